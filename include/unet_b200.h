@@ -1,0 +1,217 @@
+/*
+ * unet_b200.h -- C ABI of the B200-native (sm_100a) U-Net hot path.
+ *
+ * The reference (FabianFalck/unet-design) is 100% Python and has no FFI of its own; its
+ * "plugin API" for this path is the nn.Module contract of its model classes.
+ * This header is the boundary a maintainer of the reference would bind instead of the
+ * ATen / pytorch_wavelets calls listed beside each entry point (file:line under the
+ * reference root).  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns all memory (inputs, outputs, workspaces); nothing is allocated here,
+ *     so a caching allocator and CUDA-graph capture keep working;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant,
+ *     and keeps no mutable global state;
+ *   - return value: 0 = ok, <0 = UB200_E_* (bad argument / unsupported shape / no device
+ *     code for this GPU), >0 = a cudaError_t from the launch.  Nothing throws or exits.
+ *   - "NCHW f32"  = contiguous float  [N, C, H, W]   (the reference's layout and dtype)
+ *     "NHWC bf16" = __nv_bfloat16 [N, H, W, C] with an explicit pixel stride `ld` (elements
+ *                   between consecutive pixels, >= C): a tensor may be a channel slice of a
+ *                   wider buffer, which is how torch.cat([h, skip], 1) disappears.
+ */
+#ifndef UNET_B200_H
+#define UNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UB200_OK 0
+#define UB200_E_BADARG (-1)       /* null pointer, non-positive extent, misaligned pointer */
+#define UB200_E_UNSUPPORTED (-2)  /* shape outside what the kernel family covers */
+#define UB200_E_NODEVICE (-3)     /* not an sm_100 device */
+
+/* Library identification; safe to call without a GPU. */
+const char *ub200_version(void);
+int ub200_abi_version(void);
+/* Name of a status code returned by any entry point ("ok", "bad argument", cudaGetErrorName...). */
+const char *ub200_status_string(int status);
+
+/* ------------------------------------------------------------------------------------------
+ * Haar wavelet (replaces pytorch_wavelets.DWTForward / DWTInverse, mode='zero', wave='haar';
+ * reference call sites diff_cifar/model.py:263-267,:310-311; diff_cifar/diffusion.py:63-66;
+ * pdearena/pdearena/modules/twod_unetbase.py:169-170,:179-180; wmh/model.py:68-69,:81-82).
+ * All NCHW f32.  planes = N*C.  h2 = ceil(H/2), w2 = ceil(W/2); an odd extent is extended by
+ * one zero at its end.
+ * ------------------------------------------------------------------------------------------ */
+
+/* One analysis level.  x [planes,H,W] -> ll [planes,h2,w2], highs [planes,3,h2,w2] in the order
+ * LH (W-low,H-high), HL (W-high,H-low), HH.  highs may be NULL (LL only).  Also the adjoint of
+ * ub200_haar_idwt2d (backward of the synthesis). */
+int ub200_haar_dwt2d_fwd(const float *x, int64_t planes, int64_t H, int64_t W,
+                         float *ll, float *highs, void *stream);
+
+/* One synthesis level.  ll [planes,h2,w2], highs [planes,3,h2,w2] (NULL = zeros) ->
+ * out [planes,Hout,Wout] with Hout in {2*h2-1, 2*h2}, Wout likewise (the crop undoes the zero
+ * extension).  Also the adjoint of ub200_haar_dwt2d_fwd (its backward). */
+int ub200_haar_idwt2d(const float *ll, const float *highs, int64_t planes, int64_t h2, int64_t w2,
+                      int64_t Hout, int64_t Wout, float *out, void *stream);
+
+/* DTWBlock / DWTBlock forward (diff_cifar/model.py:270-323; diff_mnist/mnist_diff/models.py:29-82;
+ * twod_unetbase.py:173-193; wmh/model.py:72-95), fused:  out[n,k] = LL_J(x[n, k mod C]) / 2^J,
+ * k < out_channels, J in [0,3] (J = 0 is the channel tile alone).  x [N,C,H,W] f32 ->
+ * out [N,out_channels,ceil(H/2^J),ceil(W/2^J)] f32. */
+int ub200_dwtblock_fwd(const float *x, int64_t N, int64_t C, int64_t H, int64_t W, int J,
+                       int64_t out_channels, float *out, void *stream);
+
+/* Adjoint of ub200_dwtblock_fwd: gx[n,c] = LL_J^T( sum_{k mod C == c} gout[n,k] ) / 2^J. */
+int ub200_dwtblock_bwd(const float *gout, int64_t N, int64_t C, int64_t H, int64_t W, int J,
+                       int64_t out_channels, float *gx, void *stream);
+
+/* Same forward, written straight into the conv blocks' layout: out NHWC bf16 with pixel stride
+ * ld_out (the skip half of a torch.cat([h, skip], 1) buffer; diff_cifar/model.py:454).
+ * chmap (device int32 [out_channels], nullable) gives the source channel of every output channel;
+ * NULL means k mod C.  A chain of DTWBlocks composes into one map, e.g. ((k mod 256) mod 128) mod 3,
+ * so the whole Haar encoder reads only the 3-channel image pyramid.  out_channels % 8 == 0. */
+int ub200_dwtblock_fwd_nhwc_bf16(const float *x, int64_t N, int64_t C, int64_t H, int64_t W, int J,
+                                 int64_t out_channels, const int32_t *chmap, void *out_bf16,
+                                 int64_t ld_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / resampling (memory-bound).
+ * ------------------------------------------------------------------------------------------ */
+
+/* NCHW f32 [N,C,H,W] -> NHWC bf16 (pixel stride ld) and back (boundary of the drop-in modules). */
+int ub200_nchw_f32_to_nhwc_bf16(const float *x, int64_t N, int64_t C, int64_t H, int64_t W,
+                                void *out_bf16, int64_t ld, void *stream);
+int ub200_nhwc_bf16_to_nchw_f32(const void *x_bf16, int64_t ld, int64_t N, int64_t C, int64_t H,
+                                int64_t W, float *out, void *stream);
+
+/* F.interpolate(scale_factor=2, mode='nearest') (diff_cifar/model.py:78-79; layers.py:219;
+ * twod_unetbase.py:243) on NHWC bf16: out[n,y,x,:] = in[n,y>>1,x>>1,:];  and its adjoint
+ * (sum of the 2x2 block, fp32 accumulate).  H, W are the extents of the LOW-resolution tensor
+ * (x of the forward, gx of the backward); the other side is [N,2H,2W,C].  C % 8 == 0. */
+int ub200_upsample2x_nhwc_bf16(const void *x, int64_t ld_in, int64_t N, int64_t H, int64_t W, int64_t C,
+                               void *out, int64_t ld_out, void *stream);
+int ub200_upsample2x_bwd_nhwc_bf16(const void *gout, int64_t ld_g, int64_t N, int64_t H, int64_t W,
+                                   int64_t C, void *gx, int64_t ld_gx, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm + activation (replaces nn.GroupNorm + Swish/SiLU/GELU [+ Dropout];
+ * diff_cifar/model.py:130-132,:139-142; layers.py:284-288,:330-334; twod_unetbase.py:30-31).
+ * NHWC bf16 activations, fp32 statistics and affine parameters (gamma/beta may be NULL = 1/0),
+ * biased variance.  C % 8 == 0, C <= 2048.
+ * ------------------------------------------------------------------------------------------ */
+#define UB200_ACT_NONE 0
+#define UB200_ACT_SILU 1
+#define UB200_ACT_GELU 2   /* exact erf form (pdearena/pdearena/modules/activations.py:3-9) */
+
+/* stats[n,g] = (sum, sum of squares) over the (C/G)*HW slab of sample n; float [N,G,2], zeroed
+ * here.  Consumers derive mean / rstd; the conv epilogue can accumulate the same layout
+ * (ub200_conv_args.gn_partial), which removes this pass. */
+int ub200_gn_stats_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, int64_t C, int G,
+                             float *stats, void *stream);
+
+/* y = dropout( act( (x - mean) * rstd * gamma[c] * (1 + scale[n,c]) + beta[c] * (1 + scale) + shift[n,c] ) )
+ * scale/shift (float [N,C]) may be NULL (diff_mnist's use_scale_shift_norm, layers.py:330-334).
+ * Dropout: keep-probability 1-p, Philox4x32-10 counter (seed, offset + *offset_dev + element index/4),
+ * scaled 1/(1-p); p = 0 disables it.  offset_dev (nullable) is a device-resident counter so that a
+ * captured CUDA graph draws a fresh mask on every replay; backward passes the same triple. */
+int ub200_gn_act_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t HW, int64_t C, int G,
+                               const float *stats, float eps, const float *gamma, const float *beta,
+                               const float *scale, const float *shift, int act,
+                               float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                               void *y, int64_t ld_y, void *stream);
+
+/* Backward of the above.  gy, x NHWC bf16 -> gx NHWC bf16 (accumulate=1 adds into gx),
+ * dgamma/dbeta float [C] (accumulated with atomics: zero them first), dscale/dshift float [N,C]
+ * (NULL when unused).  ws is a float workspace of ub200_gn_act_bwd_ws_floats(N, C, G) elements. */
+size_t ub200_gn_act_bwd_ws_floats(int64_t N, int64_t C, int G);
+int ub200_gn_act_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int64_t ld_x,
+                               int64_t N, int64_t HW, int64_t C, int G,
+                               const float *stats, float eps, const float *gamma, const float *beta,
+                               const float *scale, const float *shift, int act,
+                               float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                               void *gx, int64_t ld_gx, int accumulate,
+                               float *dgamma, float *dbeta, float *dscale, float *dshift,
+                               float *ws, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3x3 / 1x1 convolution, stride 1, "same" zero padding, as tcgen05/TMEM implicit GEMM fed by TMA
+ * (replaces nn.Conv2d fprop / dgrad / wgrad; diff_cifar/model.py:69,:133,:143,:146,:396;
+ * layers.py:286,:300,:305-312; twod_unetbase.py:19-24).  Activations NHWC bf16, weights packed
+ * bf16 [Cout, kh, kw, Cin] (ub200_pack_conv_weight), fp32 accumulation in TMEM.
+ *
+ *   out[n,y,x,co] = bias[co] + rowadd[n,co] + residual[n,y,x,co]
+ *                 + sum_{ky,kx,ci} a [n,y+ky-p,x+kx-p,ci] * w [co,ky,kx,ci]
+ *                 + sum_{ci2}      a2[n,y,x,ci2]          * w2[co,ci2]          (optional 1x1 term:
+ *                   the ResBlock shortcut folded in as extra K slices; model.py:145-148,:167)
+ *
+ * bias / rowadd (the temb projection, model.py:164) / residual / a2+w2 may be NULL.
+ * Cin, Cin2 multiples of 16.  Cout is arbitrary for the fp32 NCHW output (the packed weights are
+ * padded to a multiple of 16 rows) and a multiple of 8 for the bf16 NHWC output.
+ * dgrad is the same entry point called with spatially flipped, transposed packed weights
+ * (ub200_pack_conv_weight with transpose_flip = 1).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ub200_conv_args {
+    const void *a;  int64_t ld_a;  int64_t Cin;      /* NHWC bf16 input, pixel stride, channels      */
+    const void *w;                                   /* packed bf16 [Cout, k, k, Cin]                 */
+    int ksize;                                       /* 3 or 1                                        */
+    const void *a2; int64_t ld_a2; int64_t Cin2;     /* optional 1x1 term                             */
+    const void *w2;                                  /* packed bf16 [Cout, Cin2]                      */
+    const float *bias;                               /* [Cout] or NULL                                */
+    const float *rowadd;                             /* [N, Cout] or NULL                             */
+    const void *residual; int64_t ld_res;            /* NHWC bf16 [N,H,W,Cout] or NULL                */
+    void *out; int64_t ld_out;                       /* NHWC bf16 output                              */
+    float *out_f32_nchw;                             /* optional: also/instead write NCHW f32 output  */
+    int64_t N, H, W, Cout;
+    float *gn_partial;                               /* optional [N, G, 2] sum / sumsq of the output  */
+    int gn_groups;                                   /*   (next layer's GroupNorm statistics) or 0    */
+} ub200_conv_args;
+
+int ub200_conv_fprop(const ub200_conv_args *args, void *stream);
+
+/* dW[co,ky,kx,ci] += sum_{n,y,x} gout[n,y,x,co] * a[n,y+ky-p,x+kx-p,ci]   (fp32, packed layout
+ * [Cout,k,k,Cin] = the channels_last memory of the torch weight).  The pixel range is split across
+ * CTAs and reduced with fp32 atomics, so the call ACCUMULATES: zero dw first for a plain gradient.
+ * Cin, Cout multiples of 16. */
+int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a,
+                     int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize,
+                     float *dw, void *stream);
+
+/* Channel sums of an NHWC bf16 tensor: per_sample[N,C] += sum_p x[n,p,c] (the time-embedding /
+ * scale-shift gradient) and/or total[C] += sum_{n,p} x (the conv bias gradient).  Accumulates. */
+int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, int64_t C,
+                            float *per_sample, float *total, void *stream);
+
+/* fp32 weight (element (co,ci,ky,kx) at w[co*s_co + ci*s_ci + ky*s_ky + kx*s_kx], so both the
+ * contiguous torch layout and channels_last work) -> packed bf16 [rows_pad,k,k,cols]:
+ * transpose_flip = 0: rows = Cout, cols = Cin (fprop / wgrad operand);
+ * transpose_flip = 1: rows = Cin, cols = Cout, taps rotated by 180 degrees (dgrad operand).
+ * rows_pad = rows rounded up to 16, padding rows are zero. */
+int ub200_pack_conv_weight(const float *w, int64_t Cout, int64_t Cin, int ksize,
+                           int64_t s_co, int64_t s_ci, int64_t s_ky, int64_t s_kx,
+                           int transpose_flip, void *out_bf16, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Train-step tail (diff_cifar/main.py:425-429, :57-77): global-norm clip + Adam + EMA over a
+ * flat fp32 parameter arena, no host synchronisation.
+ * ------------------------------------------------------------------------------------------ */
+/* sumsq[0] += sum(g^2) */
+int ub200_sumsq_f32(const float *g, int64_t n, float *sumsq, void *stream);
+/* g' = g * grad_scale * min(1, max_norm / (sqrt(sumsq[0]) * grad_scale + 1e-6))  (sumsq NULL or
+ * max_norm <= 0: no clip); torch.optim.Adam update with bias correction for the 1-based step_host;
+ * ema = decay*ema + (1-decay)*p (ema NULL to skip). */
+int ub200_adam_ema_step_f32(float *p, const float *g, float *m, float *v, float *ema, int64_t n,
+                            const float *sumsq, float max_norm, float grad_scale,
+                            float lr, float beta1, float beta2, float eps, float ema_decay,
+                            int64_t step_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNET_B200_H */

@@ -1,0 +1,98 @@
+"""CPU checks of the diff_cifar drop-in's Python side (level bookkeeping, channel maps, autograd glue,
+state_dict surface) against the golden vectors of the reference's own classes, with the kernels replaced
+by the test-only emulation of their contract.  Tolerances are bf16-level: activations are bf16 here."""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+TOL = 2e-2   # bf16 activations between layers (north_star: <= 1e-2 relative for the CUDA path per block)
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), map_location="cpu", weights_only=False)
+
+
+def test_state_dict_surface_matches_reference(golden_dir, emulated_ops):
+    from unet_design_b200.diff_cifar.model import UNetWaveletEnc
+    for tag in ("multiresnet", "unet"):
+        g = _load(golden_dir, f"cifar_{tag}.pt")
+        net = UNetWaveletEnc(**g["cfg"])
+        ours = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        ref = {k: tuple(v.shape) for k, v in g["state"].items()}
+        assert ours == ref
+        res = net.load_state_dict(g["state"], strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        # conv weights stay in [Cout, kh, kw, Cin] memory order after loading
+        w = net.upblocks[0][0].block1[2].weight
+        assert w.permute(0, 2, 3, 1).is_contiguous()
+
+
+@pytest.mark.parametrize("tag", ["resblock_sc", "resblock_id", "resblock_attn"])
+def test_resblock(golden_dir, emulated_ops, tag):
+    from unet_design_b200.diff_cifar.model import ResBlock
+    g = _load(golden_dir, f"cifar_{tag}.pt")
+    blk = ResBlock(**g["cfg"])
+    blk.load_state_dict(g["state"])
+    x = g["x"].clone().requires_grad_(True)
+    temb = g["temb"].clone().requires_grad_(True)
+    y = blk(x, temb)
+    y.backward(g["gy"])
+    assert rel_err(y, g["y"]) < TOL
+    assert rel_err(x.grad, g["gx"]) < TOL
+    assert rel_err(temb.grad, g["gtemb"]) < TOL
+    for n, p in blk.named_parameters():
+        if n.endswith("proj_k.bias"):      # exactly zero in exact arithmetic (softmax shift invariance)
+            continue
+        assert rel_err(p.grad, g["gparams"][n]) < 3 * TOL, n
+
+
+def test_upsample(golden_dir, emulated_ops):
+    from unet_design_b200.diff_cifar.model import UpSample
+    g = _load(golden_dir, "cifar_upsample.pt")
+    up = UpSample(32)
+    up.load_state_dict(g["state"])
+    x = g["x"].clone().requires_grad_(True)
+    y = up(x, None)
+    y.backward(g["gy"])
+    assert rel_err(y, g["y"]) < TOL and rel_err(x.grad, g["gx"]) < TOL
+    for n, p in up.named_parameters():
+        assert rel_err(p.grad, g["gparams"][n]) < TOL, n
+
+
+def test_dtwblock(golden_dir, emulated_ops):
+    from unet_design_b200.diff_cifar.model import DTWBlock
+    for case in _load(golden_dir, "cifar_dtwblock.pt"):
+        y = DTWBlock(case["J"], case["out_channels"])(case["x"])
+        assert y.shape == case["y"].shape and rel_err(y, case["y"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["multiresnet", "unet"])
+def test_model_forward_backward(golden_dir, emulated_ops, tag):
+    from unet_design_b200.diff_cifar.diffusion import GaussianDiffusionTrainer
+    from unet_design_b200.diff_cifar.model import UNetWaveletEnc
+    g = _load(golden_dir, f"cifar_{tag}.pt")
+    net = UNetWaveletEnc(**g["cfg"])
+    net.load_state_dict(g["state"])
+    with torch.no_grad():
+        out = net(g["x_t"], g["t"])
+        out1 = net(g["x_t"][:, :, ::2, ::2].contiguous(), g["t"], n_levels_used=1)
+    outs = out if isinstance(out, list) else [out]
+    gouts = g["out"] if isinstance(g["out"], list) else [g["out"]]
+    assert len(outs) == len(gouts)
+    for a, b in zip(outs, gouts):
+        assert a.shape == b.shape and rel_err(a, b) < 3 * TOL
+    a1 = out1[-1] if isinstance(out1, list) else out1
+    b1 = g["out_1lvl"][-1] if isinstance(g["out_1lvl"], list) else g["out_1lvl"]
+    assert rel_err(a1, b1) < 3 * TOL
+    trainer = GaussianDiffusionTrainer(net, 1e-4, 0.02, g["cfg"]["T"], g["cfg"]["multi_res_loss"], False, "cpu")
+    loss, loss_list = trainer.loss_from(g["x0"], g["t"], g["noise"])
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) < 2e-2 * abs(float(g["loss"]))
+    params = dict(net.named_parameters())
+    for n, gr in g["gparams"].items():
+        if n.endswith("proj_k.bias"):
+            continue
+        assert rel_err(params[n].grad, gr, floor=1e-4) < 6e-2, n

@@ -50,8 +50,8 @@ def cifar_goldens():
     d = load_reference_module("ref_cifar_diffusion", f"{REF}/diff_cifar/diffusion.py")
 
     # --- one ResBlock with a 1x1 shortcut, and one without (reference diff_cifar/model.py:122-169)
-    for tag, cin, cout, attn in (("resblock_sc", 96, 32, False), ("resblock_id", 32, 32, False),
-                                 ("resblock_attn", 32, 32, True)):
+    for tag, cin, cout, attn in (("resblock_sc", 96, 64, False), ("resblock_id", 64, 64, False),
+                                 ("resblock_attn", 64, 64, True)):
         torch.manual_seed(1234)
         blk = m.ResBlock(cin, cout, tdim=128, dropout=0.0, attn=attn).double().float()
         # conv2 starts at gain 1e-5: give it weight so its gradient path is exercised

@@ -1,0 +1,327 @@
+// 3x3 / 1x1 stride-1 "same" convolution forward (and, with transposed+rotated weights, dgrad) as an
+// implicit GEMM on the 5th-generation tensor cores:
+//
+//   D[128 pixels, BN channels] (fp32, TMEM)  +=  A[128 pixels, BK] (bf16, smem)  x  W[BN, BK]^T (bf16, smem)
+//
+// * A is never materialised as an im2col matrix.  The activation tensor is NHWC bf16; a pixel tile is a
+//   BW x BH x BNI box of (x, y, n) with BW*BH*BNI = 128, and the tile of filter tap (ky, kx) is the SAME box
+//   shifted by (kx-1, ky-1): one 4-D TMA tiled load with signed coordinates, whose out-of-bounds elements
+//   (the zero padding, and the ragged edge of the last tile) are zero-filled by the TMA unit.  The box
+//   lands in shared memory as 128 rows x BK channels with the 128/64/32-byte swizzle tcgen05 expects
+//   (K-major canonical layout), so there is no register staging at all.
+// * W is the packed weight matrix [Cout_pad, k*k*Cin] (K contiguous), a 2-D TMA box [BN, BK].
+// * An optional second operand pair (a2, w2) appends the K slices of a 1x1 convolution of another tensor
+//   (the ResBlock shortcut, diff_cifar/model.py:145-148,:167), and the epilogue adds bias, a per-sample
+//   per-channel row (the time-embedding projection, model.py:164) and a residual tensor.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+//   warps 2..5 = epilogue (tcgen05.ld -> registers -> bf16 NHWC / fp32 NCHW global stores).
+//   smem ring of `stages` (A, W) slots with full/empty mbarriers; tcgen05.commit releases slots.
+//
+// Replaces nn.Conv2d forward/backward-data at diff_cifar/model.py:69,:133,:143,:146,:396;
+// diff_mnist/torch_ddpm/ddpm/models/unet/layers.py:286,:300,:305-312; pdearena twod_unetbase.py:19-24.
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace {
+using namespace ub;
+using namespace ub::tc;
+
+struct FpropParams {
+    int N, H, W, Cout;
+    int BW, BH, BNI, tiles_w, tiles_h;
+    int BN, Cin, cblocks, taps, kb_main, kb_extra, stages;
+    uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
+    const float *bias, *rowadd;
+    const __nv_bfloat16 *residual; int64_t ld_res;
+    __nv_bfloat16 *out; int64_t ld_out;
+    float *out_nchw;
+    float *gn_partial; int gn_groups;
+};
+
+constexpr int kThreads = 192;
+
+template <int BK>
+__global__ void __launch_bounds__(kThreads) conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_a,
+                                                             const __grid_constant__ CUtensorMap tm_w,
+                                                             const __grid_constant__ CUtensorMap tm_a2,
+                                                             const __grid_constant__ CUtensorMap tm_w2,
+                                                             const FpropParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages x A][stages x B][full barriers][empty barriers][tmem_full][tmem ptr]
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem_a + (size_t)p.stages * p.a_stage_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_b + (size_t)p.stages * p.b_stage_bytes);
+    uint64_t *empty = full + p.stages;
+    uint64_t *tmem_full = empty + p.stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int mt = blockIdx.x;
+    const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+    const int th = mt % p.tiles_h; mt /= p.tiles_h;
+    const int x0 = tw * p.BW, y0 = th * p.BH, n0 = mt * p.BNI;
+    const int co0 = blockIdx.y * p.BN;
+    const int num_kb = p.kb_main + p.kb_extra;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_a);
+        prefetch_tmap(&tm_w);
+        if (p.kb_extra) { prefetch_tmap(&tm_a2); prefetch_tmap(&tm_w2); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t tx_bytes = 128u * BK * 2u + (uint32_t)p.BN * BK * 2u;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(empty + s, ph ^ 1u);
+                mbar_arrive_expect_tx(full + s, tx_bytes);
+                uint8_t *dst_a = smem_a + (size_t)s * p.a_stage_bytes;
+                uint8_t *dst_b = smem_b + (size_t)s * p.b_stage_bytes;
+                if (kb < p.kb_main) {
+                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                    const int ky = p.taps == 9 ? tap / 3 - 1 : 0, kx = p.taps == 9 ? tap % 3 - 1 : 0;
+                    tma_load_4d(dst_a, &tm_a, full + s, cb * BK, x0 + kx, y0 + ky, n0);
+                    tma_load_2d(dst_b, &tm_w, full + s, tap * p.Cin + cb * BK, co0);
+                } else {
+                    const int cb = kb - p.kb_main;
+                    tma_load_4d(dst_a, &tm_a2, full + s, cb * BK, x0, y0, n0);
+                    tma_load_2d(dst_b, &tm_w2, full + s, cb * BK, co0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, p.BN, 0, 0);
+            constexpr uint32_t swz = swizzle_code(BK * 2);
+            constexpr uint32_t sbo = 8u * BK * 2u;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(full + s, ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem_a + (size_t)s * p.a_stage_bytes);
+                const uint32_t b_addr = smem_u32(smem_b + (size_t)s * p.b_stage_bytes);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, swz);
+                    const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, swz);
+                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(empty + s);                       // slot reusable once these MMAs have read it
+                if (kb == num_kb - 1) umma_commit(tmem_full); // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue: 4 warps, one TMEM lane quadrant each =====================
+        const int qd = warp & 3;
+        const int r = qd * 32 + lane;                 // row of the tile == TMEM lane
+        const int wi = r % p.BW, hi = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
+        const int x = x0 + wi, y = y0 + hi, n = n0 + ni;
+        const bool valid = x < p.W && y < p.H && n < p.N;
+        const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16);
+        for (int cg = 0; cg < p.BN / 16; ++cg) {
+            float v[16];
+            tmem_ld16(trow + cg * 16, v);
+            const int co = co0 + cg * 16;
+            if (!valid || co >= p.Cout) continue;
+            const int nv = p.Cout - co < 16 ? p.Cout - co : 16;
+            if (p.bias) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (i < nv) v[i] += __ldg(p.bias + co + i);
+            }
+            if (p.rowadd) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (i < nv) v[i] += __ldg(p.rowadd + (int64_t)n * p.Cout + co + i);
+            }
+            if (p.residual) {
+                const __nv_bfloat16 *rp = p.residual + pix * p.ld_res + co;
+                if (nv == 16) {
+                    float f[8];
+                    unpack8(*reinterpret_cast<const uint4 *>(rp), f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += f[i];
+                    unpack8(*reinterpret_cast<const uint4 *>(rp + 8), f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
+                } else {
+                    for (int i = 0; i < nv; ++i) v[i] += __bfloat162float(rp[i]);
+                }
+            }
+            if (p.out) {
+                __nv_bfloat16 *op = p.out + pix * p.ld_out + co;
+                if (nv == 16) {
+                    float f[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = v[i];
+                    *reinterpret_cast<uint4 *>(op) = pack8(f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = v[8 + i];
+                    *reinterpret_cast<uint4 *>(op + 8) = pack8(f);
+                } else {
+                    for (int i = 0; i < nv; ++i) op[i] = __float2bfloat16_rn(v[i]);
+                }
+            }
+            if (p.out_nchw) {
+                const int64_t hw = (int64_t)p.H * p.W;
+                float *op = p.out_nchw + ((int64_t)n * p.Cout + co) * hw + (int64_t)y * p.W + x;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) if (i < nv) op[i * hw] = v[i];
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------------
+struct PixelTile { int BW, BH, BNI; };
+
+// box of 128 pixels (powers of two per axis) that wastes the fewest rows on ragged edges
+PixelTile pick_pixel_tile(int64_t N, int64_t H, int64_t W) {
+    PixelTile best{1, 1, 128};
+    double best_cost = 1e300;
+    for (int bw = 1; bw <= 128; bw *= 2)
+        for (int bh = 1; bw * bh <= 128; bh *= 2) {
+            const int bn = 128 / (bw * bh);
+            const double cost = (double)((W + bw - 1) / bw * bw) * (double)((H + bh - 1) / bh * bh) *
+                                (double)((N + bn - 1) / bn * bn);
+            // ties: prefer wide boxes (longer contiguous runs per TMA row)
+            if (cost < best_cost - 0.5 || (cost < best_cost + 0.5 && bw > best.BW)) { best_cost = cost; best = {bw, bh, bn}; }
+        }
+    return best;
+}
+
+int pick_bk(int64_t Cin, int64_t Cin2) {
+    for (int bk : {64, 32, 16})
+        if (Cin % bk == 0 && (Cin2 == 0 || Cin2 % bk == 0)) return bk;
+    return 0;
+}
+
+uint32_t pow2_at_least(uint32_t v, uint32_t lo) { uint32_t r = lo; while (r < v) r <<= 1; return r; }
+
+template <int BK>
+int launch_fprop(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &ta2, const CUtensorMap &tw2,
+                 const FpropParams &p, dim3 grid, size_t smem, cudaStream_t s) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(conv_fprop_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
+    if (attr_err != cudaSuccess) return (int)attr_err;
+    conv_fprop_kernel<BK><<<grid, kThreads, smem, s>>>(ta, tw, ta2, tw2, p);
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+}  // namespace
+
+extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
+    UB_REQUIRE(a && a->a && a->w && (a->out || a->out_f32_nchw), UB200_E_BADARG);
+    UB_REQUIRE(a->N > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, UB200_E_BADARG);
+    UB_REQUIRE(a->ksize == 1 || a->ksize == 3, UB200_E_UNSUPPORTED);
+    const bool extra = a->a2 != nullptr;
+    UB_REQUIRE(!extra || (a->w2 && a->Cin2 > 0), UB200_E_BADARG);
+    const int bk = pick_bk(a->Cin, extra ? a->Cin2 : 0);
+    UB_REQUIRE(bk != 0, UB200_E_UNSUPPORTED);
+    UB_REQUIRE(a->ld_a % 8 == 0 && a->ld_a >= a->Cin && ub::aligned16(a->a), UB200_E_UNSUPPORTED);
+    UB_REQUIRE(!extra || (a->ld_a2 % 8 == 0 && a->ld_a2 >= a->Cin2 && ub::aligned16(a->a2)), UB200_E_UNSUPPORTED);
+    UB_REQUIRE(!a->out || (a->Cout % 8 == 0 && a->ld_out % 8 == 0 && a->ld_out >= a->Cout && ub::aligned16(a->out)),
+               UB200_E_UNSUPPORTED);
+    UB_REQUIRE(!a->residual || (a->ld_res % 8 == 0 && a->ld_res >= a->Cout && ub::aligned16(a->residual) && a->Cout % 8 == 0),
+               UB200_E_UNSUPPORTED);
+    UB_REQUIRE(a->N < (1 << 24) && a->H < (1 << 15) && a->W < (1 << 15) && a->Cin <= 16384 && a->Cout <= 16384,
+               UB200_E_UNSUPPORTED);
+
+    const int64_t cout_pad = (a->Cout + 15) / 16 * 16;
+    FpropParams p{};
+    p.N = (int)a->N; p.H = (int)a->H; p.W = (int)a->W; p.Cout = (int)a->Cout;
+    const PixelTile pt = pick_pixel_tile(a->N, a->H, a->W);
+    p.BW = pt.BW; p.BH = pt.BH; p.BNI = pt.BNI;
+    p.tiles_w = (p.W + p.BW - 1) / p.BW;
+    p.tiles_h = (p.H + p.BH - 1) / p.BH;
+    const int tiles_n = (p.N + p.BNI - 1) / p.BNI;
+    p.BN = (int)(cout_pad < 128 ? cout_pad : 128);
+    p.Cin = (int)a->Cin;
+    p.cblocks = (int)(a->Cin / bk);
+    p.taps = a->ksize * a->ksize;
+    p.kb_main = p.taps * p.cblocks;
+    p.kb_extra = extra ? (int)(a->Cin2 / bk) : 0;
+    p.a_stage_bytes = 128u * bk * 2u;
+    p.b_stage_bytes = ((uint32_t)p.BN * bk * 2u + 1023u) & ~1023u;
+    const uint32_t stage = p.a_stage_bytes + p.b_stage_bytes;
+    int stages = (int)((100u * 1024u) / stage);
+    if (stages > 8) stages = 8;
+    if (stages > p.kb_main + p.kb_extra) stages = p.kb_main + p.kb_extra;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    p.tmem_cols = pow2_at_least((uint32_t)p.BN, 32);
+    p.bias = a->bias; p.rowadd = a->rowadd;
+    p.residual = reinterpret_cast<const __nv_bfloat16 *>(a->residual); p.ld_res = a->ld_res;
+    p.out = reinterpret_cast<__nv_bfloat16 *>(a->out); p.ld_out = a->ld_out;
+    p.out_nchw = a->out_f32_nchw;
+    p.gn_partial = a->gn_partial; p.gn_groups = a->gn_groups;
+    UB_REQUIRE(!a->gn_partial, UB200_E_UNSUPPORTED);   // epilogue statistics: not in this build yet
+
+    // tensor maps
+    CUtensorMap ta, tw, ta2, tw2;
+    {
+        const int64_t dims[4] = {a->Cin, a->W, a->H, a->N};
+        const int64_t str[3] = {a->ld_a, a->ld_a * a->W, a->ld_a * a->W * a->H};
+        const int box[4] = {bk, p.BW, p.BH, p.BNI};
+        int rc = encode_bf16_tensor_map(&ta, a->a, 4, dims, str, box);
+        if (rc) return rc;
+        const int64_t wd[2] = {(int64_t)p.taps * a->Cin, cout_pad};
+        const int64_t ws[1] = {(int64_t)p.taps * a->Cin};
+        const int wb[2] = {bk, p.BN};
+        rc = encode_bf16_tensor_map(&tw, a->w, 2, wd, ws, wb);
+        if (rc) return rc;
+    }
+    if (extra) {
+        const int64_t dims[4] = {a->Cin2, a->W, a->H, a->N};
+        const int64_t str[3] = {a->ld_a2, a->ld_a2 * a->W, a->ld_a2 * a->W * a->H};
+        const int box[4] = {bk, p.BW, p.BH, p.BNI};
+        int rc = encode_bf16_tensor_map(&ta2, a->a2, 4, dims, str, box);
+        if (rc) return rc;
+        const int64_t wd[2] = {a->Cin2, cout_pad};
+        const int64_t ws[1] = {a->Cin2};
+        const int wb[2] = {bk, p.BN};
+        rc = encode_bf16_tensor_map(&tw2, a->w2, 2, wd, ws, wb);
+        if (rc) return rc;
+    } else {
+        ta2 = ta; tw2 = tw;
+    }
+
+    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)((cout_pad + p.BN - 1) / p.BN), 1);
+    const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
+    cudaStream_t s = ub::as_stream(stream);
+    switch (bk) {
+        case 64: return launch_fprop<64>(ta, tw, ta2, tw2, p, grid, smem, s);
+        case 32: return launch_fprop<32>(ta, tw, ta2, tw2, p, grid, smem, s);
+        default: return launch_fprop<16>(ta, tw, ta2, tw2, p, grid, smem, s);
+    }
+}

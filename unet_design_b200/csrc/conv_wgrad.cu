@@ -1,0 +1,316 @@
+// Weight gradient of the 3x3 / 1x1 stride-1 "same" convolution on tcgen05 tensor cores.
+//
+//   dW[co, (ky,kx), ci] += sum over pixels  G[pix, co] * A[pix + (ky-1, kx-1), ci]
+//
+// is a GEMM whose reduction dimension is the PIXEL index, so both operands are "MN-major" for the tensor
+// core: a TMA box of 64 pixels x CW channels of an NHWC tensor lands in shared memory as 64 rows (K) of
+// CW contiguous channels (M or N) -- exactly the canonical MN-major swizzled layout -- and is consumed
+// in place.  One CTA owns a [128 co] x [<=128 ci] x [3 taps of one filter row] slab of dW: three fp32
+// accumulators in TMEM (3 x 128 columns), fed by one G tile and three shifted A tiles per 64-pixel stage
+// (the shifts are TMA coordinates; zero padding is the TMA out-of-bounds fill).  The pixel range is split
+// across CTAs (split-K) and the partial slabs are reduced with 128-bit fp32 atomics into dW, which is kept
+// in the packed [Cout, k, k, Cin] layout (= the channels_last memory of the torch weight).
+//
+// Replaces the wgrad half of nn.Conv2d backward at the sites listed in conv_fprop.cu.
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace {
+using namespace ub;
+using namespace ub::tc;
+
+constexpr int kThreads = 192;
+constexpr int kPix = 64;   // pixels (GEMM K) per pipeline stage
+
+struct WgradParams {
+    int N, H, W, Cin, Cout, ksize;
+    int BW, BH, BNI, tiles_w, tiles_h, pix_tiles, tiles_per_split;
+    int ci_tiles, ky_groups, ntaps;     // ntaps = taps handled by one CTA (3 or 1)
+    int cw_g, cw_a;                     // channel chunk width (elements) of the G and A boxes
+    int stages;
+    uint32_t g_stage_bytes, a_tap_bytes, tmem_cols;
+    float *dw;
+};
+
+__global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g,
+                                                             const __grid_constant__ CUtensorMap tm_a,
+                                                             const WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t stage_bytes = p.g_stage_bytes + p.ntaps * p.a_tap_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t *empty = full + p.stages;
+    uint64_t *tmem_full = empty + p.stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // blockIdx.x -> (ci tile, ky group, co tile); blockIdx.y -> pixel split
+    int t = blockIdx.x;
+    const int cit = t % p.ci_tiles; t /= p.ci_tiles;
+    const int kyg = t % p.ky_groups; t /= p.ky_groups;
+    const int co0 = t * 128, ci0 = cit * 128;
+    const int ncols = (p.Cin - ci0 < 128 ? p.Cin - ci0 : 128);          // multiple of 16
+    const int mrows = (p.Cout - co0 < 128 ? p.Cout - co0 : 128);
+    const int chunks_g = (mrows + p.cw_g - 1) / p.cw_g, chunks_a = (ncols + p.cw_a - 1) / p.cw_a;
+    const int pt0 = blockIdx.y * p.tiles_per_split;
+    int pt1 = pt0 + p.tiles_per_split;
+    if (pt1 > p.pix_tiles) pt1 = p.pix_tiles;
+    const int iters = pt1 - pt0;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tm_g);
+        prefetch_tmap(&tm_a);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t g_chunk_bytes = kPix * p.cw_g * 2, a_chunk_bytes = kPix * p.cw_a * 2;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx_bytes = chunks_g * g_chunk_bytes + p.ntaps * chunks_a * a_chunk_bytes;
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                int pt = pt0 + it;
+                const int tw = pt % p.tiles_w; pt /= p.tiles_w;
+                const int th = pt % p.tiles_h; pt /= p.tiles_h;
+                const int x0 = tw * p.BW, y0 = th * p.BH, n0 = pt * p.BNI;
+                mbar_wait(empty + s, ph ^ 1u);
+                mbar_arrive_expect_tx(full + s, tx_bytes);
+                uint8_t *sg = smem + (size_t)s * stage_bytes;
+                for (int c = 0; c < chunks_g; ++c)
+                    tma_load_4d(sg + c * g_chunk_bytes, &tm_g, full + s, co0 + c * p.cw_g, x0, y0, n0);
+                for (int tp = 0; tp < p.ntaps; ++tp) {
+                    const int ky = p.ksize == 3 ? kyg - 1 : 0, kx = p.ksize == 3 ? tp - 1 : 0;
+                    uint8_t *sa = sg + p.g_stage_bytes + tp * p.a_tap_bytes;
+                    for (int c = 0; c < chunks_a; ++c)
+                        tma_load_4d(sa + c * a_chunk_bytes, &tm_a, full + s, ci0 + c * p.cw_a, x0 + kx, y0 + ky, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, ncols, 1, 1);
+            const uint32_t swz_g = swizzle_code(p.cw_g * 2), swz_a = swizzle_code(p.cw_a * 2);
+            const uint32_t row_g = p.cw_g * 2, row_a = p.cw_a * 2;
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(full + s, ph);
+                tc_fence_after();
+                const uint32_t g_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                for (int tp = 0; tp < p.ntaps; ++tp) {
+                    const uint32_t a_addr = g_addr + p.g_stage_bytes + tp * p.a_tap_bytes;
+#pragma unroll
+                    for (int k = 0; k < kPix / 16; ++k) {
+                        const uint64_t da = make_smem_desc(g_addr + k * 16 * row_g, g_chunk_bytes, 8 * row_g, swz_g);
+                        const uint64_t db = make_smem_desc(a_addr + k * 16 * row_a, a_chunk_bytes, 8 * row_a, swz_a);
+                        umma_bf16(tmem_base + tp * 128, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(empty + s);
+                if (it == iters - 1) umma_commit(tmem_full);
+            }
+        }
+    } else if (iters > 0) {
+        const int qd = warp & 3;
+        const int co = co0 + qd * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16);
+        const int taps_total = p.ksize * p.ksize;
+        for (int tp = 0; tp < p.ntaps; ++tp) {
+            const int tap = p.ksize == 3 ? kyg * 3 + tp : 0;
+            for (int cg = 0; cg < ncols / 16; ++cg) {
+                float v[16];
+                tmem_ld16(trow + tp * 128 + cg * 16, v);
+                if (co < p.Cout) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.dw + ((int64_t)co * taps_total + tap) * p.Cin + ci0 + cg * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        atomicAdd(dst + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// per-channel sums of an NHWC bf16 tensor: per_sample[N,C] and/or total[C] (atomics; caller zeroes)
+__global__ void __launch_bounds__(256) chansum_kernel(const __nv_bfloat16 *__restrict__ x, int64_t ld, int64_t HW, int C,
+                                                     int chunks, int rows, int64_t pix_per_cta,
+                                                     float *__restrict__ per_sample, float *__restrict__ total) {
+    const int64_t n = blockIdx.y;
+    const int q = threadIdx.x % chunks, r = threadIdx.x / chunks;
+    if (r >= rows) return;
+    float s[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] = 0.f;
+    const int64_t p0 = (int64_t)blockIdx.x * pix_per_cta;
+    int64_t p1 = p0 + pix_per_cta;
+    if (p1 > HW) p1 = HW;
+    for (int64_t pp = p0 + r; pp < p1; pp += rows) {
+        float f[8];
+        unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(x + (n * HW + pp) * ld + 8 * q)), f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += f[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        if (per_sample) atomicAdd(per_sample + n * C + 8 * q + u, s[u]);
+        if (total) atomicAdd(total + 8 * q + u, s[u]);
+    }
+}
+
+// fp32 weights with arbitrary strides -> packed bf16 [rows_pad, k, k, cols] (rows padded to 16 with zeros)
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, int Cout, int Cin, int k,
+                                                         int64_t s_co, int64_t s_ci, int64_t s_ky, int64_t s_kx,
+                                                         int transpose_flip, __nv_bfloat16 *__restrict__ out,
+                                                         int64_t total) {
+    const int rows = transpose_flip ? Cin : Cout, cols = transpose_flip ? Cout : Cin;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols);
+        int64_t t = i / cols;
+        const int kx = (int)(t % k); t /= k;
+        const int ky = (int)(t % k);
+        const int r = (int)(t / k);
+        float v = 0.f;
+        if (r < rows) {
+            if (!transpose_flip) v = __ldg(w + r * s_co + c * s_ci + ky * s_ky + kx * s_kx);
+            else v = __ldg(w + c * s_co + r * s_ci + (k - 1 - ky) * s_ky + (k - 1 - kx) * s_kx);
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+void pick_pixel_tile64(int64_t N, int64_t H, int64_t W, int &BW, int &BH, int &BNI) {
+    double best_cost = 1e300;
+    BW = 1; BH = 1; BNI = kPix;
+    for (int bw = 1; bw <= kPix; bw *= 2)
+        for (int bh = 1; bw * bh <= kPix; bh *= 2) {
+            const int bn = kPix / (bw * bh);
+            const double cost = (double)((W + bw - 1) / bw * bw) * (double)((H + bh - 1) / bh * bh) *
+                                (double)((N + bn - 1) / bn * bn);
+            if (cost < best_cost - 0.5 || (cost < best_cost + 0.5 && bw > BW)) { best_cost = cost; BW = bw; BH = bh; BNI = bn; }
+        }
+}
+
+int chunk_width(int64_t C) { return C % 64 == 0 ? 64 : C % 32 == 0 ? 32 : C % 16 == 0 ? 16 : 0; }
+
+}  // namespace
+
+extern "C" {
+
+int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a, int64_t N, int64_t H, int64_t W,
+                     int64_t Cin, int64_t Cout, int ksize, float *dw, void *stream) {
+    UB_REQUIRE(gout && a && dw && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, UB200_E_BADARG);
+    UB_REQUIRE(ksize == 1 || ksize == 3, UB200_E_UNSUPPORTED);
+    WgradParams p{};
+    p.cw_g = chunk_width(Cout); p.cw_a = chunk_width(Cin);
+    UB_REQUIRE(p.cw_g && p.cw_a, UB200_E_UNSUPPORTED);
+    UB_REQUIRE(ld_g % 8 == 0 && ld_a % 8 == 0 && ld_g >= Cout && ld_a >= Cin && ub::aligned16(gout) && ub::aligned16(a) &&
+                   ub::aligned16(dw),
+               UB200_E_UNSUPPORTED);
+    UB_REQUIRE(N < (1 << 24) && H < (1 << 15) && W < (1 << 15) && Cin <= 16384 && Cout <= 16384, UB200_E_UNSUPPORTED);
+    p.N = (int)N; p.H = (int)H; p.W = (int)W; p.Cin = (int)Cin; p.Cout = (int)Cout; p.ksize = ksize;
+    pick_pixel_tile64(N, H, W, p.BW, p.BH, p.BNI);
+    p.tiles_w = (p.W + p.BW - 1) / p.BW;
+    p.tiles_h = (p.H + p.BH - 1) / p.BH;
+    p.pix_tiles = p.tiles_w * p.tiles_h * ((p.N + p.BNI - 1) / p.BNI);
+    p.ci_tiles = (int)((Cin + 127) / 128);
+    p.ky_groups = ksize == 3 ? 3 : 1;
+    p.ntaps = ksize == 3 ? 3 : 1;
+    const int co_tiles = (int)((Cout + 127) / 128);
+    const int out_tiles = p.ci_tiles * p.ky_groups * co_tiles;
+    int splits = (2 * ub::kSMs + out_tiles - 1) / out_tiles;
+    if (splits > p.pix_tiles) splits = p.pix_tiles;
+    if (splits < 1) splits = 1;
+    p.tiles_per_split = (p.pix_tiles + splits - 1) / splits;
+    splits = (p.pix_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    const int ncols_max = (int)(Cin < 128 ? Cin : 128);
+    p.g_stage_bytes = kPix * 128 * 2;                       // room for a full 128-channel G tile
+    p.a_tap_bytes = (uint32_t)((kPix * ncols_max * 2 + 1023) & ~1023);
+    const uint32_t stage = p.g_stage_bytes + p.ntaps * p.a_tap_bytes;
+    int stages = (int)((200u * 1024u) / stage);
+    if (stages > 6) stages = 6;
+    if (stages > p.tiles_per_split) stages = p.tiles_per_split;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    p.tmem_cols = p.ntaps == 3 ? 512 : 128;
+    p.dw = dw;
+
+    CUtensorMap tg, ta;
+    {
+        const int64_t dims[4] = {Cout, W, H, N};
+        const int64_t str[3] = {ld_g, ld_g * W, ld_g * W * H};
+        const int box[4] = {p.cw_g, p.BW, p.BH, p.BNI};
+        int rc = encode_bf16_tensor_map(&tg, gout, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        const int64_t dims[4] = {Cin, W, H, N};
+        const int64_t str[3] = {ld_a, ld_a * W, ld_a * W * H};
+        const int box[4] = {p.cw_a, p.BW, p.BH, p.BNI};
+        int rc = encode_bf16_tensor_map(&ta, a, 4, dims, str, box);
+        if (rc) return rc;
+    }
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    });
+    if (attr_err != cudaSuccess) return (int)attr_err;
+    const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
+    dim3 grid((unsigned)out_tiles, (unsigned)splits, 1);
+    conv_wgrad_kernel<<<grid, kThreads, smem, ub::as_stream(stream)>>>(tg, ta, p);
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, int64_t C, float *per_sample, float *total,
+                            void *stream) {
+    UB_REQUIRE(x && (per_sample || total) && N > 0 && HW > 0 && C > 0, UB200_E_BADARG);
+    UB_REQUIRE(C % 8 == 0 && C <= 2048 && ld % 8 == 0 && ld >= C && ub::aligned16(x) && N <= 65535, UB200_E_UNSUPPORTED);
+    const int chunks = (int)(C / 8), rows = 256 / chunks;
+    int64_t splits = (148 * 8 + N - 1) / N;
+    const int64_t max_splits = (HW + rows - 1) / rows;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    const int64_t ppc = (HW + splits - 1) / splits;
+    splits = (HW + ppc - 1) / ppc;
+    dim3 grid((unsigned)splits, (unsigned)N, 1);
+    chansum_kernel<<<grid, 256, 0, ub::as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16 *>(x), ld, HW, (int)C,
+                                                           chunks, rows, ppc, per_sample, total);
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+int ub200_pack_conv_weight(const float *w, int64_t Cout, int64_t Cin, int ksize, int64_t s_co, int64_t s_ci,
+                           int64_t s_ky, int64_t s_kx, int transpose_flip, void *out_bf16, void *stream) {
+    UB_REQUIRE(w && out_bf16 && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3), UB200_E_BADARG);
+    const int64_t rows = transpose_flip ? Cin : Cout, cols = transpose_flip ? Cout : Cin;
+    const int64_t rows_pad = (rows + 15) / 16 * 16;
+    const int64_t total = rows_pad * ksize * ksize * cols;
+    int grid = ub::grid_for(total, 256, 8);
+    pack_weight_kernel<<<grid, 256, 0, ub::as_stream(stream)>>>(w, (int)Cout, (int)Cin, ksize, s_co, s_ci, s_ky, s_kx,
+                                                               transpose_flip, reinterpret_cast<__nv_bfloat16 *>(out_bf16),
+                                                               total);
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+// Train-step tail as flat-arena kernels: gradient sum of squares, then global-norm clip + Adam + EMA in
+// one pass, with no host synchronisation (the clip factor is computed on the device from sumsq[0]).
+// Replaces torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step + ema() at diff_cifar/main.py:425-429,
+// :57-77.  Memory-bound: reads p, g, m, v, ema and writes p, m, v, ema once (36 bytes per parameter).
+#include "common.cuh"
+
+namespace {
+using namespace ub;
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float *__restrict__ g, int64_t n, float *__restrict__ out) {
+    float acc = 0.f;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = ld_stream(reinterpret_cast<const float4 *>(g) + i);
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float t = g[(n4 << 2) + threadIdx.x]; acc += t * t; }
+    __shared__ float part[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float t = part[threadIdx.x];
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
+        if (threadIdx.x == 0) atomicAdd(out, t);
+    }
+}
+
+struct AdamArgs {
+    float max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, bc1, bc2;
+};
+
+__device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, float *ema, const AdamArgs &a, float clip) {
+    g *= clip;
+    m = a.beta1 * m + (1.f - a.beta1) * g;
+    v = a.beta2 * v + (1.f - a.beta2) * g * g;
+    // torch.optim.Adam: p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+    p -= (a.lr / a.bc1) * m / (sqrtf(v) / a.bc2 + a.eps);
+    if (ema) *ema = a.ema_decay * *ema + (1.f - a.ema_decay) * p;
+}
+
+__global__ void __launch_bounds__(256) adam_ema_kernel(float *__restrict__ p, const float *__restrict__ g,
+                                                      float *__restrict__ m, float *__restrict__ v,
+                                                      float *__restrict__ ema, int64_t n,
+                                                      const float *__restrict__ sumsq, AdamArgs a) {
+    // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1; grads arrive scaled by 1/grad_scale
+    float clip = a.grad_scale;
+    if (sumsq && a.max_norm > 0.f) {
+        const float norm = sqrtf(__ldg(sumsq)) * a.grad_scale;
+        clip *= fminf(1.f, a.max_norm / (norm + 1e-6f));
+    }
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 pp = reinterpret_cast<float4 *>(p)[i], mm = reinterpret_cast<float4 *>(m)[i], vv = reinterpret_cast<float4 *>(v)[i];
+        const float4 gg = ld_stream(reinterpret_cast<const float4 *>(g) + i);
+        float4 ee = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ema) ee = reinterpret_cast<float4 *>(ema)[i];
+        adam1(pp.x, gg.x, mm.x, vv.x, ema ? &ee.x : nullptr, a, clip);
+        adam1(pp.y, gg.y, mm.y, vv.y, ema ? &ee.y : nullptr, a, clip);
+        adam1(pp.z, gg.z, mm.z, vv.z, ema ? &ee.z : nullptr, a, clip);
+        adam1(pp.w, gg.w, mm.w, vv.w, ema ? &ee.w : nullptr, a, clip);
+        reinterpret_cast<float4 *>(p)[i] = pp; reinterpret_cast<float4 *>(m)[i] = mm; reinterpret_cast<float4 *>(v)[i] = vv;
+        if (ema) reinterpret_cast<float4 *>(ema)[i] = ee;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (n4 << 2) + threadIdx.x;
+        adam1(p[i], g[i], m[i], v[i], ema ? ema + i : nullptr, a, clip);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ub200_sumsq_f32(const float *g, int64_t n, float *sumsq, void *stream) {
+    UB_REQUIRE(g && sumsq && n > 0, UB200_E_BADARG);
+    UB_REQUIRE(ub::aligned16(g), UB200_E_UNSUPPORTED);
+    sumsq_kernel<<<ub::grid_for((n + 3) / 4, 256, 8, 2), 256, 0, ub::as_stream(stream)>>>(g, n, sumsq);
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+int ub200_adam_ema_step_f32(float *p, const float *g, float *m, float *v, float *ema, int64_t n, const float *sumsq,
+                            float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
+                            float ema_decay, int64_t step_host, void *stream) {
+    UB_REQUIRE(p && g && m && v && n > 0 && step_host >= 1, UB200_E_BADARG);
+    UB_REQUIRE(ub::aligned16(p) && ub::aligned16(g) && ub::aligned16(m) && ub::aligned16(v) && (!ema || ub::aligned16(ema)),
+               UB200_E_UNSUPPORTED);
+    AdamArgs a{max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, 0.f, 0.f};
+    a.bc1 = (float)(1.0 - pow((double)beta1, (double)step_host));
+    a.bc2 = (float)sqrt(1.0 - pow((double)beta2, (double)step_host));
+    adam_ema_kernel<<<ub::grid_for((n + 3) / 4, 256, 8, 2), 256, 0, ub::as_stream(stream)>>>(p, g, m, v, ema, n, sumsq, a);
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+}  // extern "C"

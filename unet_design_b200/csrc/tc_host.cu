@@ -1,0 +1,101 @@
+// Host-side CUtensorMap encoding for the TMA-fed kernels.  cuTensorMapEncodeTiled is a DRIVER entry
+// point: it is resolved at run time through cudaGetDriverEntryPoint so that the library links against
+// the CUDA runtime only and still loads (and exports every symbol) on a machine without a driver.
+// Encoded maps are cached by (address, shape, strides, box): the caching allocator hands the same
+// buffers back every step, so steady-state training encodes nothing.  The cache is the library's only
+// global state; it is immutable per key and guarded by a mutex (threading).
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "tc_common.cuh"
+
+namespace ub {
+namespace tc {
+namespace {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn resolve_encoder() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+struct Key {
+    uint64_t v[14];
+    bool operator==(const Key &o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct KeyHash {
+    size_t operator()(const Key &k) const {
+        uint64_t h = 1469598103934665603ull;
+        for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; }
+        return (size_t)h;
+    }
+};
+
+std::mutex g_mu;
+std::unordered_map<Key, CUtensorMap, KeyHash> g_cache;
+
+}  // namespace
+
+int encode_bf16_tensor_map(CUtensorMap *out, const void *base, int rank, const int64_t *dims,
+                           const int64_t *strides_elems, const int *box) {
+    if (!out || !base || rank < 2 || rank > 4) return UB200_E_BADARG;
+    Key key{};
+    key.v[0] = reinterpret_cast<uint64_t>(base);
+    key.v[1] = (uint64_t)rank;
+    for (int i = 0; i < rank; ++i) {
+        key.v[2 + i] = (uint64_t)dims[i];
+        key.v[6 + i] = (uint64_t)box[i];
+        if (i + 1 < rank) key.v[10 + i] = (uint64_t)strides_elems[i];
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_cache.find(key);
+        if (it != g_cache.end()) { *out = it->second; return UB200_OK; }
+    }
+    EncodeTiledFn enc = resolve_encoder();
+    if (!enc) return UB200_E_NODEVICE;
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t gbox[4], estr[4];
+    for (int i = 0; i < rank; ++i) {
+        if (dims[i] <= 0 || box[i] <= 0 || box[i] > 256) return UB200_E_UNSUPPORTED;
+        gdim[i] = (cuuint64_t)dims[i];
+        gbox[i] = (cuuint32_t)box[i];
+        estr[i] = 1;
+        if (i + 1 < rank) {
+            if (strides_elems[i] <= 0 || (strides_elems[i] * 2) % 16 != 0) return UB200_E_UNSUPPORTED;
+            gstr[i] = (cuuint64_t)strides_elems[i] * 2;
+        }
+    }
+    const int row_bytes = box[0] * 2;
+    CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                           : row_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                           : row_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
+                                              : CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (swz == CU_TENSOR_MAP_SWIZZLE_NONE) return UB200_E_UNSUPPORTED;
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, gbox,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return UB200_E_UNSUPPORTED;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_cache.size() > 65536) g_cache.clear();   // bounded; a changing allocator pattern just re-encodes
+        g_cache.emplace(key, m);
+    }
+    *out = m;
+    return UB200_OK;
+}
+
+}  // namespace tc
+}  // namespace ub

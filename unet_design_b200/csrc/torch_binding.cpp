@@ -1,0 +1,298 @@
+// PyTorch C++ extension: torch.ops.unet_b200.* over the C ABI of include/unet_b200.h.
+// PyTorch is plumbing here (device memory, current stream, autograd glue lives in Python); every op
+// validates device / dtype / strides, fetches the current CUDA stream and calls one extern "C" entry
+// point.  Errors surface as c10::Error on the Python side; there is no CPU or eager fallback.
+//
+// NHWC bf16 activations are torch tensors of logical shape [N, H, W, C] whose last stride is 1 and whose
+// pixel stride `ld` = stride(2) may exceed C (a channel slice of a wider buffer: torch.cat elided).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+#include <torch/types.h>
+
+#include "unet_b200.h"
+
+namespace {
+
+using at::Tensor;
+
+// fail loudly (no CPU fallback) before touching the device
+#define UB_GUARD(t)                                                                                         \
+    TORCH_CHECK((t).is_cuda(), "unet_b200: expected a CUDA tensor; this build has no CPU path");            \
+    const c10::cuda::CUDAGuard guard((t).device())
+
+
+void check_rc(int rc, const char *what) {
+    TORCH_CHECK(rc == 0, "unet_b200::", what, " failed: ", ub200_status_string(rc), " (", rc, ")");
+}
+
+void *cur_stream() { return (void *)at::cuda::getCurrentCUDAStream().stream(); }
+
+struct Nhwc {
+    void *ptr; int64_t N, H, W, C, ld;
+};
+
+Nhwc nhwc(const Tensor &t, const char *name) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.dim() == 4, name, ": expected a CUDA bf16 [N,H,W,C] tensor");
+    const int64_t N = t.size(0), H = t.size(1), W = t.size(2), C = t.size(3);
+    const int64_t ld = W > 1 ? t.stride(2) : (H > 1 ? t.stride(1) : (N > 1 ? t.stride(0) : C));
+    TORCH_CHECK(C == 1 || t.stride(3) == 1, name, ": channel stride must be 1");
+    TORCH_CHECK((W == 1 || t.stride(2) == ld) && (H == 1 || t.stride(1) == W * ld) && (N == 1 || t.stride(0) == H * W * ld),
+                name, ": not a dense NHWC view (pixel stride ", ld, ")");
+    return {t.data_ptr(), N, H, W, C, ld};
+}
+
+const float *f32(const Tensor &t, const char *name) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kFloat && t.is_contiguous(), name, ": expected a contiguous CUDA fp32 tensor");
+    return t.data_ptr<float>();
+}
+const float *f32_opt(const c10::optional<Tensor> &t, const char *name) { return t.has_value() ? f32(*t, name) : nullptr; }
+float *f32_mut(const Tensor &t, const char *name) { return const_cast<float *>(f32(t, name)); }
+const uint64_t *i64_opt(const c10::optional<Tensor> &t) {
+    if (!t.has_value()) return nullptr;
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->numel() >= 1, "offset_dev: expected a CUDA int64 tensor");
+    return reinterpret_cast<const uint64_t *>(t->data_ptr<int64_t>());
+}
+
+// ---------------------------------------------------------------- Haar
+std::tuple<Tensor, Tensor> haar_dwt2d_fwd(const Tensor &x, bool want_highs) {
+    TORCH_CHECK(x.dim() == 4, "haar_dwt2d_fwd: expected [N,C,H,W]");
+    UB_GUARD(x);
+    const float *xp = f32(x, "x");
+    const int64_t N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3), h2 = (H + 1) / 2, w2 = (W + 1) / 2;
+    Tensor ll = at::empty({N, C, h2, w2}, x.options());
+    Tensor highs = want_highs ? at::empty({N, C, 3, h2, w2}, x.options()) : at::empty({0}, x.options());
+    check_rc(ub200_haar_dwt2d_fwd(xp, N * C, H, W, ll.data_ptr<float>(), want_highs ? highs.data_ptr<float>() : nullptr,
+                                  cur_stream()), "haar_dwt2d_fwd");
+    return {ll, highs};
+}
+
+Tensor haar_idwt2d(const Tensor &ll, const c10::optional<Tensor> &highs, int64_t Hout, int64_t Wout) {
+    TORCH_CHECK(ll.dim() == 4, "haar_idwt2d: expected ll [N,C,h,w]");
+    UB_GUARD(ll);
+    const int64_t N = ll.size(0), C = ll.size(1), h2 = ll.size(2), w2 = ll.size(3);
+    if (highs.has_value())
+        TORCH_CHECK(highs->dim() == 5 && highs->size(0) == N && highs->size(1) == C && highs->size(2) == 3 &&
+                    highs->size(3) == h2 && highs->size(4) == w2, "haar_idwt2d: highs must be [N,C,3,h,w]");
+    Tensor out = at::empty({N, C, Hout, Wout}, ll.options());
+    check_rc(ub200_haar_idwt2d(f32(ll, "ll"), f32_opt(highs, "highs"), N * C, h2, w2, Hout, Wout, out.data_ptr<float>(),
+                               cur_stream()), "haar_idwt2d");
+    return out;
+}
+
+Tensor dwtblock_fwd(const Tensor &x, int64_t J, int64_t out_channels) {
+    TORCH_CHECK(x.dim() == 4, "dwtblock_fwd: expected [N,C,H,W]");
+    UB_GUARD(x);
+    const int64_t N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3);
+    int64_t h = H, w = W;
+    for (int j = 0; j < J; ++j) { h = (h + 1) / 2; w = (w + 1) / 2; }
+    Tensor out = at::empty({N, out_channels, h, w}, x.options());
+    check_rc(ub200_dwtblock_fwd(f32(x, "x"), N, C, H, W, (int)J, out_channels, out.data_ptr<float>(), cur_stream()), "dwtblock_fwd");
+    return out;
+}
+
+Tensor dwtblock_bwd(const Tensor &gout, int64_t C, int64_t H, int64_t W, int64_t J) {
+    TORCH_CHECK(gout.dim() == 4, "dwtblock_bwd: expected [N,K,h,w]");
+    UB_GUARD(gout);
+    const int64_t N = gout.size(0);
+    Tensor gx = at::empty({N, C, H, W}, gout.options());
+    check_rc(ub200_dwtblock_bwd(f32(gout, "gout"), N, C, H, W, (int)J, gout.size(1), gx.data_ptr<float>(), cur_stream()), "dwtblock_bwd");
+    return gx;
+}
+
+void dwtblock_fwd_nhwc(const Tensor &x, int64_t J, const c10::optional<Tensor> &chmap, const Tensor &out) {
+    UB_GUARD(x);
+    const Nhwc o = nhwc(out, "out");
+    const int32_t *mp = nullptr;
+    if (chmap.has_value()) {
+        TORCH_CHECK(chmap->is_cuda() && chmap->scalar_type() == at::kInt && chmap->is_contiguous() && chmap->numel() == o.C,
+                    "dwtblock_fwd_nhwc: chmap must be a CUDA int32 tensor with one entry per output channel");
+        mp = chmap->data_ptr<int32_t>();
+    }
+    check_rc(ub200_dwtblock_fwd_nhwc_bf16(f32(x, "x"), x.size(0), x.size(1), x.size(2), x.size(3), (int)J, o.C, mp, o.ptr, o.ld,
+                                          cur_stream()), "dwtblock_fwd_nhwc_bf16");
+}
+
+// ---------------------------------------------------------------- layout / resampling
+void nchw_to_nhwc(const Tensor &x, const Tensor &out) {
+    UB_GUARD(x);
+    const Nhwc o = nhwc(out, "out");
+    TORCH_CHECK(x.dim() == 4 && x.size(0) == o.N && x.size(1) == o.C && x.size(2) == o.H && x.size(3) == o.W, "nchw_to_nhwc: shape mismatch");
+    check_rc(ub200_nchw_f32_to_nhwc_bf16(f32(x, "x"), o.N, o.C, o.H, o.W, o.ptr, o.ld, cur_stream()), "nchw_f32_to_nhwc_bf16");
+}
+
+Tensor nhwc_to_nchw(const Tensor &x) {
+    UB_GUARD(x);
+    const Nhwc i = nhwc(x, "x");
+    Tensor out = at::empty({i.N, i.C, i.H, i.W}, x.options().dtype(at::kFloat));
+    check_rc(ub200_nhwc_bf16_to_nchw_f32(i.ptr, i.ld, i.N, i.C, i.H, i.W, out.data_ptr<float>(), cur_stream()), "nhwc_bf16_to_nchw_f32");
+    return out;
+}
+
+void upsample2x(const Tensor &x, const Tensor &out) {
+    UB_GUARD(x);
+    const Nhwc i = nhwc(x, "x"), o = nhwc(out, "out");
+    TORCH_CHECK(o.N == i.N && o.H == 2 * i.H && o.W == 2 * i.W && o.C == i.C, "upsample2x: shape mismatch");
+    check_rc(ub200_upsample2x_nhwc_bf16(i.ptr, i.ld, i.N, i.H, i.W, i.C, o.ptr, o.ld, cur_stream()), "upsample2x");
+}
+
+void upsample2x_bwd(const Tensor &gout, const Tensor &gx) {
+    UB_GUARD(gout);
+    const Nhwc g = nhwc(gout, "gout"), o = nhwc(gx, "gx");
+    TORCH_CHECK(g.N == o.N && g.H == 2 * o.H && g.W == 2 * o.W && g.C == o.C, "upsample2x_bwd: shape mismatch");
+    check_rc(ub200_upsample2x_bwd_nhwc_bf16(g.ptr, g.ld, o.N, o.H, o.W, o.C, o.ptr, o.ld, cur_stream()), "upsample2x_bwd");
+}
+
+// ---------------------------------------------------------------- GroupNorm + activation
+void gn_stats(const Tensor &x, int64_t G, const Tensor &stats) {
+    UB_GUARD(x);
+    const Nhwc i = nhwc(x, "x");
+    TORCH_CHECK(stats.numel() == i.N * G * 2, "gn_stats: stats must hold N*G*2 floats");
+    check_rc(ub200_gn_stats_nhwc_bf16(i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_mut(stats, "stats"), cur_stream()), "gn_stats");
+}
+
+void gn_act_fwd(const Tensor &x, int64_t G, const Tensor &stats, double eps, const c10::optional<Tensor> &gamma,
+                const c10::optional<Tensor> &beta, const c10::optional<Tensor> &scale, const c10::optional<Tensor> &shift,
+                int64_t act, double dropout_p, int64_t seed, int64_t offset, const c10::optional<Tensor> &offset_dev,
+                const Tensor &y) {
+    UB_GUARD(x);
+    const Nhwc i = nhwc(x, "x"), o = nhwc(y, "y");
+    TORCH_CHECK(o.N == i.N && o.H == i.H && o.W == i.W && o.C == i.C, "gn_act_fwd: shape mismatch");
+    check_rc(ub200_gn_act_fwd_nhwc_bf16(i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32(stats, "stats"), (float)eps,
+                                        f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
+                                        f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed, (uint64_t)offset,
+                                        i64_opt(offset_dev), o.ptr, o.ld, cur_stream()), "gn_act_fwd");
+}
+
+void gn_act_bwd(const Tensor &gy, const Tensor &x, int64_t G, const Tensor &stats, double eps,
+                const c10::optional<Tensor> &gamma, const c10::optional<Tensor> &beta, const c10::optional<Tensor> &scale,
+                const c10::optional<Tensor> &shift, int64_t act, double dropout_p, int64_t seed, int64_t offset,
+                const c10::optional<Tensor> &offset_dev, const Tensor &gx, bool accumulate, const c10::optional<Tensor> &dgamma, const c10::optional<Tensor> &dbeta,
+                const c10::optional<Tensor> &dscale, const c10::optional<Tensor> &dshift) {
+    UB_GUARD(x);
+    const Nhwc g = nhwc(gy, "gy"), i = nhwc(x, "x"), o = nhwc(gx, "gx");
+    TORCH_CHECK(g.N == i.N && g.H == i.H && g.W == i.W && g.C == i.C && o.N == i.N && o.H == i.H && o.W == i.W && o.C == i.C,
+                "gn_act_bwd: shape mismatch");
+    Tensor ws = at::empty({(int64_t)ub200_gn_act_bwd_ws_floats(i.N, i.C, (int)G)}, stats.options());
+    auto mut = [](const c10::optional<Tensor> &t, const char *n) -> float * { return t.has_value() ? f32_mut(*t, n) : nullptr; };
+    check_rc(ub200_gn_act_bwd_nhwc_bf16(g.ptr, g.ld, i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32(stats, "stats"), (float)eps,
+                                        f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
+                                        f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed, (uint64_t)offset,
+                                        i64_opt(offset_dev), o.ptr, o.ld, accumulate ? 1 : 0, mut(dgamma, "dgamma"), mut(dbeta, "dbeta"),
+                                        mut(dscale, "dscale"), mut(dshift, "dshift"), ws.data_ptr<float>(), cur_stream()),
+             "gn_act_bwd");
+}
+
+// ---------------------------------------------------------------- convolution
+// w / w2: packed bf16 weights (flat); out: NHWC bf16 view or None; out_nchw: fp32 [N,Cout,H,W] or None
+void conv_fprop(const Tensor &a, const Tensor &w, int64_t ksize, int64_t Cout, const c10::optional<Tensor> &a2,
+                const c10::optional<Tensor> &w2, const c10::optional<Tensor> &bias, const c10::optional<Tensor> &rowadd,
+                const c10::optional<Tensor> &residual, const c10::optional<Tensor> &out,
+                const c10::optional<Tensor> &out_nchw) {
+    UB_GUARD(a);
+    const Nhwc A = nhwc(a, "a");
+    ub200_conv_args args{};
+    args.a = A.ptr; args.ld_a = A.ld; args.Cin = A.C;
+    TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kBFloat16 && w.is_contiguous(), "conv_fprop: w must be packed bf16");
+    const int64_t cout_pad = (Cout + 15) / 16 * 16;
+    TORCH_CHECK(w.numel() == cout_pad * ksize * ksize * A.C, "conv_fprop: packed weight has ", w.numel(), " elements, expected ",
+                cout_pad * ksize * ksize * A.C);
+    args.w = w.data_ptr(); args.ksize = (int)ksize;
+    if (a2.has_value()) {
+        const Nhwc A2 = nhwc(*a2, "a2");
+        TORCH_CHECK(A2.N == A.N && A2.H == A.H && A2.W == A.W, "conv_fprop: a2 shape mismatch");
+        TORCH_CHECK(w2.has_value() && w2->scalar_type() == at::kBFloat16 && w2->is_contiguous() && w2->numel() == cout_pad * A2.C,
+                    "conv_fprop: w2 must be packed bf16 [Cout_pad, Cin2]");
+        args.a2 = A2.ptr; args.ld_a2 = A2.ld; args.Cin2 = A2.C; args.w2 = w2->data_ptr();
+    }
+    if (bias.has_value()) { TORCH_CHECK(bias->numel() == Cout, "conv_fprop: bias size"); args.bias = f32(*bias, "bias"); }
+    if (rowadd.has_value()) { TORCH_CHECK(rowadd->numel() == A.N * Cout, "conv_fprop: rowadd size"); args.rowadd = f32(*rowadd, "rowadd"); }
+    if (residual.has_value()) {
+        const Nhwc R = nhwc(*residual, "residual");
+        TORCH_CHECK(R.N == A.N && R.H == A.H && R.W == A.W && R.C == Cout, "conv_fprop: residual shape mismatch");
+        args.residual = R.ptr; args.ld_res = R.ld;
+    }
+    if (out.has_value()) {
+        const Nhwc O = nhwc(*out, "out");
+        TORCH_CHECK(O.N == A.N && O.H == A.H && O.W == A.W && O.C == Cout, "conv_fprop: out shape mismatch");
+        args.out = O.ptr; args.ld_out = O.ld;
+    }
+    if (out_nchw.has_value()) {
+        TORCH_CHECK(out_nchw->numel() == A.N * Cout * A.H * A.W, "conv_fprop: out_nchw size");
+        args.out_f32_nchw = f32_mut(*out_nchw, "out_nchw");
+    }
+    args.N = A.N; args.H = A.H; args.W = A.W; args.Cout = Cout;
+    check_rc(ub200_conv_fprop(&args, cur_stream()), "conv_fprop");
+}
+
+void conv_wgrad(const Tensor &gout, const Tensor &a, int64_t ksize, const Tensor &dw) {
+    UB_GUARD(a);
+    const Nhwc G = nhwc(gout, "gout"), A = nhwc(a, "a");
+    TORCH_CHECK(G.N == A.N && G.H == A.H && G.W == A.W, "conv_wgrad: shape mismatch");
+    TORCH_CHECK(dw.is_cuda() && dw.scalar_type() == at::kFloat && dw.numel() == G.C * ksize * ksize * A.C, "conv_wgrad: dw size");
+    // dw is the fp32 gradient in [Cout,k,k,Cin] memory order (channels_last view of [Cout,Cin,k,k] accepted)
+    TORCH_CHECK(dw.is_contiguous() || dw.is_contiguous(at::MemoryFormat::ChannelsLast), "conv_wgrad: dw must be dense");
+    check_rc(ub200_conv_wgrad(G.ptr, G.ld, A.ptr, A.ld, A.N, A.H, A.W, A.C, G.C, (int)ksize, (float *)dw.data_ptr(), cur_stream()),
+             "conv_wgrad");
+}
+
+void chansum(const Tensor &x, const c10::optional<Tensor> &per_sample, const c10::optional<Tensor> &total) {
+    UB_GUARD(x);
+    const Nhwc X = nhwc(x, "x");
+    float *ps = per_sample.has_value() ? f32_mut(*per_sample, "per_sample") : nullptr;
+    float *tt = total.has_value() ? f32_mut(*total, "total") : nullptr;
+    check_rc(ub200_chansum_nhwc_bf16(X.ptr, X.ld, X.N, X.H * X.W, X.C, ps, tt, cur_stream()), "chansum");
+}
+
+// w: fp32 [Cout,Cin,k,k] with any dense strides (contiguous or channels_last)
+void pack_conv_weight(const Tensor &w, bool transpose_flip, const Tensor &out) {
+    UB_GUARD(w);
+    TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kFloat && w.dim() == 4 && w.size(2) == w.size(3), "pack_conv_weight: w must be fp32 [Cout,Cin,k,k]");
+    const int64_t Cout = w.size(0), Cin = w.size(1), k = w.size(2);
+    const int64_t rows = transpose_flip ? Cin : Cout, cols = transpose_flip ? Cout : Cin;
+    TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kBFloat16 && out.is_contiguous() &&
+                out.numel() == (rows + 15) / 16 * 16 * k * k * cols, "pack_conv_weight: out size");
+    check_rc(ub200_pack_conv_weight(w.data_ptr<float>(), Cout, Cin, (int)k, w.stride(0), w.stride(1), w.stride(2), w.stride(3),
+                                    transpose_flip ? 1 : 0, out.data_ptr(), cur_stream()), "pack_conv_weight");
+}
+
+// ---------------------------------------------------------------- optimiser tail
+void sumsq(const Tensor &g, const Tensor &acc) {
+    UB_GUARD(g);
+    check_rc(ub200_sumsq_f32(f32(g, "g"), g.numel(), f32_mut(acc, "acc"), cur_stream()), "sumsq");
+}
+
+void adam_ema_step(const Tensor &p, const Tensor &g, const Tensor &m, const Tensor &v, const c10::optional<Tensor> &ema,
+                   const c10::optional<Tensor> &sumsq_t, double max_norm, double grad_scale, double lr, double beta1,
+                   double beta2, double eps, double ema_decay, int64_t step) {
+    UB_GUARD(p);
+    const int64_t n = p.numel();
+    TORCH_CHECK(g.numel() == n && m.numel() == n && v.numel() == n && (!ema.has_value() || ema->numel() == n), "adam_ema_step: size mismatch");
+    check_rc(ub200_adam_ema_step_f32(f32_mut(p, "p"), f32(g, "g"), f32_mut(m, "m"), f32_mut(v, "v"),
+                                     ema.has_value() ? f32_mut(*ema, "ema") : nullptr, n, f32_opt(sumsq_t, "sumsq"),
+                                     (float)max_norm, (float)grad_scale, (float)lr, (float)beta1, (float)beta2, (float)eps,
+                                     (float)ema_decay, step, cur_stream()), "adam_ema_step");
+}
+
+}  // namespace
+
+TORCH_LIBRARY(unet_b200, m) {
+    m.def("haar_dwt2d_fwd", &haar_dwt2d_fwd);
+    m.def("haar_idwt2d", &haar_idwt2d);
+    m.def("dwtblock_fwd", &dwtblock_fwd);
+    m.def("dwtblock_bwd", &dwtblock_bwd);
+    m.def("dwtblock_fwd_nhwc", &dwtblock_fwd_nhwc);
+    m.def("nchw_to_nhwc", &nchw_to_nhwc);
+    m.def("nhwc_to_nchw", &nhwc_to_nchw);
+    m.def("upsample2x", &upsample2x);
+    m.def("upsample2x_bwd", &upsample2x_bwd);
+    m.def("gn_stats", &gn_stats);
+    m.def("gn_act_fwd", &gn_act_fwd);
+    m.def("gn_act_bwd", &gn_act_bwd);
+    m.def("conv_fprop", &conv_fprop);
+    m.def("conv_wgrad", &conv_wgrad);
+    m.def("chansum", &chansum);
+    m.def("pack_conv_weight", &pack_conv_weight);
+    m.def("sumsq", &sumsq);
+    m.def("adam_ema_step", &adam_ema_step);
+}

@@ -1,0 +1,407 @@
+"""Drop-in for the reference's diff_cifar/model.py, backed by the sm_100a kernels.
+
+Same class names, constructor signatures, `forward` signatures / return structure, attribute names,
+ModuleList nesting and `state_dict` keys and shapes as the reference (file:line under
+/root/reference): Swish :9-11, TimeEmbedding :14-43, DownSample :46-63, UpSample :66-81,
+AttnBlock :84-119, ResBlock :122-169, DTWBlock :253-323, UNetWaveletEnc :326-496, and the commented
+plain `UNet` :172-246 as a thin alias.
+
+Public `forward`s take and return the reference's NCHW fp32 tensors.  Inside a model every activation is
+NHWC bf16 and every hot op is one of our kernels:
+
+    GroupNorm statistics + (normalise, SiLU, dropout)      -> ops.gn_act      (groupnorm.cu)
+    3x3 conv + bias + time-embedding row + 1x1 shortcut /
+      identity residual, forward, dgrad and wgrad           -> ops.conv        (conv_fprop.cu, conv_wgrad.cu)
+    nearest x2                                              -> ops.upsample2x  (layout.cu)
+    Haar pyramid + DTWBlock chain                           -> ops.dwtblock*   (haar.cu)
+
+Conv weights live in fp32 with channels_last strides, i.e. the memory order [Cout, kh, kw, Cin] the
+tensor-core kernels consume; `state_dict` / `load_state_dict` are unaffected by strides.
+AttnBlock (2.2% of the FLOPs, out of scope per SURVEY.md §2.1) runs on PyTorch's SDPA in bf16.
+"""
+from __future__ import annotations
+
+import math
+from typing import List
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn import init
+
+from .. import ops
+
+
+class Swish(nn.Module):
+    def forward(self, x):
+        return x * torch.sigmoid(x)
+
+
+def _conv_param(conv: nn.Conv2d) -> nn.Conv2d:
+    """Keep the weight in [Cout, kh, kw, Cin] memory order (channels_last strides of [Cout, Cin, kh, kw])."""
+    conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)
+    return conv
+
+
+class _HaarFilterBuffers(nn.Module):
+    """State-dict stand-in for pytorch_wavelets.DWTForward / DWTInverse: same buffer names and shapes
+    (the reference's checkpoints carry them), no computation -- the taps are constants of haar.cu."""
+
+    def __init__(self, names):
+        super().__init__()
+        s = 1.0 / math.sqrt(2.0)
+        for name in names:
+            taps = torch.tensor([s, s] if name[1] == "0" else [s, -s], dtype=torch.float32)
+            self.register_buffer(name, taps.reshape(1, 1, 2, 1) if name.endswith("col") else taps.reshape(1, 1, 1, 2))
+
+
+class TimeEmbedding(nn.Module):
+    def __init__(self, T, d_model, dim):
+        assert d_model % 2 == 0
+        super().__init__()
+        emb = torch.arange(0, d_model, step=2) / d_model * math.log(10000)
+        emb = torch.exp(-emb)
+        pos = torch.arange(T).float()
+        emb = pos[:, None] * emb[None, :]
+        emb = torch.stack([torch.sin(emb), torch.cos(emb)], dim=-1).view(T, d_model)
+        self.timembedding = nn.Sequential(
+            nn.Embedding.from_pretrained(emb),
+            nn.Linear(d_model, dim),
+            Swish(),
+            nn.Linear(dim, dim),
+        )
+        self.initialize()
+
+    def initialize(self):
+        for module in self.modules():
+            if isinstance(module, nn.Linear):
+                init.xavier_uniform_(module.weight)
+                init.zeros_(module.bias)
+
+    def forward(self, t):
+        return self.timembedding(t)
+
+
+class DownSample(nn.Module):
+    """Strided 3x3 conv or 2x2 average pool; only the non-Haar U-Net arm uses it (model.py:369)."""
+
+    def __init__(self, in_ch, type="conv"):
+        super().__init__()
+        self.type = type
+        if type == "conv":
+            self.main = _conv_param(nn.Conv2d(in_ch, in_ch, 3, stride=2, padding=1))
+            self.initialize()
+        elif type == "avg_pool":
+            self.main = nn.AvgPool2d(2)
+        else:
+            raise NotImplementedError
+
+    def initialize(self):
+        init.xavier_uniform_(self.main.weight)
+        init.zeros_(self.main.bias)
+
+    def forward_nhwc(self, x, temb=None):
+        if self.type == "conv":
+            # stride-2 pad-1 conv == every second pixel of the stride-1 conv (baseline arm only)
+            return ops.conv(x, self.main.weight, self.main.bias)[:, ::2, ::2, :].contiguous()
+        n, h, w, c = x.shape
+        return x.reshape(n, h // 2, 2, w // 2, 2, c).float().mean(dim=(2, 4)).to(torch.bfloat16)
+
+    def forward(self, x, temb):
+        return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x), temb))
+
+
+class UpSample(nn.Module):
+    def __init__(self, in_ch):
+        super().__init__()
+        self.main = _conv_param(nn.Conv2d(in_ch, in_ch, 3, stride=1, padding=1))
+        self.initialize()
+
+    def initialize(self):
+        init.xavier_uniform_(self.main.weight)
+        init.zeros_(self.main.bias)
+
+    def forward_nhwc(self, x, temb=None):
+        return ops.conv(ops.upsample2x(x), self.main.weight, self.main.bias)
+
+    def forward(self, x, temb):
+        return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x), temb))
+
+
+class AttnBlock(nn.Module):
+    def __init__(self, in_ch):
+        super().__init__()
+        self.group_norm = nn.GroupNorm(32, in_ch)
+        self.proj_q = nn.Conv2d(in_ch, in_ch, 1, stride=1, padding=0)
+        self.proj_k = nn.Conv2d(in_ch, in_ch, 1, stride=1, padding=0)
+        self.proj_v = nn.Conv2d(in_ch, in_ch, 1, stride=1, padding=0)
+        self.proj = nn.Conv2d(in_ch, in_ch, 1, stride=1, padding=0)
+        self.initialize()
+
+    def initialize(self):
+        for module in [self.proj_q, self.proj_k, self.proj_v, self.proj]:
+            init.xavier_uniform_(module.weight)
+            init.zeros_(module.bias)
+        init.xavier_uniform_(self.proj.weight, gain=1e-5)
+
+    def forward_nhwc(self, x):
+        n, h, w, c = x.shape
+        y = ops.gn_act(x, self.group_norm.weight, self.group_norm.bias, 32, act="none", eps=self.group_norm.eps)
+        y = y.reshape(n, h * w, c)
+
+        def lin(conv, t):
+            return F.linear(t, conv.weight.reshape(c, c).to(torch.bfloat16), conv.bias.to(torch.bfloat16))
+
+        q, k, v = lin(self.proj_q, y), lin(self.proj_k, y), lin(self.proj_v, y)
+        o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None], scale=int(c) ** (-0.5))[:, 0]
+        return x + lin(self.proj, o).reshape(n, h, w, c)
+
+    def forward(self, x):
+        return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x)))
+
+
+class ResBlock(nn.Module):
+    def __init__(self, in_ch, out_ch, tdim, dropout, attn=False):
+        super().__init__()
+        self.in_ch = in_ch
+        self.out_ch = out_ch
+        self.block1 = nn.Sequential(
+            nn.GroupNorm(32, in_ch),
+            Swish(),
+            _conv_param(nn.Conv2d(in_ch, out_ch, 3, stride=1, padding=1)),
+        )
+        self.temb_proj = nn.Sequential(
+            Swish(),
+            nn.Linear(tdim, out_ch),
+        )
+        self.block2 = nn.Sequential(
+            nn.GroupNorm(32, out_ch),
+            Swish(),
+            nn.Dropout(dropout),
+            _conv_param(nn.Conv2d(out_ch, out_ch, 3, stride=1, padding=1)),
+        )
+        if in_ch != out_ch:
+            self.shortcut = _conv_param(nn.Conv2d(in_ch, out_ch, 1, stride=1, padding=0))
+        else:
+            self.shortcut = nn.Identity()
+        self.attn = AttnBlock(out_ch) if attn else nn.Identity()
+        self.initialize()
+
+    def initialize(self):
+        for module in self.modules():
+            if isinstance(module, (nn.Conv2d, nn.Linear)):
+                init.xavier_uniform_(module.weight)
+                init.zeros_(module.bias)
+        init.xavier_uniform_(self.block2[-1].weight, gain=1e-5)
+
+    def forward_nhwc(self, x, temb):
+        gn1, conv1 = self.block1[0], self.block1[2]
+        gn2, drop, conv2 = self.block2[0], self.block2[2], self.block2[3]
+        a1 = ops.gn_act(x, gn1.weight, gn1.bias, gn1.num_groups, act="silu", eps=gn1.eps)
+        # h = conv1(a1) + bias + temb_proj(temb)[:, :, None, None]   (model.py:163-164), one kernel
+        h = ops.conv(a1, conv1.weight, conv1.bias, rowadd=self.temb_proj(temb).float().contiguous())
+        p = drop.p if self.training else 0.0
+        a2 = ops.gn_act(h, gn2.weight, gn2.bias, gn2.num_groups, act="silu", eps=gn2.eps, dropout_p=p)
+        if isinstance(self.shortcut, nn.Conv2d):
+            # conv2(a2) + shortcut(x): the 1x1 conv rides along as extra K slices of the same GEMM
+            h = ops.conv(a2, conv2.weight, conv2.bias + self.shortcut.bias, a2=x, w2=self.shortcut.weight)
+        else:
+            h = ops.conv(a2, conv2.weight, conv2.bias, residual=x)
+        if isinstance(self.attn, AttnBlock):
+            h = self.attn.forward_nhwc(h)
+        return h
+
+    def forward(self, x, temb):
+        return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x), temb))
+
+
+class DTWBlock(nn.Module):
+    """LL_J(x) / 2^J followed by a channel tile to `out_channels`; J = 0 is the tile alone (version 1,
+    the only live branch of the reference)."""
+
+    def __init__(self, J, out_channels, mode="zero", wave="haar") -> None:
+        super().__init__()
+        if mode != "zero" or wave != "haar":
+            raise NotImplementedError("the B200 kernels implement mode='zero', wave='haar' (the reference's defaults)")
+        if not 0 <= J <= 3:
+            raise NotImplementedError("fused DTWBlock supports J in [0, 3]")
+        self.version = 1
+        self.J = J
+        self.out_channels = out_channels
+        self.xfm = _HaarFilterBuffers(["h0_col", "h1_col", "h0_row", "h1_row"])
+        self.ifm = _HaarFilterBuffers(["g0_col", "g1_col", "g0_row", "g1_row"])
+
+    def forward(self, x):
+        return ops.dwtblock(x.float(), self.J, self.out_channels)
+
+
+class _PyramidView:
+    """A DTWBlock-chain output that was never materialised: pyramid level + channel map."""
+
+    __slots__ = ("level", "chmap")
+
+    def __init__(self, level: int, chmap: List[int]):
+        self.level, self.chmap = level, chmap
+
+    def tiled(self, out_channels: int) -> "_PyramidView":
+        c = len(self.chmap)
+        return _PyramidView(self.level, [self.chmap[k % c] for k in range(out_channels)])
+
+
+class UNetWaveletEnc(nn.Module):
+    def __init__(self, T, ch, ch_mult, attn, num_res_blocks, dropout, dwt_encoder=False, multi_res_loss=False,
+                 downsample_type="conv"):
+        super().__init__()
+        assert all([i < len(ch_mult) for i in attn]), "attn index out of bound"
+        tdim = ch * 4
+        self.n_levels = len(ch_mult)
+        self.dwt_encoder = dwt_encoder
+        self.multi_res_loss = multi_res_loss
+        self.downsample_type = downsample_type
+
+        self.time_embedding_list = nn.ModuleList(TimeEmbedding(T, ch, tdim) for _ in range(self.n_levels))
+        self.head_list = nn.ModuleList([])
+        self.downblocks = nn.ModuleList([nn.ModuleList() for _ in range(self.n_levels)])
+        chs = [ch]
+        now_ch = ch
+        for l, mult in enumerate(ch_mult):
+            self.head_list.append(DTWBlock(J=0, out_channels=now_ch))
+            out_ch = ch * mult
+            for _ in range(num_res_blocks):
+                if self.dwt_encoder:
+                    self.downblocks[l].append(DTWBlock(J=0, out_channels=out_ch))
+                else:
+                    self.downblocks[l].append(ResBlock(in_ch=now_ch, out_ch=out_ch, tdim=tdim, dropout=dropout,
+                                                       attn=(l in attn)))
+                now_ch = out_ch
+                chs.append(now_ch)
+            if l != len(ch_mult) - 1:
+                if self.dwt_encoder:
+                    self.downblocks[l].append(DTWBlock(J=1, out_channels=now_ch))
+                else:
+                    self.downblocks[l].append(DownSample(now_ch, type=self.downsample_type))
+                chs.append(now_ch)
+
+        self.middleblocks = nn.ModuleList([
+            ResBlock(now_ch, now_ch, tdim, dropout, attn=True),
+            ResBlock(now_ch, now_ch, tdim, dropout, attn=False),
+        ])
+
+        self.upblocks = nn.ModuleList([nn.ModuleList() for _ in range(self.n_levels)])
+        for l, mult in reversed(list(enumerate(ch_mult))):
+            out_ch = ch * mult
+            for j in range(num_res_blocks + 1):
+                chs_pop = chs.pop()
+                self.upblocks[l].append(ResBlock(in_ch=chs_pop + now_ch, out_ch=out_ch, tdim=tdim, dropout=dropout,
+                                                 attn=(l in attn)))
+                now_ch = out_ch
+            if l != 0:
+                self.upblocks[l].append(UpSample(now_ch))
+        assert len(chs) == 0
+
+        self.tail_list = nn.ModuleList([nn.Sequential(
+            nn.GroupNorm(32, ch * mult),
+            Swish(),
+            _conv_param(nn.Conv2d(ch * mult, 3, 3, stride=1, padding=1))
+        ) for mult in ch_mult])
+        self.initialize()
+        self._chmap_cache = {}
+
+    def initialize(self):
+        for tail in self.tail_list:
+            init.xavier_uniform_(tail[-1].weight, gain=1e-5)
+            init.zeros_(tail[-1].bias)
+
+    # ---- internals ---------------------------------------------------------------------------
+    def _tail(self, level, h):
+        gn, conv = self.tail_list[level][0], self.tail_list[level][2]
+        a = ops.gn_act(h, gn.weight, gn.bias, gn.num_groups, act="silu", eps=gn.eps)
+        return ops.conv(a, conv.weight, conv.bias, out_nchw=True)      # fp32 NCHW [N,3,H,W] straight from TMEM
+
+    def _materialise(self, pyramid, view: _PyramidView) -> torch.Tensor:
+        base = pyramid[view.level]
+        n, _, h, w = base.shape
+        key = (tuple(view.chmap), base.device)
+        cm = self._chmap_cache.get(key)
+        if cm is None:
+            cm = torch.tensor(view.chmap, dtype=torch.int32, device=base.device)
+            self._chmap_cache[key] = cm
+        out = torch.empty((n, h, w, len(view.chmap)), dtype=torch.bfloat16, device=base.device)
+        return ops.dwtblock_nhwc(base, 0, out, cm)
+
+    def _encode_haar(self, x, first):
+        """Haar encoder: every skip tensor is a channel tile of one level of the image pyramid
+        LL_l(x)/2^l, so only the 3-channel pyramid is computed; skips are written once, in NHWC bf16."""
+        pyramid = {first: x}
+        view = _PyramidView(first, list(range(x.shape[1]))).tiled(self.head_list[first].out_channels)
+        views = [view]
+        for level in range(first, self.n_levels):
+            for layer in self.downblocks[level]:
+                if layer.J == 1:
+                    src = pyramid[view.level]
+                    pyramid[view.level + 1] = ops.dwtblock(src, 1, src.shape[1])      # LL/2 of the 3-channel image
+                    view = _PyramidView(view.level + 1, view.chmap)
+                elif layer.J != 0:
+                    raise NotImplementedError
+                view = view.tiled(layer.out_channels)
+                views.append(view)
+        return pyramid, views
+
+    def forward(self, x, t, n_levels_used=-1):
+        if n_levels_used == -1:
+            n_levels_used = self.n_levels
+        first = self.n_levels - n_levels_used            # finest level in use
+        x = x.float().contiguous()
+
+        # ---- encoder
+        if self.dwt_encoder:
+            pyramid, views = self._encode_haar(x, first)
+            hs = views
+            h = self._materialise(pyramid, views[-1])
+            fetch = lambda v: self._materialise(pyramid, v)
+        else:
+            h = ops.dwtblock_nhwc(x, 0, torch.empty((x.shape[0], x.shape[2], x.shape[3], self.head_list[first].out_channels),
+                                                    dtype=torch.bfloat16, device=x.device))
+            hs = [h]
+            for level in range(first, self.n_levels):
+                temb = self.time_embedding_list[level](t)
+                for layer in self.downblocks[level]:
+                    h = layer.forward_nhwc(h, temb)
+                    hs.append(h)
+            fetch = lambda v: v
+
+        # ---- middle
+        temb = self.time_embedding_list[self.n_levels - 1](t)
+        for layer in self.middleblocks:
+            h = layer.forward_nhwc(h, temb)
+
+        # ---- decoder
+        model_out_list = []
+        for l in range(self.n_levels - 1, first - 1, -1):
+            temb = self.time_embedding_list[l](t)
+            for layer in self.upblocks[l]:
+                if isinstance(layer, ResBlock):
+                    h = torch.cat([h, fetch(hs.pop())], dim=3)
+                    h = layer.forward_nhwc(h, temb)
+                elif l != first:                         # UpSample; skipped on the finest level in use
+                    if self.multi_res_loss:
+                        model_out_list.append(self._tail(l, h))
+                    h = layer.forward_nhwc(h)
+        model_out_list.append(self._tail(first, h))
+        assert len(hs) == 0
+
+        if self.multi_res_loss:
+            assert len(model_out_list) == n_levels_used
+            return model_out_list
+        return model_out_list[-1]
+
+
+class UNet(UNetWaveletEnc):
+    """The plain U-Net the reference keeps commented out (model.py:172-246): `UNet(T, ch, ch_mult, attn,
+    num_res_blocks, dropout).forward(x, t)` -- the residual-encoder arm of the merged class."""
+
+    def __init__(self, T, ch, ch_mult, attn, num_res_blocks, dropout):
+        super().__init__(T, ch, ch_mult, attn, num_res_blocks, dropout, dwt_encoder=False)
+
+    def forward(self, x, t):
+        return super().forward(x, t)

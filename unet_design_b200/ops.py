@@ -1,0 +1,415 @@
+"""Autograd glue over `torch.ops.unet_b200` (the C++ extension over the C ABI).
+
+Internal activation format ("NHWC bf16"): a torch bf16 tensor of logical shape [N, H, W, C] with channel
+stride 1; it may be a channel slice of a wider buffer.  Public modules take and return the reference's
+NCHW fp32 tensors and convert at the boundary.
+
+Nothing here has a CPU or eager fallback: every function ends in a hand-written sm_100a kernel.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from ._lib import ops as _ops
+
+ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+_ACT = {"none": ACT_NONE, "silu": ACT_SILU, "swish": ACT_SILU, "gelu": ACT_GELU}
+
+
+# --------------------------------------------------------------------------------------------------
+# launch accounting (bench.py reports how many of OUR kernels ran in the timed region)
+# --------------------------------------------------------------------------------------------------
+class _Counter:
+    launches = 0
+
+
+def launches() -> int:
+    return _Counter.launches
+
+
+def _count(n: int = 1) -> None:
+    _Counter.launches += n
+
+
+def _dense_nhwc(t: torch.Tensor) -> torch.Tensor:
+    """Return `t` if it is a valid NHWC view (channel stride 1, uniform pixel stride), else a packed copy."""
+    n, h, w, c = t.shape
+    ld = t.stride(2) if w > 1 else (t.stride(1) if h > 1 else (t.stride(0) if n > 1 else c))
+    ok = (c == 1 or t.stride(3) == 1) and (w == 1 or t.stride(2) == ld) and (h == 1 or t.stride(1) == w * ld) \
+        and (n == 1 or t.stride(0) == h * w * ld) and ld % 8 == 0 and t.data_ptr() % 16 == 0
+    return t if ok else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# dropout RNG state: (seed, host offset, device offset tensor).  The device counter lets a captured CUDA
+# graph draw fresh masks on every replay (bumped once per training step by `advance_dropout_state`).
+# --------------------------------------------------------------------------------------------------
+class _DropoutState:
+    seed = 0x5DEECE66D
+    host_offset = 0
+    dev_offset: Optional[torch.Tensor] = None
+
+
+def seed_dropout(seed: int) -> None:
+    _DropoutState.seed = int(seed) & 0x7FFFFFFFFFFFFFFF
+    _DropoutState.host_offset = 0
+
+
+def dropout_device_counter(device) -> torch.Tensor:
+    d = _DropoutState.dev_offset
+    if d is None or d.device != torch.device(device):
+        _DropoutState.dev_offset = torch.zeros(1, dtype=torch.int64, device=device)
+    return _DropoutState.dev_offset
+
+
+def advance_dropout_state(device, amount: int = 1 << 32) -> None:
+    dropout_device_counter(device).add_(amount)
+
+
+def _next_dropout_offset(numel: int) -> int:
+    off = _DropoutState.host_offset
+    _DropoutState.host_offset += (numel + 3) // 4 + 1
+    return off
+
+
+# --------------------------------------------------------------------------------------------------
+# layout at the module boundary
+# --------------------------------------------------------------------------------------------------
+class _ToNhwc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pad_to):
+        n, c, h, w = x.shape
+        cp = max(pad_to, c)
+        buf = torch.zeros((n, h, w, cp), dtype=torch.bfloat16, device=x.device) if cp != c else \
+            torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+        _ops().nchw_to_nhwc(x.contiguous().float(), buf[..., :c] if cp != c else buf)
+        _count()
+        ctx.c = c
+        return buf
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _dense_nhwc(g)
+        _count()
+        return _ops().nhwc_to_nchw(g[..., : ctx.c]), None
+
+
+class _ToNchw(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _count()
+        return _ops().nhwc_to_nchw(_dense_nhwc(x))
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, h, w = g.shape
+        out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=g.device)
+        _ops().nchw_to_nhwc(g.contiguous().float(), out)
+        _count()
+        return out
+
+
+def to_nhwc(x: torch.Tensor, pad_to: int = 0) -> torch.Tensor:
+    """NCHW fp32 -> NHWC bf16; channels zero-padded up to `pad_to` (conv operands need C % 16 == 0)."""
+    return _ToNhwc.apply(x, pad_to)
+
+
+def to_nchw(x: torch.Tensor) -> torch.Tensor:
+    """NHWC bf16 -> NCHW fp32."""
+    return _ToNchw.apply(x)
+
+
+# --------------------------------------------------------------------------------------------------
+# Haar
+# --------------------------------------------------------------------------------------------------
+class _HaarDwtLevel(torch.autograd.Function):
+    """One analysis level; backward is the synthesis bank cropped to the input (pytorch_wavelets AFB2D)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.hw = x.shape[-2:]
+        ll, highs = _ops().haar_dwt2d_fwd(x.contiguous(), True)
+        _count()
+        return ll, highs
+
+    @staticmethod
+    def backward(ctx, gll, ghighs):
+        h, w = ctx.hw
+        if gll is None:
+            gll = torch.zeros(ghighs.shape[:2] + ghighs.shape[3:], dtype=ghighs.dtype, device=ghighs.device)
+        _count()
+        return _ops().haar_idwt2d(gll.contiguous(), None if ghighs is None else ghighs.contiguous(), h, w)
+
+
+class _HaarIdwtLevel(torch.autograd.Function):
+    """One synthesis level; backward is the analysis bank (zero extension of a cropped gradient)."""
+
+    @staticmethod
+    def forward(ctx, ll, highs, hout, wout):
+        _count()
+        ctx.has_highs = highs is not None
+        return _ops().haar_idwt2d(ll.contiguous(), None if highs is None else highs.contiguous(), hout, wout)
+
+    @staticmethod
+    def backward(ctx, g):
+        gll, ghighs = _ops().haar_dwt2d_fwd(g.contiguous(), True)
+        _count()
+        return gll, (ghighs if ctx.has_highs else None), None, None
+
+
+def haar_dwt2d(x: torch.Tensor, J: int):
+    """`(Yl, [Yh_1..Yh_J])`, the contract of `pytorch_wavelets.DWTForward(J, mode='zero', wave='haar')`."""
+    highs = []
+    ll = x
+    for _ in range(J):
+        ll, hi = _HaarDwtLevel.apply(ll)
+        highs.append(hi)
+    return ll, highs
+
+
+def haar_idwt2d(yl: torch.Tensor, highs) -> torch.Tensor:
+    """`pytorch_wavelets.DWTInverse(mode='zero', wave='haar')((Yl, Yh))`; identity for an empty list."""
+    ll = yl
+    for band in highs[::-1]:
+        if band is None:
+            band_hw = ll.shape[-2:]
+        else:
+            band_hw = band.shape[-2:]
+        if ll.shape[-2] > band_hw[0]:
+            ll = ll[..., :-1, :]
+        if ll.shape[-1] > band_hw[1]:
+            ll = ll[..., :-1]
+        ll = _HaarIdwtLevel.apply(ll, band, 2 * ll.shape[-2], 2 * ll.shape[-1])
+    return ll
+
+
+class _DwtBlock(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, J, out_channels):
+        ctx.meta = (x.shape[1], x.shape[2], x.shape[3], J)
+        _count()
+        return _ops().dwtblock_fwd(x.contiguous(), J, out_channels)
+
+    @staticmethod
+    def backward(ctx, g):
+        c, h, w, J = ctx.meta
+        _count()
+        return _ops().dwtblock_bwd(g.contiguous(), c, h, w, J), None, None
+
+
+def dwtblock(x: torch.Tensor, J: int, out_channels: int) -> torch.Tensor:
+    """Fused DTWBlock / DWTBlock: LL_J(x)/2^J then channel tile, NCHW fp32 (diff_cifar/model.py:270-323)."""
+    return _DwtBlock.apply(x, J, out_channels)
+
+
+def dwtblock_nhwc(x: torch.Tensor, J: int, out: torch.Tensor, chmap: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Same forward written into an NHWC bf16 view (no autograd: the diffusion encoders see data only).
+    `chmap` (int32 [C_out]) names the source channel of each output channel; None = k mod C."""
+    _ops().dwtblock_fwd_nhwc(x.contiguous(), J, chmap, out)
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# GroupNorm + activation (+ scale/shift, + dropout)
+# --------------------------------------------------------------------------------------------------
+class _GnAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, scale, shift, G, eps, act, p_drop):
+        x = _dense_nhwc(x)
+        n, h, w, c = x.shape
+        stats = torch.empty((n, G, 2), dtype=torch.float32, device=x.device)
+        _ops().gn_stats(x, G, stats)
+        y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+        seed = off = 0
+        dev = None
+        if p_drop > 0.0:
+            seed, off, dev = _DropoutState.seed, _next_dropout_offset(x.numel()), dropout_device_counter(x.device)
+        _ops().gn_act_fwd(x, G, stats, eps, gamma, beta, scale, shift, act, p_drop, seed, off, dev, y)
+        _count(3)
+        ctx.save_for_backward(x, stats, gamma, beta, scale, shift)
+        ctx.cfg = (G, eps, act, p_drop, seed, off, dev)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, stats, gamma, beta, scale, shift = ctx.saved_tensors
+        G, eps, act, p_drop, seed, off, dev = ctx.cfg
+        gy = _dense_nhwc(gy)
+        gx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        dgamma = torch.zeros_like(gamma) if gamma is not None else None
+        dbeta = torch.zeros_like(beta) if beta is not None else None
+        dscale = torch.empty_like(scale) if scale is not None else None
+        dshift = torch.empty_like(shift) if shift is not None else None
+        _ops().gn_act_bwd(gy, x, G, stats, eps, gamma, beta, scale, shift, act, p_drop, seed, off, dev, gx, False,
+                          dgamma, dbeta, dscale, dshift)
+        _count(3)
+        return gx, dgamma, dbeta, dscale, dshift, None, None, None, None
+
+
+def gn_act(x, gamma, beta, groups: int, act: str = "silu", eps: float = 1e-5, dropout_p: float = 0.0,
+           scale=None, shift=None) -> torch.Tensor:
+    """act(GroupNorm(x) * (1 + scale) + shift) with optional dropout; NHWC bf16 in and out."""
+    return _GnAct.apply(x, gamma, beta, scale, shift, groups, eps, _ACT[act], float(dropout_p))
+
+
+# --------------------------------------------------------------------------------------------------
+# nearest x2 up-sampling
+# --------------------------------------------------------------------------------------------------
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _dense_nhwc(x)
+        n, h, w, c = x.shape
+        out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+        _ops().upsample2x(x, out)
+        _count()
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _dense_nhwc(g)
+        n, h2, w2, c = g.shape
+        gx = torch.empty((n, h2 // 2, w2 // 2, c), dtype=torch.bfloat16, device=g.device)
+        _ops().upsample2x_bwd(g, gx)
+        _count()
+        return gx
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    return _Upsample2x.apply(x)
+
+
+# --------------------------------------------------------------------------------------------------
+# convolution (3x3 / 1x1, stride 1, same padding) on tcgen05
+# --------------------------------------------------------------------------------------------------
+def _pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+def pack_weight(w: torch.Tensor, transpose_flip: bool = False) -> torch.Tensor:
+    """fp32 [Cout,Cin,k,k] (any dense strides) -> packed bf16 operand of the implicit GEMM."""
+    cout, cin, k, _ = w.shape
+    rows, cols = (cin, cout) if transpose_flip else (cout, cin)
+    out = torch.empty(_pad16(rows) * k * k * cols, dtype=torch.bfloat16, device=w.device)
+    _ops().pack_conv_weight(w.detach(), transpose_flip, out)
+    _count()
+    return out
+
+
+class _Conv(torch.autograd.Function):
+    """out = conv_k(a, w) [+ conv_1(a2, w2)] + bias + rowadd[:, :, None, None] + residual.
+
+    `out_nchw=True` returns fp32 NCHW [N, Cout, H, W] (any Cout: the network tails); otherwise bf16 NHWC.
+    """
+
+    @staticmethod
+    def forward(ctx, a, w, bias, rowadd, a2, w2, residual, out_nchw):
+        o = _ops()
+        a = _dense_nhwc(a)
+        n, h, wd, cin = a.shape
+        cout, k = w.shape[0], w.shape[2]
+        assert w.shape[1] == cin, f"conv: weight expects {w.shape[1]} input channels, activation has {cin}"
+        wp = pack_weight(w)
+        a2d = w2p = None
+        if a2 is not None:
+            a2d = _dense_nhwc(a2)
+            w2p = pack_weight(w2)
+        res = _dense_nhwc(residual) if residual is not None else None
+        if out_nchw:
+            out = torch.empty((n, cout, h, wd), dtype=torch.float32, device=a.device)
+            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, None, out)
+        else:
+            out = torch.empty((n, h, wd, cout), dtype=torch.bfloat16, device=a.device)
+            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, out, None)
+        _count()
+        ctx.save_for_backward(a, w, a2d, w2)
+        ctx.flags = (bias is not None, rowadd is not None, residual is not None, out_nchw)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        o = _ops()
+        a, w, a2, w2 = ctx.saved_tensors
+        has_bias, has_rowadd, has_res, out_nchw = ctx.flags
+        n, h, wd, cin = a.shape
+        cout, k = w.shape[0], w.shape[2]
+        cpad = _pad16(cout)
+        if out_nchw:      # fp32 NCHW gradient of a narrow tail: pad the channel dim for the tensor cores
+            gp = torch.zeros((n, h, wd, cpad), dtype=torch.bfloat16, device=g.device)
+            o.nchw_to_nhwc(g.contiguous().float(), gp[..., :cout])
+            _count()
+            g_full, g_valid = gp, gp[..., :cout]
+        else:
+            g_full = g_valid = _dense_nhwc(g)
+            if cpad != cout:
+                gp = torch.zeros((n, h, wd, cpad), dtype=torch.bfloat16, device=g.device)
+                gp[..., :cout].copy_(g_valid)
+                g_full = gp
+        needs = ctx.needs_input_grad
+        ga = gw = gbias = growadd = ga2 = gw2 = gres = None
+        if needs[0]:
+            # dgrad = the same implicit GEMM with transposed, 180-degree-rotated weights
+            if cpad != cout:
+                w_t = torch.zeros((cpad, cin, k, k), dtype=torch.float32, device=w.device)
+                w_t[:cout].copy_(w.detach())
+            else:
+                w_t = w
+            wtp = pack_weight(w_t, transpose_flip=True)
+            ga = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=a.device)
+            o.conv_fprop(g_full, wtp, k, cin, None, None, None, None, None, ga, None)
+            _count()
+        if needs[1]:
+            dw = torch.zeros((cpad, k, k, cin), dtype=torch.float32, device=w.device)
+            o.conv_wgrad(g_full, a, k, dw)
+            _count(2)
+            gw = dw[:cout].permute(0, 3, 1, 2)          # [Cout,Cin,k,k] view with channels_last strides
+        if (has_bias and needs[2]) or (has_rowadd and needs[3]):
+            if cout % 8 == 0:
+                per = torch.zeros((n, cout), dtype=torch.float32, device=g.device) if has_rowadd else None
+                tot = torch.zeros((cout,), dtype=torch.float32, device=g.device) if has_bias else None
+                o.chansum(g_valid, per, tot)
+                _count(2)
+                growadd, gbias = per, tot
+            else:
+                per = torch.zeros((n, cpad), dtype=torch.float32, device=g.device)
+                o.chansum(g_full, per, None)
+                _count(2)
+                growadd = per[:, :cout].contiguous() if has_rowadd else None
+                gbias = per[:, :cout].sum(0) if has_bias else None
+        if a2 is not None:
+            if needs[4]:
+                w2tp = pack_weight(w2, transpose_flip=True)
+                ga2 = torch.empty(a2.shape, dtype=torch.bfloat16, device=a.device)
+                o.conv_fprop(g_full, w2tp, 1, a2.shape[3], None, None, None, None, None, ga2, None)
+                _count()
+            if needs[5]:
+                dw2 = torch.zeros((cpad, 1, 1, a2.shape[3]), dtype=torch.float32, device=w.device)
+                o.conv_wgrad(g_full, a2, 1, dw2)
+                _count(2)
+                gw2 = dw2[:cout].permute(0, 3, 1, 2)
+        if has_res and needs[6]:
+            gres = g_valid
+        return ga, gw, gbias, growadd, ga2, gw2, gres, None
+
+
+def conv(a: torch.Tensor, w: torch.Tensor, bias=None, rowadd=None, a2=None, w2=None, residual=None,
+         out_nchw: bool = False) -> torch.Tensor:
+    """Fused stride-1 same-padding convolution (k = 1 or 3).  `a` NHWC bf16 with C % 16 == 0."""
+    return _Conv.apply(a, w, bias, rowadd, a2, w2, residual, out_nchw)
+
+
+# --------------------------------------------------------------------------------------------------
+# optimiser tail
+# --------------------------------------------------------------------------------------------------
+def sumsq_(g: torch.Tensor, acc: torch.Tensor) -> None:
+    _ops().sumsq(g, acc)
+    _count()
+
+
+def adam_ema_step_(p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, step) -> None:
+    _ops().adam_ema_step(p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, step)
+    _count()
