@@ -1,0 +1,141 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution (fprop, dgrad, wgrad, fused epilogue terms, 1x1
+shortcut K-extension) against torch fp32 convolution of the SAME bf16-rounded operands.
+Stated tolerance (north_star): <= 1e-2 relative for bf16; observed error is bf16 output rounding."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from unet_design_b200 import ops as o
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return o
+
+
+def _mk(n, h, w, cin, cout, k, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5)
+    wt = wt.to(torch.bfloat16).float().contiguous(memory_format=torch.channels_last)
+    return a, wt
+
+
+CASES = [
+    # n, h, w, cin, cout, k
+    (2, 8, 8, 64, 64, 3), (2, 8, 8, 64, 64, 1), (8, 4, 4, 256, 256, 3), (2, 16, 16, 384, 256, 3), (2, 32, 32, 128, 128, 3),
+    (2, 32, 32, 256, 128, 3), (1, 32, 32, 128, 16, 3), (3, 7, 9, 32, 48, 3), (2, 25, 13, 16, 32, 3), (1, 13, 13, 144, 80, 3),
+    (2, 16, 16, 512, 256, 1), (1, 128, 128, 64, 64, 3), (1, 96, 192, 64, 64, 3), (1, 200, 200, 16, 16, 3), (5, 4, 4, 512, 256, 3),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fprop_plain(ops, case):
+    n, h, w, cin, cout, k = case
+    a, wt = _mk(*case)
+    y = ops.conv(a, wt)
+    ref = F.conv2d(a.float().permute(0, 3, 1, 2), wt, padding=k // 2).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < TOL, f"max abs {float((y.float() - ref).abs().max())}"
+
+
+@pytest.mark.parametrize("case", [(2, 8, 8, 64, 64, 3), (2, 16, 16, 384, 256, 3), (4, 4, 4, 512, 256, 3), (2, 32, 32, 384, 128, 3),
+                                  (3, 7, 9, 32, 48, 3)])
+def test_fprop_fused_epilogue_and_shortcut(ops, case):
+    n, h, w, cin, cout, k = case
+    a, wt = _mk(*case)
+    torch.manual_seed(1)
+    bias = torch.randn(cout, device="cuda")
+    rowadd = torch.randn(n, cout, device="cuda")
+    res = torch.randn(n, h, w, cout, device="cuda").to(torch.bfloat16)
+    ref = F.conv2d(a.float().permute(0, 3, 1, 2), wt, bias, padding=1) + rowadd[:, :, None, None]
+    y = ops.conv(a, wt, bias, rowadd=rowadd, residual=res)
+    assert rel_err(y, (ref + res.float().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)) < TOL
+    # 1x1 shortcut of a second tensor as extra K slices
+    cin2 = 2 * cout if cout <= 128 else 512
+    a2, w2 = _mk(n, h, w, cin2, cout, 1, seed=3)
+    y = ops.conv(a, wt, bias, rowadd=rowadd, a2=a2, w2=w2)
+    ref2 = ref + F.conv2d(a2.float().permute(0, 3, 1, 2), w2)
+    assert rel_err(y, ref2.permute(0, 2, 3, 1)) < TOL
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 128, 3, 3), (2, 8, 8, 64, 1, 1), (1, 25, 13, 32, 3, 3), (2, 16, 16, 256, 3, 3)])
+def test_fprop_narrow_tail_to_nchw(ops, case):
+    n, h, w, cin, cout, k = case
+    a, wt = _mk(*case)
+    bias = torch.randn(cout, device="cuda")
+    y = ops.conv(a, wt, bias, out_nchw=True)
+    ref = F.conv2d(a.float().permute(0, 3, 1, 2), wt, bias, padding=k // 2)
+    assert y.dtype == torch.float32 and y.shape == ref.shape
+    assert rel_err(y, ref) < 2e-5          # fp32 accumulate, fp32 store: no bf16 output rounding
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_backward_dgrad_wgrad_bias(ops, case):
+    n, h, w, cin, cout, k = case
+    a, wt = _mk(*case)
+    torch.manual_seed(2)
+    a = a.requires_grad_(True)
+    wt = wt.requires_grad_(True)
+    bias = torch.zeros(cout, device="cuda", requires_grad=True)
+    rowadd = torch.zeros(n, cout, device="cuda", requires_grad=True)
+    y = ops.conv(a, wt, bias, rowadd=rowadd)
+    g = torch.randn_like(y)
+    y.backward(g)
+    ar = a.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.detach().clone().requires_grad_(True)
+    br = torch.zeros(cout, device="cuda", requires_grad=True)
+    rr = torch.zeros(n, cout, device="cuda", requires_grad=True)
+    yr = F.conv2d(ar, wr, br, padding=k // 2) + rr[:, :, None, None]
+    yr.backward(g.float().permute(0, 3, 1, 2))
+    assert rel_err(a.grad, ar.grad.permute(0, 2, 3, 1)) < TOL
+    assert rel_err(wt.grad, wr.grad) < TOL
+    assert rel_err(bias.grad, br.grad) < TOL
+    assert rel_err(rowadd.grad, rr.grad) < TOL
+
+
+def test_backward_with_shortcut_residual_and_tail(ops):
+    n, h, w, cin, cout = 2, 16, 16, 128, 64
+    a, wt = _mk(n, h, w, cin, cout, 3)
+    a2, w2 = _mk(n, h, w, 256, cout, 1, seed=5)
+    for t in (a, wt, a2, w2):
+        t.requires_grad_(True)
+    y = ops.conv(a, wt, None, a2=a2, w2=w2)
+    g = torch.randn_like(y)
+    y.backward(g)
+    ar, a2r = (t.detach().float().permute(0, 3, 1, 2).requires_grad_(True) for t in (a, a2))
+    wr, w2r = (t.detach().clone().requires_grad_(True) for t in (wt, w2))
+    (F.conv2d(ar, wr, padding=1) + F.conv2d(a2r, w2r)).backward(g.float().permute(0, 3, 1, 2))
+    assert rel_err(a2.grad, a2r.grad.permute(0, 2, 3, 1)) < TOL and rel_err(w2.grad, w2r.grad) < TOL
+    assert rel_err(a.grad, ar.grad.permute(0, 2, 3, 1)) < TOL and rel_err(wt.grad, wr.grad) < TOL
+    # fp32 NCHW tail (Cout = 3): gradient arrives as NCHW fp32
+    a, wt = _mk(2, 16, 16, 128, 3, 3, seed=7)
+    a.requires_grad_(True); wt.requires_grad_(True)
+    bias = torch.zeros(3, device="cuda", requires_grad=True)
+    y = ops.conv(a, wt, bias, out_nchw=True)
+    g = torch.randn_like(y)
+    y.backward(g)
+    ar = a.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.detach().clone().requires_grad_(True)
+    br = torch.zeros(3, device="cuda", requires_grad=True)
+    F.conv2d(ar, wr, br, padding=1).backward(g.to(torch.bfloat16).float())
+    assert rel_err(a.grad, ar.grad.permute(0, 2, 3, 1)) < TOL
+    assert rel_err(wt.grad, wr.grad) < TOL and rel_err(bias.grad, br.grad) < TOL
+
+
+def test_linearity_at_full_config_size(ops):
+    """BASELINE config-2 size (batch 128, 32x32, 384 -> 128): conv(a1 + a2) == conv(a1) + conv(a2) and a
+    spot check of 64 output pixels against torch fp32."""
+    a1, wt = _mk(128, 32, 32, 384, 128, 3)
+    a2, _ = _mk(128, 32, 32, 384, 128, 3, seed=9)
+    y1, y2 = ops.conv(a1, wt), ops.conv(a2, wt)
+    ysum = ops.conv((a1.float() + a2.float()).to(torch.bfloat16), wt)
+    assert rel_err(ysum, y1.float() + y2.float()) < 2e-2
+    ref = F.conv2d(a1[:2].float().permute(0, 3, 1, 2), wt, padding=1).permute(0, 2, 3, 1)
+    assert rel_err(y1[:2], ref) < TOL

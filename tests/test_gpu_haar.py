@@ -1,0 +1,127 @@
+"""GPU parity of the Haar kernels (through torch.ops.unet_b200 -> C ABI) against the CPU oracle.
+Bar: fp32, bit-exact against oracle/haar_np.py (same expression order, no contraction); the north_star's
+1e-6 relative bound against the conv-form restatement of pytorch_wavelets."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import haar_np
+from oracle.pytorch_wavelets_restated import DWTForward, DWTInverse
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(2, 3, 32, 32), (4, 16, 16, 16), (2, 8, 8, 8), (1, 5, 7, 9), (2, 2, 25, 13), (1, 4, 1, 1), (1, 1, 32, 2),
+          (3, 2, 200, 6), (2, 16, 200, 200), (1, 3, 96, 192), (1, 128, 25, 25), (8, 64, 64, 64)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from unet_design_b200 import ops as o
+    return o
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_dwt_level_bit_exact_and_roundtrip(ops, shape):
+    torch.manual_seed(0)
+    x = torch.randn(*shape)
+    yl, yh = ops.haar_dwt2d(x.cuda(), 1)
+    ll, lh, hl, hh = haar_np.dwt2_level(x.numpy())
+    np.testing.assert_array_equal(yl.cpu().numpy(), ll)
+    np.testing.assert_array_equal(yh[0].cpu().numpy(), np.stack([lh, hl, hh], axis=2))
+    rec = ops.haar_idwt2d(yl, yh)
+    np.testing.assert_array_equal(rec.cpu().numpy(), haar_np.idwt2_level(ll, lh, hl, hh))
+    h, w = shape[-2:]
+    assert rel_err(rec[..., :h, :w], x) < 1e-6
+
+
+@pytest.mark.parametrize("shape", SHAPES[:8])
+@pytest.mark.parametrize("J", [1, 2, 3])
+def test_multilevel_matches_conv_restatement(ops, shape, J):
+    torch.manual_seed(1)
+    x = torch.randn(*shape)
+    yl, yh = ops.haar_dwt2d(x.cuda(), J)
+    ref_l, ref_h = DWTForward(J=J)(x)
+    assert yl.shape == ref_l.shape and rel_err(yl, ref_l) < 1e-6
+    for a, b in zip(yh, ref_h):
+        assert a.shape == b.shape and rel_err(a, b, floor=1e-7) < 1e-6
+    rec = ops.haar_idwt2d(yl, yh)
+    ref = DWTInverse()((ref_l, ref_h))
+    assert rec.shape == ref.shape and rel_err(rec, ref) < 1e-6
+    # the reference's only use of the inverse: an empty list is the identity
+    assert ops.haar_idwt2d(yl, []) is yl
+
+
+@pytest.mark.parametrize("shape,J,out_ch", [((2, 3, 32, 32), 0, 128), ((2, 128, 32, 32), 1, 128), ((2, 128, 16, 16), 0, 256),
+                                            ((1, 5, 7, 9), 1, 12), ((1, 3, 16, 16), 2, 7), ((1, 2, 25, 13), 3, 2),
+                                            ((2, 16, 200, 200), 1, 16), ((2, 128, 25, 25), 1, 128), ((2, 3, 33, 31), 0, 8),
+                                            ((4, 3, 32, 32), 3, 3), ((4, 3, 32, 32), 2, 3)])
+def test_dwtblock_forward_backward_bit_exact(ops, shape, J, out_ch):
+    torch.manual_seed(2)
+    x = torch.randn(*shape)
+    xg = x.cuda().requires_grad_(True)
+    y = ops.dwtblock(xg, J, out_ch)
+    want = haar_np.dwtblock(x.numpy(), J, out_ch)
+    np.testing.assert_array_equal(y.detach().cpu().numpy(), want)
+    g = torch.randn(*want.shape)
+    y.backward(g.cuda())
+    np.testing.assert_array_equal(xg.grad.cpu().numpy(), haar_np.dwtblock_bwd(g.numpy(), shape, J))
+
+
+def test_dwt_backward_is_the_adjoint(ops):
+    torch.manual_seed(3)
+    for shape in [(2, 3, 16, 16), (1, 2, 7, 9)]:
+        x = torch.randn(*shape, device="cuda", requires_grad=True)
+        yl, yh = ops.haar_dwt2d(x, 2)
+        gl, gh = torch.randn_like(yl), [torch.randn_like(b) for b in yh]
+        (yl * gl).sum().add(sum((a * b).sum() for a, b in zip(yh, gh))).backward()
+        xr = x.detach().cpu().requires_grad_(True)
+        rl, rh = DWTForward(J=2)(xr)
+        (rl * gl.cpu()).sum().add(sum((a * b.cpu()).sum() for a, b in zip(rh, gh))).backward()
+        assert rel_err(x.grad, xr.grad) < 1e-6
+        # synthesis backward
+        ylr = yl.detach().clone().requires_grad_(True)
+        yhr = [b.detach().clone().requires_grad_(True) for b in yh]
+        rec = ops.haar_idwt2d(ylr, yhr)
+        gr = torch.randn_like(rec)
+        rec.backward(gr)
+        cl = yl.detach().cpu().requires_grad_(True)
+        ch = [b.detach().cpu().requires_grad_(True) for b in yh]
+        DWTInverse()((cl, ch)).backward(gr.cpu())
+        assert rel_err(ylr.grad, cl.grad) < 1e-6
+        for a, b in zip(yhr, ch):
+            assert rel_err(a.grad, b.grad) < 1e-6
+
+
+def test_dwtblock_nhwc_with_channel_map(ops):
+    torch.manual_seed(4)
+    x = torch.randn(3, 3, 16, 16)
+    chmap = [((k % 256) % 128) % 3 for k in range(256)]
+    out = torch.empty(3, 16, 16, 256, dtype=torch.bfloat16, device="cuda")
+    ops.dwtblock_nhwc(x.cuda(), 0, out, torch.tensor(chmap, dtype=torch.int32, device="cuda"))
+    want = x[:, chmap].permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(out.cpu(), want)
+    # J = 1 into a channel slice of a wider buffer (the skip half of a cat buffer)
+    buf = torch.zeros(3, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+    ops.dwtblock_nhwc(x.cuda(), 1, buf[..., 32:])
+    want = torch.from_numpy(haar_np.dwtblock(x.numpy(), 1, 32)).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(buf[..., 32:].cpu(), want) and float(buf[..., :32].abs().max()) == 0.0
+
+
+def test_full_size_properties(ops):
+    """Size-independent properties at BASELINE sweep sizes (no CPU oracle needed): perfect reconstruction,
+    energy preservation, LL/2 == avg_pool2d, linearity."""
+    torch.manual_seed(5)
+    x = torch.randn(64, 64, 256, 256, device="cuda")          # 1 GiB
+    yl, yh = ops.haar_dwt2d(x, 1)
+    rec = ops.haar_idwt2d(yl, yh)
+    assert float((rec - x).abs().max()) < 5e-6
+    e_in = float(x.double().pow(2).sum())
+    e_out = float(yl.double().pow(2).sum() + yh[0].double().pow(2).sum())
+    assert abs(e_in - e_out) < 1e-5 * e_in
+    assert float((yl * 0.5 - torch.nn.functional.avg_pool2d(x, 2)).abs().max()) < 1e-6
+    del rec, yh
+    z = torch.randn_like(x)
+    lhs = ops.haar_dwt2d(x + 2 * z, 1)[0]
+    rhs = yl + 2 * ops.haar_dwt2d(z, 1)[0]
+    assert float((lhs - rhs).abs().max()) < 2e-5
