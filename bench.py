@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- Multi-ResNet (Haar encoder) DDPM train throughput on B200, BASELINE.json's headline metric.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port)
+
+Workload (N = 1 and every N: weak scaling): BASELINE configs[1] = diff_cifar Multi-ResNet DDPM U-Net,
+`UNetWaveletEnc(T=1000, ch=128, ch_mult=[1,2,2,2], attn=[1], num_res_blocks=2, dropout=0.1, dwt_encoder=True)`,
+synthetic 3x32x32, batch 128 per GPU, bf16 compute / fp32 master weights, Adam 2e-4 + warm-up + clip 1.0 +
+EMA 0.9999 (diff_cifar/hyperparams.py:36-55).  A "step" = noise draw, q-sample, forward, MSE, backward,
+(all-reduce,) clip + Adam + EMA.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(T=1000, ch=128, ch_mult=[1, 2, 2, 2], attn=[1], num_res_blocks=2, dropout=0.1, dwt_encoder=True)
+BATCH_PER_GPU = 128
+IMG = (3, 32, 32)
+METRIC = "multi_resnet_ddpm_train_images_per_sec"
+WORKLOAD = "diff_cifar Multi-ResNet (Haar encoder) DDPM train step, synthetic 3x32x32, batch 128 per GPU, bf16"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle/torch_ref.py, pinned against the reference's own classes by
+# tests/golden) on the host cores.  Used for `cpu_baseline` (bounded sample) and for --impl reference.
+# ------------------------------------------------------------------------------------------------
+def cpu_train_steps(batch: int, steps: int, warmup: int):
+    from oracle import torch_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    net = torch_ref.UNetWaveletEnc(**CFG)
+    trainer = torch_ref.GaussianDiffusionTrainer(net, 1e-4, 0.02, CFG["T"])
+    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=2e-4)
+    ema = [p.detach().clone() for p in net.parameters() if p.requires_grad]
+    x0 = torch.rand(batch, *IMG) * 2 - 1
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss, _ = trainer(x0)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt.step()
+        with torch.no_grad():
+            for e, p in zip(ema, (q for q in net.parameters() if q.requires_grad)):
+                e.mul_(0.9999).add_(p, alpha=1 - 0.9999)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 16
+    times, cores = cpu_train_steps(batch, args.steps, args.warmup)
+    total = sum(times)
+    value = batch * len(times) / total
+    sample = f"{len(times)} steps of batch {batch} (of the 128-per-GPU workload), fp32, PyTorch CPU, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference algorithm on host cores via oracle/torch_ref.py (the reference is "
+                   "pure Python and /root/reference does not travel to the GPU box)"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel timing proxy (CUDA events around every conv launch of one eager step)
+# ------------------------------------------------------------------------------------------------
+class KernelTimer:
+    def __init__(self, real):
+        self._real, self.records = real, []
+
+    def __getattr__(self, name):
+        fn = getattr(self._real, name)
+        if name not in ("conv_fprop", "conv_wgrad"):
+            return fn
+
+        def timed(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a)
+            e1.record()
+            if name == "conv_fprop":
+                act, _, k, cout, a2 = a[0], a[1], a[2], a[3], a[4]
+                n, h, w, cin = act.shape
+                flops = 2.0 * n * h * w * cout * (k * k * cin + (a2.shape[3] if a2 is not None else 0))
+            else:
+                g, act, k = a[0], a[1], a[2]
+                n, h, w, cin = act.shape
+                flops = 2.0 * n * h * w * g.shape[3] * k * k * cin
+            self.records.append((name, flops, e0, e1))
+            return out
+        return timed
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, flops, e0, e1 in self.records:
+            d = out.setdefault(name, {"launches": 0, "flops": 0.0, "ms": 0.0})
+            d["launches"] += 1; d["flops"] += flops; d["ms"] += e0.elapsed_time(e1)
+        return out
+
+
+def haar_roofline(peaks):
+    """Haar DWT GB/s at a beyond-L2 size (64x64x256x256 fp32 = 1 GiB in, 1 GiB out per launch)."""
+    from unet_design_b200._lib import ops as raw
+    o = raw()
+    x = torch.randn(64, 64, 256, 256, device="cuda")
+    res = {}
+
+    def timeit(fn, bytes_per_launch, reps=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        return {"ms": ms, "GBps": bytes_per_launch / ms / 1e6, "bytes": bytes_per_launch}
+
+    E = x.numel() * 4
+    res["dwt_4band_1GiB"] = timeit(lambda: o.haar_dwt2d_fwd(x, True), 2 * E)
+    ll, hi = o.haar_dwt2d_fwd(x, True)
+    res["idwt_4band_1GiB"] = timeit(lambda: o.haar_idwt2d(ll, hi, 256, 256), 2 * E)
+    res["dwtblock_J1_LL_tile1"] = timeit(lambda: o.dwtblock_fwd(x, 1, 64), E * 1.25)
+    del ll, hi
+    x2 = torch.randn(128, 128, 32, 32, device="cuda")          # config-2 encoder shape (67 MB: lives in L2)
+    res["dwtblock_J1_cfg2_128x128x32x32_L2resident"] = timeit(lambda: o.dwtblock_fwd(x2, 1, 128), x2.numel() * 4 * 1.25, reps=50)
+    best = res["dwt_4band_1GiB"]
+    return {"bound": "hbm", "kernel": "haar_dwt_vec4<true>", "achieved": best["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": best["GBps"] / peaks["hbm_gbs"], "frac_of_8TBps_nominal": best["GBps"] / 8000.0, "traffic": None,
+            "peak_source": peaks["source"], "cases": res}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from unet_design_b200 import _lib, ops
+    from unet_design_b200.diff_cifar.model import UNetWaveletEnc
+    from unet_design_b200.train import DDPMTrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback in the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = measured_peaks()
+    torch.manual_seed(1234)
+    net = UNetWaveletEnc(**CFG).to(dev)
+    net.train()
+    ops.seed_dropout(1234 + rank)
+    step = DDPMTrainStep(net, T=CFG["T"], lr=2e-4, warmup=5000, grad_clip=1.0, ema_decay=0.9999,
+                         use_cuda_graph=not args.no_graph)
+    gen = torch.Generator().manual_seed(rank)
+    host_batches = [(torch.rand(BATCH_PER_GPU, *IMG, generator=gen) * 2 - 1).pin_memory() for _ in range(4)]
+    dev_batches = [b.to(dev) for b in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # kernel launches of one step, counted on an eager pass (graph replays do not go through Python)
+    l0 = ops.launches()
+    step._body(dev_batches[0])
+    launches_per_step = ops.launches() - l0
+    torch.cuda.synchronize()
+
+    # ---- device-resident inputs: W warm-up + K timed steps
+    for i in range(max(args.warmup, 3)):
+        step(dev_batches[i % 4])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(dev_batches[i % 4])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(loss)
+
+    # ---- end to end through the public API: pinned host batch in, loss float out, every step
+    for i in range(3):
+        step.step_from_host(host_batches[i % 4])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step.step_from_host(host_batches[i % 4])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+
+    line = None
+    if rank == 0:
+        imgs = BATCH_PER_GPU * world * args.steps
+        # ---- roofline of the dominant kernel, measured live (one eager step with events around every conv launch)
+        timer = KernelTimer(_lib.ops())
+        _lib._ops = timer
+        step._body(dev_batches[0])
+        ksum = timer.summary()
+        _lib._ops = timer._real
+        fp = ksum.get("conv_fprop", {"flops": 0.0, "ms": 1.0, "launches": 0})
+        wg = ksum.get("conv_wgrad", {"flops": 0.0, "ms": 1.0, "launches": 0})
+        peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        ach = fp["flops"] / (fp["ms"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "conv_fprop_kernel (fprop + dgrad launches)", "achieved": ach, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "launches_per_step": fp["launches"],
+                    "flops_per_step": fp["flops"], "ms_per_step": fp["ms"],
+                    "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                    "wgrad": {"achieved": wg["flops"] / (wg["ms"] * 1e-3) / 1e12, "launches_per_step": wg["launches"],
+                              "ms_per_step": wg["ms"], "frac": wg["flops"] / (wg["ms"] * 1e-3) / 1e12 / peak_tf},
+                    "conv_share_of_step": (fp["ms"] + wg["ms"]) / (ms / args.steps)}
+        haar = haar_roofline(peaks) if not args.skip_haar else None
+        cpu = None
+        if not args.skip_cpu:
+            times, cores = cpu_train_steps(16, 2, 1)
+            cpu = {"value": 16 * len(times) / sum(times), "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": f"{len(times)} steps of batch 16 of the same model and optimiser, fp32 PyTorch CPU (oracle/torch_ref.py)"}
+        line = {
+            "metric": METRIC, "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}",
+                       "cuda_graph": not args.no_graph, "l2_policy": "4 rotating input batches; activations+weights per step "
+                       "(~3 GB) exceed the 126 MB L2", "loss": loss_val},
+            "clocks": clocks,
+            "e2e": {"value": imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": BATCH_PER_GPU * 3 * 32 * 32 * 4,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "haar_roofline": haar, "cpu_baseline": cpu,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-haar", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -205,11 +205,15 @@ int ub200_pack_conv_weight(const float *w, int64_t Cout, int64_t Cin, int ksize,
 int ub200_sumsq_f32(const float *g, int64_t n, float *sumsq, void *stream);
 /* g' = g * grad_scale * min(1, max_norm / (sqrt(sumsq[0]) * grad_scale + 1e-6))  (sumsq NULL or
  * max_norm <= 0: no clip); torch.optim.Adam update with bias correction for the 1-based step_host;
- * ema = decay*ema + (1-decay)*p (ema NULL to skip). */
+ * ema = decay*ema + (1-decay)*p (ema NULL to skip).  warmup_steps > 0 scales lr by
+ * min(step-1, warmup)/warmup (the LambdaLR of diff_cifar/main.py:90-91, stepped after the optimiser).
+ * step_dev (nullable) is a device-resident step counter that overrides step_host, so that a
+ * captured CUDA graph replays with the right bias correction and learning rate. */
 int ub200_adam_ema_step_f32(float *p, const float *g, float *m, float *v, float *ema, int64_t n,
                             const float *sumsq, float max_norm, float grad_scale,
                             float lr, float beta1, float beta2, float eps, float ema_decay,
-                            int64_t step_host, void *stream);
+                            int64_t step_host, int64_t warmup_steps, const int64_t *step_dev,
+                            void *stream);
 
 #ifdef __cplusplus
 }

@@ -183,7 +183,12 @@ class EmulatedOps:
     def sumsq(self, g, acc):
         acc.add_((g.double() ** 2).sum().float())
 
-    def adam_ema_step(self, p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, b1, b2, eps, decay, step):
+    def adam_ema_step(self, p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, b1, b2, eps, decay, step,
+                      warmup_steps=0, step_dev=None):
+        if step_dev is not None:
+            step = int(step_dev)
+        if warmup_steps > 0:
+            lr = lr * min(step - 1, warmup_steps) / warmup_steps
         clip = grad_scale
         if sumsq is not None and max_norm > 0:
             norm = float(sumsq.sqrt()) * grad_scale

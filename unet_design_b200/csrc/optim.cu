@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float *__restrict__ g,
 
 struct AdamArgs {
     float max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, bc1, bc2;
+    long long warmup;               // > 0: lr *= min(step - 1, warmup) / warmup   (LambdaLR of diff_cifar/main.py:90-91)
+    const long long *step_dev;      // device-resident 1-based step (CUDA-graph replays); NULL = host value baked in
 };
 
 __device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, float *ema, const AdamArgs &a, float clip) {
@@ -44,6 +46,12 @@ __global__ void __launch_bounds__(256) adam_ema_kernel(float *__restrict__ p, co
                                                       float *__restrict__ m, float *__restrict__ v,
                                                       float *__restrict__ ema, int64_t n,
                                                       const float *__restrict__ sumsq, AdamArgs a) {
+    if (a.step_dev) {               // bias corrections and warm-up from the device-side step counter
+        const float st = (float)__ldg(a.step_dev);
+        a.bc1 = 1.f - powf(a.beta1, st);
+        a.bc2 = sqrtf(1.f - powf(a.beta2, st));
+        if (a.warmup > 0) a.lr *= fminf(st - 1.f, (float)a.warmup) / (float)a.warmup;
+    }
     // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1; grads arrive scaled by 1/grad_scale
     float clip = a.grad_scale;
     if (sumsq && a.max_norm > 0.f) {
@@ -83,13 +91,21 @@ int ub200_sumsq_f32(const float *g, int64_t n, float *sumsq, void *stream) {
 
 int ub200_adam_ema_step_f32(float *p, const float *g, float *m, float *v, float *ema, int64_t n, const float *sumsq,
                             float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
-                            float ema_decay, int64_t step_host, void *stream) {
-    UB_REQUIRE(p && g && m && v && n > 0 && step_host >= 1, UB200_E_BADARG);
+                            float ema_decay, int64_t step_host, int64_t warmup_steps, const int64_t *step_dev,
+                            void *stream) {
+    UB_REQUIRE(p && g && m && v && n > 0 && (step_dev || step_host >= 1), UB200_E_BADARG);
     UB_REQUIRE(ub::aligned16(p) && ub::aligned16(g) && ub::aligned16(m) && ub::aligned16(v) && (!ema || ub::aligned16(ema)),
                UB200_E_UNSUPPORTED);
-    AdamArgs a{max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, 0.f, 0.f};
-    a.bc1 = (float)(1.0 - pow((double)beta1, (double)step_host));
-    a.bc2 = (float)sqrt(1.0 - pow((double)beta2, (double)step_host));
+    AdamArgs a{max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, 1.f, 1.f, (long long)warmup_steps,
+               reinterpret_cast<const long long *>(step_dev)};
+    if (!step_dev) {
+        a.bc1 = (float)(1.0 - pow((double)beta1, (double)step_host));
+        a.bc2 = (float)sqrt(1.0 - pow((double)beta2, (double)step_host));
+        if (warmup_steps > 0) {
+            const double s1 = (double)(step_host - 1);
+            a.lr *= (float)((s1 < (double)warmup_steps ? s1 : (double)warmup_steps) / (double)warmup_steps);
+        }
+    }
     adam_ema_kernel<<<ub::grid_for((n + 3) / 4, 256, 8, 2), 256, 0, ub::as_stream(stream)>>>(p, g, m, v, ema, n, sumsq, a);
     UB_LAUNCH_CHECK();
     return UB200_OK;

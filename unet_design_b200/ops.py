@@ -410,6 +410,8 @@ def sumsq_(g: torch.Tensor, acc: torch.Tensor) -> None:
     _count()
 
 
-def adam_ema_step_(p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, step) -> None:
-    _ops().adam_ema_step(p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, step)
+def adam_ema_step_(p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, step,
+                   warmup_steps: int = 0, step_dev=None) -> None:
+    _ops().adam_ema_step(p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, step,
+                         warmup_steps, step_dev)
     _count()

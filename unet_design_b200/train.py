@@ -1,0 +1,214 @@
+"""Training step of the Multi-ResNet DDPM (the hot loop of diff_cifar/main.py:397-429) on one B200 or,
+data-parallel, on the GPUs of one box.
+
+    step = DDPMTrainStep(model, T=1000, lr=2e-4, warmup=5000, grad_clip=1.0, ema_decay=0.9999)
+    loss = step(x0)                       # x0 already on the device
+    loss = step.step_from_host(x0_pinned) # the end-to-end call: H2D copy, step, loss read-back
+
+What is B200-first about it (reference file:line in parentheses):
+
+* parameters, gradients, Adam moments and the EMA copy live in four flat fp32 arenas; conv weights keep
+  their [Cout, kh, kw, Cin] order inside the arena, so the tensor-core kernels read them in place;
+* `clip_grad_norm_` + `Adam.step` + `LambdaLR` warm-up + `ema()` (main.py:425-429, :57-77, :90-91) are TWO
+  kernels over the arena (sum of squares, then clip+Adam+EMA), with the step counter, learning-rate
+  warm-up and dropout counter on the device: no host synchronisation anywhere in the step;
+* the whole step (noise draw, q-sample, forward, loss, backward, all-reduce, optimiser) is captured in ONE
+  CUDA graph and replayed, because the network is ~400 small-to-medium kernels and launch-bound otherwise;
+* data parallel (`nn.DataParallel` at main.py:235-238 in the reference): one process per GPU, gradients
+  all-reduced in arena buckets by NCCL from post-accumulate hooks as backward produces them, on a side
+  stream, overlapping the rest of backward; the mean over ranks is folded into the optimiser's grad_scale.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import ops
+from .diff_cifar.diffusion import GaussianDiffusionTrainer
+
+
+class FlatArena:
+    """Trainable parameters of `model` re-homed into one flat fp32 buffer (and a matching gradient buffer).
+    Conv weights (4-D) keep channels_last order: the arena slice is viewed as [Cout,kh,kw,Cin] and permuted."""
+
+    def __init__(self, model: nn.Module):
+        params = [p for p in model.parameters() if p.requires_grad]
+        assert params, "model has no trainable parameters"
+        dev = params[0].device
+        self.params = params
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]          # keep every slice 16-byte aligned
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + s)
+        total = self.offsets[-1]
+        self.p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.g = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, off in zip(params, self.offsets):
+            view = self._view(self.p, p, off)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self._view(self.g, p, off)
+
+    @staticmethod
+    def _view(flat, p, off):
+        n = p.numel()
+        if p.dim() == 4:
+            co, ci, kh, kw = p.shape
+            return flat[off:off + n].view(co, kh, kw, ci).permute(0, 3, 1, 2)
+        return flat[off:off + n].view(p.shape)
+
+    def rebind_grads(self):
+        """Point every .grad back at the arena (after anything that may have replaced it)."""
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self._view(self.g, p, off)
+
+
+class DDPMTrainStep:
+    def __init__(self, model: nn.Module, T: int = 1000, beta_1: float = 1e-4, beta_T: float = 0.02, lr: float = 2e-4,
+                 warmup: int = 5000, grad_clip: float = 1.0, ema_decay: float = 0.9999, multi_res_loss: bool = False,
+                 betas=(0.9, 0.999), eps: float = 1e-8, use_cuda_graph: bool = True, process_group=None,
+                 bucket_mb: float = 16.0):
+        self.model = model
+        self.device = next(model.parameters()).device
+        self.trainer = GaussianDiffusionTrainer(model, beta_1, beta_T, T, multi_res_loss, False, self.device).to(self.device)
+        self.lr, self.warmup, self.grad_clip, self.ema_decay = lr, warmup, grad_clip, ema_decay
+        self.betas, self.eps = betas, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or
+                                                              (dist.is_available() and dist.is_initialized())) else 1
+        if self.world > 1:      # identical replicas: rank 0's initial weights everywhere (one broadcast)
+            for t in list(model.parameters()) + list(model.buffers()):
+                dist.broadcast(t.data, src=0, group=process_group)
+        self.arena = FlatArena(model)
+        n = self.arena.p.numel()
+        self.m = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.v = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.ema = self.arena.p.clone()
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)       # 1-based after the first bump
+        self.steps_done = 0
+        self.use_graph = use_cuda_graph and self.device.type == "cuda"
+        self._graph = None
+        self._static_x0 = None
+        self._static_loss = None
+        self._buckets: List[tuple] = []
+        self._comm_stream = None
+        if self.world > 1:
+            self._build_buckets(int(bucket_mb * (1 << 20) / 4))
+
+    # ------------------------------------------------------------------ data parallel
+    def _build_buckets(self, bucket_elems: int):
+        """Arena ranges in REVERSE parameter order (the order backward fills them); each range is all-reduced
+        as soon as its last gradient has been accumulated."""
+        offs, params = self.arena.offsets, self.arena.params
+        hi = offs[-1]
+        members: List[int] = []
+        for i in range(len(params) - 1, -1, -1):
+            members.append(i)
+            if hi - offs[i] >= bucket_elems or i == 0:
+                self._buckets.append((offs[i], hi, tuple(members)))
+                hi = offs[i]
+                members = []
+        self._bucket_of = {}
+        for b, (_, _, mem) in enumerate(self._buckets):
+            for i in mem:
+                self._bucket_of[i] = b
+        self._pending = [0] * len(self._buckets)
+        if self.device.type == "cuda":
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        for i, p in enumerate(params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_hook(self, i: int):
+        def hook(_param):
+            b = self._bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch_allreduce(b)
+        return hook
+
+    def _launch_allreduce(self, b: int):
+        lo, hi, _ = self._buckets[b]
+        view = self.arena.g[lo:hi]
+        if self._comm_stream is not None:
+            self._comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._comm_stream):
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg)
+        else:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _arm_buckets(self):
+        for b, (_, _, mem) in enumerate(self._buckets):
+            self._pending[b] = len(mem)
+
+    def _finish_allreduce(self):
+        """After backward: reduce the buckets that hold parameters this step did not touch (e.g. the coarse
+        tails without the multi-resolution loss; their hooks never fire), then join the side stream.  The set of
+        untouched parameters is the same on every rank, so the collective order stays consistent."""
+        for b in range(len(self._buckets)):
+            if self._pending[b] > 0:
+                self._pending[b] = 0
+                self._launch_allreduce(b)
+        if self._comm_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+
+    # ------------------------------------------------------------------ one step
+    def _body(self, x0: torch.Tensor) -> torch.Tensor:
+        self.arena.g.zero_()
+        self.step_dev.add_(1)
+        if self.world > 1:
+            self._arm_buckets()
+        loss, _ = self.trainer(x0)
+        loss.backward()
+        if self.world > 1:
+            self._finish_allreduce()
+        self.sumsq.zero_()
+        ops.sumsq_(self.arena.g, self.sumsq)
+        # gradients hold the SUM over ranks: the mean (what DataParallel / DDP produce) is a grad_scale of 1/world
+        ops.adam_ema_step_(self.arena.p, self.arena.g, self.m, self.v, self.ema, self.sumsq, self.grad_clip,
+                           1.0 / self.world, self.lr, self.betas[0], self.betas[1], self.eps, self.ema_decay, 1,
+                           self.warmup, self.step_dev)
+        ops.advance_dropout_state(self.device)
+        return loss.detach()
+
+    def __call__(self, x0: torch.Tensor) -> torch.Tensor:
+        self.steps_done += 1
+        if not self.use_graph:
+            return self._body(x0)
+        if self._graph is None:
+            self._capture(x0)
+        self._static_x0.copy_(x0, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
+
+    def _capture(self, x0: torch.Tensor):
+        self._static_x0 = x0.clone()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):           # warm-up on a side stream: allocator, tensor maps, cuBLAS handles
+            for _ in range(3):
+                self._body(self._static_x0)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._body(self._static_x0)
+        self.launches_per_step = None
+
+    def step_from_host(self, x0_pinned: torch.Tensor) -> float:
+        """The end-to-end call a user makes: batch in pinned host memory in, loss (a Python float) out."""
+        x0 = x0_pinned.to(self.device, non_blocking=True)
+        loss = self(x0)
+        return float(loss.cpu())
+
+    # ------------------------------------------------------------------ checkpoint surface
+    def ema_state_dict(self):
+        """`state_dict` of the EMA model (the reference keeps a deep copy, main.py:207-219)."""
+        sd = {k: v.clone() for k, v in self.model.state_dict().items()}
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        for p, off in zip(self.arena.params, self.arena.offsets):
+            sd[names[id(p)]] = FlatArena._view(self.ema, p, off).clone()
+        return sd
