@@ -183,8 +183,9 @@ int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a
                      int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize,
                      float *dw, void *stream);
 
-/* Channel sums of an NHWC bf16 tensor: per_sample[N,C] += sum_p x[n,p,c] (the time-embedding /
- * scale-shift gradient) and/or total[C] += sum_{n,p} x (the conv bias gradient).  Accumulates. */
+/* Channel sums of an NHWC bf16 tensor: per_sample[N,C] = sum_p x[n,p,c] (overwritten; the
+ * time-embedding / scale-shift gradient, and the workspace of the second pass) and, when total is
+ * not NULL, total[C] += sum_n per_sample[n,c] (the conv bias gradient; accumulates). */
 int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, int64_t C,
                             float *per_sample, float *total, void *stream);
 

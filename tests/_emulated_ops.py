@@ -163,8 +163,7 @@ class EmulatedOps:
 
     def chansum(self, x, per_sample, total):
         s = x.float().sum(dim=(1, 2))
-        if per_sample is not None:
-            per_sample.add_(s)
+        per_sample.copy_(s)
         if total is not None:
             total.add_(s.sum(0))
 

@@ -126,7 +126,7 @@ def test_dropout_mask_statistics_and_backward_consistency(ops):
 def test_chansum(ops):
     torch.manual_seed(5)
     x = torch.randn(4, 16, 16, 256, device="cuda").to(torch.bfloat16)
-    per = torch.zeros(4, 256, device="cuda")
+    per = torch.full((4, 256), 7.0, device="cuda")     # overwritten
     tot = torch.zeros(256, device="cuda")
     from unet_design_b200._lib import ops as raw
     raw().chansum(x, per, tot)

@@ -150,30 +150,44 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     }
 }
 
-// per-channel sums of an NHWC bf16 tensor: per_sample[N,C] and/or total[C] (atomics; caller zeroes)
+// per-channel sums of an NHWC bf16 tensor.  Pass 1: every CTA streams a pixel range of one sample (16 bytes per
+// thread), reduces across its threads in shared memory and issues ONE atomic per channel into per_sample[n, c].
+// Pass 2 (tiny): total[c] += sum_n per_sample[n, c].
 __global__ void __launch_bounds__(256) chansum_kernel(const __nv_bfloat16 *__restrict__ x, int64_t ld, int64_t HW, int C,
                                                      int chunks, int rows, int64_t pix_per_cta,
-                                                     float *__restrict__ per_sample, float *__restrict__ total) {
+                                                     float *__restrict__ per_sample) {
+    extern __shared__ float acc[];   // [C]
     const int64_t n = blockIdx.y;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
     const int q = threadIdx.x % chunks, r = threadIdx.x / chunks;
-    if (r >= rows) return;
-    float s[8];
+    if (r < rows) {
+        float s[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s[u] = 0.f;
-    const int64_t p0 = (int64_t)blockIdx.x * pix_per_cta;
-    int64_t p1 = p0 + pix_per_cta;
-    if (p1 > HW) p1 = HW;
-    for (int64_t pp = p0 + r; pp < p1; pp += rows) {
-        float f[8];
-        unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(x + (n * HW + pp) * ld + 8 * q)), f);
+        for (int u = 0; u < 8; ++u) s[u] = 0.f;
+        const int64_t p0 = (int64_t)blockIdx.x * pix_per_cta;
+        int64_t p1 = p0 + pix_per_cta;
+        if (p1 > HW) p1 = HW;
+        for (int64_t pp = p0 + r; pp < p1; pp += rows) {
+            float f[8];
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(x + (n * HW + pp) * ld + 8 * q)), f);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s[u] += f[u];
+            for (int u = 0; u < 8; ++u) s[u] += f[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) atomicAdd(&acc[8 * q + u], s[u]);
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        if (per_sample) atomicAdd(per_sample + n * C + 8 * q + u, s[u]);
-        if (total) atomicAdd(total + 8 * q + u, s[u]);
-    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(per_sample + n * C + i, acc[i]);
+}
+
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const float *__restrict__ per_sample, int64_t N, int C,
+                                                         float *__restrict__ total) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int64_t n = 0; n < N; ++n) s += per_sample[n * C + c];
+    total[c] += s;
 }
 
 // fp32 weights with arbitrary strides -> packed bf16 [rows_pad, k, k, cols] (rows padded to 16 with zeros)
@@ -283,8 +297,11 @@ int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a
 
 int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, int64_t C, float *per_sample, float *total,
                             void *stream) {
-    UB_REQUIRE(x && (per_sample || total) && N > 0 && HW > 0 && C > 0, UB200_E_BADARG);
+    UB_REQUIRE(x && per_sample && N > 0 && HW > 0 && C > 0, UB200_E_BADARG);
     UB_REQUIRE(C % 8 == 0 && C <= 2048 && ld % 8 == 0 && ld >= C && ub::aligned16(x) && N <= 65535, UB200_E_UNSUPPORTED);
+    cudaStream_t s = ub::as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(per_sample, 0, sizeof(float) * N * C, s);
+    if (e != cudaSuccess) return (int)e;
     const int chunks = (int)(C / 8), rows = 256 / chunks;
     int64_t splits = (148 * 8 + N - 1) / N;
     const int64_t max_splits = (HW + rows - 1) / rows;
@@ -293,9 +310,13 @@ int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, in
     const int64_t ppc = (HW + splits - 1) / splits;
     splits = (HW + ppc - 1) / ppc;
     dim3 grid((unsigned)splits, (unsigned)N, 1);
-    chansum_kernel<<<grid, 256, 0, ub::as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16 *>(x), ld, HW, (int)C,
-                                                           chunks, rows, ppc, per_sample, total);
+    chansum_kernel<<<grid, 256, C * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16 *>(x), ld, HW, (int)C, chunks,
+                                                       rows, ppc, per_sample);
     UB_LAUNCH_CHECK();
+    if (total) {
+        colsum_rows_kernel<<<(unsigned)((C + 255) / 256), 256, 0, s>>>(per_sample, N, (int)C, total);
+        UB_LAUNCH_CHECK();
+    }
     return UB200_OK;
 }
 

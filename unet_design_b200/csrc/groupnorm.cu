@@ -167,40 +167,46 @@ __global__ void __launch_bounds__(256) gn_act_bwd_reduce(const __nv_bfloat16 *__
                                                         const float *__restrict__ shift, float eps, float p_drop,
                                                         uint64_t seed, uint64_t offset, const uint64_t *__restrict__ off_dev,
                                                         float *__restrict__ Q) {
+    extern __shared__ float qs[];   // [C][2]: CTA-level partial sums, one global atomic per entry afterwards
     const int64_t n = blockIdx.y;
+    for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) qs[i] = 0.f;
+    __syncthreads();
     const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
-    if (r >= sh.rows) return;
-    const Coef k = make_coef(sh, n, q, stats, gamma, beta, scale, shift, eps);
-    if (DROP && off_dev) offset += __ldg(off_dev);   // device-resident counter: CUDA-graph replays draw fresh masks
-    float mean[8], rstd[8];
-    const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
+    if (r < sh.rows) {
+        const Coef k = make_coef(sh, n, q, stats, gamma, beta, scale, shift, eps);
+        if (DROP && off_dev) offset += __ldg(off_dev);   // device-resident counter: CUDA-graph replays draw fresh masks
+        float mean[8], rstd[8];
+        const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) mean_rstd(stats, n, sh.G, (8 * q + u) / sh.cpg, inv_cnt, eps, mean[u], rstd[u]);
-    float q1[8], q2[8];
+        for (int u = 0; u < 8; ++u) mean_rstd(stats, n, sh.G, (8 * q + u) / sh.cpg, inv_cnt, eps, mean[u], rstd[u]);
+        float q1[8], q2[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) q1[u] = q2[u] = 0.f;
-    const int64_t p0 = (int64_t)blockIdx.x * sh.pix_per_cta;
-    int64_t p1 = p0 + sh.pix_per_cta;
-    if (p1 > sh.HW) p1 = sh.HW;
-    for (int64_t p = p0 + r; p < p1; p += sh.rows) {
-        const int64_t pix = n * sh.HW + p;
-        float f[8], g[8], m[8];
-        unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(x + pix * ld_x + 8 * q)), f);
-        unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(gy + pix * ld_gy + 8 * q)), g);
-        if (DROP) dropout_mask8(seed, offset, pix * sh.C + 8 * q, p_drop, m);
+        for (int u = 0; u < 8; ++u) q1[u] = q2[u] = 0.f;
+        const int64_t p0 = (int64_t)blockIdx.x * sh.pix_per_cta;
+        int64_t p1 = p0 + sh.pix_per_cta;
+        if (p1 > sh.HW) p1 = sh.HW;
+        for (int64_t p = p0 + r; p < p1; p += sh.rows) {
+            const int64_t pix = n * sh.HW + p;
+            float f[8], g[8], m[8];
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(x + pix * ld_x + 8 * q)), f);
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(gy + pix * ld_gy + 8 * q)), g);
+            if (DROP) dropout_mask8(seed, offset, pix * sh.C + 8 * q, p_drop, m);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
+                if (DROP) dz *= m[u];
+                q1[u] += dz;
+                q2[u] += dz * (f[u] - mean[u]) * rstd[u];
+            }
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
-            if (DROP) dz *= m[u];
-            q1[u] += dz;
-            q2[u] += dz * (f[u] - mean[u]) * rstd[u];
+            atomicAdd(&qs[(8 * q + u) * 2], q1[u]);
+            atomicAdd(&qs[(8 * q + u) * 2 + 1], q2[u]);
         }
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        atomicAdd(Q + (n * sh.C + 8 * q + u) * 2, q1[u]);
-        atomicAdd(Q + (n * sh.C + 8 * q + u) * 2 + 1, q2[u]);
-    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) atomicAdd(Q + n * sh.C * 2 + i, qs[i]);
 }
 
 // backward pass 2: dx = rstd * (dxhat - mean_g(dxhat) - xhat * mean_g(dxhat*xhat)),  dxhat = dz*gamma*(1+scale)
@@ -362,7 +368,7 @@ int ub200_gn_act_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int
     const bool drop = dropout_p > 0.f;
     const __nv_bfloat16 *gyp = reinterpret_cast<const __nv_bfloat16 *>(gy), *xp = reinterpret_cast<const __nv_bfloat16 *>(x);
     DISPATCH_ACT_DROP(gn_act_bwd_reduce, act, drop,
-                      <<<grid, 256, 0, s>>>(gyp, ld_gy, xp, ld_x, sh, stats, gamma, beta, scale, shift, eps, dropout_p,
+                      <<<grid, 256, 2 * C * sizeof(float), s>>>(gyp, ld_gy, xp, ld_x, sh, stats, gamma, beta, scale, shift, eps, dropout_p,
                                             seed, offset, offset_dev, ws));
     UB_LAUNCH_CHECK();
     DISPATCH_ACT_DROP(gn_act_bwd_apply, act, drop,

@@ -236,10 +236,11 @@ void conv_wgrad(const Tensor &gout, const Tensor &a, int64_t ksize, const Tensor
              "conv_wgrad");
 }
 
-void chansum(const Tensor &x, const c10::optional<Tensor> &per_sample, const c10::optional<Tensor> &total) {
+void chansum(const Tensor &x, const Tensor &per_sample, const c10::optional<Tensor> &total) {
     UB_GUARD(x);
     const Nhwc X = nhwc(x, "x");
-    float *ps = per_sample.has_value() ? f32_mut(*per_sample, "per_sample") : nullptr;
+    TORCH_CHECK(per_sample.numel() == X.N * X.C, "chansum: per_sample must hold N*C floats");
+    float *ps = f32_mut(per_sample, "per_sample");
     float *tt = total.has_value() ? f32_mut(*total, "total") : nullptr;
     check_rc(ub200_chansum_nhwc_bf16(X.ptr, X.ld, X.N, X.H * X.W, X.C, ps, tt, cur_stream()), "chansum");
 }

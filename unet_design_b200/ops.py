@@ -369,17 +369,18 @@ class _Conv(torch.autograd.Function):
             gw = dw[:cout].permute(0, 3, 1, 2)          # [Cout,Cin,k,k] view with channels_last strides
         if (has_bias and needs[2]) or (has_rowadd and needs[3]):
             if cout % 8 == 0:
-                per = torch.zeros((n, cout), dtype=torch.float32, device=g.device) if has_rowadd else None
+                per = torch.empty((n, cout), dtype=torch.float32, device=g.device)
                 tot = torch.zeros((cout,), dtype=torch.float32, device=g.device) if has_bias else None
                 o.chansum(g_valid, per, tot)
-                _count(2)
-                growadd, gbias = per, tot
+                _count(3)
+                growadd, gbias = (per if has_rowadd else None), tot
             else:
-                per = torch.zeros((n, cpad), dtype=torch.float32, device=g.device)
-                o.chansum(g_full, per, None)
-                _count(2)
+                per = torch.empty((n, cpad), dtype=torch.float32, device=g.device)
+                tot = torch.zeros((cpad,), dtype=torch.float32, device=g.device) if has_bias else None
+                o.chansum(g_full, per, tot)
+                _count(3)
                 growadd = per[:, :cout].contiguous() if has_rowadd else None
-                gbias = per[:, :cout].sum(0) if has_bias else None
+                gbias = tot[:cout] if has_bias else None
         if a2 is not None:
             if needs[4]:
                 w2tp = pack_weight(w2, transpose_flip=True)
