@@ -31,7 +31,7 @@ CASES = [
     # n, h, w, cin, cout, k
     (2, 8, 8, 64, 64, 3), (2, 8, 8, 64, 64, 1), (8, 4, 4, 256, 256, 3), (2, 16, 16, 384, 256, 3), (2, 32, 32, 128, 128, 3),
     (2, 32, 32, 256, 128, 3), (1, 32, 32, 128, 16, 3), (3, 7, 9, 32, 48, 3), (2, 25, 13, 16, 32, 3), (1, 13, 13, 144, 80, 3),
-    (2, 16, 16, 512, 256, 1), (1, 128, 128, 64, 64, 3), (1, 96, 192, 64, 64, 3), (1, 200, 200, 16, 16, 3), (5, 4, 4, 512, 256, 3),
+    (2, 16, 16, 512, 256, 1), (2, 8, 8, 128, 512, 3), (1, 16, 16, 64, 320, 3), (64, 16, 16, 64, 320, 1), (1, 128, 128, 64, 64, 3), (1, 96, 192, 64, 64, 3), (1, 200, 200, 16, 16, 3), (5, 4, 4, 512, 256, 3),
 ]
 
 

@@ -1,5 +1,5 @@
-// 3x3 / 1x1 stride-1 "same" convolution forward (and, with transposed+rotated weights, dgrad) as an
-// implicit GEMM on the 5th-generation tensor cores:
+// 3x3 / 1x1 stride-1 "same" convolution forward (and, with transposed+rotated weights, dgrad) as a
+// PERSISTENT implicit GEMM on the 5th-generation tensor cores:
 //
 //   D[128 pixels, BN channels] (fp32, TMEM)  +=  A[128 pixels, BK] (bf16, smem)  x  W[BN, BK]^T (bf16, smem)
 //
@@ -13,9 +13,12 @@
 // * An optional second operand pair (a2, w2) appends the K slices of a 1x1 convolution of another tensor
 //   (the ResBlock shortcut, diff_cifar/model.py:145-148,:167), and the epilogue adds bias, a per-sample
 //   per-channel row (the time-embedding projection, model.py:164) and a residual tensor.
-// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-//   warps 2..5 = epilogue (tcgen05.ld -> registers -> bf16 NHWC / fp32 NCHW global stores).
-//   smem ring of `stages` (A, W) slots with full/empty mbarriers; tcgen05.commit releases slots.
+// * One CTA per SM walks the (pixel tile, channel tile) list.  Warp roles: warp 0 = TMA producer,
+//   warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue.  Three pipelines:
+//   the smem ring of (A, W) stages (full/empty mbarriers, slots released by tcgen05.commit), TWO TMEM
+//   accumulators (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1, and the
+//   epilogue's own double-buffered staging tile: tcgen05.ld -> +bias/row/residual -> bf16 -> swizzled smem
+//   -> TMA tiled store (which also clips ragged tiles), or direct fp32 NCHW stores for the narrow tails.
 //
 // Replaces nn.Conv2d forward/backward-data at diff_cifar/model.py:69,:133,:143,:146,:396;
 // diff_mnist/torch_ddpm/ddpm/models/unet/layers.py:286,:300,:305-312; pdearena twod_unetbase.py:19-24.
@@ -30,49 +33,48 @@ using namespace ub::tc;
 struct FpropParams {
     int N, H, W, Cout;
     int BW, BH, BNI, tiles_w, tiles_h;
-    int BN, Cin, cblocks, taps, kb_main, kb_extra, stages;
+    int BN, n_tiles, num_tiles;
+    int Cin, cblocks, taps, kb_main, kb_extra, stages;
     uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
     const float *bias, *rowadd;
     const __nv_bfloat16 *residual; int64_t ld_res;
-    __nv_bfloat16 *out; int64_t ld_out;
+    int has_out;                      // bf16 NHWC output through the TMA store
     float *out_nchw;
-    float *gn_partial; int gn_groups;
 };
 
 constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr uint32_t kStagingBytes = 128 * 64 * 2;      // one [128 pixels][64 channels] bf16 box
 
 template <int BK>
-__global__ void __launch_bounds__(kThreads) conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_a,
-                                                             const __grid_constant__ CUtensorMap tm_w,
-                                                             const __grid_constant__ CUtensorMap tm_a2,
-                                                             const __grid_constant__ CUtensorMap tm_w2,
-                                                             const FpropParams p) {
+__global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_a,
+                                                                const __grid_constant__ CUtensorMap tm_w,
+                                                                const __grid_constant__ CUtensorMap tm_a2,
+                                                                const __grid_constant__ CUtensorMap tm_w2,
+                                                                const __grid_constant__ CUtensorMap tm_out,
+                                                                const FpropParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages x A][stages x B][full barriers][empty barriers][tmem_full][tmem ptr]
+    // carve: [2 x output staging][stages x A][stages x B][full][empty][tmem_full x2][tmem_empty x2][tmem ptr]
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *smem_a = smem;
+    uint8_t *smem_out = smem;
+    uint8_t *smem_a = smem_out + 2 * kStagingBytes;
     uint8_t *smem_b = smem_a + (size_t)p.stages * p.a_stage_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_b + (size_t)p.stages * p.b_stage_bytes);
     uint64_t *empty = full + p.stages;
     uint64_t *tmem_full = empty + p.stages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // tile coordinates
-    int mt = blockIdx.x;
-    const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-    const int th = mt % p.tiles_h; mt /= p.tiles_h;
-    const int x0 = tw * p.BW, y0 = th * p.BH, n0 = mt * p.BNI;
-    const int co0 = blockIdx.y * p.BN;
     const int num_kb = p.kb_main + p.kb_extra;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_a);
         prefetch_tmap(&tm_w);
         if (p.kb_extra) { prefetch_tmap(&tm_a2); prefetch_tmap(&tm_w2); }
+        if (p.has_out) prefetch_tmap(&tm_out);
         for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -85,22 +87,30 @@ __global__ void __launch_bounds__(kThreads) conv_fprop_kernel(const __grid_const
         // ===================== TMA producer =====================
         if (lane == 0) {
             const uint32_t tx_bytes = 128u * BK * 2u + (uint32_t)p.BN * BK * 2u;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(empty + s, ph ^ 1u);
-                mbar_arrive_expect_tx(full + s, tx_bytes);
-                uint8_t *dst_a = smem_a + (size_t)s * p.a_stage_bytes;
-                uint8_t *dst_b = smem_b + (size_t)s * p.b_stage_bytes;
-                if (kb < p.kb_main) {
-                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-                    const int ky = p.taps == 9 ? tap / 3 - 1 : 0, kx = p.taps == 9 ? tap % 3 - 1 : 0;
-                    tma_load_4d(dst_a, &tm_a, full + s, cb * BK, x0 + kx, y0 + ky, n0);
-                    tma_load_2d(dst_b, &tm_w, full + s, tap * p.Cin + cb * BK, co0);
-                } else {
-                    const int cb = kb - p.kb_main;
-                    tma_load_4d(dst_a, &tm_a2, full + s, cb * BK, x0, y0, n0);
-                    tma_load_2d(dst_b, &tm_w2, full + s, cb * BK, co0);
+            uint32_t it = 0;                                  // running k-block counter across tiles
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                int mt = tile / p.n_tiles;
+                const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+                const int th = mt % p.tiles_h; mt /= p.tiles_h;
+                const int x0 = tw * p.BW, y0 = th * p.BH, n0 = mt * p.BNI, co0 = nt * p.BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    mbar_wait(empty + s, ph ^ 1u);
+                    mbar_arrive_expect_tx(full + s, tx_bytes);
+                    uint8_t *dst_a = smem_a + (size_t)s * p.a_stage_bytes;
+                    uint8_t *dst_b = smem_b + (size_t)s * p.b_stage_bytes;
+                    if (kb < p.kb_main) {
+                        const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                        const int ky = p.taps == 9 ? tap / 3 - 1 : 0, kx = p.taps == 9 ? tap % 3 - 1 : 0;
+                        tma_load_4d(dst_a, &tm_a, full + s, cb * BK, x0 + kx, y0 + ky, n0);
+                        tma_load_2d(dst_b, &tm_w, full + s, tap * p.Cin + cb * BK, co0);
+                    } else {
+                        const int cb = kb - p.kb_main;
+                        tma_load_4d(dst_a, &tm_a2, full + s, cb * BK, x0, y0, n0);
+                        tma_load_2d(dst_b, &tm_w2, full + s, cb * BK, co0);
+                    }
                 }
             }
         }
@@ -110,21 +120,28 @@ __global__ void __launch_bounds__(kThreads) conv_fprop_kernel(const __grid_const
             const uint32_t idesc = make_idesc(128, p.BN, 0, 0);
             constexpr uint32_t swz = swizzle_code(BK * 2);
             constexpr uint32_t sbo = 8u * BK * 2u;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(full + s, ph);
+            uint32_t it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+                const uint32_t acc = local & 1u, use = local >> 1;
+                mbar_wait(tmem_empty + acc, (use & 1u) ^ 1u);          // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem_a + (size_t)s * p.a_stage_bytes);
-                const uint32_t b_addr = smem_u32(smem_b + (size_t)s * p.b_stage_bytes);
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    mbar_wait(full + s, ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_a + (size_t)s * p.a_stage_bytes);
+                    const uint32_t b_addr = smem_u32(smem_b + (size_t)s * p.b_stage_bytes);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, swz);
-                    const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, swz);
-                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, swz);
+                        const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, swz);
+                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty + s);                            // slot reusable once these MMAs have read it
                 }
-                umma_commit(empty + s);                       // slot reusable once these MMAs have read it
-                if (kb == num_kb - 1) umma_commit(tmem_full); // accumulator complete
+                umma_commit(tmem_full + acc);                          // accumulator complete
             }
         }
     } else {
@@ -132,63 +149,93 @@ __global__ void __launch_bounds__(kThreads) conv_fprop_kernel(const __grid_const
         const int qd = warp & 3;
         const int r = qd * 32 + lane;                 // row of the tile == TMEM lane
         const int wi = r % p.BW, hi = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
-        const int x = x0 + wi, y = y0 + hi, n = n0 + ni;
-        const bool valid = x < p.W && y < p.H && n < p.N;
-        const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16);
-        for (int cg = 0; cg < p.BN / 16; ++cg) {
-            float v[16];
-            tmem_ld16(trow + cg * 16, v);
-            const int co = co0 + cg * 16;
-            if (!valid || co >= p.Cout) continue;
-            const int nv = p.Cout - co < 16 ? p.Cout - co : 16;
-            if (p.bias) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) if (i < nv) v[i] += __ldg(p.bias + co + i);
-            }
-            if (p.rowadd) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) if (i < nv) v[i] += __ldg(p.rowadd + (int64_t)n * p.Cout + co + i);
-            }
-            if (p.residual) {
-                const __nv_bfloat16 *rp = p.residual + pix * p.ld_res + co;
-                if (nv == 16) {
-                    float f[8];
-                    unpack8(*reinterpret_cast<const uint4 *>(rp), f);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] += f[i];
-                    unpack8(*reinterpret_cast<const uint4 *>(rp + 8), f);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
-                } else {
-                    for (int i = 0; i < nv; ++i) v[i] += __bfloat162float(rp[i]);
+        const bool issuer = (warp == 2 && lane == 0);
+        const int64_t hw = (int64_t)p.H * p.W;
+        uint32_t local = 0, chunk_ctr = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+            const int nt = tile % p.n_tiles;
+            int mt = tile / p.n_tiles;
+            const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+            const int th = mt % p.tiles_h; mt /= p.tiles_h;
+            const int x0 = tw * p.BW, y0 = th * p.BH, n0 = mt * p.BNI, co0 = nt * p.BN;
+            const int x = x0 + wi, y = y0 + hi, n = n0 + ni;
+            const bool valid = x < p.W && y < p.H && n < p.N;
+            const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
+            const uint32_t acc = local & 1u, use = local >> 1;
+            mbar_wait(tmem_full + acc, use & 1u);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + acc * (uint32_t)p.BN;
+            const int nchunks = (p.BN + 63) / 64;
+            for (int ch = 0; ch < nchunks; ++ch, ++chunk_ctr) {
+                uint8_t *stage = smem_out + (chunk_ctr & 1u) * kStagingBytes;
+                if (p.has_out) {
+                    if (issuer) tma_store_wait_read<1>();           // the store that last used this buffer has read it
+                    named_barrier_sync(1, kEpiThreads);
                 }
-            }
-            if (p.out) {
-                __nv_bfloat16 *op = p.out + pix * p.ld_out + co;
-                if (nv == 16) {
-                    float f[8];
+                const int groups = (p.BN - ch * 64) >= 64 ? 4 : (p.BN - ch * 64) / 16;
+                for (int cg = 0; cg < groups; ++cg) {
+                    float v[16];
+                    tmem_ld16(trow + ch * 64 + cg * 16, v);
+                    const int co = co0 + ch * 64 + cg * 16;
+                    const int nv = p.Cout - co < 16 ? p.Cout - co : 16;    // may be <= 0 in the padded tail
+                    if (valid && nv > 0) {
+                        if (p.bias) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = v[i];
-                    *reinterpret_cast<uint4 *>(op) = pack8(f);
+                            for (int i = 0; i < 16; ++i) if (i < nv) v[i] += __ldg(p.bias + co + i);
+                        }
+                        if (p.rowadd) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = v[8 + i];
-                    *reinterpret_cast<uint4 *>(op + 8) = pack8(f);
-                } else {
-                    for (int i = 0; i < nv; ++i) op[i] = __float2bfloat16_rn(v[i]);
+                            for (int i = 0; i < 16; ++i) if (i < nv) v[i] += __ldg(p.rowadd + (int64_t)n * p.Cout + co + i);
+                        }
+                        if (p.residual) {
+                            const __nv_bfloat16 *rp = p.residual + pix * p.ld_res + co;
+                            if (nv == 16) {
+                                float f[8];
+                                unpack8(*reinterpret_cast<const uint4 *>(rp), f);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] += f[i];
+                                unpack8(*reinterpret_cast<const uint4 *>(rp + 8), f);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
+                            } else {
+                                for (int i = 0; i < nv; ++i) v[i] += __bfloat162float(rp[i]);
+                            }
+                        }
+                        if (p.out_nchw) {
+                            float *op = p.out_nchw + ((int64_t)n * p.Cout + co) * hw + (int64_t)y * p.W + x;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) if (i < nv) op[i * hw] = v[i];
+                        }
+                    }
+                    if (p.has_out) {
+                        // two 16-byte pieces of row r, 128-byte swizzle: piece index XOR (row & 7)
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = v[i];
+                        *reinterpret_cast<uint4 *>(stage + r * 128 + (((2 * cg) ^ (r & 7)) << 4)) = pack8(f);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = v[8 + i];
+                        *reinterpret_cast<uint4 *>(stage + r * 128 + (((2 * cg + 1) ^ (r & 7)) << 4)) = pack8(f);
+                    }
                 }
-            }
-            if (p.out_nchw) {
-                const int64_t hw = (int64_t)p.H * p.W;
-                float *op = p.out_nchw + ((int64_t)n * p.Cout + co) * hw + (int64_t)y * p.W + x;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) if (i < nv) op[i * hw] = v[i];
+                if (ch == nchunks - 1) {             // all tcgen05.ld of this accumulator are done: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty + acc);
+                }
+                if (p.has_out) {
+                    fence_proxy_async();
+                    named_barrier_sync(1, kEpiThreads);
+                    if (issuer) {
+                        tma_store_4d(&tm_out, stage, co0 + ch * 64, x0, y0, n0);
+                        tma_store_commit();
+                    }
+                }
             }
         }
-        tc_fence_before();
+        if (issuer && p.has_out) tma_store_wait_all();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
@@ -226,14 +273,14 @@ uint32_t pow2_at_least(uint32_t v, uint32_t lo) { uint32_t r = lo; while (r < v)
 
 template <int BK>
 int launch_fprop(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &ta2, const CUtensorMap &tw2,
-                 const FpropParams &p, dim3 grid, size_t smem, cudaStream_t s) {
+                 const CUtensorMap &tout, const FpropParams &p, int grid, size_t smem, cudaStream_t s) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_fprop_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_err = cudaFuncSetAttribute(conv_fprop_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return (int)attr_err;
-    conv_fprop_kernel<BK><<<grid, kThreads, smem, s>>>(ta, tw, ta2, tw2, p);
+    conv_fprop_kernel<BK><<<grid, kThreads, smem, s>>>(ta, tw, ta2, tw2, tout, p);
     UB_LAUNCH_CHECK();
     return UB200_OK;
 }
@@ -256,6 +303,7 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
                UB200_E_UNSUPPORTED);
     UB_REQUIRE(a->N < (1 << 24) && a->H < (1 << 15) && a->W < (1 << 15) && a->Cin <= 16384 && a->Cout <= 16384,
                UB200_E_UNSUPPORTED);
+    UB_REQUIRE(!a->gn_partial, UB200_E_UNSUPPORTED);   // epilogue statistics: not in this build yet
 
     const int64_t cout_pad = (a->Cout + 15) / 16 * 16;
     FpropParams p{};
@@ -264,8 +312,16 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     p.BW = pt.BW; p.BH = pt.BH; p.BNI = pt.BNI;
     p.tiles_w = (p.W + p.BW - 1) / p.BW;
     p.tiles_h = (p.H + p.BH - 1) / p.BH;
-    const int tiles_n = (p.N + p.BNI - 1) / p.BNI;
-    p.BN = (int)(cout_pad < 128 ? cout_pad : 128);
+    const int m_tiles = p.tiles_w * p.tiles_h * ((p.N + p.BNI - 1) / p.BNI);
+    // channel tile: as wide as possible (up to 256 TMEM columns per accumulator) while the tile list still fills
+    // most of the 148 SMs; narrow tiles re-read A and make the single-thread MMA issue rate the limit
+    int bn_max = 256;
+    while (bn_max > 64 && (int64_t)m_tiles * ((cout_pad + bn_max - 1) / bn_max) < 120) bn_max >>= 1;
+    p.n_tiles = (int)((cout_pad + bn_max - 1) / bn_max);
+    // several channel tiles: keep BN a multiple of the 64-channel store box so no tile writes columns it did not
+    // compute; a single tile may be any multiple of 16 (columns past Cout fall outside the tensor and are clipped)
+    p.BN = p.n_tiles > 1 ? (int)(((cout_pad + p.n_tiles - 1) / p.n_tiles + 63) / 64 * 64) : (int)cout_pad;
+    p.num_tiles = m_tiles * p.n_tiles;
     p.Cin = (int)a->Cin;
     p.cblocks = (int)(a->Cin / bk);
     p.taps = a->ksize * a->ksize;
@@ -274,21 +330,19 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     p.a_stage_bytes = 128u * bk * 2u;
     p.b_stage_bytes = ((uint32_t)p.BN * bk * 2u + 1023u) & ~1023u;
     const uint32_t stage = p.a_stage_bytes + p.b_stage_bytes;
-    int stages = (int)((100u * 1024u) / stage);
+    const uint32_t budget = 227u * 1024u - 1024u - 2u * kStagingBytes - 512u;
+    int stages = (int)(budget / stage);
     if (stages > 8) stages = 8;
-    if (stages > p.kb_main + p.kb_extra) stages = p.kb_main + p.kb_extra;
-    if (stages < 1) stages = 1;
+    if (stages < 2) stages = 2;
     p.stages = stages;
-    p.tmem_cols = pow2_at_least((uint32_t)p.BN, 32);
+    p.tmem_cols = pow2_at_least(2u * (uint32_t)p.BN, 32);
     p.bias = a->bias; p.rowadd = a->rowadd;
     p.residual = reinterpret_cast<const __nv_bfloat16 *>(a->residual); p.ld_res = a->ld_res;
-    p.out = reinterpret_cast<__nv_bfloat16 *>(a->out); p.ld_out = a->ld_out;
+    p.has_out = a->out != nullptr;
     p.out_nchw = a->out_f32_nchw;
-    p.gn_partial = a->gn_partial; p.gn_groups = a->gn_groups;
-    UB_REQUIRE(!a->gn_partial, UB200_E_UNSUPPORTED);   // epilogue statistics: not in this build yet
 
     // tensor maps
-    CUtensorMap ta, tw, ta2, tw2;
+    CUtensorMap ta, tw, ta2, tw2, tout;
     {
         const int64_t dims[4] = {a->Cin, a->W, a->H, a->N};
         const int64_t str[3] = {a->ld_a, a->ld_a * a->W, a->ld_a * a->W * a->H};
@@ -315,13 +369,22 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     } else {
         ta2 = ta; tw2 = tw;
     }
+    if (a->out) {
+        const int64_t dims[4] = {a->Cout, a->W, a->H, a->N};
+        const int64_t str[3] = {a->ld_out, a->ld_out * a->W, a->ld_out * a->W * a->H};
+        const int box[4] = {64, p.BW, p.BH, p.BNI};
+        int rc = encode_bf16_tensor_map(&tout, a->out, 4, dims, str, box);
+        if (rc) return rc;
+    } else {
+        tout = ta;
+    }
 
-    dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_n), (unsigned)((cout_pad + p.BN - 1) / p.BN), 1);
-    const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
+    const int grid = p.num_tiles < ub::kSMs ? p.num_tiles : ub::kSMs;
+    const size_t smem = 1024 + 2 * kStagingBytes + (size_t)stages * stage + (2 * stages + 4) * sizeof(uint64_t) + 16;
     cudaStream_t s = ub::as_stream(stream);
     switch (bk) {
-        case 64: return launch_fprop<64>(ta, tw, ta2, tw2, p, grid, smem, s);
-        case 32: return launch_fprop<32>(ta, tw, ta2, tw2, p, grid, smem, s);
-        default: return launch_fprop<16>(ta, tw, ta2, tw2, p, grid, smem, s);
+        case 64: return launch_fprop<64>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
+        case 32: return launch_fprop<32>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
+        default: return launch_fprop<16>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
     }
 }
