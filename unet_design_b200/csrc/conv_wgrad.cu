@@ -183,11 +183,21 @@ __global__ void __launch_bounds__(256) chansum_kernel(const __nv_bfloat16 *__res
 
 __global__ void __launch_bounds__(256) colsum_rows_kernel(const float *__restrict__ per_sample, int64_t N, int C,
                                                          float *__restrict__ total) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    // 32 channels x 8 row-lanes per CTA; rows strided by 8, combined through shared memory
+    __shared__ float part[8][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     float s = 0.f;
-    for (int64_t n = 0; n < N; ++n) s += per_sample[n * C + c];
-    total[c] += s;
+    if (c < C)
+        for (int64_t n = rl; n < N; n += 8) s += __ldg(per_sample + n * C + c);
+    part[rl][cl] = s;
+    __syncthreads();
+    if (rl == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][cl];
+        total[c] += t;
+    }
 }
 
 // fp32 weights with arbitrary strides -> packed bf16 [rows_pad, k, k, cols] (rows padded to 16 with zeros)
@@ -314,7 +324,7 @@ int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, in
                                                        rows, ppc, per_sample);
     UB_LAUNCH_CHECK();
     if (total) {
-        colsum_rows_kernel<<<(unsigned)((C + 255) / 256), 256, 0, s>>>(per_sample, N, (int)C, total);
+        colsum_rows_kernel<<<(unsigned)((C + 31) / 32), 256, 0, s>>>(per_sample, N, (int)C, total);
         UB_LAUNCH_CHECK();
     }
     return UB200_OK;

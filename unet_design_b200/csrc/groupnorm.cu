@@ -41,15 +41,15 @@ __device__ __forceinline__ void dropout_mask8(uint64_t seed, uint64_t offset, in
 
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float z) {
-    if constexpr (ACT == UB200_ACT_SILU) return z / (1.0f + __expf(-z));
+    if constexpr (ACT == UB200_ACT_SILU) return __fdividef(z, 1.0f + __expf(-z));
     else if constexpr (ACT == UB200_ACT_GELU) return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f));
     else return z;
 }
 template <int ACT>
 __device__ __forceinline__ float act_bwd(float z) {   // d act / d z
     if constexpr (ACT == UB200_ACT_SILU) {
-        const float s = 1.0f / (1.0f + __expf(-z));
-        return s * (1.0f + z * (1.0f - s));
+        const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+        return s * fmaf(z, 1.0f - s, 1.0f);
     } else if constexpr (ACT == UB200_ACT_GELU) {
         return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
     } else return 1.0f;
@@ -158,15 +158,16 @@ __global__ void __launch_bounds__(256) gn_act_fwd_kernel(const __nv_bfloat16 *__
     }
 }
 
-// backward pass 1: Q[n,c] = (sum_p dz, sum_p dz*xhat)   with dz = gy * mask * act'(z)
+// backward pass 1: Q[n,c] = (sum_p dz, sum_p dz*x)   with dz = gy * mask * act'(z);  sum_p dz*xhat is derived from
+// the two in pass 2, which keeps this loop at one fma + act' per element.
 template <int ACT, bool DROP>
-__global__ void __launch_bounds__(256) gn_act_bwd_reduce(const __nv_bfloat16 *__restrict__ gy, int64_t ld_gy,
-                                                        const __nv_bfloat16 *__restrict__ x, int64_t ld_x, Shape sh,
-                                                        const float *__restrict__ stats, const float *__restrict__ gamma,
-                                                        const float *__restrict__ beta, const float *__restrict__ scale,
-                                                        const float *__restrict__ shift, float eps, float p_drop,
-                                                        uint64_t seed, uint64_t offset, const uint64_t *__restrict__ off_dev,
-                                                        float *__restrict__ Q) {
+__global__ void __launch_bounds__(256, 3) gn_act_bwd_reduce(const __nv_bfloat16 *__restrict__ gy, int64_t ld_gy,
+                                                           const __nv_bfloat16 *__restrict__ x, int64_t ld_x, Shape sh,
+                                                           const float *__restrict__ stats, const float *__restrict__ gamma,
+                                                           const float *__restrict__ beta, const float *__restrict__ scale,
+                                                           const float *__restrict__ shift, float eps, float p_drop,
+                                                           uint64_t seed, uint64_t offset, const uint64_t *__restrict__ off_dev,
+                                                           float *__restrict__ Q) {
     extern __shared__ float qs[];   // [C][2]: CTA-level partial sums, one global atomic per entry afterwards
     const int64_t n = blockIdx.y;
     for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) qs[i] = 0.f;
@@ -175,28 +176,49 @@ __global__ void __launch_bounds__(256) gn_act_bwd_reduce(const __nv_bfloat16 *__
     if (r < sh.rows) {
         const Coef k = make_coef(sh, n, q, stats, gamma, beta, scale, shift, eps);
         if (DROP && off_dev) offset += __ldg(off_dev);   // device-resident counter: CUDA-graph replays draw fresh masks
-        float mean[8], rstd[8];
-        const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) mean_rstd(stats, n, sh.G, (8 * q + u) / sh.cpg, inv_cnt, eps, mean[u], rstd[u]);
         float q1[8], q2[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) q1[u] = q2[u] = 0.f;
         const int64_t p0 = (int64_t)blockIdx.x * sh.pix_per_cta;
         int64_t p1 = p0 + sh.pix_per_cta;
         if (p1 > sh.HW) p1 = sh.HW;
-        for (int64_t p = p0 + r; p < p1; p += sh.rows) {
-            const int64_t pix = n * sh.HW + p;
+        const __nv_bfloat16 *xb = x + n * sh.HW * ld_x + 8 * q;
+        const __nv_bfloat16 *gb = gy + n * sh.HW * ld_gy + 8 * q;
+        int64_t p = p0 + r;
+        // two pixels per iteration: four independent 16-byte loads in flight per thread
+        for (; p + sh.rows < p1; p += 2 * sh.rows) {
+            const uint4 xa = ld_stream_u4(reinterpret_cast<const uint4 *>(xb + p * ld_x));
+            const uint4 ga = ld_stream_u4(reinterpret_cast<const uint4 *>(gb + p * ld_gy));
+            const uint4 xc = ld_stream_u4(reinterpret_cast<const uint4 *>(xb + (p + sh.rows) * ld_x));
+            const uint4 gc = ld_stream_u4(reinterpret_cast<const uint4 *>(gb + (p + sh.rows) * ld_gy));
             float f[8], g[8], m[8];
-            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(x + pix * ld_x + 8 * q)), f);
-            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(gy + pix * ld_gy + 8 * q)), g);
-            if (DROP) dropout_mask8(seed, offset, pix * sh.C + 8 * q, p_drop, m);
+            unpack8(xa, f); unpack8(ga, g);
+            if (DROP) dropout_mask8(seed, offset, (n * sh.HW + p) * sh.C + 8 * q, p_drop, m);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
                 if (DROP) dz *= m[u];
-                q1[u] += dz;
-                q2[u] += dz * (f[u] - mean[u]) * rstd[u];
+                q1[u] += dz; q2[u] = fmaf(dz, f[u], q2[u]);
+            }
+            unpack8(xc, f); unpack8(gc, g);
+            if (DROP) dropout_mask8(seed, offset, (n * sh.HW + p + sh.rows) * sh.C + 8 * q, p_drop, m);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
+                if (DROP) dz *= m[u];
+                q1[u] += dz; q2[u] = fmaf(dz, f[u], q2[u]);
+            }
+        }
+        for (; p < p1; p += sh.rows) {
+            float f[8], g[8], m[8];
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(xb + p * ld_x)), f);
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(gb + p * ld_gy)), g);
+            if (DROP) dropout_mask8(seed, offset, (n * sh.HW + p) * sh.C + 8 * q, p_drop, m);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
+                if (DROP) dz *= m[u];
+                q1[u] += dz; q2[u] = fmaf(dz, f[u], q2[u]);
             }
         }
 #pragma unroll
@@ -209,26 +231,32 @@ __global__ void __launch_bounds__(256) gn_act_bwd_reduce(const __nv_bfloat16 *__
     for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) atomicAdd(Q + n * sh.C * 2 + i, qs[i]);
 }
 
-// backward pass 2: dx = rstd * (dxhat - mean_g(dxhat) - xhat * mean_g(dxhat*xhat)),  dxhat = dz*gamma*(1+scale)
+// backward pass 2.  With Q1 = sum dz, Q2x = sum dz*x per (n,c):  sum dz*xhat = rstd*(Q2x - mean*Q1), and
+//   dx = rstd*(dz*gs - m1 - xhat*m2) = dz*P + x*Qc + R     (P, Qc, R per channel; gs = gamma*(1+scale))
+// so the streaming loop is act' + three fmas per element.
 template <int ACT, bool DROP>
-__global__ void __launch_bounds__(256) gn_act_bwd_apply(const __nv_bfloat16 *__restrict__ gy, int64_t ld_gy,
-                                                       const __nv_bfloat16 *__restrict__ x, int64_t ld_x, Shape sh,
-                                                       const float *__restrict__ stats, const float *__restrict__ gamma,
-                                                       const float *__restrict__ beta, const float *__restrict__ scale,
-                                                       const float *__restrict__ shift, float eps, float p_drop,
-                                                       uint64_t seed, uint64_t offset, const uint64_t *__restrict__ off_dev,
-                                                       const float *__restrict__ Q,
-                                                       __nv_bfloat16 *__restrict__ gx, int64_t ld_gx, int accumulate,
-                                                       float *__restrict__ dgamma, float *__restrict__ dbeta,
-                                                       float *__restrict__ dscale, float *__restrict__ dshift) {
-    extern __shared__ float sg[];   // [G][2]: sum_c gamma*(1+scale)*Q1, ... *Q2
+__global__ void __launch_bounds__(256, 3) gn_act_bwd_apply(const __nv_bfloat16 *__restrict__ gy, int64_t ld_gy,
+                                                          const __nv_bfloat16 *__restrict__ x, int64_t ld_x, Shape sh,
+                                                          const float *__restrict__ stats, const float *__restrict__ gamma,
+                                                          const float *__restrict__ beta, const float *__restrict__ scale,
+                                                          const float *__restrict__ shift, float eps, float p_drop,
+                                                          uint64_t seed, uint64_t offset, const uint64_t *__restrict__ off_dev,
+                                                          const float *__restrict__ Q,
+                                                          __nv_bfloat16 *__restrict__ gx, int64_t ld_gx, int accumulate,
+                                                          float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                                          float *__restrict__ dscale, float *__restrict__ dshift) {
+    extern __shared__ float sg[];   // [G][2]: sum_c gs*Q1, sum_c gs*(sum dz*xhat)
     const int64_t n = blockIdx.y;
+    const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
     for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) sg[i] = 0.f;
     __syncthreads();
     for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
         const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
         const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f;
-        const float Q1 = __ldg(Q + (n * sh.C + c) * 2), Q2 = __ldg(Q + (n * sh.C + c) * 2 + 1);
+        float mean, rstd;
+        mean_rstd(stats, n, sh.G, c / sh.cpg, inv_cnt, eps, mean, rstd);
+        const float Q1 = __ldg(Q + (n * sh.C + c) * 2);
+        const float Q2 = rstd * (__ldg(Q + (n * sh.C + c) * 2 + 1) - mean * Q1);      // sum dz * xhat
         atomicAdd(&sg[2 * (c / sh.cpg)], ga * sc * Q1);
         atomicAdd(&sg[2 * (c / sh.cpg) + 1], ga * sc * Q2);
         if (blockIdx.x == 0) {   // parameter gradients: once per sample
@@ -242,16 +270,18 @@ __global__ void __launch_bounds__(256) gn_act_bwd_apply(const __nv_bfloat16 *__r
     const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
     if (r >= sh.rows) return;
     const Coef k = make_coef(sh, n, q, stats, gamma, beta, scale, shift, eps);
-    if (DROP && off_dev) offset += __ldg(off_dev);   // device-resident counter: CUDA-graph replays draw fresh masks
-    const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
-    float mean[8], rstd[8], m1[8], m2[8], gs[8];
+    if (DROP && off_dev) offset += __ldg(off_dev);
+    float P[8], Qc[8], R[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         const int c = 8 * q + u, g = c / sh.cpg;
-        mean_rstd(stats, n, sh.G, g, inv_cnt, eps, mean[u], rstd[u]);
-        m1[u] = sg[2 * g] * inv_cnt;
-        m2[u] = sg[2 * g + 1] * inv_cnt;
-        gs[u] = (gamma ? __ldg(gamma + c) : 1.f) * (scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f);
+        float mean, rstd;
+        mean_rstd(stats, n, sh.G, g, inv_cnt, eps, mean, rstd);
+        const float m1 = sg[2 * g] * inv_cnt, m2 = sg[2 * g + 1] * inv_cnt;
+        const float gs = (gamma ? __ldg(gamma + c) : 1.f) * (scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f);
+        P[u] = rstd * gs;
+        Qc[u] = -rstd * rstd * m2;
+        R[u] = -rstd * m1 - mean * Qc[u];
     }
     const int64_t p0 = (int64_t)blockIdx.x * sh.pix_per_cta;
     int64_t p1 = p0 + sh.pix_per_cta;
@@ -259,16 +289,16 @@ __global__ void __launch_bounds__(256) gn_act_bwd_apply(const __nv_bfloat16 *__r
     for (int64_t p = p0 + r; p < p1; p += sh.rows) {
         const int64_t pix = n * sh.HW + p;
         float f[8], g[8], m[8], o[8];
-        unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(x + pix * ld_x + 8 * q)), f);
-        unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(gy + pix * ld_gy + 8 * q)), g);
+        const uint4 xv = ld_stream_u4(reinterpret_cast<const uint4 *>(x + pix * ld_x + 8 * q));
+        const uint4 gv = ld_stream_u4(reinterpret_cast<const uint4 *>(gy + pix * ld_gy + 8 * q));
+        unpack8(xv, f); unpack8(gv, g);
         if (DROP) dropout_mask8(seed, offset, pix * sh.C + 8 * q, p_drop, m);
         if (accumulate) unpack8(*reinterpret_cast<const uint4 *>(gx + pix * ld_gx + 8 * q), o);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
             if (DROP) dz *= m[u];
-            const float xhat = (f[u] - mean[u]) * rstd[u];
-            const float dx = rstd[u] * (dz * gs[u] - m1[u] - xhat * m2[u]);
+            const float dx = fmaf(dz, P[u], fmaf(f[u], Qc[u], R[u]));
             o[u] = accumulate ? o[u] + dx : dx;
         }
         *reinterpret_cast<uint4 *>(gx + pix * ld_gx + 8 * q) = pack8(o);

@@ -147,14 +147,15 @@ class AttnBlock(nn.Module):
     def forward_nhwc(self, x):
         n, h, w, c = x.shape
         y = ops.gn_act(x, self.group_norm.weight, self.group_norm.bias, 32, act="none", eps=self.group_norm.eps)
-        y = y.reshape(n, h * w, c)
-
-        def lin(conv, t):
-            return F.linear(t, conv.weight.reshape(c, c).to(torch.bfloat16), conv.bias.to(torch.bfloat16))
-
-        q, k, v = lin(self.proj_q, y), lin(self.proj_k, y), lin(self.proj_v, y)
-        o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None], scale=int(c) ** (-0.5))[:, 0]
-        return x + lin(self.proj, o).reshape(n, h, w, c)
+        # q, k, v projections as ONE 1x1 conv on the tensor cores (weights concatenated on the fly: the
+        # state_dict keeps the reference's three separate convs); softmax(QK^T/sqrt(C))V on PyTorch SDPA
+        wqkv = torch.cat([self.proj_q.weight, self.proj_k.weight, self.proj_v.weight], dim=0)
+        bqkv = torch.cat([self.proj_q.bias, self.proj_k.bias, self.proj_v.bias], dim=0)
+        qkv = ops.conv(y, wqkv, bqkv).reshape(n, 1, h * w, 3 * c)
+        q, k, v = ops.split3(qkv)
+        o = F.scaled_dot_product_attention(q, k, v, scale=int(c) ** (-0.5))
+        # x + proj(o): the residual add rides in the conv epilogue
+        return ops.conv(o.reshape(n, h, w, c), self.proj.weight, self.proj.bias, residual=x)
 
     def forward(self, x):
         return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x)))

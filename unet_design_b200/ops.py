@@ -403,6 +403,33 @@ def conv(a: torch.Tensor, w: torch.Tensor, bias=None, rowadd=None, a2=None, w2=N
     return _Conv.apply(a, w, bias, rowadd, a2, w2, residual, out_nchw)
 
 
+class _Split3(torch.autograd.Function):
+    """Three channel-slice views of a fused q|k|v projection; backward gathers the three gradients into one
+    buffer with strided copies (no zero-fill + add chain as plain slicing would record)."""
+
+    @staticmethod
+    def forward(ctx, qkv):
+        c = qkv.shape[-1] // 3
+        ctx.shape = qkv.shape
+        return qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
+
+    @staticmethod
+    def backward(ctx, gq, gk, gv):
+        c = ctx.shape[-1] // 3
+        ref = next(g for g in (gq, gk, gv) if g is not None)
+        out = torch.empty(ctx.shape, dtype=ref.dtype, device=ref.device)
+        for i, g in enumerate((gq, gk, gv)):
+            if g is None:
+                out[..., i * c:(i + 1) * c].zero_()
+            else:
+                out[..., i * c:(i + 1) * c].copy_(g)
+        return out
+
+
+def split3(qkv: torch.Tensor):
+    return _Split3.apply(qkv)
+
+
 # --------------------------------------------------------------------------------------------------
 # optimiser tail
 # --------------------------------------------------------------------------------------------------
