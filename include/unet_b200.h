@@ -81,6 +81,15 @@ int ub200_dwtblock_fwd_nhwc_bf16(const float *x, int64_t N, int64_t C, int64_t H
                                  int64_t out_channels, const int32_t *chmap, void *out_bf16,
                                  int64_t ld_out, void *stream);
 
+/* DWTBlock inside a network whose head is learned (pdearena twod_unetbase.py:173-193,:203;
+ * wmh/model.py:72-95): NHWC bf16 in and out, J in {0,1}, fp32 arithmetic.
+ * fwd: out[n,i,j,k] = LL_J(x[n,:,:,k mod C])[i,j] / 2^J;  bwd: its adjoint.  H, W are the INPUT extents,
+ * the output is ceil(H/2^J) x ceil(W/2^J) (zero extension of an odd extent).  C, out_channels % 8 == 0. */
+int ub200_dwtblock_nhwc_bf16_fwd(const void *x, int64_t ld_x, int64_t N, int64_t H, int64_t W, int64_t C, int J,
+                                 void *out, int64_t ld_out, int64_t out_channels, void *stream);
+int ub200_dwtblock_nhwc_bf16_bwd(const void *gout, int64_t ld_g, int64_t N, int64_t H, int64_t W, int64_t C,
+                                 int J, int64_t out_channels, void *gx, int64_t ld_gx, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Layout / resampling (memory-bound).
  * ------------------------------------------------------------------------------------------ */
@@ -116,7 +125,10 @@ int ub200_upsample2x_bwd_nhwc_bf16(const void *gout, int64_t ld_g, int64_t N, in
 int ub200_gn_stats_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, int64_t C, int G,
                              float *stats, void *stream);
 
-/* y = dropout( act( (x - mean) * rstd * gamma[c] * (1 + scale[n,c]) + beta[c] * (1 + scale) + shift[n,c] ) )
+/* y = addend + dropout( act( (x - mean) * rstd * gamma[c] * (1 + scale[n,c]) + beta[c] * (1 + scale) + shift[n,c] ) )
+ * addend (NHWC bf16, nullable) is the residual of the post-norm blocks: h1 + act(GN(conv2(h1)))
+ * (pdearena twod_unetbase.py:149-151,:158-161).  stats == NULL means "no normalisation" (mean 0,
+ * rstd 1: the norm=False blocks, which are a plain activation); pass G = 1 then.
  * scale/shift (float [N,C]) may be NULL (diff_mnist's use_scale_shift_norm, layers.py:330-334).
  * Dropout: keep-probability 1-p, Philox4x32-10 counter (seed, offset + *offset_dev + element index/4),
  * scaled 1/(1-p); p = 0 disables it.  offset_dev (nullable) is a device-resident counter so that a
@@ -125,6 +137,7 @@ int ub200_gn_act_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t H
                                const float *stats, float eps, const float *gamma, const float *beta,
                                const float *scale, const float *shift, int act,
                                float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                               const void *addend, int64_t ld_add,
                                void *y, int64_t ld_y, void *stream);
 
 /* Backward of the above.  gy, x NHWC bf16 -> gx NHWC bf16 (accumulate=1 adds into gx),

@@ -89,6 +89,9 @@ class EmulatedOps:
     def _gn_forward_fp32(self, x, G, stats, eps, gamma, beta, scale, shift, act, p, seed, off):
         n, h, w, c = x.shape
         cnt = (c // G) * h * w
+        if stats is None:
+            stats = torch.tensor([0.0, float(cnt)]).expand(n, G, 2)      # mean 0, var 1 (eps folded below)
+            eps = 0.0
         mean = (stats[..., 0] / cnt).repeat_interleave(c // G, dim=1)[:, None, None, :]
         var = (stats[..., 1] / cnt).repeat_interleave(c // G, dim=1)[:, None, None, :] - mean * mean
         rstd = torch.rsqrt(var.clamp_min(0) + eps)
@@ -102,8 +105,21 @@ class EmulatedOps:
         m = self._mask(x.shape, p, seed, off)
         return y * m if m is not None else y
 
-    def gn_act_fwd(self, x, G, stats, eps, gamma, beta, scale, shift, act, p, seed, off, off_dev, y):
-        y.copy_(_bf(self._gn_forward_fp32(x, G, stats, eps, gamma, beta, scale, shift, act, p, seed, off)))
+    def gn_act_fwd(self, x, G, stats, eps, gamma, beta, scale, shift, act, p, seed, off, off_dev, addend, y):
+        out = self._gn_forward_fp32(x, G, stats, eps, gamma, beta, scale, shift, act, p, seed, off)
+        if addend is not None:
+            out = out + addend.float()
+        y.copy_(_bf(out))
+
+    def dwtblock_nhwc_fwd(self, x, J, out_channels):
+        xn = x.float().permute(0, 3, 1, 2).contiguous().numpy()
+        y = haar_np.dwtblock(xn, J, out_channels)
+        return _bf(torch.from_numpy(y).permute(0, 2, 3, 1)).contiguous()
+
+    def dwtblock_nhwc_bwd(self, g, h, w, c, J):
+        gn = g.float().permute(0, 3, 1, 2).contiguous().numpy()
+        gx = haar_np.dwtblock_bwd(gn, (g.shape[0], c, h, w), J)
+        return _bf(torch.from_numpy(np.ascontiguousarray(gx)).permute(0, 2, 3, 1)).contiguous()
 
     def gn_act_bwd(self, gy, x, G, stats, eps, gamma, beta, scale, shift, act, p, seed, off, off_dev, gx, accumulate,
                    dgamma, dbeta, dscale, dshift):
@@ -117,7 +133,7 @@ class EmulatedOps:
             n, h, w, c = x.shape
             # statistics are functions of x: recompute them differentiably
             xf = xr.reshape(n, h * w, G, c // G)
-            st = torch.stack([xf.sum(dim=(1, 3)), (xf * xf).sum(dim=(1, 3))], dim=-1)
+            st = torch.stack([xf.sum(dim=(1, 3)), (xf * xf).sum(dim=(1, 3))], dim=-1) if stats is not None else None
             y = self._gn_forward_fp32(xr, G, st, eps, ga, be, sc, sf, act, p, seed, off)
             leaves += [t for t in (ga, be, sc, sf) if t is not None]
             grads = torch.autograd.grad(y, leaves, gy.float())

@@ -1,0 +1,122 @@
+"""Shared golden-vector checks: the same replay runs against (a) the torch fp32 oracle on CPU, (b) the drop-in
+modules over the CPU emulation of the op contract, (c) the drop-in modules over the real sm_100a kernels.
+Fixtures come from the reference's own classes (tools/make_golden.py); parameters from tests/det_init.py."""
+import os
+
+import torch
+
+from conftest import GOLDEN, rel_err
+from det_init import apply_det_init
+
+ZERO_IN_EXACT_ARITHMETIC = ("proj_k.bias",)      # softmax is invariant to a key bias: gradient is round-off only
+
+
+def load(name):
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+
+
+def _dev(t, device):
+    return t.to(device) if torch.is_tensor(t) else t
+
+
+def _check_grads(module, gparams, tol, floor=1e-4, loose=()):
+    params = dict(module.named_parameters())
+    assert gparams, "fixture holds no parameter gradients"
+    for n, g in gparams.items():
+        if n.endswith(ZERO_IN_EXACT_ARITHMETIC):
+            continue
+        assert params[n].grad is not None, n
+        limit = 3 * tol if any(k in n for k in loose) else tol
+        assert rel_err(params[n].grad, g, floor=floor) < limit, (n, rel_err(params[n].grad, g, floor=floor))
+
+
+def check_cifar_resblock(ns, tag, device, tol):
+    g = load(f"cifar_{tag}.pt")
+    blk = apply_det_init(ns.ResBlock(**g["cfg"])).to(device)
+    x = g["x"].to(device).requires_grad_(True)
+    temb = g["temb"].to(device).requires_grad_(True)
+    y = blk(x, temb)
+    y.backward(g["gy"].to(device))
+    assert rel_err(y, g["y"]) < tol
+    assert rel_err(x.grad, g["gx"]) < 2 * tol
+    assert rel_err(temb.grad, g["gtemb"]) < 2 * tol
+    _check_grads(blk, g["gparams"], 3 * tol, loose=("attn.proj_q.bias",))
+
+
+def check_cifar_upsample(ns, device, tol):
+    g = load("cifar_upsample.pt")
+    up = apply_det_init(ns.UpSample(32)).to(device)
+    x = g["x"].to(device).requires_grad_(True)
+    y = up(x, None)
+    y.backward(g["gy"].to(device))
+    assert rel_err(y, g["y"]) < tol and rel_err(x.grad, g["gx"]) < tol
+    _check_grads(up, g["gparams"], tol)
+
+
+def check_cifar_dtwblock(ns, device, tol=2e-6):
+    for case in load("cifar_dtwblock.pt"):
+        y = ns.DTWBlock(case["J"], case["out_channels"]).to(device)(case["x"].to(device))
+        assert y.shape == case["y"].shape and rel_err(y, case["y"]) < tol
+
+
+def check_cifar_model(ns, trainer_cls, tag, device, tol_out, tol_grad):
+    g = load(f"cifar_{tag}.pt")
+    net = apply_det_init(ns.UNetWaveletEnc(**g["cfg"])).to(device)
+    with torch.no_grad():
+        out = net(g["x_t"].to(device), g["t"].to(device))
+        out1 = net(g["x_t"][:, :, ::2, ::2].contiguous().to(device), g["t"].to(device), n_levels_used=1)
+    outs = out if isinstance(out, list) else [out]
+    gouts = g["out"] if isinstance(g["out"], list) else [g["out"]]
+    assert len(outs) == len(gouts)
+    for a, b in zip(outs, gouts):
+        assert a.shape == b.shape and rel_err(a, b) < tol_out
+    a1 = out1[-1] if isinstance(out1, list) else out1
+    b1 = g["out_1lvl"][-1] if isinstance(g["out_1lvl"], list) else g["out_1lvl"]
+    assert rel_err(a1, b1) < tol_out
+    trainer = trainer_cls(net, 1e-4, 0.02, g["cfg"]["T"], g["cfg"]["multi_res_loss"], False, device).to(device)
+    loss, loss_list = trainer.loss_from(g["x0"].to(device), g["t"].to(device), g["noise"].to(device))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) < max(tol_out, 1e-5) * abs(float(g["loss"]))
+    for a, b in zip(loss_list, g["loss_list"]):
+        assert abs(float(a.detach()) - float(b)) < max(tol_out, 1e-5) * abs(float(b))
+    _check_grads(net, g["gparams"], tol_grad, loose=("attn.proj_q.bias", "time_embedding"))
+
+
+def check_pdearena_blocks(base_ns, unet_ns, device, tol):
+    blocks = load("pdearena_blocks.pt")
+    ctors = {"conv": lambda: base_ns.ConvBlock(32, 48),
+             "partial": lambda: base_ns.PartialResnetConvBlock(32, 48, activation="silu"),
+             "full": lambda: base_ns.FullResnetConvBlock(32, 32),
+             "conv_nonorm": lambda: base_ns.ConvBlock(32, 32, norm=False),
+             "residual_sc": lambda: unet_ns.ResidualBlock(32, 64, norm=True, n_groups=8),
+             "residual_id": lambda: unet_ns.ResidualBlock(32, 32, norm=False)}
+    for tag, g in blocks.items():
+        blk = apply_det_init(ctors[tag]()).to(device)
+        x = g["x"].to(device).requires_grad_(True)
+        y = blk(x)
+        y.backward(g["gy"].to(device))
+        assert rel_err(y, g["y"]) < tol, tag
+        assert rel_err(x.grad, g["gx"]) < 2 * tol, tag
+        _check_grads(blk, g["gparams"], 3 * tol)
+
+
+def check_unetbase_g(cls, fixture, device, tol_out, tol_grad):
+    g = load(fixture)
+    net = apply_det_init(cls(**g["cfg"])).to(device)
+    x = g["x"].float().to(device)
+    out = net(x)
+    outs = out if isinstance(out, list) else [out]
+    gouts = g["out"] if isinstance(g["out"], list) else [g["out"]]
+    gys = g["gy"] if isinstance(g["gy"], list) else [g["gy"]]
+    assert len(outs) == len(gouts)
+    for a, b in zip(outs, gouts):
+        assert a.shape == b.shape, (a.shape, b.shape)
+        assert rel_err(a, b.float()) < tol_out, rel_err(a, b.float())
+    sum((o * gy.float().to(device)).sum() for o, gy in zip(outs, gys)).backward()
+    _check_grads(net, g["gparams"], tol_grad)
+    if g.get("out_2lvl") is not None:
+        with torch.no_grad():
+            out2 = net(x[..., ::4, ::4].contiguous(), n_levels_used=2)
+        assert len(out2) == len(g["out_2lvl"])
+        for a, b in zip(out2, g["out_2lvl"]):
+            assert a.shape == b.shape and rel_err(a, b) < tol_out

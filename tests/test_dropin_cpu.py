@@ -1,0 +1,65 @@
+"""CPU checks of the drop-in modules' Python side (level bookkeeping, channel maps, odd-extent handling, autograd
+glue, state_dict surface) against golden vectors of the reference's own classes, with the kernels replaced by the
+test-only emulation of their contract (tests/_emulated_ops.py).  Tolerances are bf16-level: activations are bf16."""
+import pytest
+import torch
+
+import golden_checks as gc
+
+TOL = 2e-2
+
+
+def test_state_dict_surface_matches_reference(emulated_ops):
+    """Keys and shapes equal the reference's (recorded by tools/make_golden.py into tests/golden/state_dict_keys.pt)."""
+    from unet_design_b200.diff_cifar.model import UNetWaveletEnc
+    from unet_design_b200.pdearena.modules.twod_unetbase import Unetbase_G
+    from unet_design_b200.wmh.model import Unetbase_G as WmhUnet
+    ref = gc.load("state_dict_keys.pt")
+    builders = {"cifar_multiresnet": lambda c: UNetWaveletEnc(**c), "cifar_unet": lambda c: UNetWaveletEnc(**c),
+                "pdearena_unetbase_g_multiresnet": lambda c: Unetbase_G(**c), "pdearena_unetbase_g_unet": lambda c: Unetbase_G(**c),
+                "wmh_unetbase_g_multiresnet": lambda c: WmhUnet(**c), "wmh_unetbase_g_unet": lambda c: WmhUnet(**c)}
+    for name, build in builders.items():
+        net = build(ref[name]["cfg"])
+        ours = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        assert ours == ref[name]["keys"], name
+    # conv weights keep the [Cout, kh, kw, Cin] memory order through load_state_dict
+    net = UNetWaveletEnc(**ref["cifar_multiresnet"]["cfg"])
+    net.load_state_dict({k: torch.zeros(s) if "timembedding.0" not in k else net.state_dict()[k]
+                         for k, s in ref["cifar_multiresnet"]["keys"].items()}, strict=True)
+    assert net.upblocks[0][0].block1[2].weight.permute(0, 2, 3, 1).is_contiguous()
+
+
+@pytest.mark.parametrize("tag", ["resblock_sc", "resblock_id", "resblock_attn"])
+def test_cifar_resblock(emulated_ops, tag):
+    from unet_design_b200.diff_cifar import model
+    gc.check_cifar_resblock(model, tag, "cpu", TOL)
+
+
+def test_cifar_upsample_and_dtwblock(emulated_ops):
+    from unet_design_b200.diff_cifar import model
+    gc.check_cifar_upsample(model, "cpu", TOL)
+    gc.check_cifar_dtwblock(model, "cpu")
+
+
+@pytest.mark.parametrize("tag", ["multiresnet", "unet"])
+def test_cifar_model(emulated_ops, tag):
+    from unet_design_b200.diff_cifar import model
+    from unet_design_b200.diff_cifar.diffusion import GaussianDiffusionTrainer
+    gc.check_cifar_model(model, GaussianDiffusionTrainer, tag, "cpu", 3 * TOL, 6e-2)
+
+
+def test_pdearena_blocks(emulated_ops):
+    from unet_design_b200.pdearena.modules import twod_unet, twod_unetbase
+    gc.check_pdearena_blocks(twod_unetbase, twod_unet, "cpu", TOL)
+
+
+@pytest.mark.parametrize("tag", ["multiresnet", "unet", "multiresnet_mrl"])
+def test_pdearena_unetbase_g(emulated_ops, tag):
+    from unet_design_b200.pdearena.modules.twod_unetbase import Unetbase_G
+    gc.check_unetbase_g(Unetbase_G, f"pdearena_unetbase_g_{tag}.pt", "cpu", 3 * TOL, 8e-2)
+
+
+@pytest.mark.parametrize("tag", ["multiresnet", "unet"])
+def test_wmh_unetbase_g_odd_extents(emulated_ops, tag):
+    from unet_design_b200.wmh.model import Unetbase_G
+    gc.check_unetbase_g(Unetbase_G, f"wmh_unetbase_g_{tag}.pt", "cpu", 3 * TOL, 8e-2)

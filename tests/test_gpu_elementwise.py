@@ -153,3 +153,47 @@ def test_adam_ema_clip_matches_torch(ops):
         assert abs(float(acc) - float(g.double().pow(2).sum())) < 1e-4 * float(acc)
         ops.adam_ema_step_(p, g, m, v, ema, acc, 1.0, 1.0, 2e-4, 0.9, 0.999, 1e-8, 0.9999, step)
         assert rel_err(p, ref) < 1e-6 and rel_err(ema, ema_ref) < 1e-6
+
+
+@pytest.mark.parametrize("shape,J,cout", [((2, 16, 16, 64), 1, 128), ((2, 25, 25, 128), 1, 256), ((1, 13, 9, 16), 1, 16),
+                                          ((2, 8, 8, 64), 0, 128), ((1, 128, 128, 64), 1, 128)])
+def test_dwtblock_on_nhwc_activations(ops, shape, J, cout):
+    """In-network DWTBlock (pdearena / wmh): NHWC bf16 in/out against the fp32 numpy oracle, forward and adjoint."""
+    import numpy as np
+    from oracle import haar_np
+    torch.manual_seed(7)
+    n, h, w, c = shape
+    x = torch.randn(*shape, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    y = ops.dwtblock_act(x, J, cout)
+    xn = x.detach().float().permute(0, 3, 1, 2).cpu().numpy()
+    want = torch.from_numpy(haar_np.dwtblock(xn, J, cout)).permute(0, 2, 3, 1)
+    assert y.shape == want.shape and rel_err(y, want) < BF16
+    g = torch.randn_like(y)
+    y.backward(g)
+    gn = g.float().permute(0, 3, 1, 2).cpu().numpy()
+    gx = torch.from_numpy(np.ascontiguousarray(haar_np.dwtblock_bwd(gn, (n, c, h, w), J))).permute(0, 2, 3, 1)
+    assert rel_err(x.grad, gx) < BF16
+
+
+def test_gn_act_addend_and_no_norm_modes(ops):
+    torch.manual_seed(8)
+    x = torch.randn(2, 8, 8, 64, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    add = torch.randn(2, 8, 8, 64, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(64, device="cuda")).requires_grad_(True)
+    beta = (0.2 * torch.randn(64, device="cuda")).requires_grad_(True)
+    y = ops.gn_act(x, gamma, beta, 1, act="gelu", addend=add)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr, ar = x.detach().float().requires_grad_(True), add.detach().float().requires_grad_(True)
+    gr, br = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    yr = _gn_ref(xr, 1, gr, br, None, None, "gelu") + ar
+    yr.backward(g.float())
+    assert rel_err(y, yr) < BF16 and rel_err(x.grad, xr.grad) < 2 * BF16 and rel_err(add.grad, ar.grad) < 1e-6
+    assert rel_err(gamma.grad, gr.grad) < 1e-2 and rel_err(beta.grad, br.grad) < 1e-2
+    # groups = 0: plain activation (norm=False blocks)
+    x2 = torch.randn(2, 8, 8, 64, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    y2 = ops.gn_act(x2, None, None, 0, act="gelu")
+    y2.backward(g)
+    x2r = x2.detach().float().requires_grad_(True)
+    F.gelu(x2r).backward(g.float())
+    assert rel_err(y2, F.gelu(x2.detach().float())) < BF16 and rel_err(x2.grad, x2r.grad) < 2 * BF16

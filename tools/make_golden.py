@@ -1,11 +1,13 @@
 """Generate tests/golden/*.pt by running the reference's OWN module classes.
 
-Runs only in the build container (needs /root/reference, read-only).  The reference's
-`pytorch_wavelets` dependency is absent from the image, so `sys.modules` maps it to
-`oracle.pytorch_wavelets_restated` (parity of the Haar arithmetic itself is therefore
-unpinned, see oracle/__init__.py); everything else -- ResBlock, UpSample, AttnBlock,
-DTWBlock's scale + channel-tile logic, UNetWaveletEnc's level bookkeeping, the DDPM loss
--- is the reference's code, unmodified.
+Runs only in the build container (needs /root/reference, read-only).  The reference's `pytorch_wavelets`
+dependency is absent from the image, so `sys.modules` maps it to `oracle.pytorch_wavelets_restated` (parity of
+the Haar arithmetic itself is therefore unpinned, see oracle/__init__.py); everything else -- ResBlock, UpSample,
+AttnBlock, DTWBlock's scale + channel-tile logic, UNetWaveletEnc's level bookkeeping, the DDPM loss, pdearena's
+conv blocks and Unetbase_G, wmh's odd-extent handling -- is the reference's code, unmodified.
+
+Parameters are set by tests/det_init.py (a pure function of name and shape) so the fixtures carry inputs, outputs
+and gradients only.
 
     python tools/make_golden.py            # rewrites tests/golden/
 """
@@ -21,7 +23,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+from det_init import apply_det_init  # noqa: E402
 from oracle import pytorch_wavelets_restated as pw  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -40,45 +44,39 @@ def load_reference_module(name: str, path: str):
     return mod
 
 
-def grads_of(module, names):
-    params = dict(module.named_parameters())
-    return {n: params[n].grad.detach().clone() for n in names}
+def small_grads(module, also=()):
+    return {n: p.grad.clone() for n, p in module.named_parameters()
+            if p.grad is not None and (p.numel() <= 4096 or any(n.endswith(a) for a in also))}
 
 
 def cifar_goldens():
     m = load_reference_module("ref_cifar_model", f"{REF}/diff_cifar/model.py")
     d = load_reference_module("ref_cifar_diffusion", f"{REF}/diff_cifar/diffusion.py")
 
-    # --- one ResBlock with a 1x1 shortcut, and one without (reference diff_cifar/model.py:122-169)
+    # --- ResBlock with a 1x1 shortcut, with an identity shortcut, with attention (diff_cifar/model.py:122-169)
     for tag, cin, cout, attn in (("resblock_sc", 96, 64, False), ("resblock_id", 64, 64, False),
                                  ("resblock_attn", 64, 64, True)):
-        torch.manual_seed(1234)
-        blk = m.ResBlock(cin, cout, tdim=128, dropout=0.0, attn=attn).double().float()
-        # conv2 starts at gain 1e-5: give it weight so its gradient path is exercised
-        with torch.no_grad():
-            blk.block2[-1].weight.mul_(1e5 * 0.5)
+        cfg = dict(in_ch=cin, out_ch=cout, tdim=128, dropout=0.0, attn=attn)
+        blk = apply_det_init(m.ResBlock(**cfg))
         torch.manual_seed(0)
         x = torch.randn(4, cin, 8, 8, requires_grad=True)
         temb = torch.randn(4, 128, requires_grad=True)
         y = blk(x, temb)
         gy = torch.randn_like(y)
         y.backward(gy)
-        torch.save({"state": blk.state_dict(), "x": x.detach(), "temb": temb.detach(), "y": y.detach(),
-                    "gy": gy, "gx": x.grad, "gtemb": temb.grad,
-                    "gparams": {n: p.grad for n, p in blk.named_parameters()},
-                    "cfg": dict(in_ch=cin, out_ch=cout, tdim=128, dropout=0.0, attn=attn)},
+        torch.save({"cfg": cfg, "x": x.detach(), "temb": temb.detach(), "y": y.detach(), "gy": gy, "gx": x.grad,
+                    "gtemb": temb.grad, "gparams": small_grads(blk, also=("block1.2.weight", "block2.3.weight"))},
                    f"{OUT}/cifar_{tag}.pt")
 
     # --- UpSample (model.py:66-81)
-    torch.manual_seed(1234)
-    up = m.UpSample(32)
+    up = apply_det_init(m.UpSample(32))
     torch.manual_seed(0)
     x = torch.randn(3, 32, 4, 4, requires_grad=True)
     y = up(x, None)
     gy = torch.randn_like(y)
     y.backward(gy)
-    torch.save({"state": up.state_dict(), "x": x.detach(), "y": y.detach(), "gy": gy, "gx": x.grad,
-                "gparams": {n: p.grad for n, p in up.named_parameters()}}, f"{OUT}/cifar_upsample.pt")
+    torch.save({"x": x.detach(), "y": y.detach(), "gy": gy, "gx": x.grad, "gparams": small_grads(up, also=("main.weight",))},
+               f"{OUT}/cifar_upsample.pt")
 
     # --- DTWBlock scale + tile logic (model.py:253-323)
     torch.manual_seed(0)
@@ -86,25 +84,18 @@ def cifar_goldens():
     for (shape, J, out_ch) in (((2, 3, 8, 8), 0, 32), ((2, 32, 8, 8), 1, 32), ((2, 32, 8, 8), 1, 80),
                                ((1, 5, 7, 9), 1, 12), ((1, 3, 16, 16), 2, 7), ((1, 2, 25, 13), 3, 2)):
         x = torch.randn(*shape)
-        y = m.DTWBlock(J=J, out_channels=out_ch)(x)
-        cases.append({"x": x, "J": J, "out_channels": out_ch, "y": y})
+        cases.append({"x": x, "J": J, "out_channels": out_ch, "y": m.DTWBlock(J=J, out_channels=out_ch)(x)})
     torch.save(cases, f"{OUT}/cifar_dtwblock.pt")
 
-    # --- whole models: Multi-ResNet (Haar encoder) and the residual U-Net arm (model.py:326-496)
+    # --- whole models: Multi-ResNet (Haar encoder, multi-res loss) and the residual U-Net arm (model.py:326-496)
     for tag, kw in (("multiresnet", dict(dwt_encoder=True, multi_res_loss=True)),
                     ("unet", dict(dwt_encoder=False, multi_res_loss=False))):
-        torch.manual_seed(1234)
-        cfg = dict(T=20, ch=32, ch_mult=[1, 1], attn=[1], num_res_blocks=1, dropout=0.0, **kw)
-        net = m.UNetWaveletEnc(**cfg)
-        with torch.no_grad():  # lift the 1e-5-gain convs so every gradient is well above round-off
-            for n, p in net.named_parameters():
-                if p.dim() == 4 and p.abs().max() < 1e-3:
-                    p.mul_(3e4)
+        cfg = dict(T=20, ch=64, ch_mult=[1, 1], attn=[1], num_res_blocks=1, dropout=0.0, **kw)
+        net = apply_det_init(m.UNetWaveletEnc(**cfg))
         trainer = d.GaussianDiffusionTrainer(net, 1e-4, 0.02, 20, kw["multi_res_loss"], False, "cpu")
         torch.manual_seed(0)
         x0 = torch.randn(4, 3, 16, 16)
-        # replay the trainer's own RNG draws so that oracle/torch_ref.loss_from can reproduce them
-        torch.manual_seed(7)
+        torch.manual_seed(7)                      # replay the trainer's own draws so the oracle can reproduce them
         t = torch.randint(20, size=(4,))
         noise = torch.randn_like(x0)
         torch.manual_seed(7)
@@ -115,17 +106,89 @@ def cifar_goldens():
         with torch.no_grad():
             out = net(x_t, t)
             out_1lvl = net(x_t[:, :, ::2, ::2].contiguous(), t, n_levels_used=1)
-        torch.save({"cfg": cfg, "state": net.state_dict(), "x0": x0, "t": t, "noise": noise, "x_t": x_t,
-                    "out": out, "out_1lvl": out_1lvl, "loss": loss.detach(),
-                    "loss_list": [l.detach() for l in loss_list],
-                    # every small gradient plus one conv weight per block kind (keeps the fixture ~1.5 MB)
-                    "gparams": {n: p.grad for n, p in net.named_parameters() if p.grad is not None
-                                and (p.numel() <= 4096 or n.endswith("block1.2.weight"))}},
-                   f"{OUT}/cifar_{tag}.pt")
+        torch.save({"cfg": cfg, "x0": x0, "t": t, "noise": noise, "x_t": x_t, "out": out, "out_1lvl": out_1lvl,
+                    "loss": loss.detach(), "loss_list": [l.detach() for l in loss_list],
+                    "gparams": small_grads(net, also=("upblocks.0.0.block1.2.weight",))}, f"{OUT}/cifar_{tag}.pt")
+
+
+def pdearena_wmh_goldens():
+    sys.modules["pytorch_wavelets"] = pw
+    sys.path.insert(0, f"{REF}/pdearena")
+    import pdearena.modules.twod_unet as ref_unet          # noqa: E402  (reference, read-only)
+    import pdearena.modules.twod_unetbase as ref_base      # noqa: E402
+    wmh = load_reference_module("ref_wmh_model", f"{REF}/wmh/model.py")
+
+    # --- post-norm conv blocks (twod_unetbase.py:12-32, :148-161) and the pre-norm ResidualBlock (twod_unet.py:16-61)
+    blocks = {}
+    for tag, ctor in (("conv", lambda: ref_base.ConvBlock(32, 48)),
+                      ("partial", lambda: ref_base.PartialResnetConvBlock(32, 48, activation="silu")),
+                      ("full", lambda: ref_base.FullResnetConvBlock(32, 32)),
+                      ("conv_nonorm", lambda: ref_base.ConvBlock(32, 32, norm=False)),
+                      ("residual_sc", lambda: ref_unet.ResidualBlock(32, 64, norm=True, n_groups=8)),
+                      ("residual_id", lambda: ref_unet.ResidualBlock(32, 32, norm=False))):
+        blk = apply_det_init(ctor())
+        torch.manual_seed(0)
+        x = torch.randn(2, 32, 12, 10, requires_grad=True)
+        y = blk(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        blocks[tag] = {"x": x.detach(), "y": y.detach(), "gy": gy, "gx": x.grad,
+                       "gparams": {n: p.grad for n, p in blk.named_parameters()}}
+    torch.save(blocks, f"{OUT}/pdearena_blocks.pt")
+
+    # --- Unetbase_G: Multi-ResNet (Haar encoder, +1 extra ResNet layer), the residual U-Net arm, multi-res loss
+    for tag, kw in (("multiresnet", dict(dwt_encoder=True, n_extra_resnet_layers=1)), ("unet", dict(dwt_encoder=False)),
+                    ("multiresnet_mrl", dict(dwt_encoder=True, multi_res_loss=True))):
+        cfg = dict(n_input_scalar_components=1, n_input_vector_components=1, n_output_scalar_components=1,
+                   n_output_vector_components=1, time_history=2, time_future=1, hidden_channels=16, **kw)
+        net = apply_det_init(ref_base.Unetbase_G(**cfg))
+        torch.manual_seed(0)
+        x = torch.randn(2, 2, 3, 32, 48)
+        out = net(x)
+        outs = out if isinstance(out, list) else [out]
+        gys = [torch.randn_like(o) for o in outs]
+        sum((o * g).sum() for o, g in zip(outs, gys)).backward()
+        with torch.no_grad():
+            out2 = net(x[..., ::4, ::4].contiguous(), n_levels_used=2) if kw.get("multi_res_loss") else None
+        torch.save({"cfg": cfg, "x": x, "out": [o.detach() for o in outs], "gy": gys, "out_2lvl": out2,
+                    "gparams": small_grads(net, also=("up.3.conv.conv1.weight",))},
+                   f"{OUT}/pdearena_unetbase_g_{tag}.pt")
+
+    # --- wmh Unetbase_G: odd extents 25 -> 13 with the decoder crop (Haar arm) / replicate pad (U-Net arm)
+    for tag, kw in (("multiresnet", dict(dwt_encoder=True)), ("unet", dict(dwt_encoder=False))):
+        cfg = dict(hidden_channels=16, **kw)
+        net = apply_det_init(wmh.Unetbase_G(**cfg))
+        torch.manual_seed(0)
+        x = torch.randn(1, 2, 200, 200).to(torch.bfloat16).float()
+        out = net(x)
+        gy = torch.randn_like(out).to(torch.bfloat16).float()
+        (out * gy).sum().backward()
+        torch.save({"cfg": cfg, "x": x.to(torch.bfloat16), "out": out.detach().to(torch.bfloat16), "gy": gy.to(torch.bfloat16),
+                    "gparams": small_grads(net)}, f"{OUT}/wmh_unetbase_g_{tag}.pt")
+
+
+def state_dict_keys():
+    """Key names and shapes of the reference's state_dicts (the checkpoint compatibility surface)."""
+    m = load_reference_module("ref_cifar_model", f"{REF}/diff_cifar/model.py")
+    sys.path.insert(0, f"{REF}/pdearena")
+    import pdearena.modules.twod_unetbase as ref_base      # noqa: E402
+    wmh = load_reference_module("ref_wmh_model", f"{REF}/wmh/model.py")
+    out = {}
+    for name, fixture, cls in (("cifar_multiresnet", "cifar_multiresnet.pt", m.UNetWaveletEnc),
+                               ("cifar_unet", "cifar_unet.pt", m.UNetWaveletEnc),
+                               ("pdearena_unetbase_g_multiresnet", "pdearena_unetbase_g_multiresnet.pt", ref_base.Unetbase_G),
+                               ("pdearena_unetbase_g_unet", "pdearena_unetbase_g_unet.pt", ref_base.Unetbase_G),
+                               ("wmh_unetbase_g_multiresnet", "wmh_unetbase_g_multiresnet.pt", wmh.Unetbase_G),
+                               ("wmh_unetbase_g_unet", "wmh_unetbase_g_unet.pt", wmh.Unetbase_G)):
+        cfg = torch.load(f"{OUT}/{fixture}", weights_only=False)["cfg"]
+        out[name] = {"cfg": cfg, "keys": {k: tuple(v.shape) for k, v in cls(**cfg).state_dict().items()}}
+    torch.save(out, f"{OUT}/state_dict_keys.pt")
 
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     cifar_goldens()
+    pdearena_wmh_goldens()
+    state_dict_keys()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

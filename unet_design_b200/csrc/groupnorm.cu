@@ -104,6 +104,7 @@ struct Coef { float A[8], B[8]; };
 
 __device__ __forceinline__ void mean_rstd(const float *stats, int64_t n, int G, int g, float inv_cnt, float eps,
                                           float &mean, float &rstd) {
+    if (!stats) { mean = 0.f; rstd = 1.f; return; }      // no normalisation: plain activation (norm=False blocks)
     const float s = __ldg(stats + (n * G + g) * 2), ss = __ldg(stats + (n * G + g) * 2 + 1);
     mean = s * inv_cnt;
     const float var = fmaxf(ss * inv_cnt - mean * mean, 0.f);
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) gn_act_fwd_kernel(const __nv_bfloat16 *__
                                                         const float *__restrict__ beta, const float *__restrict__ scale,
                                                         const float *__restrict__ shift, float eps, float p_drop,
                                                         uint64_t seed, uint64_t offset, const uint64_t *__restrict__ off_dev,
+                                                        const __nv_bfloat16 *__restrict__ addend, int64_t ld_add,
                                                         __nv_bfloat16 *__restrict__ y,
                                                         int64_t ld_y) {
     const int64_t n = blockIdx.y;
@@ -153,6 +155,12 @@ __global__ void __launch_bounds__(256) gn_act_fwd_kernel(const __nv_bfloat16 *__
         for (int u = 0; u < 8; ++u) {
             f[u] = act_fwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
             if (DROP) f[u] *= m[u];
+        }
+        if (addend) {
+            float r8[8];
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(addend + pix * ld_add + 8 * q)), r8);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] += r8[u];
         }
         *reinterpret_cast<uint4 *>(y + pix * ld_y + 8 * q) = pack8(f);
     }
@@ -257,8 +265,10 @@ __global__ void __launch_bounds__(256, 3) gn_act_bwd_apply(const __nv_bfloat16 *
         mean_rstd(stats, n, sh.G, c / sh.cpg, inv_cnt, eps, mean, rstd);
         const float Q1 = __ldg(Q + (n * sh.C + c) * 2);
         const float Q2 = rstd * (__ldg(Q + (n * sh.C + c) * 2 + 1) - mean * Q1);      // sum dz * xhat
-        atomicAdd(&sg[2 * (c / sh.cpg)], ga * sc * Q1);
-        atomicAdd(&sg[2 * (c / sh.cpg) + 1], ga * sc * Q2);
+        if (stats) {      // without normalisation the statistics do not depend on x: no mean-subtraction terms
+            atomicAdd(&sg[2 * (c / sh.cpg)], ga * sc * Q1);
+            atomicAdd(&sg[2 * (c / sh.cpg) + 1], ga * sc * Q2);
+        }
         if (blockIdx.x == 0) {   // parameter gradients: once per sample
             if (dgamma) atomicAdd(dgamma + c, sc * Q2);
             if (dbeta) atomicAdd(dbeta + c, sc * Q1);
@@ -356,19 +366,21 @@ int ub200_gn_stats_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, i
 int ub200_gn_act_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t HW, int64_t C, int G, const float *stats,
                                float eps, const float *gamma, const float *beta, const float *scale, const float *shift,
                                int act, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
-                               void *y, int64_t ld_y, void *stream) {
-    UB_REQUIRE(x && y && stats && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
+                               const void *addend, int64_t ld_add, void *y, int64_t ld_y, void *stream) {
+    UB_REQUIRE(x && y && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
     UB_REQUIRE(act == UB200_ACT_NONE || act == UB200_ACT_SILU || act == UB200_ACT_GELU, UB200_E_BADARG);
     Shape sh; dim3 grid;
     int rc = make_shape(N, HW, C, G, sh, grid);
     if (rc) return rc;
     UB_REQUIRE(ld_x % 8 == 0 && ld_y % 8 == 0 && ld_x >= C && ld_y >= C && ub::aligned16(x) && ub::aligned16(y),
                UB200_E_UNSUPPORTED);
+    UB_REQUIRE(!addend || (ld_add % 8 == 0 && ld_add >= C && ub::aligned16(addend)), UB200_E_UNSUPPORTED);
     cudaStream_t s = ub::as_stream(stream);
     const bool drop = dropout_p > 0.f;
     DISPATCH_ACT_DROP(gn_act_fwd_kernel, act, drop,
                       <<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16 *>(x), ld_x, sh, stats, gamma, beta,
                                             scale, shift, eps, dropout_p, seed, offset, offset_dev,
+                                            reinterpret_cast<const __nv_bfloat16 *>(addend), ld_add,
                                             reinterpret_cast<__nv_bfloat16 *>(y), ld_y));
     UB_LAUNCH_CHECK();
     return UB200_OK;
@@ -384,7 +396,7 @@ int ub200_gn_act_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int
                                const float *scale, const float *shift, int act, float dropout_p, uint64_t seed,
                                uint64_t offset, const uint64_t *offset_dev, void *gx, int64_t ld_gx, int accumulate, float *dgamma, float *dbeta,
                                float *dscale, float *dshift, float *ws, void *stream) {
-    UB_REQUIRE(gy && x && gx && stats && ws && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
+    UB_REQUIRE(gy && x && gx && ws && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
     UB_REQUIRE(act == UB200_ACT_NONE || act == UB200_ACT_SILU || act == UB200_ACT_GELU, UB200_E_BADARG);
     Shape sh; dim3 grid;
     int rc = make_shape(N, HW, C, G, sh, grid);

@@ -308,9 +308,105 @@ __global__ void __launch_bounds__(256) dwtblock_nhwc_bf16(const float *__restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// DWTBlock on NHWC bf16 activations (pdearena / wmh: the head conv is learned, so the block sits inside the
+// network and has a backward).  J in {0, 1}; fp32 arithmetic, bf16 storage.  One work item = one 16-byte channel
+// chunk of one output (forward) / input (backward) pixel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dwtblock_nhwc_fwd(const __nv_bfloat16 *__restrict__ x, int64_t ld_x, int64_t N,
+                                                        int H, int W, int C, int J, __nv_bfloat16 *__restrict__ out,
+                                                        int64_t ld_o, int Cout) {
+    const int ho = J ? (H + 1) >> 1 : H, wo = J ? (W + 1) >> 1 : W, chunks = C >> 3;
+    const int64_t items = N * ho * (int64_t)wo * chunks;
+    for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(it % chunks);
+        const int64_t pix = it / chunks;
+        const int j = (int)(pix % wo);
+        int64_t t = pix / wo;
+        const int i = (int)(t % ho);
+        const int64_t n = t / ho;
+        float f[8];
+        if (J == 0) {
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(x + pix * ld_x + 8 * q)), f);
+        } else {
+            float a[8], b[8], c[8], d[8];
+            const bool r1 = 2 * i + 1 < H, c1 = 2 * j + 1 < W;
+            const __nv_bfloat16 *p00 = x + ((n * H + 2 * i) * (int64_t)W + 2 * j) * ld_x + 8 * q;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(p00)), a);
+            unpack8(c1 ? ld_stream_u4(reinterpret_cast<const uint4 *>(p00 + ld_x)) : z, b);
+            unpack8(r1 ? ld_stream_u4(reinterpret_cast<const uint4 *>(p00 + (int64_t)W * ld_x)) : z, c);
+            unpack8((r1 && c1) ? ld_stream_u4(reinterpret_cast<const uint4 *>(p00 + (int64_t)W * ld_x + ld_x)) : z, d);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] = analyse_ll(a[u], b[u], c[u], d[u]) * 0.5f;
+        }
+        const uint4 v = pack8(f);
+        for (int k0 = 8 * q; k0 < Cout; k0 += C) *reinterpret_cast<uint4 *>(out + pix * ld_o + k0) = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) dwtblock_nhwc_bwd(const __nv_bfloat16 *__restrict__ g, int64_t ld_g, int64_t N,
+                                                        int H, int W, int C, int J, int Cout,
+                                                        __nv_bfloat16 *__restrict__ gx, int64_t ld_gx) {
+    const int wo = J ? (W + 1) >> 1 : W, ho = J ? (H + 1) >> 1 : H, chunks = C >> 3;
+    const int64_t items = N * H * (int64_t)W * chunks;
+    for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(it % chunks);
+        const int64_t pix = it / chunks;
+        const int xw = (int)(pix % W);
+        int64_t t = pix / W;
+        const int y = (int)(t % H);
+        const int64_t n = t / H;
+        const int64_t opix = (n * ho + (y >> J)) * wo + (xw >> J);
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+        for (int k0 = 8 * q; k0 < Cout; k0 += C) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4 *>(g + opix * ld_g + k0), f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] += f[u];
+        }
+        if (J) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] = mul_s(mul_s(acc[u])) * 0.5f;
+        }
+        *reinterpret_cast<uint4 *>(gx + pix * ld_gx + 8 * q) = pack8(acc);
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int ub200_dwtblock_nhwc_bf16_fwd(const void *x, int64_t ld_x, int64_t N, int64_t H, int64_t W, int64_t C, int J,
+                                 void *out, int64_t ld_out, int64_t out_channels, void *stream) {
+    UB_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && C > 0 && out_channels > 0, UB200_E_BADARG);
+    UB_REQUIRE((J == 0 || J == 1) && C % 8 == 0 && out_channels % 8 == 0 && ld_x % 8 == 0 && ld_out % 8 == 0 && ld_x >= C &&
+                   ld_out >= out_channels && ub::aligned16(x) && ub::aligned16(out) && H < (1 << 29) && W < (1 << 29),
+               UB200_E_UNSUPPORTED);
+    const int64_t ho = J ? (H + 1) / 2 : H, wo = J ? (W + 1) / 2 : W;
+    int grid = ub::grid_for(N * ho * wo * (C / 8), 256, 8);
+    dwtblock_nhwc_fwd<<<grid, 256, 0, ub::as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16 *>(x), ld_x, N, (int)H, (int)W,
+                                                              (int)C, J, reinterpret_cast<__nv_bfloat16 *>(out), ld_out,
+                                                              (int)out_channels);
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+int ub200_dwtblock_nhwc_bf16_bwd(const void *gout, int64_t ld_g, int64_t N, int64_t H, int64_t W, int64_t C, int J,
+                                 int64_t out_channels, void *gx, int64_t ld_gx, void *stream) {
+    UB_REQUIRE(gout && gx && N > 0 && H > 0 && W > 0 && C > 0 && out_channels > 0, UB200_E_BADARG);
+    UB_REQUIRE((J == 0 || J == 1) && C % 8 == 0 && out_channels % 8 == 0 && ld_g % 8 == 0 && ld_gx % 8 == 0 && ld_gx >= C &&
+                   ld_g >= out_channels && ub::aligned16(gout) && ub::aligned16(gx) && H < (1 << 29) && W < (1 << 29),
+               UB200_E_UNSUPPORTED);
+    int grid = ub::grid_for(N * H * W * (C / 8), 256, 8);
+    dwtblock_nhwc_bwd<<<grid, 256, 0, ub::as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16 *>(gout), ld_g, N, (int)H,
+                                                              (int)W, (int)C, J, (int)out_channels,
+                                                              reinterpret_cast<__nv_bfloat16 *>(gx), ld_gx);
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
 
 int ub200_haar_dwt2d_fwd(const float *x, int64_t planes, int64_t H, int64_t W, float *ll, float *highs, void *stream) {
     UB_REQUIRE(x && ll && planes > 0 && H > 0 && W > 0, UB200_E_BADARG);

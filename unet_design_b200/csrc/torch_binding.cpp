@@ -113,6 +113,25 @@ void dwtblock_fwd_nhwc(const Tensor &x, int64_t J, const c10::optional<Tensor> &
                                           cur_stream()), "dwtblock_fwd_nhwc_bf16");
 }
 
+Tensor dwtblock_nhwc_fwd(const Tensor &x, int64_t J, int64_t out_channels) {
+    UB_GUARD(x);
+    const Nhwc i = nhwc(x, "x");
+    const int64_t ho = J ? (i.H + 1) / 2 : i.H, wo = J ? (i.W + 1) / 2 : i.W;
+    Tensor out = at::empty({i.N, ho, wo, out_channels}, x.options());
+    check_rc(ub200_dwtblock_nhwc_bf16_fwd(i.ptr, i.ld, i.N, i.H, i.W, i.C, (int)J, out.data_ptr(), out_channels, out_channels,
+                                          cur_stream()), "dwtblock_nhwc_bf16_fwd");
+    return out;
+}
+
+Tensor dwtblock_nhwc_bwd(const Tensor &gout, int64_t H, int64_t W, int64_t C, int64_t J) {
+    UB_GUARD(gout);
+    const Nhwc g = nhwc(gout, "gout");
+    Tensor gx = at::empty({g.N, H, W, C}, gout.options());
+    check_rc(ub200_dwtblock_nhwc_bf16_bwd(g.ptr, g.ld, g.N, H, W, C, (int)J, g.C, gx.data_ptr(), C, cur_stream()),
+             "dwtblock_nhwc_bf16_bwd");
+    return gx;
+}
+
 // ---------------------------------------------------------------- layout / resampling
 void nchw_to_nhwc(const Tensor &x, const Tensor &out) {
     UB_GUARD(x);
@@ -151,20 +170,26 @@ void gn_stats(const Tensor &x, int64_t G, const Tensor &stats) {
     check_rc(ub200_gn_stats_nhwc_bf16(i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_mut(stats, "stats"), cur_stream()), "gn_stats");
 }
 
-void gn_act_fwd(const Tensor &x, int64_t G, const Tensor &stats, double eps, const c10::optional<Tensor> &gamma,
+void gn_act_fwd(const Tensor &x, int64_t G, const c10::optional<Tensor> &stats, double eps, const c10::optional<Tensor> &gamma,
                 const c10::optional<Tensor> &beta, const c10::optional<Tensor> &scale, const c10::optional<Tensor> &shift,
                 int64_t act, double dropout_p, int64_t seed, int64_t offset, const c10::optional<Tensor> &offset_dev,
-                const Tensor &y) {
+                const c10::optional<Tensor> &addend, const Tensor &y) {
     UB_GUARD(x);
     const Nhwc i = nhwc(x, "x"), o = nhwc(y, "y");
     TORCH_CHECK(o.N == i.N && o.H == i.H && o.W == i.W && o.C == i.C, "gn_act_fwd: shape mismatch");
-    check_rc(ub200_gn_act_fwd_nhwc_bf16(i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32(stats, "stats"), (float)eps,
+    const void *addp = nullptr; int64_t ld_add = 0;
+    if (addend.has_value()) {
+        const Nhwc a = nhwc(*addend, "addend");
+        TORCH_CHECK(a.N == i.N && a.H == i.H && a.W == i.W && a.C == i.C, "gn_act_fwd: addend shape mismatch");
+        addp = a.ptr; ld_add = a.ld;
+    }
+    check_rc(ub200_gn_act_fwd_nhwc_bf16(i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_opt(stats, "stats"), (float)eps,
                                         f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
                                         f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed, (uint64_t)offset,
-                                        i64_opt(offset_dev), o.ptr, o.ld, cur_stream()), "gn_act_fwd");
+                                        i64_opt(offset_dev), addp, ld_add, o.ptr, o.ld, cur_stream()), "gn_act_fwd");
 }
 
-void gn_act_bwd(const Tensor &gy, const Tensor &x, int64_t G, const Tensor &stats, double eps,
+void gn_act_bwd(const Tensor &gy, const Tensor &x, int64_t G, const c10::optional<Tensor> &stats, double eps,
                 const c10::optional<Tensor> &gamma, const c10::optional<Tensor> &beta, const c10::optional<Tensor> &scale,
                 const c10::optional<Tensor> &shift, int64_t act, double dropout_p, int64_t seed, int64_t offset,
                 const c10::optional<Tensor> &offset_dev, const Tensor &gx, bool accumulate, const c10::optional<Tensor> &dgamma, const c10::optional<Tensor> &dbeta,
@@ -173,9 +198,9 @@ void gn_act_bwd(const Tensor &gy, const Tensor &x, int64_t G, const Tensor &stat
     const Nhwc g = nhwc(gy, "gy"), i = nhwc(x, "x"), o = nhwc(gx, "gx");
     TORCH_CHECK(g.N == i.N && g.H == i.H && g.W == i.W && g.C == i.C && o.N == i.N && o.H == i.H && o.W == i.W && o.C == i.C,
                 "gn_act_bwd: shape mismatch");
-    Tensor ws = at::empty({(int64_t)ub200_gn_act_bwd_ws_floats(i.N, i.C, (int)G)}, stats.options());
+    Tensor ws = at::empty({(int64_t)ub200_gn_act_bwd_ws_floats(i.N, i.C, (int)G)}, x.options().dtype(at::kFloat));
     auto mut = [](const c10::optional<Tensor> &t, const char *n) -> float * { return t.has_value() ? f32_mut(*t, n) : nullptr; };
-    check_rc(ub200_gn_act_bwd_nhwc_bf16(g.ptr, g.ld, i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32(stats, "stats"), (float)eps,
+    check_rc(ub200_gn_act_bwd_nhwc_bf16(g.ptr, g.ld, i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_opt(stats, "stats"), (float)eps,
                                         f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
                                         f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed, (uint64_t)offset,
                                         i64_opt(offset_dev), o.ptr, o.ld, accumulate ? 1 : 0, mut(dgamma, "dgamma"), mut(dbeta, "dbeta"),
@@ -285,6 +310,8 @@ TORCH_LIBRARY(unet_b200, m) {
     m.def("dwtblock_fwd", &dwtblock_fwd);
     m.def("dwtblock_bwd", &dwtblock_bwd);
     m.def("dwtblock_fwd_nhwc", &dwtblock_fwd_nhwc);
+    m.def("dwtblock_nhwc_fwd", &dwtblock_nhwc_fwd);
+    m.def("dwtblock_nhwc_bwd", &dwtblock_nhwc_bwd);
     m.def("nchw_to_nhwc", &nchw_to_nhwc);
     m.def("nhwc_to_nchw", &nhwc_to_nchw);
     m.def("upsample2x", &upsample2x);

@@ -218,18 +218,24 @@ def dwtblock_nhwc(x: torch.Tensor, J: int, out: torch.Tensor, chmap: Optional[to
 # --------------------------------------------------------------------------------------------------
 class _GnAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, shift, G, eps, act, p_drop):
+    def forward(ctx, x, gamma, beta, scale, shift, G, eps, act, p_drop, addend):
         x = _dense_nhwc(x)
         n, h, w, c = x.shape
-        stats = torch.empty((n, G, 2), dtype=torch.float32, device=x.device)
-        _ops().gn_stats(x, G, stats)
+        stats = None
+        if G > 0:
+            stats = torch.empty((n, G, 2), dtype=torch.float32, device=x.device)
+            _ops().gn_stats(x, G, stats)
+        else:
+            G = 1                      # G <= 0: no normalisation, plain activation (norm=False blocks)
         y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
         seed = off = 0
         dev = None
         if p_drop > 0.0:
             seed, off, dev = _DropoutState.seed, _next_dropout_offset(x.numel()), dropout_device_counter(x.device)
-        _ops().gn_act_fwd(x, G, stats, eps, gamma, beta, scale, shift, act, p_drop, seed, off, dev, y)
+        _ops().gn_act_fwd(x, G, stats, eps, gamma, beta, scale, shift, act, p_drop, seed, off, dev,
+                          _dense_nhwc(addend) if addend is not None else None, y)
         _count(3)
+        ctx.has_addend = addend is not None
         ctx.save_for_backward(x, stats, gamma, beta, scale, shift)
         ctx.cfg = (G, eps, act, p_drop, seed, off, dev)
         return y
@@ -247,13 +253,35 @@ class _GnAct(torch.autograd.Function):
         _ops().gn_act_bwd(gy, x, G, stats, eps, gamma, beta, scale, shift, act, p_drop, seed, off, dev, gx, False,
                           dgamma, dbeta, dscale, dshift)
         _count(3)
-        return gx, dgamma, dbeta, dscale, dshift, None, None, None, None
+        return gx, dgamma, dbeta, dscale, dshift, None, None, None, None, (gy if ctx.has_addend else None)
 
 
 def gn_act(x, gamma, beta, groups: int, act: str = "silu", eps: float = 1e-5, dropout_p: float = 0.0,
-           scale=None, shift=None) -> torch.Tensor:
-    """act(GroupNorm(x) * (1 + scale) + shift) with optional dropout; NHWC bf16 in and out."""
-    return _GnAct.apply(x, gamma, beta, scale, shift, groups, eps, _ACT[act], float(dropout_p))
+           scale=None, shift=None, addend=None) -> torch.Tensor:
+    """addend + dropout(act(GroupNorm(x) * (1 + scale) + shift)); NHWC bf16 in and out.
+    `groups = 0` skips the normalisation (gamma / beta still apply if given)."""
+    return _GnAct.apply(x, gamma, beta, scale, shift, groups, eps, _ACT[act], float(dropout_p), addend)
+
+
+class _DwtBlockNhwc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, J, out_channels):
+        x = _dense_nhwc(x)
+        ctx.meta = (x.shape[1], x.shape[2], x.shape[3], J)
+        _count()
+        return _ops().dwtblock_nhwc_fwd(x, J, out_channels)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w, c, J = ctx.meta
+        _count()
+        return _ops().dwtblock_nhwc_bwd(_dense_nhwc(g), h, w, c, J), None, None
+
+
+def dwtblock_act(x: torch.Tensor, J: int, out_channels: int) -> torch.Tensor:
+    """DWTBlock on an NHWC bf16 activation (J in {0, 1}) with its adjoint as backward
+    (pdearena twod_unetbase.py:173-193; wmh/model.py:72-95)."""
+    return _DwtBlockNhwc.apply(x, J, out_channels)
 
 
 # --------------------------------------------------------------------------------------------------
