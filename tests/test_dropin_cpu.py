@@ -63,3 +63,14 @@ def test_pdearena_unetbase_g(emulated_ops, tag):
 def test_wmh_unetbase_g_odd_extents(emulated_ops, tag):
     from unet_design_b200.wmh.model import Unetbase_G
     gc.check_unetbase_g(Unetbase_G, f"wmh_unetbase_g_{tag}.pt", "cpu", 3 * TOL, 8e-2)
+
+
+def test_mnist_blocks(emulated_ops):
+    from unet_design_b200.diff_mnist import layers
+    gc.check_mnist_blocks(layers, "cpu", TOL)
+
+
+@pytest.mark.parametrize("tag", ["multiresnet", "multiresnet_mrl", "unet", "unet_pool"])
+def test_mnist_unet_wavelet(emulated_ops, tag):
+    from unet_design_b200.diff_mnist.unet import get_unet_wavelet
+    gc.check_mnist_unet(get_unet_wavelet, tag, "cpu", 3 * TOL, 0.12)   # 4 levels deep through 1-channel bottlenecks

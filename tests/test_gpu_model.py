@@ -78,3 +78,14 @@ def test_config2_architecture_against_oracle():
         if e > worst:
             worst, name = e, n
     assert worst < 0.1, (worst, name)
+
+
+def test_mnist_blocks_golden():
+    from unet_design_b200.diff_mnist import layers
+    gc.check_mnist_blocks(layers, "cuda", TOL)
+
+
+@pytest.mark.parametrize("tag", ["multiresnet", "multiresnet_mrl", "unet", "unet_pool"])
+def test_mnist_unet_wavelet_golden(tag):
+    from unet_design_b200.diff_mnist.unet import get_unet_wavelet
+    gc.check_mnist_unet(get_unet_wavelet, tag, "cuda", 3 * TOL, 0.12)   # 4 levels deep through 1-channel bottlenecks

@@ -167,6 +167,52 @@ def pdearena_wmh_goldens():
                     "gparams": small_grads(net)}, f"{OUT}/wmh_unetbase_g_{tag}.pt")
 
 
+def mnist_goldens():
+    """diff_mnist: guided-diffusion ResBlock with scale-shift norm (layers.py:250-338), AttentionBlock (:341-368),
+    Upsample / Downsample (:195-247) and the UNet_wavelet container (mnist_diff/unet.py:75-556)."""
+    sys.modules["pytorch_wavelets"] = pw
+    load_reference_module("_mpl_stub_probe", f"{REF}/diff_cifar/model.py")     # installs the matplotlib stub
+    sys.path.insert(0, f"{REF}/diff_mnist")
+    import mnist_diff.unet as ref_unet                             # noqa: E402  (reference, read-only)
+    import torch_ddpm.ddpm.models.unet.layers as ref_layers        # noqa: E402
+
+    blocks = {}
+    for tag, ctor, cin in (("res_scale_shift", lambda: ref_layers.ResBlock(128, 128, 0.0, out_channels=64, use_scale_shift_norm=True), 128),
+                           ("res_plain_id", lambda: ref_layers.ResBlock(64, 128, 0.0, use_scale_shift_norm=False), 64),
+                           ("attention", lambda: ref_layers.AttentionBlock(64, num_heads=4), 64),
+                           ("upsample", lambda: ref_layers.Upsample(64, True), 64),
+                           ("downsample_conv", lambda: ref_layers.Downsample(64, True), 64),
+                           ("downsample_pool", lambda: ref_layers.Downsample(64, False), 64)):
+        blk = apply_det_init(ctor())            # also replaces the zero-initialised convs, so every path carries signal
+        torch.manual_seed(0)
+        x = torch.randn(3, cin, 8, 8, requires_grad=True)
+        emb = torch.randn(3, 128, requires_grad=True)
+        y = blk(x, emb) if tag.startswith("res_") else blk(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        blocks[tag] = {"x": x.detach(), "emb": emb.detach(), "y": y.detach(), "gy": gy, "gx": x.grad,
+                       "gemb": emb.grad, "gparams": {n: p.grad for n, p in blk.named_parameters()}}
+    torch.save(blocks, f"{OUT}/mnist_blocks.pt")
+
+    for tag, kw in (("multiresnet", dict(dwt_encoder=True)), ("multiresnet_mrl", dict(dwt_encoder=True, multi_res_loss=True)),
+                    ("unet", dict(dwt_encoder=False)), ("unet_pool", dict(dwt_encoder=False, avg_pool_down=True))):
+        cfg = dict(image_size=32, image_channels=1, num_channels=32, dropout=0.0, num_res_blocks=1, **kw)
+        net = apply_det_init(ref_unet.get_unet_wavelet(**cfg))
+        torch.manual_seed(0)
+        x = torch.randn(2, 1, 32, 32)
+        t = torch.randint(30, (2, 1))
+        out, _ = net(x, t)
+        outs = out if isinstance(out, list) else [out]
+        gys = [torch.randn_like(o) for o in outs]
+        sum((o * g).sum() for o, g in zip(outs, gys)).backward()
+        with torch.no_grad():
+            out2, _ = net(x[..., ::4, ::4].contiguous(), t, n_levels_used=2)
+        torch.save({"cfg": cfg, "x": x, "t": t, "out": [o.detach() for o in outs], "gy": gys,
+                    "out_2lvl": out2 if isinstance(out2, list) else [out2],
+                    "gparams": small_grads(net, also=("out_f_list.0.0.0.in_layers.2.weight",)),
+                    "keys": {k: tuple(v.shape) for k, v in net.state_dict().items()}}, f"{OUT}/mnist_unet_wavelet_{tag}.pt")
+
+
 def state_dict_keys():
     """Key names and shapes of the reference's state_dicts (the checkpoint compatibility surface)."""
     m = load_reference_module("ref_cifar_model", f"{REF}/diff_cifar/model.py")
@@ -189,6 +235,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     cifar_goldens()
     pdearena_wmh_goldens()
+    mnist_goldens()
     state_dict_keys()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

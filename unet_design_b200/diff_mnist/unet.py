@@ -1,0 +1,255 @@
+"""Drop-in for diff_mnist/mnist_diff/unet.py (`get_unet_wavelet` :11-68, `UNet_wavelet` :75-556) and
+diff_mnist/mnist_diff/models.py (`DTWBlock` :12-82), backed by the sm_100a kernels.
+
+Same constructor arguments, attribute names (`time_embed_list`, `input_blocks`, `middle_block`, `out_f_list`,
+`out_upsample_list`, `out_activation_list`, `out_reduce_channels_list` -- the staged-training freeze code walks them,
+diff_mnist/main.py:258-308) and state_dict keys.  `forward(x, t, y=None, n_levels_used=-1, u_net_norm=False)`
+returns `(tensor or list coarse->fine, norms or None)` exactly as the reference, including its quirk of forcing
+`model_out_passed_on = True` (:457): at every level the state is collapsed to `out_channels` by GN+SiLU + a 1x1
+conv, emitted, and channel-tiled back (:498-510).
+"""
+from __future__ import annotations
+
+import torch
+import torch as th
+from torch import nn
+
+from .. import ops
+from ..diff_cifar.model import DTWBlock, _PyramidView, _conv_param  # DTWBlock: same logic as mnist_diff/models.py:12-82
+from .layers import (AttentionBlock, Downsample, ResBlock, SiLU, TimestepEmbedSequential, Upsample, linear, normalization,
+                     timestep_embedding)
+
+
+def compute_norm(tensor):
+    """diff_mnist/utils.py:59-68 (layout independent: works on NHWC as well)."""
+    dim = 1
+    for sub_dim in tensor.shape[1:]:
+        dim *= sub_dim
+    return torch.linalg.norm(torch.flatten(tensor.float(), start_dim=1), dim=1) * (1 / dim)
+
+
+def get_unet_wavelet(image_size, image_channels, num_channels=32, dropout=0.0, num_res_blocks=2, dwt_encoder=False,
+                     multi_res_loss=False, model_out_passed_on=False, avg_pool_down=False):
+    num_heads = 4
+    num_heads_upsample = -1
+    attention_resolutions = "168"
+    channel_mult = {256: (1, 1, 2, 2, 4, 4), 64: (2, 2, 2, 2), 32: (2, 2, 2, 2), 28: (1, 2, 2), 16: (1, 2, 2, 2),
+                    8: (1, 2, 2), 4: (1, 1, 1), 2: (1, 2), 1: (1,)}.get(image_size)
+    if channel_mult is None:
+        raise ValueError(f"unsupported image size: {image_size}")
+    attention_ds = [image_size // int(res) for res in attention_resolutions.split(",")]
+    return UNet_wavelet(in_channels=image_channels, model_channels=num_channels, out_channels=image_channels,
+                        num_res_blocks=num_res_blocks, attention_resolutions=tuple(attention_ds), dropout=dropout,
+                        channel_mult=channel_mult, num_classes=None, use_checkpoint=False, num_heads=num_heads,
+                        num_heads_upsample=num_heads_upsample, use_scale_shift_norm=True, dwt_encoder=dwt_encoder,
+                        multi_res_loss=multi_res_loss, model_out_passed_on=model_out_passed_on,
+                        conv_resample=not avg_pool_down)
+
+
+class _TileToNhwc(torch.autograd.Function):
+    """`h.repeat(1, n/C + 1, 1, 1)[:, :n]` of an NCHW fp32 tensor written straight into NHWC bf16 (unet.py:498-510);
+    backward folds the replicas back."""
+
+    @staticmethod
+    def forward(ctx, x, out_channels):
+        n, c, h, w = x.shape
+        out = torch.empty((n, h, w, out_channels), dtype=torch.bfloat16, device=x.device)
+        ops.dwtblock_nhwc(x.contiguous(), 0, out)
+        ctx.meta = (c, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from .._lib import ops as raw
+        c, h, w = ctx.meta
+        g_nchw = raw().nhwc_to_nchw(ops._dense_nhwc(g))
+        return raw().dwtblock_bwd(g_nchw, c, h, w, 0), None
+
+
+class UNet_wavelet(nn.Module):
+    def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
+                 channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False, num_heads=1,
+                 num_heads_upsample=-1, use_scale_shift_norm=False, dwt_encoder=False, multi_res_loss=False,
+                 model_out_passed_on=False):
+        super().__init__()
+        if num_heads_upsample == -1:
+            num_heads_upsample = num_heads
+        if num_classes is not None:
+            raise NotImplementedError("class conditioning is not on the hot path (the reference passes num_classes=None)")
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.num_res_blocks, self.attention_resolutions, self.dropout = num_res_blocks, attention_resolutions, dropout
+        self.channel_mult, self.conv_resample, self.num_classes = channel_mult, conv_resample, num_classes
+        self.use_checkpoint, self.num_heads, self.num_heads_upsample = use_checkpoint, num_heads, num_heads_upsample
+        self.n_levels = len(channel_mult)
+        self.dwt_encoder, self.multi_res_loss, self.model_out_passed_on = dwt_encoder, multi_res_loss, model_out_passed_on
+
+        time_embed_dim = model_channels * 4
+        self.time_embed_list = nn.ModuleList([nn.Sequential(
+            linear(model_channels, time_embed_dim), SiLU(), linear(time_embed_dim, time_embed_dim),
+        ) for _ in range(self.n_levels)])
+
+        ch = model_channels * channel_mult[0]
+        ds = 1
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(DTWBlock(J=0, out_channels=ch))])
+        input_block_chans = [ch]
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                if self.dwt_encoder:
+                    ch = int(mult * model_channels)
+                    self.input_blocks.append(TimestepEmbedSequential(DTWBlock(J=0, out_channels=ch)))
+                else:
+                    layers = [ResBlock(ch, time_embed_dim, dropout, out_channels=mult * model_channels, dims=dims,
+                                       use_checkpoint=use_checkpoint, use_scale_shift_norm=use_scale_shift_norm)]
+                    ch = mult * model_channels
+                    if ds in attention_resolutions:
+                        layers.append(AttentionBlock(ch, use_checkpoint=use_checkpoint, num_heads=num_heads))
+                    self.input_blocks.append(TimestepEmbedSequential(*layers))
+                input_block_chans.append(ch)
+            if level != len(channel_mult) - 1:
+                if self.dwt_encoder:
+                    ch_downsample = int(channel_mult[level + 1] * model_channels)
+                    self.input_blocks.append(TimestepEmbedSequential(DTWBlock(J=1, out_channels=ch_downsample)))
+                    input_block_chans.append(ch_downsample)
+                else:
+                    self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, dims=dims)))
+                    input_block_chans.append(ch)
+                ds *= 2
+
+        self.middle_block = TimestepEmbedSequential(
+            ResBlock(ch, time_embed_dim, dropout, dims=dims, use_checkpoint=use_checkpoint,
+                     use_scale_shift_norm=use_scale_shift_norm),
+            AttentionBlock(ch, use_checkpoint=use_checkpoint, num_heads=num_heads),
+            ResBlock(ch, time_embed_dim, dropout, dims=dims, use_checkpoint=use_checkpoint,
+                     use_scale_shift_norm=use_scale_shift_norm),
+        )
+
+        self.out_f_list = nn.ModuleList([nn.ModuleList() for _ in range(len(channel_mult))])
+        self.out_upsample_list = nn.ModuleList([nn.ModuleList() for _ in range(len(channel_mult))])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                layers = [ResBlock(ch + input_block_chans.pop(), time_embed_dim, dropout, out_channels=model_channels * mult,
+                                   dims=dims, use_checkpoint=use_checkpoint, use_scale_shift_norm=use_scale_shift_norm)]
+                ch = model_channels * mult
+                if ds in attention_resolutions:
+                    layers.append(AttentionBlock(ch, use_checkpoint=use_checkpoint, num_heads=num_heads_upsample))
+                self.out_f_list[level].append(TimestepEmbedSequential(*layers))
+                if i == num_res_blocks:
+                    if level:
+                        self.out_upsample_list[level].append(TimestepEmbedSequential(Upsample(ch, conv_resample, dims=dims)))
+                        ds //= 2
+                    else:
+                        self.out_upsample_list[level].append(TimestepEmbedSequential(nn.Identity()))
+
+        self.out_reduce_channels_list = nn.ModuleList([
+            _conv_param(nn.Conv2d(in_channels=ch, out_channels=out_channels, kernel_size=1, stride=1))
+            for _ in range(len(channel_mult))])
+        self.out_activation_list = nn.ModuleList([nn.Sequential(normalization(ch), SiLU()) for _ in range(len(channel_mult))])
+        self._chmap_cache = {}
+
+    def compute_time_embedding(self, timesteps, level, y=None):
+        if level == -1:
+            level = 0
+        return self.time_embed_list[level](timestep_embedding(timesteps, self.model_channels))
+
+    # ---- internals
+    def _materialise(self, pyramid, view: _PyramidView):
+        base = pyramid[view.level]
+        n, _, h, w = base.shape
+        key = (tuple(view.chmap), base.device)
+        cm = self._chmap_cache.get(key)
+        if cm is None:
+            cm = torch.tensor(view.chmap, dtype=torch.int32, device=base.device)
+            self._chmap_cache[key] = cm
+        out = torch.empty((n, h, w, len(view.chmap)), dtype=torch.bfloat16, device=base.device)
+        return ops.dwtblock_nhwc(base, 0, out, cm)
+
+    def forward(self, x, t, y=None, n_levels_used=-1, u_net_norm=False):
+        if n_levels_used == -1:
+            n_levels_used = len(self.channel_mult)
+        timesteps = t.squeeze()
+        if timesteps.dim() == 0:
+            timesteps = timesteps[None]
+        assert y is None, "must specify y if and only if the model is class-conditional"
+        norms = {"down": {k: [] for k in range(self.n_levels)}, "middle": [],
+                 "up": {k: [] for k in range(self.n_levels)}} if u_net_norm else None
+        x = x.float().contiguous()
+        lowest_level = len(self.channel_mult) - n_levels_used
+        if u_net_norm:
+            norms["down"][lowest_level].append(compute_norm(x))
+        upper_range = n_levels_used * (self.num_res_blocks + 1) - 1
+        ins = [self.input_blocks[0]] + list(self.input_blocks[::-1][:upper_range][::-1])
+        start_level = self.n_levels - n_levels_used
+
+        hs = []
+        if self.dwt_encoder:
+            # every encoder tensor is a channel tile of the image pyramid LL_l(x)/2^l: compute the pyramid only
+            pyramid = {0: x}
+            view = _PyramidView(0, list(range(x.shape[1])))
+            for i, module in enumerate(ins):
+                blk = module[0]
+                if blk.J == 1:
+                    src = pyramid[view.level]
+                    pyramid[view.level + 1] = ops.dwtblock(src, 1, src.shape[1])
+                    view = _PyramidView(view.level + 1, view.chmap)
+                view = view.tiled(blk.out_channels)
+                hs.append(view)
+                if u_net_norm:
+                    level = start_level + int((i - 1) / (self.num_res_blocks + 1))
+                    norms["down"][level].append(compute_norm(self._materialise(pyramid, view)))
+            fetch = lambda v: self._materialise(pyramid, v)
+            h = fetch(hs[-1])
+        else:
+            h = None
+            for i, module in enumerate(ins):
+                level = start_level + int((i - 1) / (self.num_res_blocks + 1))
+                emb = self.compute_time_embedding(timesteps=timesteps, level=level, y=y)
+                if i == 0:
+                    blk = module[0]
+                    h = ops.dwtblock_nhwc(x, 0, torch.empty((x.shape[0], x.shape[2], x.shape[3], blk.out_channels),
+                                                            dtype=torch.bfloat16, device=x.device))
+                else:
+                    h = module.forward_nhwc(h, emb)
+                if u_net_norm:
+                    norms["down"][level].append(compute_norm(h))
+                hs.append(h)
+            fetch = lambda v: v
+
+        emb = self.compute_time_embedding(timesteps=timesteps, level=self.n_levels - 1, y=y)
+        h = self.middle_block.forward_nhwc(h, emb)
+        if u_net_norm:
+            norms["middle"].append(compute_norm(h))
+
+        self.model_out_passed_on = True            # the reference forces this (unet.py:457)
+        model_out_list = []
+        out = None
+        level_inv = 0
+        for i, level in enumerate(list(range(len(self.channel_mult)))[::-1][:n_levels_used]):
+            for out_block in self.out_f_list[level]:
+                cat_in = th.cat([h, fetch(hs.pop())], dim=3)
+                emb = self.compute_time_embedding(timesteps=timesteps, level=level, y=y)
+                h = out_block.forward_nhwc(cat_in, emb)
+                if u_net_norm:
+                    norms["up"][level].append(compute_norm(h))
+            gn = self.out_activation_list[i][0]
+            a = ops.gn_act(h, gn.weight, gn.bias, gn.num_groups, act="silu", eps=gn.eps)
+            n_state_channels = a.shape[3]
+            red = self.out_reduce_channels_list[i]
+            out = ops.conv(a, red.weight, red.bias, out_nchw=True)          # fp32 NCHW [N, out_channels, H, W]
+            if self.multi_res_loss:
+                model_out_list.append(out)
+            if u_net_norm:
+                norms["up"][level].append(compute_norm(out))
+            last = level_inv == n_levels_used - 1
+            if self.multi_res_loss or not last:
+                h = _TileToNhwc.apply(out, n_state_channels)
+                if u_net_norm:
+                    norms["up"][level].append(compute_norm(h))
+            if not last:
+                emb = self.compute_time_embedding(timesteps=timesteps, level=level - 1, y=y)
+                h = self.out_upsample_list[level][0].forward_nhwc(h, emb)
+                if u_net_norm:
+                    norms["up"][level].append(compute_norm(h))
+            level_inv += 1
+        if self.multi_res_loss:
+            return model_out_list, norms
+        return out.type(x.dtype), norms
