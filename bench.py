@@ -228,7 +228,7 @@ def run_gpu_arm(args):
     net.train()
     ops.seed_dropout(1234 + rank)
     step = DDPMTrainStep(net, T=CFG["T"], lr=2e-4, warmup=5000, grad_clip=1.0, ema_decay=0.9999,
-                         use_cuda_graph=not args.no_graph)
+                         use_cuda_graph=not args.no_graph, overlap_allreduce=not args.no_overlap)
     gen = torch.Generator().manual_seed(rank)
     host_batches = [(torch.rand(BATCH_PER_GPU, *IMG, generator=gen) * 2 - 1).pin_memory() for _ in range(4)]
     dev_batches = [b.to(dev) for b in host_batches]
@@ -277,15 +277,18 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
 
+    # ---- roofline of the dominant kernel, measured live: one eager step with CUDA events around every conv launch.
+    # Every rank runs it (the step contains the gradient all-reduce); rank 0 reports.
+    timer = KernelTimer(_lib.ops())
+    _lib._ops = timer
+    step._body(dev_batches[0])
+    ksum = timer.summary()
+    _lib._ops = timer._real
+    barrier()
+
     line = None
     if rank == 0:
         imgs = BATCH_PER_GPU * world * args.steps
-        # ---- roofline of the dominant kernel, measured live (one eager step with events around every conv launch)
-        timer = KernelTimer(_lib.ops())
-        _lib._ops = timer
-        step._body(dev_batches[0])
-        ksum = timer.summary()
-        _lib._ops = timer._real
         fp = ksum.get("conv_fprop", {"flops": 0.0, "ms": 1.0, "launches": 0})
         wg = ksum.get("conv_wgrad", {"flops": 0.0, "ms": 1.0, "launches": 0})
         peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
@@ -308,7 +311,7 @@ def run_gpu_arm(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}",
-                       "cuda_graph": not args.no_graph, "l2_policy": "4 rotating input batches; activations+weights per step "
+                       "cuda_graph": not args.no_graph, "allreduce": ("none" if world == 1 else ("one NCCL all-reduce of the gradient arena after the forward+backward graph" if not args.no_graph else ("tail" if args.no_overlap else "bucketed, overlapped with backward"))), "l2_policy": "4 rotating input batches; activations+weights per step "
                        "(~3 GB) exceed the 126 MB L2", "loss": loss_val},
             "clocks": clocks,
             "e2e": {"value": imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": BATCH_PER_GPU * 3 * 32 * 32 * 4,
@@ -330,6 +333,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after backward instead of bucketed overlap")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-haar", action="store_true")
     args = ap.parse_args()

@@ -112,7 +112,7 @@ def _dp_worker(rank, world, port, state, x0, ret):
     torch.manual_seed(5)
     t = torch.randint(CFG["T"], size=(x0.shape[0],)).chunk(world)[rank]
     noise = torch.randn_like(x0).chunk(world)[rank]
-    step.arena.g.zero_(); step.step_dev.add_(1); step._arm_buckets()
+    step.arena.g.zero_(); step.step_dev.add_(1); step._arm_buckets(); step._hooks_live = True
     loss, _ = step.trainer.loss_from(shard, t, noise)
     loss.backward()
     step._finish_allreduce()

@@ -12,11 +12,14 @@ What is B200-first about it (reference file:line in parentheses):
 * `clip_grad_norm_` + `Adam.step` + `LambdaLR` warm-up + `ema()` (main.py:425-429, :57-77, :90-91) are TWO
   kernels over the arena (sum of squares, then clip+Adam+EMA), with the step counter, learning-rate
   warm-up and dropout counter on the device: no host synchronisation anywhere in the step;
-* the whole step (noise draw, q-sample, forward, loss, backward, all-reduce, optimiser) is captured in ONE
-  CUDA graph and replayed, because the network is ~400 small-to-medium kernels and launch-bound otherwise;
-* data parallel (`nn.DataParallel` at main.py:235-238 in the reference): one process per GPU, gradients
-  all-reduced in arena buckets by NCCL from post-accumulate hooks as backward produces them, on a side
-  stream, overlapping the rest of backward; the mean over ranks is folded into the optimiser's grad_scale.
+* the whole step (noise draw, q-sample, forward, loss, backward, optimiser) is captured in ONE CUDA graph and
+  replayed, because the network is several hundred small-to-medium kernels and launch-bound otherwise;
+* data parallel (`nn.DataParallel` at main.py:235-238 in the reference): one process per GPU, identical
+  replicas, sum all-reduce of the gradient arena, the 1/world mean folded into the optimiser's grad_scale.
+  Two modes: (a) CUDA graph of forward+backward, then ONE all-reduce of the 106 MB arena and the 2-kernel
+  optimiser tail (default; ~0.4 ms of NVLink time per step); (b) eager (`use_cuda_graph=False`): arena buckets
+  all-reduced by NCCL from post-accumulate hooks on a side stream as backward produces them, overlapping the
+  rest of backward.
 """
 from __future__ import annotations
 
@@ -70,7 +73,7 @@ class DDPMTrainStep:
     def __init__(self, model: nn.Module, T: int = 1000, beta_1: float = 1e-4, beta_T: float = 0.02, lr: float = 2e-4,
                  warmup: int = 5000, grad_clip: float = 1.0, ema_decay: float = 0.9999, multi_res_loss: bool = False,
                  betas=(0.9, 0.999), eps: float = 1e-8, use_cuda_graph: bool = True, process_group=None,
-                 bucket_mb: float = 16.0):
+                 bucket_mb: float = 16.0, overlap_allreduce: bool = True):
         self.model = model
         self.device = next(model.parameters()).device
         self.trainer = GaussianDiffusionTrainer(model, beta_1, beta_T, T, multi_res_loss, False, self.device).to(self.device)
@@ -96,7 +99,9 @@ class DDPMTrainStep:
         self._static_loss = None
         self._buckets: List[tuple] = []
         self._comm_stream = None
-        if self.world > 1:
+        self._hooks_live = False
+        self.overlap = overlap_allreduce
+        if self.world > 1 and self.overlap:
             self._build_buckets(int(bucket_mb * (1 << 20) / 4))
 
     # ------------------------------------------------------------------ data parallel
@@ -124,6 +129,8 @@ class DDPMTrainStep:
 
     def _make_hook(self, i: int):
         def hook(_param):
+            if not self._hooks_live:
+                return
             b = self._bucket_of[i]
             self._pending[b] -= 1
             if self._pending[b] == 0:
@@ -156,15 +163,22 @@ class DDPMTrainStep:
             torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
 
     # ------------------------------------------------------------------ one step
-    def _body(self, x0: torch.Tensor) -> torch.Tensor:
+    def _fwd_bwd(self, x0: torch.Tensor, overlap: bool) -> torch.Tensor:
         self.arena.g.zero_()
         self.step_dev.add_(1)
-        if self.world > 1:
+        self._hooks_live = overlap
+        if overlap:
             self._arm_buckets()
         loss, _ = self.trainer(x0)
         loss.backward()
+        return loss.detach()
+
+    def _reduce_and_update(self, overlapped: bool):
         if self.world > 1:
-            self._finish_allreduce()
+            if overlapped:
+                self._finish_allreduce()
+            else:                      # one all-reduce of the whole arena after backward
+                dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM, group=self.pg)
         self.sumsq.zero_()
         ops.sumsq_(self.arena.g, self.sumsq)
         # gradients hold the SUM over ranks: the mean (what DataParallel / DDP produce) is a grad_scale of 1/world
@@ -172,7 +186,13 @@ class DDPMTrainStep:
                            1.0 / self.world, self.lr, self.betas[0], self.betas[1], self.eps, self.ema_decay, 1,
                            self.warmup, self.step_dev)
         ops.advance_dropout_state(self.device)
-        return loss.detach()
+
+    def _body(self, x0: torch.Tensor) -> torch.Tensor:
+        """Eager step; with several ranks the bucketed all-reduce overlaps backward."""
+        overlap = self.world > 1 and self.overlap
+        loss = self._fwd_bwd(x0, overlap)
+        self._reduce_and_update(overlap)
+        return loss
 
     def __call__(self, x0: torch.Tensor) -> torch.Tensor:
         self.steps_done += 1
@@ -182,21 +202,28 @@ class DDPMTrainStep:
             self._capture(x0)
         self._static_x0.copy_(x0, non_blocking=True)
         self._graph.replay()
+        if self.world > 1:             # the collective and the optimiser tail stay outside the graph (3 launches)
+            self._reduce_and_update(False)
         return self._static_loss
 
     def _capture(self, x0: torch.Tensor):
+        """One CUDA graph for the whole step on a single GPU; forward + backward only when data-parallel (NCCL work
+        captured into a graph dead-locked on this stack, so the gradient all-reduce is issued right after the replay)."""
         self._static_x0 = x0.clone()
+        whole = self.world == 1
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):           # warm-up on a side stream: allocator, tensor maps, cuBLAS handles
             for _ in range(3):
-                self._body(self._static_x0)
+                self._fwd_bwd(self._static_x0, False)
+                self._reduce_and_update(False)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self._static_loss = self._body(self._static_x0)
-        self.launches_per_step = None
+            self._static_loss = self._fwd_bwd(self._static_x0, False)
+            if whole:
+                self._reduce_and_update(False)
 
     def step_from_host(self, x0_pinned: torch.Tensor) -> float:
         """The end-to-end call a user makes: batch in pinned host memory in, loss (a Python float) out."""
