@@ -159,14 +159,23 @@ class KernelTimer:
                 g, act, k = a[0], a[1], a[2]
                 n, h, w, cin = act.shape
                 flops = 2.0 * n * h * w * g.shape[3] * k * k * cin
-            self.records.append((name, flops, e0, e1))
+            self.records.append((name, flops, e0, e1, (n, h, w, cin, (cout if name == "conv_fprop" else g.shape[3]), k,
+                                                       (a2.shape[3] if name == "conv_fprop" and a2 is not None else 0))))
             return out
         return timed
+
+    def table(self):
+        torch.cuda.synchronize()
+        rows = []
+        for name, flops, e0, e1, shape in self.records:
+            ms = e0.elapsed_time(e1)
+            rows.append({"kernel": name, "n_h_w_cin_cout_k_cin2": shape, "us": 1e3 * ms, "tflops": flops / (ms * 1e-3) / 1e12})
+        return rows
 
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for name, flops, e0, e1 in self.records:
+        for name, flops, e0, e1, _ in self.records:
             d = out.setdefault(name, {"launches": 0, "flops": 0.0, "ms": 0.0})
             d["launches"] += 1; d["flops"] += flops; d["ms"] += e0.elapsed_time(e1)
         return out
@@ -283,6 +292,9 @@ def run_gpu_arm(args):
     _lib._ops = timer
     step._body(dev_batches[0])
     ksum = timer.summary()
+    if args.dump_kernels and rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(timer.table(), open(os.path.join(ROOT, "gpurun_out", "conv_launch_table.json"), "w"), indent=0)
     _lib._ops = timer._real
     barrier()
 
@@ -334,6 +346,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after backward instead of bucketed overlap")
+    ap.add_argument("--dump-kernels", action="store_true", help="write per-launch conv timings to gpurun_out/conv_launch_table.json")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-haar", action="store_true")
     args = ap.parse_args()

@@ -223,11 +223,20 @@ int ub200_sumsq_f32(const float *g, int64_t n, float *sumsq, void *stream);
  * min(step-1, warmup)/warmup (the LambdaLR of diff_cifar/main.py:90-91, stepped after the optimiser).
  * step_dev (nullable) is a device-resident step counter that overrides step_host, so that a
  * captured CUDA graph replays with the right bias correction and learning rate. */
+
 int ub200_adam_ema_step_f32(float *p, const float *g, float *m, float *v, float *ema, int64_t n,
                             const float *sumsq, float max_norm, float grad_scale,
                             float lr, float beta1, float beta2, float eps, float ema_decay,
                             int64_t step_host, int64_t warmup_steps, const int64_t *step_dev,
-                            void *stream);
+                            void *shadow_bf16, void *stream);
+
+/* shadow_bf16 (nullable, n bf16 elements) receives bf16(p) from the optimiser kernel: conv weights keep
+ * the [Cout,kh,kw,Cin] order in the arena, so their shadow slice IS the packed fprop / wgrad operand.
+ * The dgrad operands ([Cin_pad,kh,kw,Cout], taps rotated) of ALL conv layers are then produced by one
+ * launch from a device table of n_convs rows (src offset in the shadow arena, dst offset in
+ * dgrad_arena_bf16, Cout, Cin, k), all in elements. */
+int ub200_pack_dgrad_weights_batched(const void *shadow_bf16, void *dgrad_arena_bf16,
+                                     const int64_t *table_dev, int n_convs, void *stream);
 
 #ifdef __cplusplus
 }

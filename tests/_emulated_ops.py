@@ -175,7 +175,10 @@ class EmulatedOps:
         xg = a.float().permute(0, 3, 1, 2)
         gg = gout.float().permute(0, 3, 1, 2)
         gw = torch.nn.grad.conv2d_weight(xg, (cout, cin, k, k), gg, padding=k // 2)     # [Cout,Cin,k,k]
-        dw.view(cout, k, k, cin).add_(gw.permute(0, 2, 3, 1))
+        if dw.dim() == 4 and tuple(dw.shape) == (cout, cin, k, k):      # a [Cout,Cin,k,k] view with channels_last strides
+            dw.add_(gw)
+        else:
+            dw.view(cout, k, k, cin).add_(gw.permute(0, 2, 3, 1))
 
     def chansum(self, x, per_sample, total):
         s = x.float().sum(dim=(1, 2))
@@ -198,8 +201,17 @@ class EmulatedOps:
     def sumsq(self, g, acc):
         acc.add_((g.double() ** 2).sum().float())
 
+    def pack_dgrad_weights_batched(self, shadow, dgrad_arena, table):
+        for src, dst, cout, cin, k in table.tolist():
+            w = shadow[src:src + cout * k * k * cin].reshape(cout, k, k, cin)
+            t = w.flip(1, 2).permute(3, 1, 2, 0)                                    # [Cin,k,k,Cout], taps rotated
+            rows = (cin + 15) // 16 * 16
+            buf = torch.zeros((rows, k, k, cout), dtype=torch.bfloat16)
+            buf[:cin] = t
+            dgrad_arena[dst:dst + buf.numel()] = buf.reshape(-1)
+
     def adam_ema_step(self, p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, b1, b2, eps, decay, step,
-                      warmup_steps=0, step_dev=None):
+                      warmup_steps=0, step_dev=None, shadow=None):
         if step_dev is not None:
             step = int(step_dev)
         if warmup_steps > 0:
@@ -215,3 +227,5 @@ class EmulatedOps:
         p.sub_((lr / bc1) * m / (v.sqrt() / bc2 + eps))
         if ema is not None:
             ema.mul_(decay).add_(p, alpha=1 - decay)
+        if shadow is not None:
+            shadow.copy_(p)

@@ -33,6 +33,14 @@ struct AdamArgs {
     const long long *step_dev;      // device-resident 1-based step (CUDA-graph replays); NULL = host value baked in
 };
 
+// bf16 "shadow" of the parameter arena, written by the optimiser: conv weights keep the [Cout,kh,kw,Cin] order in
+// the arena, so their shadow slice IS the packed fprop / wgrad GEMM operand -- no per-layer re-packing.
+__device__ __forceinline__ void store_shadow4(__nv_bfloat16 *shadow, int64_t i4, const float4 &p) {
+    if (!shadow) return;
+    uint2 v = make_uint2(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w));
+    *reinterpret_cast<uint2 *>(shadow + 4 * i4) = v;
+}
+
 __device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, float *ema, const AdamArgs &a, float clip) {
     g *= clip;
     m = a.beta1 * m + (1.f - a.beta1) * g;
@@ -45,7 +53,8 @@ __device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, flo
 __global__ void __launch_bounds__(256) adam_ema_kernel(float *__restrict__ p, const float *__restrict__ g,
                                                       float *__restrict__ m, float *__restrict__ v,
                                                       float *__restrict__ ema, int64_t n,
-                                                      const float *__restrict__ sumsq, AdamArgs a) {
+                                                      const float *__restrict__ sumsq, AdamArgs a,
+                                                      __nv_bfloat16 *__restrict__ shadow) {
     if (a.step_dev) {               // bias corrections and warm-up from the device-side step counter
         const float st = (float)__ldg(a.step_dev);
         a.bc1 = 1.f - powf(a.beta1, st);
@@ -70,10 +79,36 @@ __global__ void __launch_bounds__(256) adam_ema_kernel(float *__restrict__ p, co
         adam1(pp.w, gg.w, mm.w, vv.w, ema ? &ee.w : nullptr, a, clip);
         reinterpret_cast<float4 *>(p)[i] = pp; reinterpret_cast<float4 *>(m)[i] = mm; reinterpret_cast<float4 *>(v)[i] = vv;
         if (ema) reinterpret_cast<float4 *>(ema)[i] = ee;
+        store_shadow4(shadow, i, pp);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const int64_t i = (n4 << 2) + threadIdx.x;
         adam1(p[i], g[i], m[i], v[i], ema ? ema + i : nullptr, a, clip);
+        if (shadow) shadow[i] = __float2bfloat16_rn(p[i]);
+    }
+}
+
+// dgrad operands of ALL conv layers in one launch: for conv j (blockIdx.y) with table row
+// (src offset in the shadow arena, dst offset, Cout, Cin, k):
+//   dst[ci][ky][kx][co] = src[co][k-1-ky][k-1-kx][ci]      (rows ci padded to a multiple of 16 with zeros)
+__global__ void __launch_bounds__(256) pack_dgrad_batched_kernel(const __nv_bfloat16 *__restrict__ shadow,
+                                                                __nv_bfloat16 *__restrict__ dst_arena,
+                                                                const long long *__restrict__ table) {
+    const long long *row = table + 5 * blockIdx.y;
+    const __nv_bfloat16 *src = shadow + row[0];
+    __nv_bfloat16 *dst = dst_arena + row[1];
+    const int Cout = (int)row[2], Cin = (int)row[3], k = (int)row[4];
+    const int rows_pad = (Cin + 15) / 16 * 16;
+    const long long total = (long long)rows_pad * k * k * Cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        long long t = i / Cout;
+        const int kx = (int)(t % k); t /= k;
+        const int ky = (int)(t % k);
+        const int ci = (int)(t / k);
+        __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+        if (ci < Cin) v = src[(((long long)co * k + (k - 1 - ky)) * k + (k - 1 - kx)) * Cin + ci];
+        dst[i] = v;
     }
 }
 
@@ -92,7 +127,7 @@ int ub200_sumsq_f32(const float *g, int64_t n, float *sumsq, void *stream) {
 int ub200_adam_ema_step_f32(float *p, const float *g, float *m, float *v, float *ema, int64_t n, const float *sumsq,
                             float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
                             float ema_decay, int64_t step_host, int64_t warmup_steps, const int64_t *step_dev,
-                            void *stream) {
+                            void *shadow_bf16, void *stream) {
     UB_REQUIRE(p && g && m && v && n > 0 && (step_dev || step_host >= 1), UB200_E_BADARG);
     UB_REQUIRE(ub::aligned16(p) && ub::aligned16(g) && ub::aligned16(m) && ub::aligned16(v) && (!ema || ub::aligned16(ema)),
                UB200_E_UNSUPPORTED);
@@ -106,7 +141,20 @@ int ub200_adam_ema_step_f32(float *p, const float *g, float *m, float *v, float 
             a.lr *= (float)((s1 < (double)warmup_steps ? s1 : (double)warmup_steps) / (double)warmup_steps);
         }
     }
-    adam_ema_kernel<<<ub::grid_for((n + 3) / 4, 256, 8, 2), 256, 0, ub::as_stream(stream)>>>(p, g, m, v, ema, n, sumsq, a);
+    UB_REQUIRE(!shadow_bf16 || (reinterpret_cast<uintptr_t>(shadow_bf16) & 7u) == 0, UB200_E_UNSUPPORTED);
+    adam_ema_kernel<<<ub::grid_for((n + 3) / 4, 256, 8, 2), 256, 0, ub::as_stream(stream)>>>(
+        p, g, m, v, ema, n, sumsq, a, reinterpret_cast<__nv_bfloat16 *>(shadow_bf16));
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+int ub200_pack_dgrad_weights_batched(const void *shadow_bf16, void *dgrad_arena_bf16, const int64_t *table_dev,
+                                     int n_convs, void *stream) {
+    UB_REQUIRE(shadow_bf16 && dgrad_arena_bf16 && table_dev && n_convs > 0 && n_convs <= 65535, UB200_E_BADARG);
+    dim3 grid(64, (unsigned)n_convs, 1);
+    pack_dgrad_batched_kernel<<<grid, 256, 0, ub::as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(shadow_bf16), reinterpret_cast<__nv_bfloat16 *>(dgrad_arena_bf16),
+        reinterpret_cast<const long long *>(table_dev));
     UB_LAUNCH_CHECK();
     return UB200_OK;
 }

@@ -48,6 +48,12 @@ const float *f32(const Tensor &t, const char *name) {
 }
 const float *f32_opt(const c10::optional<Tensor> &t, const char *name) { return t.has_value() ? f32(*t, name) : nullptr; }
 float *f32_mut(const Tensor &t, const char *name) { return const_cast<float *>(f32(t, name)); }
+void *bf16_opt(const c10::optional<Tensor> &t, int64_t n) {
+    if (!t.has_value()) return nullptr;
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kBFloat16 && t->is_contiguous() && t->numel() == n,
+                "shadow: expected a contiguous CUDA bf16 tensor with one element per parameter");
+    return t->data_ptr();
+}
 const uint64_t *i64_opt(const c10::optional<Tensor> &t) {
     if (!t.has_value()) return nullptr;
     TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->numel() >= 1, "offset_dev: expected a CUDA int64 tensor");
@@ -291,7 +297,7 @@ void sumsq(const Tensor &g, const Tensor &acc) {
 void adam_ema_step(const Tensor &p, const Tensor &g, const Tensor &m, const Tensor &v, const c10::optional<Tensor> &ema,
                    const c10::optional<Tensor> &sumsq_t, double max_norm, double grad_scale, double lr, double beta1,
                    double beta2, double eps, double ema_decay, int64_t step, int64_t warmup_steps,
-                   const c10::optional<Tensor> &step_dev) {
+                   const c10::optional<Tensor> &step_dev, const c10::optional<Tensor> &shadow) {
     UB_GUARD(p);
     const int64_t n = p.numel();
     TORCH_CHECK(g.numel() == n && m.numel() == n && v.numel() == n && (!ema.has_value() || ema->numel() == n), "adam_ema_step: size mismatch");
@@ -299,7 +305,18 @@ void adam_ema_step(const Tensor &p, const Tensor &g, const Tensor &m, const Tens
                                      ema.has_value() ? f32_mut(*ema, "ema") : nullptr, n, f32_opt(sumsq_t, "sumsq"),
                                      (float)max_norm, (float)grad_scale, (float)lr, (float)beta1, (float)beta2, (float)eps,
                                      (float)ema_decay, step, warmup_steps,
-                                     reinterpret_cast<const int64_t *>(i64_opt(step_dev)), cur_stream()), "adam_ema_step");
+                                     reinterpret_cast<const int64_t *>(i64_opt(step_dev)), bf16_opt(shadow, n), cur_stream()),
+             "adam_ema_step");
+}
+
+void pack_dgrad_weights_batched(const Tensor &shadow, const Tensor &dgrad_arena, const Tensor &table) {
+    UB_GUARD(shadow);
+    TORCH_CHECK(shadow.scalar_type() == at::kBFloat16 && dgrad_arena.scalar_type() == at::kBFloat16 && shadow.is_contiguous() &&
+                dgrad_arena.is_contiguous(), "pack_dgrad_weights_batched: bf16 contiguous arenas expected");
+    TORCH_CHECK(table.is_cuda() && table.scalar_type() == at::kLong && table.is_contiguous() && table.dim() == 2 && table.size(1) == 5,
+                "pack_dgrad_weights_batched: table must be a CUDA int64 [n,5] tensor");
+    check_rc(ub200_pack_dgrad_weights_batched(shadow.data_ptr(), dgrad_arena.data_ptr(), table.data_ptr<int64_t>(),
+                                              (int)table.size(0), cur_stream()), "pack_dgrad_weights_batched");
 }
 
 }  // namespace
@@ -325,4 +342,5 @@ TORCH_LIBRARY(unet_b200, m) {
     m.def("pack_conv_weight", &pack_conv_weight);
     m.def("sumsq", &sumsq);
     m.def("adam_ema_step", &adam_ema_step);
+    m.def("pack_dgrad_weights_batched", &pack_dgrad_weights_batched);
 }

@@ -34,6 +34,42 @@ def _count(n: int = 1) -> None:
     _Counter.launches += n
 
 
+# --------------------------------------------------------------------------------------------------
+# per-parameter fast paths installed by the training step (train.DDPMTrainStep):
+#   * gradient sinks: kernels that already ACCUMULATE (wgrad atomics, GroupNorm dgamma/dbeta atomics, the bias
+#     column sum) write straight into the parameter's slice of the flat gradient arena, instead of allocating a
+#     zeroed temporary that autograd then adds into .grad (two launches and three passes over memory per parameter);
+#   * packed weights: the bf16 GEMM operands of every conv weight ([Cout,kh,kw,Cin] for fprop/wgrad, the
+#     transposed + rotated [Cin,kh,kw,Cout] for dgrad) are refreshed once per optimiser step by the optimiser
+#     kernel itself, not re-packed by every forward and backward call.
+# Without a registered entry every op falls back to its self-contained path (standalone use, tests).
+# --------------------------------------------------------------------------------------------------
+class _Registry:
+    sinks = {}      # id(param) -> (grad view in the arena, on_ready callback or None)
+    packed = {}     # id(param) -> (fprop/wgrad operand, dgrad operand)  bf16, flat
+
+
+def register_grad_sink(param: torch.Tensor, grad_view: torch.Tensor, on_ready=None) -> None:
+    _Registry.sinks[id(param)] = (grad_view, on_ready)
+
+
+def register_packed_weight(param: torch.Tensor, fwd: torch.Tensor, bwd: torch.Tensor) -> None:
+    _Registry.packed[id(param)] = (fwd, bwd)
+
+
+def clear_registry() -> None:
+    _Registry.sinks.clear()
+    _Registry.packed.clear()
+
+
+def _sink_of(key):
+    return _Registry.sinks.get(key) if key is not None else None
+
+
+def _key(t):
+    return id(t) if isinstance(t, torch.nn.Parameter) else None
+
+
 def _dense_nhwc(t: torch.Tensor) -> torch.Tensor:
     """Return `t` if it is a valid NHWC view (channel stride 1, uniform pixel stride), else a packed copy."""
     n, h, w, c = t.shape
@@ -236,6 +272,7 @@ class _GnAct(torch.autograd.Function):
                           _dense_nhwc(addend) if addend is not None else None, y)
         _count(3)
         ctx.has_addend = addend is not None
+        ctx.keys = (_key(gamma), _key(beta))
         ctx.save_for_backward(x, stats, gamma, beta, scale, shift)
         ctx.cfg = (G, eps, act, p_drop, seed, off, dev)
         return y
@@ -246,14 +283,19 @@ class _GnAct(torch.autograd.Function):
         G, eps, act, p_drop, seed, off, dev = ctx.cfg
         gy = _dense_nhwc(gy)
         gx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-        dgamma = torch.zeros_like(gamma) if gamma is not None else None
-        dbeta = torch.zeros_like(beta) if beta is not None else None
+        sg, sb = _sink_of(ctx.keys[0]), _sink_of(ctx.keys[1])
+        dgamma = (sg[0] if sg else torch.zeros_like(gamma)) if gamma is not None else None
+        dbeta = (sb[0] if sb else torch.zeros_like(beta)) if beta is not None else None
         dscale = torch.empty_like(scale) if scale is not None else None
         dshift = torch.empty_like(shift) if shift is not None else None
         _ops().gn_act_bwd(gy, x, G, stats, eps, gamma, beta, scale, shift, act, p_drop, seed, off, dev, gx, False,
                           dgamma, dbeta, dscale, dshift)
         _count(3)
-        return gx, dgamma, dbeta, dscale, dshift, None, None, None, None, (gy if ctx.has_addend else None)
+        for sink in (sg, sb):
+            if sink and sink[1] is not None:
+                sink[1]()
+        return (gx, None if sg else dgamma, None if sb else dbeta, dscale, dshift, None, None, None, None,
+                (gy if ctx.has_addend else None))
 
 
 def gn_act(x, gamma, beta, groups: int, act: str = "silu", eps: float = 1e-5, dropout_p: float = 0.0,
@@ -341,11 +383,13 @@ class _Conv(torch.autograd.Function):
         n, h, wd, cin = a.shape
         cout, k = w.shape[0], w.shape[2]
         assert w.shape[1] == cin, f"conv: weight expects {w.shape[1]} input channels, activation has {cin}"
-        wp = pack_weight(w)
+        pk = _Registry.packed.get(_key(w))
+        wp = pk[0] if pk else pack_weight(w)
         a2d = w2p = None
         if a2 is not None:
             a2d = _dense_nhwc(a2)
-            w2p = pack_weight(w2)
+            pk2 = _Registry.packed.get(_key(w2))
+            w2p = pk2[0] if pk2 else pack_weight(w2)
         res = _dense_nhwc(residual) if residual is not None else None
         if out_nchw:
             out = torch.empty((n, cout, h, wd), dtype=torch.float32, device=a.device)
@@ -356,6 +400,7 @@ class _Conv(torch.autograd.Function):
         _count()
         ctx.save_for_backward(a, w, a2d, w2)
         ctx.flags = (bias is not None, rowadd is not None, residual is not None, out_nchw)
+        ctx.keys = (_key(w), _key(bias), _key(w2))
         return out
 
     @staticmethod
@@ -379,29 +424,47 @@ class _Conv(torch.autograd.Function):
                 g_full = gp
         needs = ctx.needs_input_grad
         ga = gw = gbias = growadd = ga2 = gw2 = gres = None
+        kw, kb, kw2 = ctx.keys
+        pk, pk2 = _Registry.packed.get(kw), _Registry.packed.get(kw2)
         if needs[0]:
             # dgrad = the same implicit GEMM with transposed, 180-degree-rotated weights
-            if cpad != cout:
-                w_t = torch.zeros((cpad, cin, k, k), dtype=torch.float32, device=w.device)
-                w_t[:cout].copy_(w.detach())
+            if pk is not None and cpad == cout:
+                wtp = pk[1]
             else:
-                w_t = w
-            wtp = pack_weight(w_t, transpose_flip=True)
+                if cpad != cout:
+                    w_t = torch.zeros((cpad, cin, k, k), dtype=torch.float32, device=w.device)
+                    w_t[:cout].copy_(w.detach())
+                else:
+                    w_t = w
+                wtp = pack_weight(w_t, transpose_flip=True)
             ga = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=a.device)
             o.conv_fprop(g_full, wtp, k, cin, None, None, None, None, None, ga, None)
             _count()
         if needs[1]:
-            dw = torch.zeros((cpad, k, k, cin), dtype=torch.float32, device=w.device)
-            o.conv_wgrad(g_full, a, k, dw)
-            _count(2)
-            gw = dw[:cout].permute(0, 3, 1, 2)          # [Cout,Cin,k,k] view with channels_last strides
+            sink = _sink_of(kw) if cpad == cout else None
+            if sink is not None:                        # accumulate straight into the gradient arena
+                o.conv_wgrad(g_full, a, k, sink[0])
+                _count()
+                if sink[1] is not None:
+                    sink[1]()
+            else:
+                dw = torch.zeros((cpad, k, k, cin), dtype=torch.float32, device=w.device)
+                o.conv_wgrad(g_full, a, k, dw)
+                _count(2)
+                gw = dw[:cout].permute(0, 3, 1, 2)      # [Cout,Cin,k,k] view with channels_last strides
         if (has_bias and needs[2]) or (has_rowadd and needs[3]):
+            bsink = _sink_of(kb) if (has_bias and needs[2] and cout % 8 == 0) else None
             if cout % 8 == 0:
                 per = torch.empty((n, cout), dtype=torch.float32, device=g.device)
-                tot = torch.zeros((cout,), dtype=torch.float32, device=g.device) if has_bias else None
+                if bsink is not None:
+                    tot = bsink[0]
+                else:
+                    tot = torch.zeros((cout,), dtype=torch.float32, device=g.device) if has_bias else None
                 o.chansum(g_valid, per, tot)
                 _count(3)
-                growadd, gbias = (per if has_rowadd else None), tot
+                growadd, gbias = (per if has_rowadd else None), (None if bsink is not None else tot)
+                if bsink is not None and bsink[1] is not None:
+                    bsink[1]()
             else:
                 per = torch.empty((n, cpad), dtype=torch.float32, device=g.device)
                 tot = torch.zeros((cpad,), dtype=torch.float32, device=g.device) if has_bias else None
@@ -411,15 +474,22 @@ class _Conv(torch.autograd.Function):
                 gbias = tot[:cout] if has_bias else None
         if a2 is not None:
             if needs[4]:
-                w2tp = pack_weight(w2, transpose_flip=True)
+                w2tp = pk2[1] if (pk2 is not None and cpad == cout) else pack_weight(w2, transpose_flip=True)
                 ga2 = torch.empty(a2.shape, dtype=torch.bfloat16, device=a.device)
                 o.conv_fprop(g_full, w2tp, 1, a2.shape[3], None, None, None, None, None, ga2, None)
                 _count()
             if needs[5]:
-                dw2 = torch.zeros((cpad, 1, 1, a2.shape[3]), dtype=torch.float32, device=w.device)
-                o.conv_wgrad(g_full, a2, 1, dw2)
-                _count(2)
-                gw2 = dw2[:cout].permute(0, 3, 1, 2)
+                sink2 = _sink_of(kw2) if cpad == cout else None
+                if sink2 is not None:
+                    o.conv_wgrad(g_full, a2, 1, sink2[0])
+                    _count()
+                    if sink2[1] is not None:
+                        sink2[1]()
+                else:
+                    dw2 = torch.zeros((cpad, 1, 1, a2.shape[3]), dtype=torch.float32, device=w.device)
+                    o.conv_wgrad(g_full, a2, 1, dw2)
+                    _count(2)
+                    gw2 = dw2[:cout].permute(0, 3, 1, 2)
         if has_res and needs[6]:
             gres = g_valid
         return ga, gw, gbias, growadd, ga2, gw2, gres, None
@@ -467,7 +537,12 @@ def sumsq_(g: torch.Tensor, acc: torch.Tensor) -> None:
 
 
 def adam_ema_step_(p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, step,
-                   warmup_steps: int = 0, step_dev=None) -> None:
+                   warmup_steps: int = 0, step_dev=None, shadow=None) -> None:
     _ops().adam_ema_step(p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, step,
-                         warmup_steps, step_dev)
+                         warmup_steps, step_dev, shadow)
+    _count()
+
+
+def pack_dgrad_weights_batched_(shadow, dgrad_arena, table) -> None:
+    _ops().pack_dgrad_weights_batched(shadow, dgrad_arena, table)
     _count()

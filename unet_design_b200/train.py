@@ -69,6 +69,45 @@ class FlatArena:
             p.grad = self._view(self.g, p, off)
 
 
+class PackedWeights:
+    """bf16 GEMM operands of every conv weight, refreshed once per optimiser step.
+
+    * `shadow`: bf16 copy of the whole parameter arena, written by the Adam kernel.  A conv weight's slice is its
+      fprop / wgrad operand ([Cout, kh, kw, Cin], same order as the fp32 master).
+    * `dgrad`: the transposed + 180-degree-rotated operands ([Cin_pad, kh, kw, Cout]) of all convs, produced by ONE
+      kernel launch from a device-resident table.
+    Registered with `ops.register_packed_weight`, so forward / backward calls pick them up instead of re-packing.
+    Call `refresh_from_master()` after loading a state_dict into a model that already has a training step.
+    """
+
+    def __init__(self, arena: FlatArena):
+        self.arena = arena
+        dev = arena.p.device
+        self.shadow = torch.empty(arena.p.numel(), dtype=torch.bfloat16, device=dev)
+        rows, doff = [], 0
+        self.entries = []
+        for p, off in zip(arena.params, arena.offsets):
+            if p.dim() == 4 and p.shape[0] % 16 == 0 and p.shape[1] % 16 == 0 and p.shape[2] == p.shape[3]:
+                cout, cin, k, _ = p.shape
+                n_fwd, n_bwd = cout * k * k * cin, (cin + 15) // 16 * 16 * k * k * cout
+                rows.append([off, doff, cout, cin, k])
+                self.entries.append((p, off, n_fwd, doff, n_bwd))
+                doff += (n_bwd + 7) // 8 * 8                    # keep every operand 16-byte aligned
+        self.dgrad = torch.empty(max(doff, 8), dtype=torch.bfloat16, device=dev)
+        self.table = torch.tensor(rows, dtype=torch.int64, device=dev) if rows else None
+        for p, off, n_fwd, d0, n_bwd in self.entries:
+            ops.register_packed_weight(p, self.shadow[off:off + n_fwd], self.dgrad[d0:d0 + n_bwd])
+        self.refresh_from_master()
+
+    def refresh_dgrad(self):
+        if self.table is not None:
+            ops.pack_dgrad_weights_batched_(self.shadow, self.dgrad, self.table)
+
+    def refresh_from_master(self):
+        self.shadow.copy_(self.arena.p)
+        self.refresh_dgrad()
+
+
 class DDPMTrainStep:
     def __init__(self, model: nn.Module, T: int = 1000, beta_1: float = 1e-4, beta_T: float = 0.02, lr: float = 2e-4,
                  warmup: int = 5000, grad_clip: float = 1.0, ema_decay: float = 0.9999, multi_res_loss: bool = False,
@@ -90,6 +129,9 @@ class DDPMTrainStep:
         self.m = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.v = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.ema = self.arena.p.clone()
+        self.packed = PackedWeights(self.arena)
+        for p, off in zip(self.arena.params, self.arena.offsets):
+            ops.register_grad_sink(p, p.grad, None)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)       # 1-based after the first bump
         self.steps_done = 0
@@ -124,6 +166,8 @@ class DDPMTrainStep:
         self._pending = [0] * len(self._buckets)
         if self.device.type == "cuda":
             self._comm_stream = torch.cuda.Stream(device=self.device)
+        # note: post-accumulate hooks also fire for parameters whose Function returned None because its kernel
+        # accumulated straight into the arena (ops gradient sinks), and they fire after that kernel was enqueued
         for i, p in enumerate(params):
             p.register_post_accumulate_grad_hook(self._make_hook(i))
 
@@ -184,7 +228,8 @@ class DDPMTrainStep:
         # gradients hold the SUM over ranks: the mean (what DataParallel / DDP produce) is a grad_scale of 1/world
         ops.adam_ema_step_(self.arena.p, self.arena.g, self.m, self.v, self.ema, self.sumsq, self.grad_clip,
                            1.0 / self.world, self.lr, self.betas[0], self.betas[1], self.eps, self.ema_decay, 1,
-                           self.warmup, self.step_dev)
+                           self.warmup, self.step_dev, self.packed.shadow)
+        self.packed.refresh_dgrad()                 # one launch: dgrad operands of every conv from the bf16 shadow
         ops.advance_dropout_state(self.device)
 
     def _body(self, x0: torch.Tensor) -> torch.Tensor:
