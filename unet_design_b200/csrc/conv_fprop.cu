@@ -33,9 +33,11 @@ using namespace ub::tc;
 struct FpropParams {
     int N, H, W, Cout;
     int BW, BH, BNI, tiles_w, tiles_h;
-    int BN, n_tiles, num_tiles;
+    int BN, n_tiles, num_tiles, m_tiles;
+    int msub;                         // pixel tiles per CTA tile (2 when Cout <= 128: both share one weight tile)
     int Cin, cblocks, taps, kb_main, kb_extra, stages;
-    uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
+    uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, tbl_bytes;
+    int cluster_tiles;                // (channel tile, pixel-tile pair) units walked by one CTA pair
     const float *bias, *rowadd;
     const __nv_bfloat16 *residual; int64_t ld_res;
     int has_out;                      // bf16 NHWC output through the TMA store
@@ -45,6 +47,8 @@ struct FpropParams {
 constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr uint32_t kStagingBytes = 128 * 64 * 2;      // one [128 pixels][64 channels] bf16 box
+constexpr int kTblRows = 8;                           // addend table: up to 8 samples per pixel tile
+constexpr int kCluster = 2;                           // CTA pair: the weight tile is loaded once and multicast to both
 
 template <int BK>
 __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_a,
@@ -57,7 +61,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
     // carve: [2 x output staging][stages x A][stages x B][full][empty][tmem_full x2][tmem_empty x2][tmem ptr]
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_out = smem;
-    uint8_t *smem_a = smem_out + 2 * kStagingBytes;
+    float *tbl = reinterpret_cast<float *>(smem_out + 2 * kStagingBytes);   // [kTblRows][BN] bias + per-sample row
+    uint8_t *smem_a = smem_out + 2 * kStagingBytes + p.tbl_bytes;
     uint8_t *smem_b = smem_a + (size_t)p.stages * p.a_stage_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_b + (size_t)p.stages * p.b_stage_bytes);
     uint64_t *empty = full + p.stages;
@@ -73,27 +78,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         prefetch_tmap(&tm_w);
         if (p.kb_extra) { prefetch_tmap(&tm_a2); prefetch_tmap(&tm_w2); }
         if (p.has_out) prefetch_tmap(&tm_out);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kCluster); }
         for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();               // the peer multicasts into our smem and arrives on our barriers: both must be ready
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int crank = (int)cluster_ctarank();
+    const int cluster_id = blockIdx.x / kCluster, num_clusters = gridDim.x / kCluster;
+    // this CTA's m unit of cluster tile ct:  (ct / n_tiles) * kCluster + crank   (may lie past the end: zero tile)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t tx_bytes = 128u * BK * 2u + (uint32_t)p.BN * BK * 2u;
+            const uint32_t tx_bytes = (uint32_t)p.msub * 128u * BK * 2u + (uint32_t)p.BN * BK * 2u;
+            const int half = p.BN / kCluster;                 // weight rows this CTA fetches for the pair
             uint32_t it = 0;                                  // running k-block counter across tiles
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles;
-                int mt = tile / p.n_tiles;
-                const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-                const int th = mt % p.tiles_h; mt /= p.tiles_h;
-                const int x0 = tw * p.BW, y0 = th * p.BH, n0 = mt * p.BNI, co0 = nt * p.BN;
+            for (int ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
+                const int nt = ct % p.n_tiles, co0 = nt * p.BN;
+                int x0[2], y0[2], n0[2];
+                for (int sub = 0; sub < p.msub; ++sub) {
+                    int mt = ((ct / p.n_tiles) * kCluster + crank) * p.msub + sub;
+                    x0[sub] = (mt % p.tiles_w) * p.BW; mt /= p.tiles_w;
+                    y0[sub] = (mt % p.tiles_h) * p.BH; mt /= p.tiles_h;
+                    n0[sub] = mt * p.BNI;                     // past the batch for a padded trailing tile: TMA zero-fills
+                }
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1u;
@@ -104,12 +117,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                     if (kb < p.kb_main) {
                         const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                         const int ky = p.taps == 9 ? tap / 3 - 1 : 0, kx = p.taps == 9 ? tap % 3 - 1 : 0;
-                        tma_load_4d(dst_a, &tm_a, full + s, cb * BK, x0 + kx, y0 + ky, n0);
-                        tma_load_2d(dst_b, &tm_w, full + s, tap * p.Cin + cb * BK, co0);
+                        for (int sub = 0; sub < p.msub; ++sub)
+                            tma_load_4d(dst_a + sub * (128 * BK * 2), &tm_a, full + s, cb * BK, x0[sub] + kx, y0[sub] + ky, n0[sub]);
+                        tma_load_2d_mcast(dst_b + crank * half * (BK * 2), &tm_w, full + s, tap * p.Cin + cb * BK,
+                                          co0 + crank * half, (uint16_t)0x3);
                     } else {
                         const int cb = kb - p.kb_main;
-                        tma_load_4d(dst_a, &tm_a2, full + s, cb * BK, x0, y0, n0);
-                        tma_load_2d(dst_b, &tm_w2, full + s, cb * BK, co0);
+                        for (int sub = 0; sub < p.msub; ++sub)
+                            tma_load_4d(dst_a + sub * (128 * BK * 2), &tm_a2, full + s, cb * BK, x0[sub], y0[sub], n0[sub]);
+                        tma_load_2d_mcast(dst_b + crank * half * (BK * 2), &tm_w2, full + s, cb * BK, co0 + crank * half,
+                                          (uint16_t)0x3);
                     }
                 }
             }
@@ -121,11 +138,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
             constexpr uint32_t swz = swizzle_code(BK * 2);
             constexpr uint32_t sbo = 8u * BK * 2u;
             uint32_t it = 0, local = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+            for (int ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, ++local) {
                 const uint32_t acc = local & 1u, use = local >> 1;
                 mbar_wait(tmem_empty + acc, (use & 1u) ^ 1u);          // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.BN;
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)(p.msub * p.BN);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1u;
@@ -133,13 +150,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem_a + (size_t)s * p.a_stage_bytes);
                     const uint32_t b_addr = smem_u32(smem_b + (size_t)s * p.b_stage_bytes);
+                    for (int sub = 0; sub < p.msub; ++sub) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = make_smem_desc(a_addr + k * 32, 16, sbo, swz);
-                        const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, swz);
-                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t da = make_smem_desc(a_addr + sub * (128 * BK * 2) + k * 32, 16, sbo, swz);
+                            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, swz);
+                            umma_bf16(d_tmem + sub * (uint32_t)p.BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
-                    umma_commit(empty + s);                            // slot reusable once these MMAs have read it
+                    umma_commit_mcast(empty + s, (uint16_t)0x3);       // slot reusable once BOTH CTAs' MMAs have read it
                 }
                 umma_commit(tmem_full + acc);                          // accumulator complete
             }
@@ -148,87 +167,130 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         // ===================== epilogue: 4 warps, one TMEM lane quadrant each =====================
         const int qd = warp & 3;
         const int r = qd * 32 + lane;                 // row of the tile == TMEM lane
+        const int et = threadIdx.x - 64;              // 0..127 within the epilogue group
         const int wi = r % p.BW, hi = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
         const bool issuer = (warp == 2 && lane == 0);
         const int64_t hw = (int64_t)p.H * p.W;
+        const bool use_tbl = (p.bias || p.rowadd) && p.BNI <= kTblRows;
         uint32_t local = 0, chunk_ctr = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
-            const int nt = tile % p.n_tiles;
-            int mt = tile / p.n_tiles;
-            const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-            const int th = mt % p.tiles_h; mt /= p.tiles_h;
-            const int x0 = tw * p.BW, y0 = th * p.BH, n0 = mt * p.BNI, co0 = nt * p.BN;
-            const int x = x0 + wi, y = y0 + hi, n = n0 + ni;
-            const bool valid = x < p.W && y < p.H && n < p.N;
-            const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
+        for (int ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, ++local) {
+            const int nt = ct % p.n_tiles, co0 = nt * p.BN;
             const uint32_t acc = local & 1u, use = local >> 1;
             mbar_wait(tmem_full + acc, use & 1u);
             tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + acc * (uint32_t)p.BN;
-            const int nchunks = (p.BN + 63) / 64;
-            for (int ch = 0; ch < nchunks; ++ch, ++chunk_ctr) {
-                uint8_t *stage = smem_out + (chunk_ctr & 1u) * kStagingBytes;
-                if (p.has_out) {
-                    if (issuer) tma_store_wait_read<1>();           // the store that last used this buffer has read it
+            for (int sub = 0; sub < p.msub; ++sub) {
+                int mt = ((ct / p.n_tiles) * kCluster + crank) * p.msub + sub;
+                const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+                const int th = mt % p.tiles_h; mt /= p.tiles_h;
+                const int x0 = tw * p.BW, y0 = th * p.BH, n0 = mt * p.BNI;
+                const int x = x0 + wi, y = y0 + hi, n = n0 + ni;
+                const bool valid = x < p.W && y < p.H && n < p.N;
+                const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
+                if (use_tbl) {
+                    // tbl[s][c] = bias[co0+c] + rowadd[n0+s][co0+c]: one smem row per sample of the pixel tile
+                    named_barrier_sync(1, kEpiThreads);             // previous readers of the table are done
+                    for (int i = et; i < p.BNI * p.BN; i += kEpiThreads) {
+                        const int sidx = i / p.BN, c = i - sidx * p.BN, co = co0 + c;
+                        float v = 0.f;
+                        if (co < p.Cout) {
+                            if (p.bias) v = __ldg(p.bias + co);
+                            if (p.rowadd && n0 + sidx < p.N) v += __ldg(p.rowadd + (int64_t)(n0 + sidx) * p.Cout + co);
+                        }
+                        tbl[i] = v;
+                    }
                     named_barrier_sync(1, kEpiThreads);
                 }
-                const int groups = (p.BN - ch * 64) >= 64 ? 4 : (p.BN - ch * 64) / 16;
-                for (int cg = 0; cg < groups; ++cg) {
-                    float v[16];
-                    tmem_ld16(trow + ch * 64 + cg * 16, v);
-                    const int co = co0 + ch * 64 + cg * 16;
-                    const int nv = p.Cout - co < 16 ? p.Cout - co : 16;    // may be <= 0 in the padded tail
-                    if (valid && nv > 0) {
-                        if (p.bias) {
+                const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + acc * (uint32_t)(p.msub * p.BN) + sub * (uint32_t)p.BN;
+                const int nchunks = (p.BN + 63) / 64;
+                for (int ch = 0; ch < nchunks; ++ch, ++chunk_ctr) {
+                    uint8_t *stage = smem_out + (chunk_ctr & 1u) * kStagingBytes;
+                    if (p.has_out) {
+                        if (issuer) tma_store_wait_read<1>();       // the store that last used this buffer has read it
+                        named_barrier_sync(1, kEpiThreads);
+                    }
+                    const int groups = (p.BN - ch * 64) >= 64 ? 4 : (p.BN - ch * 64) / 16;
+                    float v[64];
+                    if (groups == 4) {
+                        tmem_ld64(trow + ch * 64, v);
+                    } else {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) if (i < nv) v[i] += __ldg(p.bias + co + i);
-                        }
-                        if (p.rowadd) {
+                        for (int cg = 0; cg < 3; ++cg) {
+                            if (cg < groups) {                   // warp-uniform
+                                float t16[16];
+                                tmem_ld16(trow + ch * 64 + cg * 16, t16);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) if (i < nv) v[i] += __ldg(p.rowadd + (int64_t)n * p.Cout + co + i);
-                        }
-                        if (p.residual) {
-                            const __nv_bfloat16 *rp = p.residual + pix * p.ld_res + co;
-                            if (nv == 16) {
-                                float f[8];
-                                unpack8(*reinterpret_cast<const uint4 *>(rp), f);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] += f[i];
-                                unpack8(*reinterpret_cast<const uint4 *>(rp + 8), f);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[8 + i] += f[i];
-                            } else {
-                                for (int i = 0; i < nv; ++i) v[i] += __bfloat162float(rp[i]);
+                                for (int i = 0; i < 16; ++i) v[cg * 16 + i] = t16[i];
                             }
                         }
-                        if (p.out_nchw) {
-                            float *op = p.out_nchw + ((int64_t)n * p.Cout + co) * hw + (int64_t)y * p.W + x;
+                    }
+                    if (ch == nchunks - 1 && sub == p.msub - 1) {   // all tcgen05.ld of this accumulator are done
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tmem_empty + acc);
+                    }
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) if (i < nv) op[i * hw] = v[i];
+                    for (int cg = 0; cg < 4; ++cg) {
+                        if (cg >= groups) continue;
+                        float *vv = v + cg * 16;
+                        const int co = co0 + ch * 64 + cg * 16;
+                        const int nv = p.Cout - co < 16 ? p.Cout - co : 16;    // may be <= 0 in the padded tail
+                        if (valid && nv > 0) {
+                            if (use_tbl) {
+                                const float4 *tp = reinterpret_cast<const float4 *>(tbl + ni * p.BN + ch * 64 + cg * 16);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float4 t = tp[i];
+                                    vv[4 * i] += t.x; vv[4 * i + 1] += t.y; vv[4 * i + 2] += t.z; vv[4 * i + 3] += t.w;
+                                }
+                            } else {
+                                if (p.bias) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) if (i < nv) vv[i] += __ldg(p.bias + co + i);
+                                }
+                                if (p.rowadd) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) if (i < nv) vv[i] += __ldg(p.rowadd + (int64_t)n * p.Cout + co + i);
+                                }
+                            }
+                            if (p.residual) {
+                                const __nv_bfloat16 *rp = p.residual + pix * p.ld_res + co;
+                                if (nv == 16) {
+                                    float f[8];
+                                    unpack8(*reinterpret_cast<const uint4 *>(rp), f);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) vv[i] += f[i];
+                                    unpack8(*reinterpret_cast<const uint4 *>(rp + 8), f);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) vv[8 + i] += f[i];
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) if (i < nv) vv[i] += __bfloat162float(rp[i]);
+                                }
+                            }
+                            if (p.out_nchw) {
+                                float *op = p.out_nchw + ((int64_t)n * p.Cout + co) * hw + (int64_t)y * p.W + x;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) if (i < nv) op[i * hw] = vv[i];
+                            }
+                        }
+                        if (p.has_out) {
+                            // two 16-byte pieces of row r, 128-byte swizzle: piece index XOR (row & 7)
+                            float f[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] = vv[i];
+                            *reinterpret_cast<uint4 *>(stage + r * 128 + (((2 * cg) ^ (r & 7)) << 4)) = pack8(f);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] = vv[8 + i];
+                            *reinterpret_cast<uint4 *>(stage + r * 128 + (((2 * cg + 1) ^ (r & 7)) << 4)) = pack8(f);
                         }
                     }
                     if (p.has_out) {
-                        // two 16-byte pieces of row r, 128-byte swizzle: piece index XOR (row & 7)
-                        float f[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = v[i];
-                        *reinterpret_cast<uint4 *>(stage + r * 128 + (((2 * cg) ^ (r & 7)) << 4)) = pack8(f);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = v[8 + i];
-                        *reinterpret_cast<uint4 *>(stage + r * 128 + (((2 * cg + 1) ^ (r & 7)) << 4)) = pack8(f);
-                    }
-                }
-                if (ch == nchunks - 1) {             // all tcgen05.ld of this accumulator are done: hand it back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty + acc);
-                }
-                if (p.has_out) {
-                    fence_proxy_async();
-                    named_barrier_sync(1, kEpiThreads);
-                    if (issuer) {
-                        tma_store_4d(&tm_out, stage, co0 + ch * 64, x0, y0, n0);
-                        tma_store_commit();
+                        fence_proxy_async();
+                        named_barrier_sync(1, kEpiThreads);
+                        if (issuer) {
+                            tma_store_4d(&tm_out, stage, co0 + ch * 64, x0, y0, n0);
+                            tma_store_commit();
+                        }
                     }
                 }
             }
@@ -237,6 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();               // nobody exits while the peer may still write our smem / arrive on our barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
@@ -280,7 +343,17 @@ int launch_fprop(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap
         attr_err = cudaFuncSetAttribute(conv_fprop_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) return (int)attr_err;
-    conv_fprop_kernel<BK><<<grid, kThreads, smem, s>>>(ta, tw, ta2, tw2, tout, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BK>, ta, tw, ta2, tw2, tout, p);
+    if (e != cudaSuccess) return (int)e;
     UB_LAUNCH_CHECK();
     return UB200_OK;
 }
@@ -321,21 +394,28 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     // several channel tiles: keep BN a multiple of the 64-channel store box so no tile writes columns it did not
     // compute; a single tile may be any multiple of 16 (columns past Cout fall outside the tensor and are clipped)
     p.BN = p.n_tiles > 1 ? (int)(((cout_pad + p.n_tiles - 1) / p.n_tiles + 63) / 64 * 64) : (int)cout_pad;
-    p.num_tiles = m_tiles * p.n_tiles;
+    p.m_tiles = m_tiles;
+    // narrow outputs (one channel tile of <= 128): two pixel tiles share each weight tile (halves the weight traffic
+    // per MAC and the k-block count per MAC); 4 accumulators x BN <= 512 TMEM columns
+    p.msub = (p.n_tiles == 1 && p.BN <= 128 && m_tiles >= 2 * ub::kSMs) ? 2 : 1;
+    const int m_units = (m_tiles + p.msub - 1) / p.msub;
+    p.num_tiles = m_units * p.n_tiles;
+    p.cluster_tiles = ((m_units + kCluster - 1) / kCluster) * p.n_tiles;
+    p.tbl_bytes = ((uint32_t)((p.BNI <= kTblRows ? p.BNI : 1) * p.BN * 4) + 1023u) & ~1023u;
     p.Cin = (int)a->Cin;
     p.cblocks = (int)(a->Cin / bk);
     p.taps = a->ksize * a->ksize;
     p.kb_main = p.taps * p.cblocks;
     p.kb_extra = extra ? (int)(a->Cin2 / bk) : 0;
-    p.a_stage_bytes = 128u * bk * 2u;
+    p.a_stage_bytes = (uint32_t)p.msub * 128u * bk * 2u;
     p.b_stage_bytes = ((uint32_t)p.BN * bk * 2u + 1023u) & ~1023u;
     const uint32_t stage = p.a_stage_bytes + p.b_stage_bytes;
-    const uint32_t budget = 227u * 1024u - 1024u - 2u * kStagingBytes - 512u;
+    const uint32_t budget = 227u * 1024u - 1024u - 2u * kStagingBytes - p.tbl_bytes - 256u;
     int stages = (int)(budget / stage);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    p.tmem_cols = pow2_at_least(2u * (uint32_t)p.BN, 32);
+    p.tmem_cols = pow2_at_least(2u * (uint32_t)(p.msub * p.BN), 32);
     p.bias = a->bias; p.rowadd = a->rowadd;
     p.residual = reinterpret_cast<const __nv_bfloat16 *>(a->residual); p.ld_res = a->ld_res;
     p.has_out = a->out != nullptr;
@@ -351,7 +431,7 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
         if (rc) return rc;
         const int64_t wd[2] = {(int64_t)p.taps * a->Cin, cout_pad};
         const int64_t ws[1] = {(int64_t)p.taps * a->Cin};
-        const int wb[2] = {bk, p.BN};
+        const int wb[2] = {bk, p.BN / kCluster};            // each CTA of the pair fetches half the rows and multicasts
         rc = encode_bf16_tensor_map(&tw, a->w, 2, wd, ws, wb);
         if (rc) return rc;
     }
@@ -363,7 +443,7 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
         if (rc) return rc;
         const int64_t wd[2] = {a->Cin2, cout_pad};
         const int64_t ws[1] = {a->Cin2};
-        const int wb[2] = {bk, p.BN};
+        const int wb[2] = {bk, p.BN / kCluster};
         rc = encode_bf16_tensor_map(&tw2, a->w2, 2, wd, ws, wb);
         if (rc) return rc;
     } else {
@@ -379,8 +459,8 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
         tout = ta;
     }
 
-    const int grid = p.num_tiles < ub::kSMs ? p.num_tiles : ub::kSMs;
-    const size_t smem = 1024 + 2 * kStagingBytes + (size_t)stages * stage + (2 * stages + 4) * sizeof(uint64_t) + 16;
+    const int grid = kCluster * (p.cluster_tiles < ub::kSMs / kCluster ? p.cluster_tiles : ub::kSMs / kCluster);
+    const size_t smem = 1024 + 2 * kStagingBytes + p.tbl_bytes + (size_t)stages * stage + (2 * stages + 4) * sizeof(uint64_t) + 16;
     cudaStream_t s = ub::as_stream(stream);
     switch (bk) {
         case 64: return launch_fprop<64>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
