@@ -140,7 +140,8 @@ int ub200_gn_act_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t H
                                const void *addend, int64_t ld_add,
                                void *y, int64_t ld_y, void *stream);
 
-/* Backward of the above.  gy, x NHWC bf16 -> gx NHWC bf16 (accumulate=1 adds into gx),
+/* Backward of the above.  gy, x NHWC bf16 -> gx NHWC bf16 (accumulate must be 0: the first pass parks
+ * dz = gy * mask * act'(z) in the gx buffer, the second pass finishes it in place; gx may not alias gy or x),
  * dgamma/dbeta float [C] (accumulated with atomics: zero them first), dscale/dshift float [N,C]
  * (NULL when unused).  ws is a float workspace of ub200_gn_act_bwd_ws_floats(N, C, G) elements. */
 size_t ub200_gn_act_bwd_ws_floats(int64_t N, int64_t C, int G);

@@ -156,10 +156,8 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
 __global__ void __launch_bounds__(256) chansum_kernel(const __nv_bfloat16 *__restrict__ x, int64_t ld, int64_t HW, int C,
                                                      int chunks, int rows, int64_t pix_per_cta,
                                                      float *__restrict__ per_sample) {
-    extern __shared__ float acc[];   // [C]
+    extern __shared__ float part[];   // [256 threads][8]: per-thread partial sums, combined without atomics
     const int64_t n = blockIdx.y;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) acc[i] = 0.f;
-    __syncthreads();
     const int q = threadIdx.x % chunks, r = threadIdx.x / chunks;
     if (r < rows) {
         float s[8];
@@ -168,17 +166,31 @@ __global__ void __launch_bounds__(256) chansum_kernel(const __nv_bfloat16 *__res
         const int64_t p0 = (int64_t)blockIdx.x * pix_per_cta;
         int64_t p1 = p0 + pix_per_cta;
         if (p1 > HW) p1 = HW;
-        for (int64_t pp = p0 + r; pp < p1; pp += rows) {
+        const __nv_bfloat16 *xb = x + n * HW * ld + 8 * q;
+        int64_t pp = p0 + r;
+        for (; pp + rows < p1; pp += 2 * rows) {
+            const uint4 a = ld_stream_u4(reinterpret_cast<const uint4 *>(xb + pp * ld));
+            const uint4 b = ld_stream_u4(reinterpret_cast<const uint4 *>(xb + (pp + rows) * ld));
+            float f[8], g[8];
+            unpack8(a, f); unpack8(b, g);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[u] += f[u] + g[u];
+        }
+        for (; pp < p1; pp += rows) {
             float f[8];
-            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(x + (n * HW + pp) * ld + 8 * q)), f);
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(xb + pp * ld)), f);
 #pragma unroll
             for (int u = 0; u < 8; ++u) s[u] += f[u];
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) atomicAdd(&acc[8 * q + u], s[u]);
+        float4 *dst = reinterpret_cast<float4 *>(part + (size_t)threadIdx.x * 8);
+        dst[0] = make_float4(s[0], s[1], s[2], s[3]); dst[1] = make_float4(s[4], s[5], s[6], s[7]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(per_sample + n * C + i, acc[i]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int rr = 0; rr < rows; ++rr) acc += part[(size_t)(rr * chunks + (c >> 3)) * 8 + (c & 7)];
+        atomicAdd(per_sample + n * C + c, acc);
+    }
 }
 
 __global__ void __launch_bounds__(256) colsum_rows_kernel(const float *__restrict__ per_sample, int64_t N, int C,
@@ -320,7 +332,7 @@ int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, in
     const int64_t ppc = (HW + splits - 1) / splits;
     splits = (HW + ppc - 1) / ppc;
     dim3 grid((unsigned)splits, (unsigned)N, 1);
-    chansum_kernel<<<grid, 256, C * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16 *>(x), ld, HW, (int)C, chunks,
+    chansum_kernel<<<grid, 256, 256 * 8 * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16 *>(x), ld, HW, (int)C, chunks,
                                                        rows, ppc, per_sample);
     UB_LAUNCH_CHECK();
     if (total) {

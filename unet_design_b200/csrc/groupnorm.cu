@@ -39,17 +39,25 @@ __device__ __forceinline__ void dropout_mask8(uint64_t seed, uint64_t offset, in
     for (int u = 0; u < 8; ++u) m[u] = r[u] >= thr ? keep_scale : 0.f;
 }
 
+// sigmoid through ONE special-function op: 0.5 * tanh(z/2) + 0.5  (tanh.approx.f32, relative error 2^-11: far below
+// the bf16 rounding of every value this feeds).  These kernels are issue-bound, not bandwidth-bound, on B200.
+__device__ __forceinline__ float fast_sigmoid(float z) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    return fmaf(t, 0.5f, 0.5f);
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float z) {
-    if constexpr (ACT == UB200_ACT_SILU) return __fdividef(z, 1.0f + __expf(-z));
+    if constexpr (ACT == UB200_ACT_SILU) return z * fast_sigmoid(z);
     else if constexpr (ACT == UB200_ACT_GELU) return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f));
     else return z;
 }
 template <int ACT>
 __device__ __forceinline__ float act_bwd(float z) {   // d act / d z
     if constexpr (ACT == UB200_ACT_SILU) {
-        const float s = __fdividef(1.0f, 1.0f + __expf(-z));
-        return s * fmaf(z, 1.0f - s, 1.0f);
+        const float s = fast_sigmoid(z);
+        return fmaf(z, fmaf(-s, s, s), s);          // s + z*s*(1-s)
     } else if constexpr (ACT == UB200_ACT_GELU) {
         return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
     } else return 1.0f;
@@ -166,8 +174,8 @@ __global__ void __launch_bounds__(256) gn_act_fwd_kernel(const __nv_bfloat16 *__
     }
 }
 
-// backward pass 1: Q[n,c] = (sum_p dz, sum_p dz*x)   with dz = gy * mask * act'(z);  sum_p dz*xhat is derived from
-// the two in pass 2, which keeps this loop at one fma + act' per element.
+// backward pass 1: dz = gy * mask * act'(z) is computed ONCE, stored (bf16) in the gx buffer, and reduced to
+// Q[n,c] = (sum_p dz, sum_p dz*x).  Pass 2 then needs no transcendental and no dropout mask.
 template <int ACT, bool DROP>
 __global__ void __launch_bounds__(256, 3) gn_act_bwd_reduce(const __nv_bfloat16 *__restrict__ gy, int64_t ld_gy,
                                                            const __nv_bfloat16 *__restrict__ x, int64_t ld_x, Shape sh,
@@ -175,11 +183,10 @@ __global__ void __launch_bounds__(256, 3) gn_act_bwd_reduce(const __nv_bfloat16 
                                                            const float *__restrict__ beta, const float *__restrict__ scale,
                                                            const float *__restrict__ shift, float eps, float p_drop,
                                                            uint64_t seed, uint64_t offset, const uint64_t *__restrict__ off_dev,
+                                                           __nv_bfloat16 *__restrict__ dzbuf, int64_t ld_dz,
                                                            float *__restrict__ Q) {
-    extern __shared__ float qs[];   // [C][2]: CTA-level partial sums, one global atomic per entry afterwards
+    extern __shared__ float part[];   // [rows][chunks][16]: per-thread partial sums, combined without atomics
     const int64_t n = blockIdx.y;
-    for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) qs[i] = 0.f;
-    __syncthreads();
     const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
     if (r < sh.rows) {
         const Coef k = make_coef(sh, n, q, stats, gamma, beta, scale, shift, eps);
@@ -192,6 +199,7 @@ __global__ void __launch_bounds__(256, 3) gn_act_bwd_reduce(const __nv_bfloat16 
         if (p1 > sh.HW) p1 = sh.HW;
         const __nv_bfloat16 *xb = x + n * sh.HW * ld_x + 8 * q;
         const __nv_bfloat16 *gb = gy + n * sh.HW * ld_gy + 8 * q;
+        __nv_bfloat16 *db = dzbuf + n * sh.HW * ld_dz + 8 * q;
         int64_t p = p0 + r;
         // two pixels per iteration: four independent 16-byte loads in flight per thread
         for (; p + sh.rows < p1; p += 2 * sh.rows) {
@@ -207,7 +215,9 @@ __global__ void __launch_bounds__(256, 3) gn_act_bwd_reduce(const __nv_bfloat16 
                 float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
                 if (DROP) dz *= m[u];
                 q1[u] += dz; q2[u] = fmaf(dz, f[u], q2[u]);
+                g[u] = dz;
             }
+            *reinterpret_cast<uint4 *>(db + p * ld_dz) = pack8(g);
             unpack8(xc, f); unpack8(gc, g);
             if (DROP) dropout_mask8(seed, offset, (n * sh.HW + p + sh.rows) * sh.C + 8 * q, p_drop, m);
 #pragma unroll
@@ -215,7 +225,9 @@ __global__ void __launch_bounds__(256, 3) gn_act_bwd_reduce(const __nv_bfloat16 
                 float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
                 if (DROP) dz *= m[u];
                 q1[u] += dz; q2[u] = fmaf(dz, f[u], q2[u]);
+                g[u] = dz;
             }
+            *reinterpret_cast<uint4 *>(db + (p + sh.rows) * ld_dz) = pack8(g);
         }
         for (; p < p1; p += sh.rows) {
             float f[8], g[8], m[8];
@@ -227,30 +239,32 @@ __global__ void __launch_bounds__(256, 3) gn_act_bwd_reduce(const __nv_bfloat16 
                 float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
                 if (DROP) dz *= m[u];
                 q1[u] += dz; q2[u] = fmaf(dz, f[u], q2[u]);
+                g[u] = dz;
             }
+            *reinterpret_cast<uint4 *>(db + p * ld_dz) = pack8(g);
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            atomicAdd(&qs[(8 * q + u) * 2], q1[u]);
-            atomicAdd(&qs[(8 * q + u) * 2 + 1], q2[u]);
-        }
+        float4 *dst = reinterpret_cast<float4 *>(part + (size_t)threadIdx.x * 16);
+        dst[0] = make_float4(q1[0], q1[1], q1[2], q1[3]); dst[1] = make_float4(q1[4], q1[5], q1[6], q1[7]);
+        dst[2] = make_float4(q2[0], q2[1], q2[2], q2[3]); dst[3] = make_float4(q2[4], q2[5], q2[6], q2[7]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) atomicAdd(Q + n * sh.C * 2 + i, qs[i]);
+    // channel c = 8q+u: sum over the `rows` threads that own chunk q, then one global atomic per (c, kind)
+    for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) {
+        const int c = i >> 1, kind = i & 1, cq = c >> 3, u = c & 7;
+        float acc = 0.f;
+        for (int rr = 0; rr < sh.rows; ++rr) acc += part[(size_t)(rr * sh.chunks + cq) * 16 + kind * 8 + u];
+        atomicAdd(Q + (n * sh.C + c) * 2 + kind, acc);
+    }
 }
 
 // backward pass 2.  With Q1 = sum dz, Q2x = sum dz*x per (n,c):  sum dz*xhat = rstd*(Q2x - mean*Q1), and
 //   dx = rstd*(dz*gs - m1 - xhat*m2) = dz*P + x*Qc + R     (P, Qc, R per channel; gs = gamma*(1+scale))
-// so the streaming loop is act' + three fmas per element.
-template <int ACT, bool DROP>
-__global__ void __launch_bounds__(256, 3) gn_act_bwd_apply(const __nv_bfloat16 *__restrict__ gy, int64_t ld_gy,
-                                                          const __nv_bfloat16 *__restrict__ x, int64_t ld_x, Shape sh,
+// dz is read back from the gx buffer (written by pass 1) and overwritten in place: three fmas per element.
+__global__ void __launch_bounds__(256, 4) gn_act_bwd_apply(const __nv_bfloat16 *__restrict__ x, int64_t ld_x, Shape sh,
                                                           const float *__restrict__ stats, const float *__restrict__ gamma,
                                                           const float *__restrict__ beta, const float *__restrict__ scale,
-                                                          const float *__restrict__ shift, float eps, float p_drop,
-                                                          uint64_t seed, uint64_t offset, const uint64_t *__restrict__ off_dev,
-                                                          const float *__restrict__ Q,
-                                                          __nv_bfloat16 *__restrict__ gx, int64_t ld_gx, int accumulate,
+                                                          float eps, const float *__restrict__ Q,
+                                                          __nv_bfloat16 *__restrict__ gx, int64_t ld_gx,
                                                           float *__restrict__ dgamma, float *__restrict__ dbeta,
                                                           float *__restrict__ dscale, float *__restrict__ dshift) {
     extern __shared__ float sg[];   // [G][2]: sum_c gs*Q1, sum_c gs*(sum dz*xhat)
@@ -279,8 +293,6 @@ __global__ void __launch_bounds__(256, 3) gn_act_bwd_apply(const __nv_bfloat16 *
     __syncthreads();
     const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
     if (r >= sh.rows) return;
-    const Coef k = make_coef(sh, n, q, stats, gamma, beta, scale, shift, eps);
-    if (DROP && off_dev) offset += __ldg(off_dev);
     float P[8], Qc[8], R[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -296,22 +308,31 @@ __global__ void __launch_bounds__(256, 3) gn_act_bwd_apply(const __nv_bfloat16 *
     const int64_t p0 = (int64_t)blockIdx.x * sh.pix_per_cta;
     int64_t p1 = p0 + sh.pix_per_cta;
     if (p1 > sh.HW) p1 = sh.HW;
-    for (int64_t p = p0 + r; p < p1; p += sh.rows) {
-        const int64_t pix = n * sh.HW + p;
-        float f[8], g[8], m[8], o[8];
-        const uint4 xv = ld_stream_u4(reinterpret_cast<const uint4 *>(x + pix * ld_x + 8 * q));
-        const uint4 gv = ld_stream_u4(reinterpret_cast<const uint4 *>(gy + pix * ld_gy + 8 * q));
-        unpack8(xv, f); unpack8(gv, g);
-        if (DROP) dropout_mask8(seed, offset, pix * sh.C + 8 * q, p_drop, m);
-        if (accumulate) unpack8(*reinterpret_cast<const uint4 *>(gx + pix * ld_gx + 8 * q), o);
+    const __nv_bfloat16 *xb = x + n * sh.HW * ld_x + 8 * q;
+    __nv_bfloat16 *gb = gx + n * sh.HW * ld_gx + 8 * q;
+    int64_t p = p0 + r;
+    for (; p + sh.rows < p1; p += 2 * sh.rows) {
+        const uint4 xa = ld_stream_u4(reinterpret_cast<const uint4 *>(xb + p * ld_x));
+        const uint4 da = *reinterpret_cast<const uint4 *>(gb + p * ld_gx);
+        const uint4 xc = ld_stream_u4(reinterpret_cast<const uint4 *>(xb + (p + sh.rows) * ld_x));
+        const uint4 dc = *reinterpret_cast<const uint4 *>(gb + (p + sh.rows) * ld_gx);
+        float f[8], d[8];
+        unpack8(xa, f); unpack8(da, d);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
-            if (DROP) dz *= m[u];
-            const float dx = fmaf(dz, P[u], fmaf(f[u], Qc[u], R[u]));
-            o[u] = accumulate ? o[u] + dx : dx;
-        }
-        *reinterpret_cast<uint4 *>(gx + pix * ld_gx + 8 * q) = pack8(o);
+        for (int u = 0; u < 8; ++u) d[u] = fmaf(d[u], P[u], fmaf(f[u], Qc[u], R[u]));
+        *reinterpret_cast<uint4 *>(gb + p * ld_gx) = pack8(d);
+        unpack8(xc, f); unpack8(dc, d);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = fmaf(d[u], P[u], fmaf(f[u], Qc[u], R[u]));
+        *reinterpret_cast<uint4 *>(gb + (p + sh.rows) * ld_gx) = pack8(d);
+    }
+    for (; p < p1; p += sh.rows) {
+        float f[8], d[8];
+        unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(xb + p * ld_x)), f);
+        unpack8(*reinterpret_cast<const uint4 *>(gb + p * ld_gx), d);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = fmaf(d[u], P[u], fmaf(f[u], Qc[u], R[u]));
+        *reinterpret_cast<uint4 *>(gb + p * ld_gx) = pack8(d);
     }
 }
 
@@ -404,20 +425,19 @@ int ub200_gn_act_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int
     UB_REQUIRE(ld_x % 8 == 0 && ld_gy % 8 == 0 && ld_gx % 8 == 0 && ld_x >= C && ld_gy >= C && ld_gx >= C &&
                    ub::aligned16(x) && ub::aligned16(gy) && ub::aligned16(gx),
                UB200_E_UNSUPPORTED);
+    UB_REQUIRE(accumulate == 0, UB200_E_UNSUPPORTED);     // pass 1 parks dz in the gx buffer
     cudaStream_t s = ub::as_stream(stream);
     cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(float) * 2 * N * C, s);
     if (e != cudaSuccess) return (int)e;
     const bool drop = dropout_p > 0.f;
     const __nv_bfloat16 *gyp = reinterpret_cast<const __nv_bfloat16 *>(gy), *xp = reinterpret_cast<const __nv_bfloat16 *>(x);
+    __nv_bfloat16 *gxp = reinterpret_cast<__nv_bfloat16 *>(gx);
     DISPATCH_ACT_DROP(gn_act_bwd_reduce, act, drop,
-                      <<<grid, 256, 2 * C * sizeof(float), s>>>(gyp, ld_gy, xp, ld_x, sh, stats, gamma, beta, scale, shift, eps, dropout_p,
-                                            seed, offset, offset_dev, ws));
+                      <<<grid, 256, 256 * 16 * sizeof(float), s>>>(gyp, ld_gy, xp, ld_x, sh, stats, gamma, beta, scale, shift,
+                                                                   eps, dropout_p, seed, offset, offset_dev, gxp, ld_gx, ws));
     UB_LAUNCH_CHECK();
-    DISPATCH_ACT_DROP(gn_act_bwd_apply, act, drop,
-                      <<<grid, 256, 2 * G * sizeof(float), s>>>(gyp, ld_gy, xp, ld_x, sh, stats, gamma, beta, scale, shift,
-                                                                eps, dropout_p, seed, offset, offset_dev, ws,
-                                                                reinterpret_cast<__nv_bfloat16 *>(gx), ld_gx, accumulate,
-                                                                dgamma, dbeta, dscale, dshift));
+    gn_act_bwd_apply<<<grid, 256, 2 * G * sizeof(float), s>>>(xp, ld_x, sh, stats, gamma, beta, scale, eps, ws, gxp, ld_gx,
+                                                             dgamma, dbeta, dscale, dshift);
     UB_LAUNCH_CHECK();
     return UB200_OK;
 }
