@@ -22,6 +22,7 @@
 //
 // Replaces nn.Conv2d forward/backward-data at diff_cifar/model.py:69,:133,:143,:146,:396;
 // diff_mnist/torch_ddpm/ddpm/models/unet/layers.py:286,:300,:305-312; pdearena twod_unetbase.py:19-24.
+#include <cstdlib>
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -37,7 +38,8 @@ struct FpropParams {
     int msub;                         // pixel tiles per CTA tile (2 when Cout <= 128: both share one weight tile)
     int Cin, cblocks, taps, kb_main, kb_extra, stages;
     uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, tbl_bytes;
-    int cluster_tiles;                // (channel tile, pixel-tile pair) units walked by one CTA pair
+    int cluster_tiles;                // (channel tile, pixel-tile group) units walked by one cluster
+    int cluster;                      // CTAs per cluster: 1, or 2 with weight multicast
     const float *bias, *rowadd;
     const __nv_bfloat16 *residual; int64_t ld_res;
     int has_out;                      // bf16 NHWC output through the TMA store
@@ -48,7 +50,9 @@ constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr uint32_t kStagingBytes = 128 * 64 * 2;      // one [128 pixels][64 channels] bf16 box
 constexpr int kTblRows = 8;                           // addend table: up to 8 samples per pixel tile
-constexpr int kCluster = 2;                           // CTA pair: the weight tile is loaded once and multicast to both
+// Optional CTA pair (cluster of 2): the weight tile is fetched once from L2 and multicast to both CTAs.  Measured
+// neutral-to-negative on B200 for these shapes: the kernel is bound by shared-memory bandwidth (tensor-core operand
+// reads + TMA writes), which multicast does not reduce; kept selectable (UB200_FPROP_CLUSTER=2) for the 2-CTA MMA work.
 
 template <int BK>
 __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_a,
@@ -78,28 +82,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         prefetch_tmap(&tm_w);
         if (p.kb_extra) { prefetch_tmap(&tm_a2); prefetch_tmap(&tm_w2); }
         if (p.has_out) prefetch_tmap(&tm_out);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kCluster); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, p.cluster); }
         for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();               // the peer multicasts into our smem and arrives on our barriers: both must be ready
+    if (p.cluster > 1) cluster_sync_all();   // the peer multicasts into our smem and arrives on our barriers
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int crank = (int)cluster_ctarank();
+    const int kCluster = p.cluster;
+    const int crank = kCluster > 1 ? (int)cluster_ctarank() : 0;
     const int cluster_id = blockIdx.x / kCluster, num_clusters = gridDim.x / kCluster;
     // this CTA's m unit of cluster tile ct:  (ct / n_tiles) * kCluster + crank   (may lie past the end: zero tile)
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (one thread; address arithmetic strength-reduced: no div/mod per k-block)
         if (lane == 0) {
             const uint32_t tx_bytes = (uint32_t)p.msub * 128u * BK * 2u + (uint32_t)p.BN * BK * 2u;
             const int half = p.BN / kCluster;                 // weight rows this CTA fetches for the pair
-            uint32_t it = 0;                                  // running k-block counter across tiles
+            const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b) + (uint32_t)(crank * half * (BK * 2));
+            const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+            const int cow = crank * half;
+            int s = 0; uint32_t ph = 0;                       // ring position, carried across tiles
             for (int ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
-                const int nt = ct % p.n_tiles, co0 = nt * p.BN;
+                const int nt = ct % p.n_tiles, co0 = nt * p.BN + cow;
                 int x0[2], y0[2], n0[2];
                 for (int sub = 0; sub < p.msub; ++sub) {
                     int mt = ((ct / p.n_tiles) * kCluster + crank) * p.msub + sub;
@@ -107,27 +115,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                     y0[sub] = (mt % p.tiles_h) * p.BH; mt /= p.tiles_h;
                     n0[sub] = mt * p.BNI;                     // past the batch for a padded trailing tile: TMA zero-fills
                 }
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1u;
-                    mbar_wait(empty + s, ph ^ 1u);
-                    mbar_arrive_expect_tx(full + s, tx_bytes);
-                    uint8_t *dst_a = smem_a + (size_t)s * p.a_stage_bytes;
-                    uint8_t *dst_b = smem_b + (size_t)s * p.b_stage_bytes;
-                    if (kb < p.kb_main) {
-                        const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-                        const int ky = p.taps == 9 ? tap / 3 - 1 : 0, kx = p.taps == 9 ? tap % 3 - 1 : 0;
-                        for (int sub = 0; sub < p.msub; ++sub)
-                            tma_load_4d(dst_a + sub * (128 * BK * 2), &tm_a, full + s, cb * BK, x0[sub] + kx, y0[sub] + ky, n0[sub]);
-                        tma_load_2d_mcast(dst_b + crank * half * (BK * 2), &tm_w, full + s, tap * p.Cin + cb * BK,
-                                          co0 + crank * half, (uint16_t)0x3);
-                    } else {
-                        const int cb = kb - p.kb_main;
-                        for (int sub = 0; sub < p.msub; ++sub)
-                            tma_load_4d(dst_a + sub * (128 * BK * 2), &tm_a2, full + s, cb * BK, x0[sub], y0[sub], n0[sub]);
-                        tma_load_2d_mcast(dst_b + crank * half * (BK * 2), &tm_w2, full + s, cb * BK, co0 + crank * half,
-                                          (uint16_t)0x3);
+                const int kdim = p.taps == 9 ? 3 : 1;
+                int wk = 0;                                   // K coordinate into the packed weights: tap * Cin + cb * BK
+                for (int ky = 0; ky < kdim; ++ky)
+                    for (int kx = 0; kx < kdim; ++kx) {
+                        const int dy = kdim == 3 ? ky - 1 : 0, dx = kdim == 3 ? kx - 1 : 0;
+                        for (int c = 0; c < p.Cin; c += BK, wk += BK) {
+                            const uint32_t fb = full0 + 8u * s, sa = a0 + (uint32_t)s * p.a_stage_bytes;
+                            mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
+                            mbar_arrive_expect_tx_a(fb, tx_bytes);
+                            tma_load_4d_a(sa, &tm_a, fb, c, x0[0] + dx, y0[0] + dy, n0[0]);
+                            if (p.msub == 2) tma_load_4d_a(sa + 128 * BK * 2, &tm_a, fb, c, x0[1] + dx, y0[1] + dy, n0[1]);
+                            if (kCluster > 1) tma_load_2d_mcast_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w, fb, wk, co0, (uint16_t)0x3);
+                            else tma_load_2d_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w, fb, wk, co0);
+                            if (++s == p.stages) { s = 0; ph ^= 1u; }
+                        }
                     }
+                for (int c = 0; c < p.kb_extra * BK; c += BK) {   // K slices of the fused 1x1 term
+                    const uint32_t fb = full0 + 8u * s, sa = a0 + (uint32_t)s * p.a_stage_bytes;
+                    mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
+                    mbar_arrive_expect_tx_a(fb, tx_bytes);
+                    tma_load_4d_a(sa, &tm_a2, fb, c, x0[0], y0[0], n0[0]);
+                    if (p.msub == 2) tma_load_4d_a(sa + 128 * BK * 2, &tm_a2, fb, c, x0[1], y0[1], n0[1]);
+                    if (kCluster > 1) tma_load_2d_mcast_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w2, fb, c, co0, (uint16_t)0x3);
+                    else tma_load_2d_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w2, fb, c, co0);
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -137,28 +149,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
             const uint32_t idesc = make_idesc(128, p.BN, 0, 0);
             constexpr uint32_t swz = swizzle_code(BK * 2);
             constexpr uint32_t sbo = 8u * BK * 2u;
-            uint32_t it = 0, local = 0;
+            // descriptors differ between stages / k-steps only in the 14-bit start-address field (units of 16 bytes)
+            const uint64_t da0 = make_smem_desc(smem_u32(smem_a), 16, sbo, swz);
+            const uint64_t db0 = make_smem_desc(smem_u32(smem_b), 16, sbo, swz);
+            const uint32_t a_step = p.a_stage_bytes >> 4, b_step = p.b_stage_bytes >> 4;
+            const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+            int s = 0; uint32_t ph = 0, local = 0;
             for (int ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, ++local) {
                 const uint32_t acc = local & 1u, use = local >> 1;
                 mbar_wait(tmem_empty + acc, (use & 1u) ^ 1u);          // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)(p.msub * p.BN);
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (it / p.stages) & 1u;
-                    mbar_wait(full + s, ph);
+                uint32_t accum = 0;                                    // first MMA of the tile overwrites
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_a(full0 + 8u * s, ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + (size_t)s * p.a_stage_bytes);
-                    const uint32_t b_addr = smem_u32(smem_b + (size_t)s * p.b_stage_bytes);
-                    for (int sub = 0; sub < p.msub; ++sub) {
+                    const uint64_t da = da0 + (uint64_t)(s * a_step), db = db0 + (uint64_t)(s * b_step);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            const uint64_t da = make_smem_desc(a_addr + sub * (128 * BK * 2) + k * 32, 16, sbo, swz);
-                            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, sbo, swz);
-                            umma_bf16(d_tmem + sub * (uint32_t)p.BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                        }
+                    for (int k = 0; k < BK / 16; ++k) {
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                        accum = 1;
                     }
-                    umma_commit_mcast(empty + s, (uint16_t)0x3);       // slot reusable once BOTH CTAs' MMAs have read it
+                    if (p.msub == 2) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16(d_tmem + (uint32_t)p.BN, da + (128 * BK * 2 / 16) + 2 * k, db + 2 * k, idesc, kb | k ? 1u : 0u);
+                    }
+                    if (kCluster > 1) umma_commit_mcast_a(empty0 + 8u * s, (uint16_t)0x3);   // both CTAs' MMAs must have read it
+                    else umma_commit_a(empty0 + 8u * s);                                     // slot reusable once read
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
                 umma_commit(tmem_full + acc);                          // accumulator complete
             }
@@ -299,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();               // nobody exits while the peer may still write our smem / arrive on our barriers
+    if (p.cluster > 1) cluster_sync_all();   // nobody exits while the peer may still write our smem / barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, p.tmem_cols);
@@ -350,7 +369,7 @@ int launch_fprop(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = (unsigned)p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BK>, ta, tw, ta2, tw2, tout, p);
     if (e != cudaSuccess) return (int)e;
@@ -388,8 +407,11 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     const int m_tiles = p.tiles_w * p.tiles_h * ((p.N + p.BNI - 1) / p.BNI);
     // channel tile: as wide as possible (up to 256 TMEM columns per accumulator) while the tile list still fills
     // most of the 148 SMs; narrow tiles re-read A and make the single-thread MMA issue rate the limit
+    static const int env_bn = [] { const char *e = getenv("UB200_FPROP_BN"); return e ? atoi(e) : 0; }();
+    static const int env_stages = [] { const char *e = getenv("UB200_FPROP_STAGES"); return e ? atoi(e) : 0; }();
     int bn_max = 256;
-    while (bn_max > 64 && (int64_t)m_tiles * ((cout_pad + bn_max - 1) / bn_max) < 120) bn_max >>= 1;
+    if (env_bn) bn_max = env_bn;
+    else while (bn_max > 64 && (int64_t)m_tiles * ((cout_pad + bn_max - 1) / bn_max) < 120) bn_max >>= 1;
     p.n_tiles = (int)((cout_pad + bn_max - 1) / bn_max);
     // several channel tiles: keep BN a multiple of the 64-channel store box so no tile writes columns it did not
     // compute; a single tile may be any multiple of 16 (columns past Cout fall outside the tensor and are clipped)
@@ -397,7 +419,11 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     p.m_tiles = m_tiles;
     // narrow outputs (one channel tile of <= 128): two pixel tiles share each weight tile (halves the weight traffic
     // per MAC and the k-block count per MAC); 4 accumulators x BN <= 512 TMEM columns
-    p.msub = (p.n_tiles == 1 && p.BN <= 128 && m_tiles >= 2 * ub::kSMs) ? 2 : 1;
+    static const int env_cluster = [] { const char *e = getenv("UB200_FPROP_CLUSTER"); return e ? atoi(e) : 1; }();
+    static const int env_msub = [] { const char *e = getenv("UB200_FPROP_MSUB"); return e ? atoi(e) : 1; }();
+    p.cluster = env_cluster == 2 ? 2 : 1;
+    const int kCluster = p.cluster;
+    p.msub = (env_msub == 2 && p.n_tiles == 1 && p.BN <= 128 && m_tiles >= 2 * ub::kSMs) ? 2 : 1;
     const int m_units = (m_tiles + p.msub - 1) / p.msub;
     p.num_tiles = m_units * p.n_tiles;
     p.cluster_tiles = ((m_units + kCluster - 1) / kCluster) * p.n_tiles;
@@ -413,6 +439,7 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     const uint32_t budget = 227u * 1024u - 1024u - 2u * kStagingBytes - p.tbl_bytes - 256u;
     int stages = (int)(budget / stage);
     if (stages > 8) stages = 8;
+    if (env_stages && stages > env_stages) stages = env_stages;
     if (stages < 2) stages = 2;
     p.stages = stages;
     p.tmem_cols = pow2_at_least(2u * (uint32_t)(p.msub * p.BN), 32);

@@ -75,51 +75,61 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     const uint32_t g_chunk_bytes = kPix * p.cw_g * 2, a_chunk_bytes = kPix * p.cw_a * 2;
 
     if (warp == 0) {
+        // ===================== TMA producer (one thread; no div/mod per stage) =====================
         if (lane == 0) {
             const uint32_t tx_bytes = chunks_g * g_chunk_bytes + p.ntaps * chunks_a * a_chunk_bytes;
+            const uint32_t base = smem_u32(smem), full0 = smem_u32(full), empty0 = smem_u32(empty);
+            // first pixel tile of this split, then advance (x fastest, then y, then image group) incrementally
+            int pt = pt0;
+            int tw = pt % p.tiles_w; pt /= p.tiles_w;
+            int th = pt % p.tiles_h; pt /= p.tiles_h;
+            int tn = pt;
+            const int ky = p.ksize == 3 ? kyg - 1 : 0;
+            int s = 0; uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                int pt = pt0 + it;
-                const int tw = pt % p.tiles_w; pt /= p.tiles_w;
-                const int th = pt % p.tiles_h; pt /= p.tiles_h;
-                const int x0 = tw * p.BW, y0 = th * p.BH, n0 = pt * p.BNI;
-                mbar_wait(empty + s, ph ^ 1u);
-                mbar_arrive_expect_tx(full + s, tx_bytes);
-                uint8_t *sg = smem + (size_t)s * stage_bytes;
+                const int x0 = tw * p.BW, y0 = th * p.BH, n0 = tn * p.BNI;
+                const uint32_t fb = full0 + 8u * s, sg = base + (uint32_t)s * stage_bytes;
+                mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
+                mbar_arrive_expect_tx_a(fb, tx_bytes);
                 for (int c = 0; c < chunks_g; ++c)
-                    tma_load_4d(sg + c * g_chunk_bytes, &tm_g, full + s, co0 + c * p.cw_g, x0, y0, n0);
+                    tma_load_4d_a(sg + c * g_chunk_bytes, &tm_g, fb, co0 + c * p.cw_g, x0, y0, n0);
                 for (int tp = 0; tp < p.ntaps; ++tp) {
-                    const int ky = p.ksize == 3 ? kyg - 1 : 0, kx = p.ksize == 3 ? tp - 1 : 0;
-                    uint8_t *sa = sg + p.g_stage_bytes + tp * p.a_tap_bytes;
+                    const int kx = p.ksize == 3 ? tp - 1 : 0;
+                    const uint32_t sa = sg + p.g_stage_bytes + tp * p.a_tap_bytes;
                     for (int c = 0; c < chunks_a; ++c)
-                        tma_load_4d(sa + c * a_chunk_bytes, &tm_a, full + s, ci0 + c * p.cw_a, x0 + kx, y0 + ky, n0);
+                        tma_load_4d_a(sa + c * a_chunk_bytes, &tm_a, fb, ci0 + c * p.cw_a, x0 + kx, y0 + ky, n0);
                 }
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+                if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
             }
         }
     } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(128, ncols, 1, 1);
             const uint32_t swz_g = swizzle_code(p.cw_g * 2), swz_a = swizzle_code(p.cw_a * 2);
             const uint32_t row_g = p.cw_g * 2, row_a = p.cw_a * 2;
+            const uint32_t base = smem_u32(smem), full0 = smem_u32(full), empty0 = smem_u32(empty);
+            const uint64_t dg0 = make_smem_desc(base, g_chunk_bytes, 8 * row_g, swz_g);
+            const uint64_t da0 = make_smem_desc(base + p.g_stage_bytes, a_chunk_bytes, 8 * row_a, swz_a);
+            const uint32_t kstep_g = (16 * row_g) >> 4, kstep_a = (16 * row_a) >> 4, tap_step = p.a_tap_bytes >> 4;
+            const uint32_t stage_step = stage_bytes >> 4;
+            int s = 0; uint32_t ph = 0, accum = 0;
             for (int it = 0; it < iters; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                mbar_wait(full + s, ph);
+                mbar_wait_a(full0 + 8u * s, ph);
                 tc_fence_after();
-                const uint32_t g_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t dg = dg0 + (uint64_t)(s * stage_step), da = da0 + (uint64_t)(s * stage_step);
                 for (int tp = 0; tp < p.ntaps; ++tp) {
-                    const uint32_t a_addr = g_addr + p.g_stage_bytes + tp * p.a_tap_bytes;
 #pragma unroll
-                    for (int k = 0; k < kPix / 16; ++k) {
-                        const uint64_t da = make_smem_desc(g_addr + k * 16 * row_g, g_chunk_bytes, 8 * row_g, swz_g);
-                        const uint64_t db = make_smem_desc(a_addr + k * 16 * row_a, a_chunk_bytes, 8 * row_a, swz_a);
-                        umma_bf16(tmem_base + tp * 128, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < kPix / 16; ++k)
+                        umma_bf16(tmem_base + tp * 128, dg + k * kstep_g, da + tp * tap_step + k * kstep_a, idesc,
+                                  (accum | (uint32_t)k) != 0 ? 1u : 0u);
                 }
-                umma_commit(empty + s);
-                if (it == iters - 1) umma_commit(tmem_full);
+                accum = 1;
+                umma_commit_a(empty0 + 8u * s);
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
+            if (iters > 0) umma_commit(tmem_full);
         }
     } else if (iters > 0) {
         const int qd = warp & 3;
