@@ -420,7 +420,7 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     // narrow outputs (one channel tile of <= 128): two pixel tiles share each weight tile (halves the weight traffic
     // per MAC and the k-block count per MAC); 4 accumulators x BN <= 512 TMEM columns
     static const int env_cluster = [] { const char *e = getenv("UB200_FPROP_CLUSTER"); return e ? atoi(e) : 1; }();
-    static const int env_msub = [] { const char *e = getenv("UB200_FPROP_MSUB"); return e ? atoi(e) : 1; }();
+    static const int env_msub = [] { const char *e = getenv("UB200_FPROP_MSUB"); return e ? atoi(e) : 2; }();
     p.cluster = env_cluster == 2 ? 2 : 1;
     const int kCluster = p.cluster;
     p.msub = (env_msub == 2 && p.n_tiles == 1 && p.BN <= 128 && m_tiles >= 2 * ub::kSMs) ? 2 : 1;
