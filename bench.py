@@ -148,7 +148,7 @@ class KernelTimer:
 
         def timed(*a):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda._sleep(30000)      # keep the GPU busy ~15 us so the launch below is queued before e0 fires:
+            torch.cuda._sleep(200000)     # keep the GPU busy ~100 us so the launch below is queued before e0 fires:
             e0.record()                   # the interval is then kernel execution, not host launch latency
             out = fn(*a)
             e1.record()

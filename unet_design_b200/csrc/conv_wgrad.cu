@@ -282,7 +282,9 @@ int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a
     p.ntaps = ksize == 3 ? 3 : 1;
     const int co_tiles = (int)((Cout + 127) / 128);
     const int out_tiles = p.ci_tiles * p.ky_groups * co_tiles;
-    int splits = (2 * ub::kSMs + out_tiles - 1) / out_tiles;
+    // one CTA per SM (the smem ring takes the whole SM): keep the grid within ONE wave of 148 CTAs so there is no
+    // tail wave, and give every split the same number of pixel tiles
+    int splits = ub::kSMs / out_tiles;
     if (splits > p.pix_tiles) splits = p.pix_tiles;
     if (splits < 1) splits = 1;
     p.tiles_per_split = (p.pix_tiles + splits - 1) / splits;

@@ -33,6 +33,18 @@ from . import ops
 from .diff_cifar.diffusion import GaussianDiffusionTrainer
 
 
+class _Tf32Matmul:
+    """fp32 nn.Linear layers of the time-embedding path (tiny GEMMs, otherwise run as SIMT sgemm) on TF32 tensor
+    cores for the duration of the step; the caller's global setting is restored afterwards."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
 class FlatArena:
     """Trainable parameters of `model` re-homed into one flat fp32 buffer (and a matching gradient buffer).
     Conv weights (4-D) keep channels_last order: the arena slice is viewed as [Cout,kh,kw,Cin] and permuted."""
@@ -213,8 +225,9 @@ class DDPMTrainStep:
         self._hooks_live = overlap
         if overlap:
             self._arm_buckets()
-        loss, _ = self.trainer(x0)
-        loss.backward()
+        with _Tf32Matmul():
+            loss, _ = self.trainer(x0)
+            loss.backward()
         return loss.detach()
 
     def _reduce_and_update(self, overlapped: bool):
