@@ -211,7 +211,10 @@ def haar_roofline(peaks):
     res["dwtblock_J1_cfg2_128x128x32x32_L2resident"] = timeit(lambda: o.dwtblock_fwd(x2, 1, 128), x2.numel() * 4 * 1.25, reps=50)
     best = res["dwt_4band_1GiB"]
     return {"bound": "hbm", "kernel": "haar_dwt_vec4<true>", "achieved": best["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": best["GBps"] / peaks["hbm_gbs"], "frac_of_8TBps_nominal": best["GBps"] / 8000.0, "traffic": None,
+            "frac": best["GBps"] / peaks["hbm_gbs"], "frac_of_8TBps_nominal": best["GBps"] / 8000.0,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this kernel on this shape
+            # (profiles/r01_ncu_full_haar_raw.csv): 1.0739 GB + 1.0263 GB vs 2.1475 GB algorithmic -> no re-reads
+            "traffic": 2.1002e9, "traffic_source": "profiles/r01_ncu_full_haar_raw.csv",
             "peak_source": peaks["source"], "cases": res}
 
 
@@ -307,7 +310,11 @@ def run_gpu_arm(args):
         peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
         ach = fp["flops"] / (fp["ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "conv_fprop_kernel (fprop + dgrad launches)", "achieved": ach, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None, "launches_per_step": fp["launches"],
+                    "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    # DRAM bytes of the largest launch (256->256 @ 32x32, batch 128) in the ncu --set full capture
+                    # profiles/r01_ncu_full_conv_fprop_v2_raw.csv: 68.4 MB read + 27.4 MB written (67 + 34 MB algorithmic)
+                    "traffic": 95.8e6, "traffic_source": "profiles/r01_ncu_full_conv_fprop_v2_raw.csv (largest launch)",
+                    "launches_per_step": fp["launches"],
                     "flops_per_step": fp["flops"], "ms_per_step": fp["ms"],
                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                     "wgrad": {"achieved": wg["flops"] / (wg["ms"] * 1e-3) / 1e12, "launches_per_step": wg["launches"],

@@ -283,6 +283,37 @@ __global__ void __launch_bounds__(256) dwtblock_bwd_any(const float *__restrict_
     }
 }
 
+// backward fast path, J = 1, W % 8 == 0, H even, aligned: one work item = 4 coefficient columns of one coefficient
+// row -> 2 input rows x 8 floats.  Every coefficient's gradient is read once (float4) instead of four times.
+__global__ void __launch_bounds__(256) dwtblock_bwd_j1_vec4(const float *__restrict__ g, int64_t N, int C, int H, int W,
+                                                           int out_channels, float *__restrict__ gx) {
+    const int h2 = H >> 1, w2 = W >> 1, wq = w2 >> 2;
+    const int64_t plane_o = (int64_t)h2 * w2;
+    const int64_t items = N * C * h2 * wq;
+    for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int jq = (int)(it % wq);
+        int64_t t = it / wq;
+        const int i = (int)(t % h2);
+        t /= h2;
+        const int c = (int)(t % C);
+        const int64_t n = t / C;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = c; k < out_channels; k += C) {
+            const float4 v = ld_stream(reinterpret_cast<const float4 *>(g + (n * out_channels + k) * plane_o + (int64_t)i * w2 + 4 * jq));
+            acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+        }
+        // same expression as the generic path: (acc * 0.5) then s*(s*.)
+        const float a = mul_s(mul_s(acc.x * 0.5f)), b = mul_s(mul_s(acc.y * 0.5f));
+        const float cc = mul_s(mul_s(acc.z * 0.5f)), d = mul_s(mul_s(acc.w * 0.5f));
+        const float4 lo = make_float4(a, a, b, b), hi = make_float4(cc, cc, d, d);
+        float *dst = gx + ((n * C + c) * H + 2 * i) * (int64_t)W + 8 * jq;
+        st_stream(reinterpret_cast<float4 *>(dst), lo);
+        st_stream(reinterpret_cast<float4 *>(dst) + 1, hi);
+        st_stream(reinterpret_cast<float4 *>(dst + W), lo);
+        st_stream(reinterpret_cast<float4 *>(dst + W) + 1, hi);
+    }
+}
+
 // forward into NHWC bf16 (pixel stride ld): one work item = 8 consecutive output channels of one pixel
 __global__ void __launch_bounds__(256) dwtblock_nhwc_bf16(const float *__restrict__ x, int64_t N, int C, Ext e, int J,
                                                          int out_channels, float scale, const int *__restrict__ chmap,
@@ -475,6 +506,12 @@ int ub200_dwtblock_bwd(const float *gout, int64_t N, int64_t C, int64_t H, int64
     UB_REQUIRE(gout && gx && N > 0 && C > 0 && H > 0 && W > 0 && out_channels > 0, UB200_E_BADARG);
     UB_REQUIRE(J >= 0 && J <= 3 && H < (1 << 30) && W < (1 << 30) && C < (1 << 30) && out_channels < (1 << 30),
                UB200_E_UNSUPPORTED);
+    if (J == 1 && W % 8 == 0 && H % 2 == 0 && ub::aligned16(gout) && ub::aligned16(gx)) {
+        int grid = ub::grid_for(N * C * (H / 2) * (W / 8), 256, 8);
+        dwtblock_bwd_j1_vec4<<<grid, 256, 0, ub::as_stream(stream)>>>(gout, N, (int)C, (int)H, (int)W, (int)out_channels, gx);
+        UB_LAUNCH_CHECK();
+        return UB200_OK;
+    }
     Ext e = make_ext(H, W);
     int grid = ub::grid_for(N * C * H * W, 256, 8);
     dwtblock_bwd_any<<<grid, 256, 0, ub::as_stream(stream)>>>(gout, N, (int)C, e, J, (int)out_channels,
