@@ -154,6 +154,25 @@ int ub200_gn_act_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int
                                float *dgamma, float *dbeta, float *dscale, float *dshift,
                                float *ws, void *stream);
 
+/* Single-pass variants of the three calls above: one thread-block cluster per sample keeps the sample's
+ * slab in distributed shared memory, so x (and gy) are read from HBM once.  forward = statistics + apply
+ * (stats [N,G,2] is an OUTPUT here, kept for the backward); backward = both backward passes.  When the
+ * slab does not fit one cluster (8 CTAs x ~200 KB) they run the multi-pass kernels instead: same results
+ * either way.  stats == NULL ("no normalisation") is only valid for the backward. */
+int ub200_gn_act_fused_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t HW, int64_t C, int G,
+                                     float *stats, float eps, const float *gamma, const float *beta,
+                                     const float *scale, const float *shift, int act,
+                                     float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                                     const void *addend, int64_t ld_add, void *y, int64_t ld_y, void *stream);
+int ub200_gn_act_fused_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int64_t ld_x,
+                                     int64_t N, int64_t HW, int64_t C, int G,
+                                     const float *stats, float eps, const float *gamma, const float *beta,
+                                     const float *scale, const float *shift, int act,
+                                     float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                                     void *gx, int64_t ld_gx,
+                                     float *dgamma, float *dbeta, float *dscale, float *dshift,
+                                     float *ws, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * 3x3 / 1x1 convolution, stride 1, "same" zero padding, as tcgen05/TMEM implicit GEMM fed by TMA
  * (replaces nn.Conv2d fprop / dgrad / wgrad; diff_cifar/model.py:69,:133,:143,:146,:396;

@@ -105,7 +105,10 @@ class EmulatedOps:
         m = self._mask(x.shape, p, seed, off)
         return y * m if m is not None else y
 
-    def gn_act_fwd(self, x, G, stats, eps, gamma, beta, scale, shift, act, p, seed, off, off_dev, addend, y):
+    def gn_act_fwd(self, x, G, stats, eps, gamma, beta, scale, shift, act, p, seed, off, off_dev, addend, y,
+                   compute_stats=False):
+        if compute_stats:
+            self.gn_stats(x, G, stats)
         out = self._gn_forward_fp32(x, G, stats, eps, gamma, beta, scale, shift, act, p, seed, off)
         if addend is not None:
             out = out + addend.float()

@@ -56,7 +56,7 @@ def _gn_ref(x, G, gamma, beta, scale, shift, act, eps=1e-5):
 
 
 @pytest.mark.parametrize("shape,G", [((4, 8, 8, 128), 32), ((2, 32, 32, 384), 32), ((3, 4, 4, 512), 32), ((2, 16, 16, 64), 32),
-                                     ((2, 16, 16, 64), 1), ((2, 25, 13, 16), 1), ((1, 128, 128, 64), 1), ((2, 8, 8, 1024), 1)])
+                                     ((2, 16, 16, 64), 1), ((2, 25, 13, 16), 1), ((3, 32, 32, 128), 32), ((2, 32, 32, 256), 32), ((2, 31, 33, 48), 3), ((1, 128, 128, 64), 1), ((2, 8, 8, 1024), 1)])
 @pytest.mark.parametrize("act", ["silu", "gelu", "none"])
 @pytest.mark.parametrize("scale_shift", [False, True])
 def test_gn_act_forward_backward(ops, shape, G, act, scale_shift):

@@ -9,7 +9,15 @@
 // stats layout: float [N, G, 2] = (sum, sum of squares) over the (C/G)*HW slab; consumers derive
 // mean / rstd (biased variance, eps) themselves, so a producer (this file's stats kernel, or the conv
 // epilogue) only ever accumulates.
-#include "common.cuh"
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+#include <mutex>
+#include <unordered_set>
+
+#include "tc_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 using namespace ub;
@@ -336,6 +344,405 @@ __global__ void __launch_bounds__(256, 4) gn_act_bwd_apply(const __nv_bfloat16 *
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused single-pass variants: one thread-block CLUSTER per sample keeps the sample's slab in (distributed) shared
+// memory, so every tensor crosses HBM once.  forward: read x, write y (2 passes instead of 3) and emit the raw
+// statistics for the backward; backward: read x and gy, write gx (3 passes instead of 6), one launch instead of
+// memset + two kernels.  The slab arrives through bulk async copies (cp.async.bulk -> mbarrier): the whole per-CTA
+// slab is in flight at once, which is what these latency-bound kernels were missing (one 16-byte load per thread
+// per iteration reached ~3 TB/s).  Sums are combined without floating-point shared atomics (those are CAS loops):
+// per-thread partials are folded through an 8 KB staging buffer, then across the cluster through DSMEM.
+// Used when the slab fits one cluster; otherwise the multi-pass kernels above run.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 256;
+constexpr int kFusedFixedBytes = 16 + 8192;      // mbarrier + fold staging (128 x 16 floats)
+constexpr uint32_t kBulkPiece = 16384;           // dense slabs are fetched in pieces of this many bytes
+
+struct FusedShape {
+    int64_t HW; int C, G, cpg, chunks, rows, cs; int64_t pix_per_cta;
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// warp 0 fetches `npx` pixels x C channels (bf16) into a dense smem slab; completion is counted on `bar`
+__device__ __forceinline__ void fetch_slab(uint32_t dst, const __nv_bfloat16 *src, int64_t ld, int C, int npx, uint32_t bar) {
+    const int lane = threadIdx.x;
+    if (ld == C) {                                   // contiguous in HBM: few large pieces
+        const uint32_t total = (uint32_t)npx * (uint32_t)C * 2u;
+        for (uint32_t o = lane * kBulkPiece; o < total; o += 32 * kBulkPiece)
+            bulk_g2s(dst + o, reinterpret_cast<const uint8_t *>(src) + o, min(kBulkPiece, total - o), bar);
+    } else {                                         // a channel slice of a wider buffer: one piece per pixel
+        const uint32_t row = (uint32_t)C * 2u;
+        for (int p = lane; p < npx; p += 32) bulk_g2s(dst + p * row, src + (int64_t)p * ld, row, bar);
+    }
+}
+
+// Sum 16 per-thread values over the threads that share chunk q (all r), for every q: out[2*c + kind], c = 8q+u,
+// value index kind*8+u.  stage: float4[4][128].  Every thread of the CTA must call this (it synchronises).
+__device__ __forceinline__ void cta_channel_sums(const float (&v)[16], float4 *stage, float *out, const FusedShape &sh,
+                                                 int q, int r) {
+    const int half = (sh.rows + 1) >> 1;
+    float w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = v[i];
+    if (r >= half && r < sh.rows) {
+        const int idx = (r - half) * sh.chunks + q;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) stage[k * 128 + idx] = make_float4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    }
+    __syncthreads();
+    if (r < half && r + half < sh.rows) {
+        const int idx = r * sh.chunks + q;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 t = stage[k * 128 + idx];
+            w[4 * k] += t.x; w[4 * k + 1] += t.y; w[4 * k + 2] += t.z; w[4 * k + 3] += t.w;
+        }
+    }
+    __syncthreads();
+    if (r < half) {
+        const int idx = r * sh.chunks + q;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) stage[k * 128 + idx] = make_float4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    }
+    __syncthreads();
+    const float *sf = reinterpret_cast<const float *>(stage);
+    for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) {     // i = (k*chunks + cq)*4 + j: conflict-free reads
+        const int j = i & 3, cq = (i >> 2) % sh.chunks, k = (i >> 2) / sh.chunks;
+        float acc = 0.f;
+        for (int rr = 0; rr < half; ++rr) acc += sf[(k * 128 + rr * sh.chunks + cq) * 4 + j];
+        const int val = 4 * k + j;
+        out[2 * (8 * cq + (val & 7)) + (val >> 3)] = acc;
+    }
+    __syncthreads();
+}
+
+template <int ACT, bool DROP>
+__global__ void __launch_bounds__(kFusedThreads) gn_fused_fwd_kernel(
+    const __nv_bfloat16 *__restrict__ x, int64_t ld_x, FusedShape sh, float *__restrict__ stats_out, float eps,
+    const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ scale,
+    const float *__restrict__ shift, float p_drop, uint64_t seed, uint64_t offset, const uint64_t *__restrict__ off_dev,
+    const __nv_bfloat16 *__restrict__ addend, int64_t ld_add, __nv_bfloat16 *__restrict__ y, int64_t ld_y) {
+    extern __shared__ __align__(128) uint8_t fsm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int64_t n = blockIdx.x / sh.cs;
+    const int gpad = (2 * sh.G + 3) & ~3;
+    float4 *stage = reinterpret_cast<float4 *>(fsm + 16);
+    float *chan = reinterpret_cast<float *>(fsm + kFusedFixedBytes);       // [C][2] this CTA
+    float *cta_gs = chan + 2 * sh.C;                                       // [G][2] this CTA
+    float *tot_gs = cta_gs + gpad;                                         // [G][2] whole sample
+    uint4 *xs = reinterpret_cast<uint4 *>(tot_gs + gpad);                  // [pix][chunks]
+    const uint32_t bar = tc::smem_u32(fsm);
+    const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
+    const int64_t p0 = (int64_t)rank * sh.pix_per_cta;
+    const int npx = (int)(min(p0 + sh.pix_per_cta, sh.HW) - p0);
+    if (threadIdx.x == 0) {
+        tc::mbar_init(reinterpret_cast<uint64_t *>(fsm), 1);
+        tc::fence_barrier_init();
+        tc::mbar_arrive_expect_tx_a(bar, (uint32_t)npx * (uint32_t)sh.C * 2u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) fetch_slab(tc::smem_u32(xs), x + (n * sh.HW + p0) * ld_x, ld_x, sh.C, npx, bar);
+    // per-channel affine parameters travel while the slab is in flight
+    float ga[8], be[8];
+    const bool active = r < sh.rows;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int c = 8 * q + u;
+        const float g0 = (active && gamma) ? __ldg(gamma + c) : 1.f, b0 = (active && beta) ? __ldg(beta + c) : 0.f;
+        const float sc = (active && scale) ? 1.f + __ldg(scale + n * sh.C + c) : 1.f;
+        const float sf = (active && shift) ? __ldg(shift + n * sh.C + c) : 0.f;
+        ga[u] = g0 * sc; be[u] = fmaf(b0, sc, sf);                         // y = act(xhat*ga + be)
+    }
+    if (DROP && off_dev) offset += __ldg(off_dev);
+    tc::mbar_wait_a(bar, 0);
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = 0.f;
+    if (active) {
+        for (int p = r; p < npx; p += sh.rows) {
+            float f[8];
+            unpack8(xs[p * sh.chunks + q], f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { v[u] += f[u]; v[8 + u] = fmaf(f[u], f[u], v[8 + u]); }
+        }
+    }
+    cta_channel_sums(v, stage, chan, sh, q, r);
+    for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) {
+        const int g = i >> 1, kind = i & 1;
+        float acc = 0.f;
+        for (int c = g * sh.cpg; c < (g + 1) * sh.cpg; ++c) acc += chan[2 * c + kind];
+        cta_gs[i] = acc;
+    }
+    cluster.sync();
+    for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) {
+        float acc = 0.f;
+        for (int rk = 0; rk < sh.cs; ++rk) acc += cluster.map_shared_rank(cta_gs, rk)[i];
+        tot_gs[i] = acc;
+        if (rank == 0) stats_out[n * 2 * sh.G + i] = acc;                   // raw sums: what the backward consumes
+    }
+    cluster.sync();                                                         // peers are done reading our cta_gs
+    if (!active) return;
+    const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
+    float A[8], B[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int g = (8 * q + u) / sh.cpg;
+        const float mean = tot_gs[2 * g] * inv_cnt;
+        const float var = fmaxf(tot_gs[2 * g + 1] * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        A[u] = rstd * ga[u];
+        B[u] = fmaf(-mean, A[u], be[u]);
+    }
+    __nv_bfloat16 *yb = y + (n * sh.HW + p0) * ld_y + 8 * q;
+    const __nv_bfloat16 *ab = addend ? addend + (n * sh.HW + p0) * ld_add + 8 * q : nullptr;
+#pragma unroll 2
+    for (int p = r; p < npx; p += sh.rows) {
+        float f[8];
+        unpack8(xs[p * sh.chunks + q], f);
+        float m[8];
+        if (DROP) dropout_mask8(seed, offset, (n * sh.HW + p0 + p) * sh.C + 8 * q, p_drop, m);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            f[u] = act_fwd<ACT>(fmaf(f[u], A[u], B[u]));
+            if (DROP) f[u] *= m[u];
+        }
+        if (ab) {
+            float r8[8];
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(ab + (int64_t)p * ld_add)), r8);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] += r8[u];
+        }
+        *reinterpret_cast<uint4 *>(yb + (int64_t)p * ld_y) = pack8(f);
+    }
+}
+
+// XSLAB: x is kept in shared memory next to dz (small slabs: shortest latency chain).  Otherwise only gy -> dz lives in
+// shared memory and x is streamed from HBM in the sums pass and read again (L2-resident: the same CTA touched it
+// microseconds earlier) in the apply pass, which halves the footprint: large layers keep 3 CTAs per SM.
+template <int ACT, bool DROP, bool XSLAB>
+__global__ void __launch_bounds__(kFusedThreads, 3) gn_fused_bwd_kernel(
+    const __nv_bfloat16 *__restrict__ gy, int64_t ld_gy, const __nv_bfloat16 *__restrict__ x, int64_t ld_x, FusedShape sh,
+    const float *__restrict__ stats, float eps, const float *__restrict__ gamma, const float *__restrict__ beta,
+    const float *__restrict__ scale, const float *__restrict__ shift, float p_drop, uint64_t seed, uint64_t offset,
+    const uint64_t *__restrict__ off_dev, __nv_bfloat16 *__restrict__ gx, int64_t ld_gx, float *__restrict__ dgamma,
+    float *__restrict__ dbeta, float *__restrict__ dscale, float *__restrict__ dshift) {
+    extern __shared__ __align__(128) uint8_t fsm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int64_t n = blockIdx.x / sh.cs;
+    float4 *stage = reinterpret_cast<float4 *>(fsm + 16);
+    float *cta_q = reinterpret_cast<float *>(fsm + kFusedFixedBytes);      // [C][2] this CTA: sum dz, sum dz*x
+    float *tot_q = cta_q + 2 * sh.C;                                       // [C][2] whole sample
+    float *sg = tot_q + 2 * sh.C;                                          // [G][2]
+    uint4 *slab = reinterpret_cast<uint4 *>(sg + ((2 * sh.G + 3) & ~3));
+    uint4 *ds = slab;                                                      // [pix][chunks] gy, then dz in place
+    uint4 *xs = slab + (size_t)sh.pix_per_cta * sh.chunks;                 // [pix][chunks] x (XSLAB only)
+    const uint32_t bar = tc::smem_u32(fsm);
+    const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
+    const bool active = r < sh.rows;
+    const int64_t p0 = (int64_t)rank * sh.pix_per_cta;
+    const int npx = (int)(min(p0 + sh.pix_per_cta, sh.HW) - p0);
+    if (threadIdx.x == 0) {
+        tc::mbar_init(reinterpret_cast<uint64_t *>(fsm), 1);
+        tc::fence_barrier_init();
+        tc::mbar_arrive_expect_tx_a(bar, (XSLAB ? 2u : 1u) * (uint32_t)npx * (uint32_t)sh.C * 2u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        fetch_slab(tc::smem_u32(ds), gy + (n * sh.HW + p0) * ld_gy, ld_gy, sh.C, npx, bar);
+        if (XSLAB) fetch_slab(tc::smem_u32(xs), x + (n * sh.HW + p0) * ld_x, ld_x, sh.C, npx, bar);
+    }
+    const __nv_bfloat16 *xb = x + (n * sh.HW + p0) * ld_x + 8 * q;
+    const int step = sh.rows;
+    uint4 xa = make_uint4(0, 0, 0, 0), xc = xa;
+    if (!XSLAB && active) {                                                // first two pixels travel with the bulk copy
+        if (r < npx) xa = *reinterpret_cast<const uint4 *>(xb + (int64_t)r * ld_x);
+        if (r + step < npx) xc = *reinterpret_cast<const uint4 *>(xb + (int64_t)(r + step) * ld_x);
+    }
+    const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
+    Coef k;
+    if (active) {
+        Shape s2; s2.HW = sh.HW; s2.C = sh.C; s2.G = sh.G; s2.cpg = sh.cpg; s2.chunks = sh.chunks; s2.rows = sh.rows; s2.pix_per_cta = 0;
+        k = make_coef(s2, n, q, stats, gamma, beta, scale, shift, eps);
+    }
+    if (DROP && off_dev) offset += __ldg(off_dev);
+    tc::mbar_wait_a(bar, 0);
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = 0.f;
+    auto one = [&](int p, const uint4 &xv) {
+        float f[8], g[8], m[8];
+        unpack8(xv, f);
+        unpack8(ds[p * sh.chunks + q], g);
+        if (DROP) dropout_mask8(seed, offset, (n * sh.HW + p0 + p) * sh.C + 8 * q, p_drop, m);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
+            if (DROP) dz *= m[u];
+            v[u] += dz; v[8 + u] = fmaf(dz, f[u], v[8 + u]);
+            g[u] = dz;
+        }
+        ds[p * sh.chunks + q] = pack8(g);
+    };
+    if (active) {
+        if (XSLAB) {
+#pragma unroll 2
+            for (int p = r; p < npx; p += step) one(p, xs[p * sh.chunks + q]);
+        } else {
+            for (int p = r; p < npx; p += 2 * step) {                      // two pixels per turn, the next two in flight
+                uint4 na = make_uint4(0, 0, 0, 0), nc = na;
+                if (p + 2 * step < npx) na = *reinterpret_cast<const uint4 *>(xb + (int64_t)(p + 2 * step) * ld_x);
+                if (p + 3 * step < npx) nc = *reinterpret_cast<const uint4 *>(xb + (int64_t)(p + 3 * step) * ld_x);
+                one(p, xa);
+                if (p + step < npx) one(p + step, xc);
+                xa = na; xc = nc;
+            }
+        }
+    }
+    cta_channel_sums(v, stage, cta_q, sh, q, r);
+    cluster.sync();
+    for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) {
+        float acc = 0.f;
+        for (int rk = 0; rk < sh.cs; ++rk) acc += cluster.map_shared_rank(cta_q, rk)[i];
+        tot_q[i] = acc;
+    }
+    cluster.sync();                                                         // peers are done reading our cta_q: reuse it
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
+        const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f;
+        float mean, rstd;
+        mean_rstd(stats, n, sh.G, c / sh.cpg, inv_cnt, eps, mean, rstd);
+        const float Q1 = tot_q[2 * c];
+        const float Q2 = rstd * (tot_q[2 * c + 1] - mean * Q1);                  // sum dz * xhat
+        cta_q[2 * c] = ga * sc * Q1;
+        cta_q[2 * c + 1] = ga * sc * Q2;
+        if (rank == 0) {                                                          // parameter gradients: once per sample
+            if (dgamma) atomicAdd(dgamma + c, sc * Q2);
+            if (dbeta) atomicAdd(dbeta + c, sc * Q1);
+            if (dscale) dscale[n * sh.C + c] = ga * Q2 + be * Q1;
+            if (dshift) dshift[n * sh.C + c] = Q1;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) {
+        const int g = i >> 1, kind = i & 1;
+        float acc = 0.f;
+        // without normalisation the statistics do not depend on x: no mean-subtraction terms
+        if (stats) for (int c = g * sh.cpg; c < (g + 1) * sh.cpg; ++c) acc += cta_q[2 * c + kind];
+        sg[i] = acc;
+    }
+    __syncthreads();
+    if (!active) return;
+    float P[8], Qc[8], R[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int c = 8 * q + u, g = c / sh.cpg;
+        float mean, rstd;
+        mean_rstd(stats, n, sh.G, g, inv_cnt, eps, mean, rstd);
+        const float m1 = sg[2 * g] * inv_cnt, m2 = sg[2 * g + 1] * inv_cnt;
+        const float gs = (gamma ? __ldg(gamma + c) : 1.f) * (scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f);
+        P[u] = rstd * gs;
+        Qc[u] = -rstd * rstd * m2;
+        R[u] = -rstd * m1 - mean * Qc[u];
+    }
+    __nv_bfloat16 *ob = gx + (n * sh.HW + p0) * ld_gx + 8 * q;
+    auto fin = [&](int p, const uint4 &xv) {
+        float f[8], d[8];
+        unpack8(xv, f);
+        unpack8(ds[p * sh.chunks + q], d);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = fmaf(d[u], P[u], fmaf(f[u], Qc[u], R[u]));
+        *reinterpret_cast<uint4 *>(ob + (int64_t)p * ld_gx) = pack8(d);
+    };
+    if (XSLAB) {
+#pragma unroll 2
+        for (int p = r; p < npx; p += step) fin(p, xs[p * sh.chunks + q]);
+    } else {
+        for (int p = r; p < npx; p += 4 * step) {                          // four L2 reads in flight per thread
+            uint4 t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (p + j * step < npx) t[j] = *reinterpret_cast<const uint4 *>(xb + (int64_t)(p + j * step) * ld_x);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (p + j * step < npx) fin(p + j * step, t[j]);
+        }
+    }
+}
+
+// cluster size / smem plan for the fused kernels; returns false when the slab does not fit
+bool plan_fused(int64_t N, int64_t HW, int64_t C, int G, int tensors, size_t extra_floats, FusedShape &sh, size_t &smem,
+                int only_single_cta = 0) {
+    static const bool enabled = [] { const char *e = getenv("UB200_GN_FUSED"); return !(e && e[0] == '0'); }();   // A/B switch
+    if (!enabled) return false;
+    if (C % 8 != 0 || C % G != 0 || C > 4 * kFusedThreads || N * 8 > 2147483647LL) return false;
+    sh.HW = HW; sh.C = (int)C; sh.G = G; sh.cpg = (int)(C / G); sh.chunks = (int)(C / 8);
+    sh.rows = (kFusedThreads / sh.chunks) & ~1;      // even, >= 2: the fold staging holds rows/2 * chunks <= 128 entries
+    const size_t fixed = (size_t)kFusedFixedBytes + extra_floats * 4;
+    if (only_single_cta) {
+        const size_t bytes = fixed + (size_t)tensors * HW * C * 2;
+        if (bytes > 73 * 1024) return false;
+        sh.cs = 1; sh.pix_per_cta = HW; smem = bytes;
+        return true;
+    }
+    static const int mode = [] { const char *e = getenv("UB200_GN_PLAN"); return e ? atoi(e) : 0; }();
+    const int cs_max = mode >= 2 ? 16 : 8;
+    if (mode >= 1) {
+        // largest cluster that still gives every CTA a full pass of its threads: more, smaller CTAs balance the SMs
+        for (int cs = cs_max; cs >= 1; cs /= 2) {
+            const int64_t ppc = (HW + cs - 1) / cs;
+            if (cs > 1 && ((int64_t)(cs - 1) * ppc >= HW || ppc < 2 * sh.rows)) continue;
+            const size_t bytes = fixed + (size_t)tensors * ppc * C * 2;
+            if (bytes <= 220 * 1024) { sh.cs = cs; sh.pix_per_cta = ppc; smem = bytes; return true; }
+        }
+        return false;
+    }
+    // smallest cluster whose per-CTA slab leaves room for 3, else 2 CTAs per SM; at 8 CTAs accept one per SM
+    static const size_t limits[3] = {73 * 1024, 110 * 1024, 220 * 1024};
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int cs = (pass == 2 ? 8 : 1); cs <= 8; cs *= 2) {
+            const int64_t ppc = (HW + cs - 1) / cs;
+            if (cs > 1 && (int64_t)(cs - 1) * ppc >= HW) continue;                 // would leave an empty CTA
+            const size_t bytes = fixed + (size_t)tensors * ppc * C * 2;
+            if (bytes <= limits[pass]) { sh.cs = cs; sh.pix_per_cta = ppc; smem = bytes; return true; }
+        }
+    }
+    return false;
+}
+
+std::mutex g_attr_mu;
+std::unordered_set<const void *> g_attr_done;
+
+template <typename K, typename... Args>
+int launch_cluster(K kernel, int grid, int cs, size_t smem, cudaStream_t s, Args... args) {
+    cudaError_t e = cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lk(g_attr_mu);
+        if (!g_attr_done.count(reinterpret_cast<const void *>(kernel))) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e == cudaSuccess) g_attr_done.insert(reinterpret_cast<const void *>(kernel));
+        }
+    }
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(kFusedThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    return e == cudaSuccess ? (int)cudaPeekAtLastError() : (int)e;
+}
+
 int make_shape(int64_t N, int64_t HW, int64_t C, int G, Shape &sh, dim3 &grid) {
     if (N <= 0 || HW <= 0 || C <= 0 || G <= 0) return UB200_E_BADARG;
     if (C % 8 != 0 || C % G != 0 || C > 2048 || G > 1024 || N > 65535) return UB200_E_UNSUPPORTED;
@@ -440,6 +847,70 @@ int ub200_gn_act_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int
                                                              dgamma, dbeta, dscale, dshift);
     UB_LAUNCH_CHECK();
     return UB200_OK;
+}
+
+#define DISPATCH_FUSED(KERNEL, act, drop, ...)                                                                  \
+    ((drop) ? ((act) == UB200_ACT_SILU   ? launch_cluster(KERNEL(UB200_ACT_SILU, true), __VA_ARGS__)            \
+               : (act) == UB200_ACT_GELU ? launch_cluster(KERNEL(UB200_ACT_GELU, true), __VA_ARGS__)            \
+                                         : launch_cluster(KERNEL(UB200_ACT_NONE, true), __VA_ARGS__))           \
+            : ((act) == UB200_ACT_SILU   ? launch_cluster(KERNEL(UB200_ACT_SILU, false), __VA_ARGS__)           \
+               : (act) == UB200_ACT_GELU ? launch_cluster(KERNEL(UB200_ACT_GELU, false), __VA_ARGS__)           \
+                                         : launch_cluster(KERNEL(UB200_ACT_NONE, false), __VA_ARGS__)))
+#define FUSED_FWD(A, D) gn_fused_fwd_kernel<A, D>
+#define FUSED_BWD_X(A, D) gn_fused_bwd_kernel<A, D, true>
+#define FUSED_BWD_S(A, D) gn_fused_bwd_kernel<A, D, false>
+
+int ub200_gn_act_fused_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t HW, int64_t C, int G, float *stats,
+                                     float eps, const float *gamma, const float *beta, const float *scale,
+                                     const float *shift, int act, float dropout_p, uint64_t seed, uint64_t offset,
+                                     const uint64_t *offset_dev, const void *addend, int64_t ld_add, void *y,
+                                     int64_t ld_y, void *stream) {
+    UB_REQUIRE(x && y && stats && N > 0 && HW > 0 && C > 0 && G > 0 && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
+    UB_REQUIRE(act == UB200_ACT_NONE || act == UB200_ACT_SILU || act == UB200_ACT_GELU, UB200_E_BADARG);
+    FusedShape sh; size_t smem = 0;
+    const size_t gpad = (size_t)((2 * G + 3) & ~3);
+    const bool ok = ld_x % 8 == 0 && ld_y % 8 == 0 && ld_x >= C && ld_y >= C && ub::aligned16(x) && ub::aligned16(y) &&
+                    (!addend || (ld_add % 8 == 0 && ld_add >= C && ub::aligned16(addend))) &&
+                    plan_fused(N, HW, C, G, 1, 2 * (size_t)C + 2 * gpad, sh, smem);
+    if (!ok) {      // slab too large for one cluster: statistics pass + apply pass
+        int rc = ub200_gn_stats_nhwc_bf16(x, ld_x, N, HW, C, G, stats, stream);
+        if (rc) return rc;
+        return ub200_gn_act_fwd_nhwc_bf16(x, ld_x, N, HW, C, G, stats, eps, gamma, beta, scale, shift, act, dropout_p, seed,
+                                          offset, offset_dev, addend, ld_add, y, ld_y, stream);
+    }
+    const bool drop = dropout_p > 0.f;
+    return DISPATCH_FUSED(FUSED_FWD, act, drop, (int)(N * sh.cs), sh.cs, smem, ub::as_stream(stream),
+                          reinterpret_cast<const __nv_bfloat16 *>(x), ld_x, sh, stats, eps, gamma, beta, scale, shift,
+                          dropout_p, seed, offset, offset_dev, reinterpret_cast<const __nv_bfloat16 *>(addend), ld_add,
+                          reinterpret_cast<__nv_bfloat16 *>(y), ld_y);
+}
+
+int ub200_gn_act_fused_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int64_t ld_x, int64_t N, int64_t HW,
+                                     int64_t C, int G, const float *stats, float eps, const float *gamma,
+                                     const float *beta, const float *scale, const float *shift, int act,
+                                     float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                                     void *gx, int64_t ld_gx, float *dgamma, float *dbeta, float *dscale, float *dshift,
+                                     float *ws, void *stream) {
+    UB_REQUIRE(gy && x && gx && ws && N > 0 && HW > 0 && C > 0 && G > 0 && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
+    UB_REQUIRE(act == UB200_ACT_NONE || act == UB200_ACT_SILU || act == UB200_ACT_GELU, UB200_E_BADARG);
+    FusedShape sh; size_t smem = 0;
+    const bool fits = ld_x % 8 == 0 && ld_gy % 8 == 0 && ld_gx % 8 == 0 && ld_x >= C && ld_gy >= C && ld_gx >= C &&
+                      ub::aligned16(x) && ub::aligned16(gy) && ub::aligned16(gx);
+    const size_t extra = (size_t)(4 * C + ((2 * G + 3) & ~3));
+    const bool xslab = fits && plan_fused(N, HW, C, G, 2, extra, sh, smem, 1);
+    const bool ok = xslab || (fits && plan_fused(N, HW, C, G, 1, extra, sh, smem));
+    if (!ok)
+        return ub200_gn_act_bwd_nhwc_bf16(gy, ld_gy, x, ld_x, N, HW, C, G, stats, eps, gamma, beta, scale, shift, act,
+                                          dropout_p, seed, offset, offset_dev, gx, ld_gx, 0, dgamma, dbeta, dscale, dshift,
+                                          ws, stream);
+    const bool drop = dropout_p > 0.f;
+#define BWD_ARGS                                                                                                      \
+    (int)(N * sh.cs), sh.cs, smem, ub::as_stream(stream), reinterpret_cast<const __nv_bfloat16 *>(gy), ld_gy,         \
+        reinterpret_cast<const __nv_bfloat16 *>(x), ld_x, sh, stats, eps, gamma, beta, scale, shift, dropout_p, seed, \
+        offset, offset_dev, reinterpret_cast<__nv_bfloat16 *>(gx), ld_gx, dgamma, dbeta, dscale, dshift
+    if (xslab) return DISPATCH_FUSED(FUSED_BWD_X, act, drop, BWD_ARGS);
+    return DISPATCH_FUSED(FUSED_BWD_S, act, drop, BWD_ARGS);
+#undef BWD_ARGS
 }
 
 }  // extern "C"

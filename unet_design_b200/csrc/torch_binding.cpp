@@ -179,7 +179,7 @@ void gn_stats(const Tensor &x, int64_t G, const Tensor &stats) {
 void gn_act_fwd(const Tensor &x, int64_t G, const c10::optional<Tensor> &stats, double eps, const c10::optional<Tensor> &gamma,
                 const c10::optional<Tensor> &beta, const c10::optional<Tensor> &scale, const c10::optional<Tensor> &shift,
                 int64_t act, double dropout_p, int64_t seed, int64_t offset, const c10::optional<Tensor> &offset_dev,
-                const c10::optional<Tensor> &addend, const Tensor &y) {
+                const c10::optional<Tensor> &addend, const Tensor &y, bool compute_stats) {
     UB_GUARD(x);
     const Nhwc i = nhwc(x, "x"), o = nhwc(y, "y");
     TORCH_CHECK(o.N == i.N && o.H == i.H && o.W == i.W && o.C == i.C, "gn_act_fwd: shape mismatch");
@@ -188,6 +188,15 @@ void gn_act_fwd(const Tensor &x, int64_t G, const c10::optional<Tensor> &stats, 
         const Nhwc a = nhwc(*addend, "addend");
         TORCH_CHECK(a.N == i.N && a.H == i.H && a.W == i.W && a.C == i.C, "gn_act_fwd: addend shape mismatch");
         addp = a.ptr; ld_add = a.ld;
+    }
+    if (compute_stats) {     // statistics + apply in one cluster kernel (falls back to two passes for huge slabs)
+        TORCH_CHECK(stats.has_value(), "gn_act_fwd: compute_stats needs a stats buffer");
+        check_rc(ub200_gn_act_fused_fwd_nhwc_bf16(i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_mut(*stats, "stats"), (float)eps,
+                                                  f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
+                                                  f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed,
+                                                  (uint64_t)offset, i64_opt(offset_dev), addp, ld_add, o.ptr, o.ld, cur_stream()),
+                 "gn_act_fused_fwd");
+        return;
     }
     check_rc(ub200_gn_act_fwd_nhwc_bf16(i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_opt(stats, "stats"), (float)eps,
                                         f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
@@ -206,11 +215,13 @@ void gn_act_bwd(const Tensor &gy, const Tensor &x, int64_t G, const c10::optiona
                 "gn_act_bwd: shape mismatch");
     Tensor ws = at::empty({(int64_t)ub200_gn_act_bwd_ws_floats(i.N, i.C, (int)G)}, x.options().dtype(at::kFloat));
     auto mut = [](const c10::optional<Tensor> &t, const char *n) -> float * { return t.has_value() ? f32_mut(*t, n) : nullptr; };
-    check_rc(ub200_gn_act_bwd_nhwc_bf16(g.ptr, g.ld, i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_opt(stats, "stats"), (float)eps,
-                                        f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
-                                        f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed, (uint64_t)offset,
-                                        i64_opt(offset_dev), o.ptr, o.ld, accumulate ? 1 : 0, mut(dgamma, "dgamma"), mut(dbeta, "dbeta"),
-                                        mut(dscale, "dscale"), mut(dshift, "dshift"), ws.data_ptr<float>(), cur_stream()),
+    TORCH_CHECK(!accumulate, "gn_act_bwd: accumulate is not supported");
+    check_rc(ub200_gn_act_fused_bwd_nhwc_bf16(g.ptr, g.ld, i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_opt(stats, "stats"),
+                                              (float)eps, f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
+                                              f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed,
+                                              (uint64_t)offset, i64_opt(offset_dev), o.ptr, o.ld, mut(dgamma, "dgamma"),
+                                              mut(dbeta, "dbeta"), mut(dscale, "dscale"), mut(dshift, "dshift"),
+                                              ws.data_ptr<float>(), cur_stream()),
              "gn_act_bwd");
 }
 

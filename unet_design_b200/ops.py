@@ -258,9 +258,8 @@ class _GnAct(torch.autograd.Function):
         x = _dense_nhwc(x)
         n, h, w, c = x.shape
         stats = None
-        if G > 0:
+        if G > 0:                      # statistics are produced by the fused forward kernel below
             stats = torch.empty((n, G, 2), dtype=torch.float32, device=x.device)
-            _ops().gn_stats(x, G, stats)
         else:
             G = 1                      # G <= 0: no normalisation, plain activation (norm=False blocks)
         y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
@@ -269,8 +268,8 @@ class _GnAct(torch.autograd.Function):
         if p_drop > 0.0:
             seed, off, dev = _DropoutState.seed, _next_dropout_offset(x.numel()), dropout_device_counter(x.device)
         _ops().gn_act_fwd(x, G, stats, eps, gamma, beta, scale, shift, act, p_drop, seed, off, dev,
-                          _dense_nhwc(addend) if addend is not None else None, y)
-        _count(3)
+                          _dense_nhwc(addend) if addend is not None else None, y, stats is not None)
+        _count(1)
         ctx.has_addend = addend is not None
         ctx.keys = (_key(gamma), _key(beta))
         ctx.save_for_backward(x, stats, gamma, beta, scale, shift)
@@ -290,7 +289,7 @@ class _GnAct(torch.autograd.Function):
         dshift = torch.empty_like(shift) if shift is not None else None
         _ops().gn_act_bwd(gy, x, G, stats, eps, gamma, beta, scale, shift, act, p_drop, seed, off, dev, gx, False,
                           dgamma, dbeta, dscale, dshift)
-        _count(3)
+        _count(1)
         for sink in (sg, sb):
             if sink and sink[1] is not None:
                 sink[1]()
