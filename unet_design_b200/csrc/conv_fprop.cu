@@ -46,15 +46,29 @@ struct FpropParams {
     float *out_nchw;
 };
 
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 320;                         // TMA warp, MMA warp, two epilogue groups of four warps
+constexpr int kEpiThreads = 128;                      // one epilogue group: one warp per TMEM lane quadrant
 constexpr uint32_t kStagingBytes = 128 * 64 * 2;      // one [128 pixels][64 channels] bf16 box
+constexpr int kStagingBufs = 4;                       // two per epilogue group
 constexpr int kTblRows = 8;                           // addend table: up to 8 samples per pixel tile
 // Optional CTA pair (cluster of 2): the weight tile is fetched once from L2 and multicast to both CTAs.  Measured
 // neutral-to-negative on B200 for these shapes: the kernel is bound by shared-memory bandwidth (tensor-core operand
 // reads + TMA writes), which multicast does not reduce; kept selectable (UB200_FPROP_CLUSTER=2) for the 2-CTA MMA work.
 
-template <int BK>
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// FAST: the common epilogue (bf16 NHWC output through TMA, Cout and BN multiples of 64) with every per-launch option
+// resolved at compile time (RES: residual tensor, TBL: bias / per-sample row through the smem table) and both
+// epilogue groups working on alternate 64-channel chunks.  The generic path keeps all runtime options and uses
+// one group.  The epilogue is what bounds the 1x1 and short-K convolutions, so its instruction count matters.
+template <int BK, bool FAST, bool RES, bool TBL>
 __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                 const __grid_constant__ CUtensorMap tm_w,
                                                                 const __grid_constant__ CUtensorMap tm_a2,
@@ -65,8 +79,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
     // carve: [2 x output staging][stages x A][stages x B][full][empty][tmem_full x2][tmem_empty x2][tmem ptr]
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_out = smem;
-    float *tbl = reinterpret_cast<float *>(smem_out + 2 * kStagingBytes);   // [kTblRows][BN] bias + per-sample row
-    uint8_t *smem_a = smem_out + 2 * kStagingBytes + p.tbl_bytes;
+    float *tbl = reinterpret_cast<float *>(smem_out + kStagingBufs * kStagingBytes);   // bias + per-sample rows
+    uint8_t *smem_a = smem_out + kStagingBufs * kStagingBytes + p.tbl_bytes;
     uint8_t *smem_b = smem_a + (size_t)p.stages * p.a_stage_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_b + (size_t)p.stages * p.b_stage_bytes);
     uint64_t *empty = full + p.stages;
@@ -83,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         if (p.kb_extra) { prefetch_tmap(&tm_a2); prefetch_tmap(&tm_w2); }
         if (p.has_out) prefetch_tmap(&tm_out);
         for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, p.cluster); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 8); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -183,7 +197,133 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
             }
         }
     } else {
-        // ===================== epilogue: 4 warps, one TMEM lane quadrant each =====================
+        // ===================== epilogue: two groups of 4 warps, one TMEM lane quadrant per warp =====================
+        const int grp = (warp - 2) >> 2;              // 0: warps 2..5, 1: warps 6..9
+        if constexpr (FAST) {
+            const int qd = warp & 3;
+            const int r = qd * 32 + lane;             // row of the tile == TMEM lane
+            const int et = threadIdx.x - 64;          // 0..255 within the epilogue warps
+            const int wi = r % p.BW, hi = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
+            const bool issuer = ((warp == 2 || warp == 6) && lane == 0);
+            const int bar_id = 1 + grp;
+            const int nchunks = p.BN >> 6, total = p.msub * nchunks;
+            const uint32_t stage0 = smem_u32(smem_out) + (uint32_t)grp * 2u * kStagingBytes;
+            const uint32_t tbl0 = smem_u32(tbl);
+            const int tbl_elems = p.msub * p.BNI * p.BN;                     // per tile parity
+            const uint32_t row_off = (uint32_t)r * 128u, sw = (uint32_t)(r & 7);
+            uint32_t local = 0, lc = 0;
+            for (int ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, ++local) {
+                const int nt = ct % p.n_tiles, co0 = nt * p.BN;
+                const uint32_t acc = local & 1u, use = local >> 1;
+                int xa, ya, na, xb = 0, yb = 0, nb = 0;
+                {
+                    int mt = ((ct / p.n_tiles) * kCluster + crank) * p.msub;
+                    xa = (mt % p.tiles_w) * p.BW; mt /= p.tiles_w;
+                    ya = (mt % p.tiles_h) * p.BH; mt /= p.tiles_h;
+                    na = mt * p.BNI;
+                    if (p.msub == 2) {
+                        mt = ((ct / p.n_tiles) * kCluster + crank) * p.msub + 1;
+                        xb = (mt % p.tiles_w) * p.BW; mt /= p.tiles_w;
+                        yb = (mt % p.tiles_h) * p.BH; mt /= p.tiles_h;
+                        nb = mt * p.BNI;
+                    }
+                }
+                if (TBL) {
+                    // tbl[parity][sub][s][c] = bias[co0+c] + rowadd[n0(sub)+s][co0+c].  The all-epilogue barrier below
+                    // also proves every reader of this parity's previous contents (tile local-2) has finished.
+                    float *tb = tbl + (local & 1u) * tbl_elems;
+                    for (int i = et; i < tbl_elems; i += 2 * kEpiThreads) {
+                        const int sub = i / (p.BNI * p.BN), rem = i - sub * (p.BNI * p.BN);
+                        const int sidx = rem / p.BN, c = rem - sidx * p.BN, co = co0 + c;
+                        const int ns = (sub ? nb : na) + sidx;
+                        float v = 0.f;
+                        if (co < p.Cout) {
+                            if (p.bias) v = __ldg(p.bias + co);
+                            if (p.rowadd && ns < p.N) v += __ldg(p.rowadd + (int64_t)ns * p.Cout + co);
+                        }
+                        tb[i] = v;
+                    }
+                    named_barrier_sync(3, 2 * kEpiThreads);
+                }
+                mbar_wait(tmem_full + acc, use & 1u);
+                tc_fence_after();
+                bool arrived = false;
+                for (int cc = grp; cc < total; cc += 2, ++lc) {
+                    const int sub = cc >= nchunks ? 1 : 0, ch = cc - sub * nchunks;
+                    const int x0 = sub ? xb : xa, y0 = sub ? yb : ya, n0 = sub ? nb : na;
+                    const uint32_t stage = stage0 + (lc & 1u) * kStagingBytes;
+                    if (issuer) tma_store_wait_read<1>();           // the store that last used this buffer has read it
+                    named_barrier_sync(bar_id, kEpiThreads);
+                    uint4 rq[8];
+                    bool valid = false;
+                    if (RES) {
+                        const int x = x0 + wi, y = y0 + hi, n = n0 + ni;
+                        valid = x < p.W && y < p.H && n < p.N;
+                        if (valid) {
+                            const uint4 *rp = reinterpret_cast<const uint4 *>(
+                                p.residual + (((int64_t)n * p.H + y) * p.W + x) * p.ld_res + co0 + ch * 64);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) rq[j] = __ldg(rp + j);
+                        }
+                    }
+                    float v[64];
+                    tmem_ld64(tmem_base + ((uint32_t)(qd * 32) << 16) + acc * (uint32_t)(p.msub * p.BN) + (uint32_t)(sub * p.BN + ch * 64), v);
+                    if (cc + 2 >= total) {                           // this group's last tcgen05.ld of the accumulator
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tmem_empty + acc);
+                        arrived = true;
+                    }
+                    if (TBL) {
+                        const uint32_t ta = tbl0 + 4u * (uint32_t)((local & 1u) * tbl_elems + (sub * p.BNI + ni) * p.BN + ch * 64);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 t = lds_f4(ta + 16u * i);
+                            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+                        }
+                    }
+                    if (RES && valid) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float f[8];
+                            unpack8(rq[j], f);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[8 * j + i] += f[i];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                    // 16-byte pieces of row r, 128-byte swizzle
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = v[8 * j + i];
+                        sts_u4(stage + row_off + (((uint32_t)j ^ sw) << 4), pack8(f));
+                    }
+                    fence_proxy_async();
+                    named_barrier_sync(bar_id, kEpiThreads);
+                    if (issuer) {
+                        tma_store_4d(&tm_out, smem_out + (stage - smem_u32(smem_out)), co0 + ch * 64, x0, y0, n0);
+                        tma_store_commit();
+                    }
+                }
+                if (!arrived) {                                      // no chunk of this tile was ours: stay in lock step
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty + acc);
+                }
+            }
+            if (issuer) tma_store_wait_all();
+        } else if (grp == 1) {
+            // generic path: the second group only keeps the accumulator hand-shake in lock step
+            uint32_t local = 0;
+            for (int ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, ++local) {
+                const uint32_t acc = local & 1u, use = local >> 1;
+                mbar_wait(tmem_full + acc, use & 1u);
+                tc_fence_after();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty + acc);
+            }
+        } else {
         const int qd = warp & 3;
         const int r = qd * 32 + lane;                 // row of the tile == TMEM lane
         const int et = threadIdx.x - 64;              // 0..127 within the epilogue group
@@ -315,6 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
             }
         }
         if (issuer && p.has_out) tma_store_wait_all();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -353,13 +494,14 @@ int pick_bk(int64_t Cin, int64_t Cin2) {
 
 uint32_t pow2_at_least(uint32_t v, uint32_t lo) { uint32_t r = lo; while (r < v) r <<= 1; return r; }
 
-template <int BK>
+template <int BK, bool FAST, bool RES, bool TBL>
 int launch_fprop(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &ta2, const CUtensorMap &tw2,
                  const CUtensorMap &tout, const FpropParams &p, int grid, size_t smem, cudaStream_t s) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_fprop_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(conv_fprop_kernel<BK, FAST, RES, TBL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        227 * 1024);
     });
     if (attr_err != cudaSuccess) return (int)attr_err;
     cudaLaunchConfig_t cfg{};
@@ -371,7 +513,7 @@ int launch_fprop(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BK>, ta, tw, ta2, tw2, tout, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BK, FAST, RES, TBL>, ta, tw, ta2, tw2, tout, p);
     if (e != cudaSuccess) return (int)e;
     UB_LAUNCH_CHECK();
     return UB200_OK;
@@ -427,7 +569,12 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     const int m_units = (m_tiles + p.msub - 1) / p.msub;
     p.num_tiles = m_units * p.n_tiles;
     p.cluster_tiles = ((m_units + kCluster - 1) / kCluster) * p.n_tiles;
-    p.tbl_bytes = ((uint32_t)((p.BNI <= kTblRows ? p.BNI : 1) * p.BN * 4) + 1023u) & ~1023u;
+    static const int env_fast = [] { const char *e = getenv("UB200_FPROP_FAST_EPI"); return e ? atoi(e) : 1; }();
+    const bool has_tbl = (a->bias || a->rowadd);
+    const bool fast = env_fast && bk == 64 && a->out && !a->out_f32_nchw && a->Cout % 64 == 0 && p.BN % 64 == 0 &&
+                      (!has_tbl || p.BNI <= kTblRows);
+    // generic: [BNI][BN]; fast: [2 tile parities][msub][BNI][BN]
+    p.tbl_bytes = ((uint32_t)((fast ? 2 * p.msub : 1) * (p.BNI <= kTblRows ? p.BNI : 1) * p.BN * 4) + 1023u) & ~1023u;
     p.Cin = (int)a->Cin;
     p.cblocks = (int)(a->Cin / bk);
     p.taps = a->ksize * a->ksize;
@@ -436,7 +583,7 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     p.a_stage_bytes = (uint32_t)p.msub * 128u * bk * 2u;
     p.b_stage_bytes = ((uint32_t)p.BN * bk * 2u + 1023u) & ~1023u;
     const uint32_t stage = p.a_stage_bytes + p.b_stage_bytes;
-    const uint32_t budget = 227u * 1024u - 1024u - 2u * kStagingBytes - p.tbl_bytes - 256u;
+    const uint32_t budget = 227u * 1024u - 1024u - kStagingBufs * kStagingBytes - p.tbl_bytes - 256u;
     int stages = (int)(budget / stage);
     if (stages > 8) stages = 8;
     if (env_stages && stages > env_stages) stages = env_stages;
@@ -487,11 +634,18 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     }
 
     const int grid = kCluster * (p.cluster_tiles < ub::kSMs / kCluster ? p.cluster_tiles : ub::kSMs / kCluster);
-    const size_t smem = 1024 + 2 * kStagingBytes + p.tbl_bytes + (size_t)stages * stage + (2 * stages + 4) * sizeof(uint64_t) + 16;
+    const size_t smem = 1024 + kStagingBufs * kStagingBytes + p.tbl_bytes + (size_t)stages * stage + (2 * stages + 4) * sizeof(uint64_t) + 16;
     cudaStream_t s = ub::as_stream(stream);
+    if (fast) {
+        const bool res = a->residual != nullptr;
+        if (res) return has_tbl ? launch_fprop<64, true, true, true>(ta, tw, ta2, tw2, tout, p, grid, smem, s)
+                                : launch_fprop<64, true, true, false>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
+        return has_tbl ? launch_fprop<64, true, false, true>(ta, tw, ta2, tw2, tout, p, grid, smem, s)
+                       : launch_fprop<64, true, false, false>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
+    }
     switch (bk) {
-        case 64: return launch_fprop<64>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
-        case 32: return launch_fprop<32>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
-        default: return launch_fprop<16>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
+        case 64: return launch_fprop<64, false, false, false>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
+        case 32: return launch_fprop<32, false, false, false>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
+        default: return launch_fprop<16, false, false, false>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
     }
 }
