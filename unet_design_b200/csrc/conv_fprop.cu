@@ -88,7 +88,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform, so the role branches are uniform
+    // control flow and the producer / MMA loops below keep their state in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int num_kb = p.kb_main + p.kb_extra;
 
     if (warp == 0 && lane == 0) {
@@ -105,15 +107,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
     __syncthreads();
     if (p.cluster > 1) cluster_sync_all();   // the peer multicasts into our smem and arrives on our barriers
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int kCluster = p.cluster;
     const int crank = kCluster > 1 ? (int)cluster_ctarank() : 0;
     const int cluster_id = blockIdx.x / kCluster, num_clusters = gridDim.x / kCluster;
     // this CTA's m unit of cluster tile ct:  (ct / n_tiles) * kCluster + crank   (may lie past the end: zero tile)
 
     if (warp == 0) {
-        // ===================== TMA producer (one thread; address arithmetic strength-reduced: no div/mod per k-block)
-        if (lane == 0) {
+        // ===================== TMA producer.  The whole warp walks the loop (uniform trip counts, so every address and
+        // coordinate is warp-uniform and lives in uniform registers: TMA / mbarrier operands need no per-lane
+        // "waterfall"); only the instructions with side effects are issued by lane 0.
+        {
+            const bool leader = lane == 0;
             const uint32_t tx_bytes = (uint32_t)p.msub * 128u * BK * 2u + (uint32_t)p.BN * BK * 2u;
             const int half = p.BN / kCluster;                 // weight rows this CTA fetches for the pair
             const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b) + (uint32_t)(crank * half * (BK * 2));
@@ -122,12 +127,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
             int s = 0; uint32_t ph = 0;                       // ring position, carried across tiles
             for (int ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
                 const int nt = ct % p.n_tiles, co0 = nt * p.BN + cow;
-                int x0[2], y0[2], n0[2];
-                for (int sub = 0; sub < p.msub; ++sub) {
-                    int mt = ((ct / p.n_tiles) * kCluster + crank) * p.msub + sub;
-                    x0[sub] = (mt % p.tiles_w) * p.BW; mt /= p.tiles_w;
-                    y0[sub] = (mt % p.tiles_h) * p.BH; mt /= p.tiles_h;
-                    n0[sub] = mt * p.BNI;                     // past the batch for a padded trailing tile: TMA zero-fills
+                int xa, ya, na, xb = 0, yb = 0, nb = 0;
+                {
+                    int mt = ((ct / p.n_tiles) * kCluster + crank) * p.msub;
+                    xa = (mt % p.tiles_w) * p.BW; mt /= p.tiles_w;
+                    ya = (mt % p.tiles_h) * p.BH; mt /= p.tiles_h;
+                    na = mt * p.BNI;                          // past the batch for a padded trailing tile: TMA zero-fills
+                    if (p.msub == 2) {
+                        mt = ((ct / p.n_tiles) * kCluster + crank) * p.msub + 1;
+                        xb = (mt % p.tiles_w) * p.BW; mt /= p.tiles_w;
+                        yb = (mt % p.tiles_h) * p.BH; mt /= p.tiles_h;
+                        nb = mt * p.BNI;
+                    }
                 }
                 const int kdim = p.taps == 9 ? 3 : 1;
                 int wk = 0;                                   // K coordinate into the packed weights: tap * Cin + cb * BK
@@ -137,29 +148,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                         for (int c = 0; c < p.Cin; c += BK, wk += BK) {
                             const uint32_t fb = full0 + 8u * s, sa = a0 + (uint32_t)s * p.a_stage_bytes;
                             mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
-                            mbar_arrive_expect_tx_a(fb, tx_bytes);
-                            tma_load_4d_a(sa, &tm_a, fb, c, x0[0] + dx, y0[0] + dy, n0[0]);
-                            if (p.msub == 2) tma_load_4d_a(sa + 128 * BK * 2, &tm_a, fb, c, x0[1] + dx, y0[1] + dy, n0[1]);
-                            if (kCluster > 1) tma_load_2d_mcast_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w, fb, wk, co0, (uint16_t)0x3);
-                            else tma_load_2d_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w, fb, wk, co0);
+                            if (leader) {
+                                mbar_arrive_expect_tx_a(fb, tx_bytes);
+                                tma_load_4d_a(sa, &tm_a, fb, c, xa + dx, ya + dy, na);
+                                if (p.msub == 2) tma_load_4d_a(sa + 128 * BK * 2, &tm_a, fb, c, xb + dx, yb + dy, nb);
+                                if (kCluster > 1) tma_load_2d_mcast_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w, fb, wk, co0, (uint16_t)0x3);
+                                else tma_load_2d_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w, fb, wk, co0);
+                            }
                             if (++s == p.stages) { s = 0; ph ^= 1u; }
                         }
                     }
                 for (int c = 0; c < p.kb_extra * BK; c += BK) {   // K slices of the fused 1x1 term
                     const uint32_t fb = full0 + 8u * s, sa = a0 + (uint32_t)s * p.a_stage_bytes;
                     mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
-                    mbar_arrive_expect_tx_a(fb, tx_bytes);
-                    tma_load_4d_a(sa, &tm_a2, fb, c, x0[0], y0[0], n0[0]);
-                    if (p.msub == 2) tma_load_4d_a(sa + 128 * BK * 2, &tm_a2, fb, c, x0[1], y0[1], n0[1]);
-                    if (kCluster > 1) tma_load_2d_mcast_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w2, fb, c, co0, (uint16_t)0x3);
-                    else tma_load_2d_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w2, fb, c, co0);
+                    if (leader) {
+                        mbar_arrive_expect_tx_a(fb, tx_bytes);
+                        tma_load_4d_a(sa, &tm_a2, fb, c, xa, ya, na);
+                        if (p.msub == 2) tma_load_4d_a(sa + 128 * BK * 2, &tm_a2, fb, c, xb, yb, nb);
+                        if (kCluster > 1) tma_load_2d_mcast_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w2, fb, c, co0, (uint16_t)0x3);
+                        else tma_load_2d_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w2, fb, c, co0);
+                    }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer: warp-uniform loop, tcgen05.mma / commit issued by lane 0 =====================
+        {
+            const bool leader = lane == 0;
             const uint32_t idesc = make_idesc(128, p.BN, 0, 0);
             constexpr uint32_t swz = swizzle_code(BK * 2);
             constexpr uint32_t sbo = 8u * BK * 2u;
@@ -174,26 +190,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                 mbar_wait(tmem_empty + acc, (use & 1u) ^ 1u);          // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)(p.msub * p.BN);
-                uint32_t accum = 0;                                    // first MMA of the tile overwrites
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait_a(full0 + 8u * s, ph);
                     tc_fence_after();
                     const uint64_t da = da0 + (uint64_t)(s * a_step), db = db0 + (uint64_t)(s * b_step);
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
-                        accum = 1;
-                    }
-                    if (p.msub == 2) {
+                        for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        if (p.msub == 2) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            umma_bf16(d_tmem + (uint32_t)p.BN, da + (128 * BK * 2 / 16) + 2 * k, db + 2 * k, idesc, kb | k ? 1u : 0u);
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_bf16(d_tmem + (uint32_t)p.BN, da + (128 * BK * 2 / 16) + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        }
+                        if (kCluster > 1) umma_commit_mcast_a(empty0 + 8u * s, (uint16_t)0x3);   // both CTAs' MMAs must have read it
+                        else umma_commit_a(empty0 + 8u * s);                                     // slot reusable once read
                     }
-                    if (kCluster > 1) umma_commit_mcast_a(empty0 + 8u * s, (uint16_t)0x3);   // both CTAs' MMAs must have read it
-                    else umma_commit_a(empty0 + 8u * s);                                     // slot reusable once read
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(tmem_full + acc);                          // accumulator complete
+                if (leader) umma_commit(tmem_full + acc);              // accumulator complete
             }
         }
     } else {
