@@ -258,6 +258,32 @@ int ub200_adam_ema_step_f32(float *p, const float *g, float *m, float *v, float 
 int ub200_pack_dgrad_weights_batched(const void *shadow_bf16, void *dgrad_arena_bf16,
                                      const int64_t *table_dev, int n_convs, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Batched fp32 row linears of the time-embedding path.  Replaces, in ONE launch per direction, the
+ * per-ResBlock `temb_proj` = Swish + Linear(tdim, Cout) (diff_cifar/model.py:134-137, used at :164) and the
+ * two Linear layers of every level's TimeEmbedding MLP (diff_cifar/model.py:29-36):
+ *     y_i[N, cout_i] = act(x_i[N, K]) @ w_i[cout_i, K]^T + bias_i        act = SiLU if `silu` else identity
+ * for i < n_items.  Several items may share one x (all ResBlocks of a level share that level's embedding).
+ * Backward, per item: gw_i += gy_i^T @ act(x_i), gbias_i += column sums of gy_i (both ACCUMULATE: they are
+ * the caller's gradient buffers), and gx = act'(x) * sum over the items sharing that gx pointer of
+ * gy_i @ w_i (OVERWRITTEN).  fp32 FMA arithmetic; cout_i % 4 == 0, K % 4 == 0, all pointers 16-byte aligned.
+ * Fields not used by a direction may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ub200_rowlin_item {
+    const float *x;      /* [N, K] */
+    const float *w;      /* [cout, K] */
+    const float *bias;   /* [cout] or NULL                                   (forward) */
+    float *y;            /* [N, cout]                                        (forward) */
+    const float *gy;     /* [N, cout]                                        (backward) */
+    float *gw;           /* [cout, K], accumulated; NULL = not wanted        (backward) */
+    float *gbias;        /* [cout], accumulated; NULL = not wanted           (backward) */
+    float *gx;           /* [N, K], overwritten with the group's sum; NULL = not wanted (backward) */
+    int64_t cout;
+} ub200_rowlin_item;
+
+int ub200_rowlin_fwd(const ub200_rowlin_item *items, int n_items, int64_t N, int64_t K, int silu, void *stream);
+int ub200_rowlin_bwd(const ub200_rowlin_item *items, int n_items, int64_t N, int64_t K, int silu, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

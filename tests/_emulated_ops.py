@@ -204,6 +204,31 @@ class EmulatedOps:
     def sumsq(self, g, acc):
         acc.add_((g.double() ** 2).sum().float())
 
+    # ---- batched row linears (time-embedding path)
+    def rowlin_fwd(self, xs, ws, bs, ys, silu):
+        for x, w, b, y in zip(xs, ws, bs, ys):
+            a = F.silu(x) if silu else x
+            y.copy_(a @ w.t() + (b if b is not None else 0.0))
+
+    def rowlin_bwd(self, xs, ws, gys, gws, gbs, gxs, silu):
+        first = {}
+        for x, w, gy, gw, gb, gx in zip(xs, ws, gys, gws, gbs, gxs):
+            a = F.silu(x) if silu else x
+            if gw is not None:
+                gw.add_((gy.t() @ a).view(gw.shape))
+            if gb is not None:
+                gb.add_(gy.sum(0))
+            if gx is not None:
+                t = gy @ w
+                if silu:
+                    s = torch.sigmoid(x)
+                    t = t * (s * (1 + x * (1 - s)))
+                if id(gx) in first:
+                    gx.add_(t)
+                else:
+                    first[id(gx)] = True
+                    gx.copy_(t)
+
     def pack_dgrad_weights_batched(self, shadow, dgrad_arena, table):
         for src, dst, cout, cin, k in table.tolist():
             w = shadow[src:src + cout * k * k * cin].reshape(cout, k, k, cin)

@@ -197,3 +197,39 @@ def test_gn_act_addend_and_no_norm_modes(ops):
     x2r = x2.detach().float().requires_grad_(True)
     F.gelu(x2r).backward(g.float())
     assert rel_err(y2, F.gelu(x2.detach().float())) < BF16 and rel_err(x2.grad, x2r.grad) < 2 * BF16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,K,couts,silu", [(128, 512, [128, 256, 256, 128], True), (5, 20, [68, 4, 132], True),
+                                            (64, 128, [512], False), (33, 512, [256] * 30, True)])
+def test_rowlin_batch_matches_torch(ops, N, K, couts, silu):
+    """Batched Swish + Linear rows (temb_proj / TimeEmbedding) against torch fp32, forward and all three gradients;
+    items alternate between two shared inputs so the input gradient is a sum over items (and over kernel chunks)."""
+    torch.manual_seed(11)
+    dev = "cuda"
+    xa = torch.randn(N, K, device=dev, requires_grad=True)
+    xb = torch.randn(N, K, device=dev, requires_grad=True)
+    ws = [torch.randn(c, K, device=dev, requires_grad=True) for c in couts]
+    bs = [torch.randn(c, device=dev, requires_grad=True) if i % 3 != 2 else None for i, c in enumerate(couts)]
+    xs = [xa if i % 2 == 0 else xb for i in range(len(couts))]
+    ys = ops.rowlin_batch(xs, ws, bs, silu=silu)
+    gys = [torch.randn_like(y) for y in ys]
+    torch.autograd.backward(ys, gys)
+    got = [None if t.grad is None else t.grad.clone() for t in [xa, xb] + ws + [b for b in bs if b is not None]]
+    for t in [xa, xb] + ws + [b for b in bs if b is not None]:
+        t.grad = None
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        act = torch.nn.functional.silu if silu else (lambda v: v)
+        refs = [act(x) @ w.t() + (b if b is not None else 0.0) for x, w, b in zip(xs, ws, bs)]
+        torch.autograd.backward(refs, gys)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    want = [t.grad for t in [xa, xb] + ws + [b for b in bs if b is not None]]
+    for y, r in zip(ys, refs):
+        assert rel_err(y, r.detach()) < 1e-5
+    for g, w_ in zip(got, want):
+        assert (g is None) == (w_ is None)
+        if g is not None:
+            assert rel_err(g, w_) < 2e-5

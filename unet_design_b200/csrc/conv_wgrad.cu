@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     uint64_t *tmem_full = empty + p.stages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // shuffled warp index: provably warp-uniform, so the role branches are uniform control flow (see conv_fprop.cu)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     // blockIdx.x -> (ci tile, ky group, co tile); blockIdx.y -> pixel split
     int t = blockIdx.x;
@@ -70,13 +71,14 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     const uint32_t g_chunk_bytes = kPix * p.cw_g * 2, a_chunk_bytes = kPix * p.cw_a * 2;
 
     if (warp == 0) {
-        // ===================== TMA producer (one thread; no div/mod per stage) =====================
-        if (lane == 0) {
+        // ===================== TMA producer: warp-uniform loop, lane 0 issues (no div/mod per stage) =====================
+        {
+            const bool leader = lane == 0;
             const uint32_t tx_bytes = chunks_g * g_chunk_bytes + p.ntaps * chunks_a * a_chunk_bytes;
             const uint32_t base = smem_u32(smem), full0 = smem_u32(full), empty0 = smem_u32(empty);
             // first pixel tile of this split, then advance (x fastest, then y, then image group) incrementally
@@ -90,22 +92,23 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                 const int x0 = tw * p.BW, y0 = th * p.BH, n0 = tn * p.BNI;
                 const uint32_t fb = full0 + 8u * s, sg = base + (uint32_t)s * stage_bytes;
                 mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
-                mbar_arrive_expect_tx_a(fb, tx_bytes);
+                if (leader) mbar_arrive_expect_tx_a(fb, tx_bytes);
                 for (int c = 0; c < chunks_g; ++c)
-                    tma_load_4d_a(sg + c * g_chunk_bytes, &tm_g, fb, co0 + c * p.cw_g, x0, y0, n0);
+                    if (leader) tma_load_4d_a(sg + c * g_chunk_bytes, &tm_g, fb, co0 + c * p.cw_g, x0, y0, n0);
                 for (int tp = 0; tp < p.ntaps; ++tp) {
                     const int kx = p.ksize == 3 ? tp - 1 : 0;
                     const uint32_t sa = sg + p.g_stage_bytes + tp * p.a_tap_bytes;
                     for (int c = 0; c < chunks_a; ++c)
-                        tma_load_4d_a(sa + c * a_chunk_bytes, &tm_a, fb, ci0 + c * p.cw_a, x0 + kx, y0 + ky, n0);
+                        if (leader) tma_load_4d_a(sa + c * a_chunk_bytes, &tm_a, fb, ci0 + c * p.cw_a, x0 + kx, y0 + ky, n0);
                 }
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
                 if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer: warp-uniform loop, lane 0 issues =====================
+        {
+            const bool leader = lane == 0;
             const uint32_t idesc = make_idesc(128, ncols, 1, 1);
             const uint32_t swz_g = swizzle_code(p.cw_g * 2), swz_a = swizzle_code(p.cw_a * 2);
             const uint32_t row_g = p.cw_g * 2, row_a = p.cw_a * 2;
@@ -120,16 +123,18 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                 tc_fence_after();
                 const uint64_t dg = dg0 + (uint64_t)(s * stage_step), da = da0 + (uint64_t)(s * stage_step);
                 for (int tp = 0; tp < p.ntaps; ++tp) {
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < kPix / 16; ++k)
-                        umma_bf16(tmem_base + tp * 128, dg + k * kstep_g, da + tp * tap_step + k * kstep_a, idesc,
-                                  (accum | (uint32_t)k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kPix / 16; ++k)
+                            umma_bf16(tmem_base + tp * 128, dg + k * kstep_g, da + tp * tap_step + k * kstep_a, idesc,
+                                      (accum | (uint32_t)k) != 0 ? 1u : 0u);
+                    }
                 }
                 accum = 1;
-                umma_commit_a(empty0 + 8u * s);
+                if (leader) umma_commit_a(empty0 + 8u * s);
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
-            if (iters > 0) umma_commit(tmem_full);
+            if (iters > 0 && leader) umma_commit(tmem_full);
         }
     } else if (iters > 0) {
         const int qd = warp & 3;

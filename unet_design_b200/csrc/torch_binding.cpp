@@ -7,6 +7,7 @@
 // pixel stride `ld` = stride(2) may exceed C (a channel slice of a wider buffer: torch.cat elided).
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
+#include <vector>
 #include <torch/library.h>
 #include <torch/types.h>
 
@@ -330,6 +331,64 @@ void pack_dgrad_weights_batched(const Tensor &shadow, const Tensor &dgrad_arena,
                                               (int)table.size(0), cur_stream()), "pack_dgrad_weights_batched");
 }
 
+const float *rl_f32(const Tensor &t, const char *what) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kFloat && t.is_contiguous(), "rowlin: ", what, " must be a contiguous CUDA fp32 tensor");
+    return t.data_ptr<float>();
+}
+
+// y_i = act(x_i) @ w_i^T + bias_i for a list of items, one launch (bias list: same length, undefined tensors = no bias)
+using OptList = c10::List<c10::optional<Tensor>>;
+const Tensor *opt_at(const OptList &l, size_t i, Tensor &hold) {
+    c10::optional<Tensor> o = l.get(i);
+    if (!o.has_value() || !o->defined()) return nullptr;
+    hold = *o;
+    return &hold;
+}
+
+void rowlin_fwd(at::TensorList x, at::TensorList w, const OptList &bias, at::TensorList y, bool silu) {
+    const size_t n = x.size();
+    TORCH_CHECK(n > 0 && w.size() == n && (size_t)bias.size() == n && y.size() == n, "rowlin_fwd: list lengths differ");
+    UB_GUARD(x[0]);
+    const int64_t N = x[0].size(0), K = x[0].size(1);
+    std::vector<ub200_rowlin_item> items(n);
+    for (size_t i = 0; i < n; ++i) {
+        TORCH_CHECK(x[i].dim() == 2 && x[i].size(0) == N && x[i].size(1) == K && w[i].dim() == 2 && w[i].size(1) == K, "rowlin_fwd: shapes");
+        const int64_t cout = w[i].size(0);
+        TORCH_CHECK(y[i].dim() == 2 && y[i].size(0) == N && y[i].size(1) == cout, "rowlin_fwd: y shape");
+        Tensor hb;
+        const Tensor *pb = opt_at(bias, i, hb);
+        items[i] = ub200_rowlin_item{rl_f32(x[i], "x"), rl_f32(w[i], "w"), pb ? rl_f32(*pb, "bias") : nullptr,
+                                     const_cast<float *>(rl_f32(y[i], "y")), nullptr, nullptr, nullptr, nullptr, cout};
+    }
+    check_rc(ub200_rowlin_fwd(items.data(), (int)n, N, K, silu ? 1 : 0, cur_stream()), "rowlin_fwd");
+}
+
+// undefined tensors in gw / gbias / gx = that gradient is not wanted; items sharing one gx tensor are summed into it
+void rowlin_bwd(at::TensorList x, at::TensorList w, at::TensorList gy, const OptList &gw, const OptList &gbias, const OptList &gx,
+                bool silu) {
+    const size_t n = x.size();
+    TORCH_CHECK(n > 0 && w.size() == n && gy.size() == n && (size_t)gw.size() == n && (size_t)gbias.size() == n && (size_t)gx.size() == n,
+                "rowlin_bwd: list lengths differ");
+    UB_GUARD(x[0]);
+    const int64_t N = x[0].size(0), K = x[0].size(1);
+    std::vector<ub200_rowlin_item> items(n);
+    for (size_t i = 0; i < n; ++i) {
+        const int64_t cout = w[i].size(0);
+        TORCH_CHECK(x[i].dim() == 2 && x[i].size(0) == N && x[i].size(1) == K && w[i].dim() == 2 && w[i].size(1) == K &&
+                        gy[i].dim() == 2 && gy[i].size(0) == N && gy[i].size(1) == cout, "rowlin_bwd: shapes");
+        Tensor h1, h2, h3;
+        const Tensor *pw = opt_at(gw, i, h1), *pb = opt_at(gbias, i, h2), *px = opt_at(gx, i, h3);
+        TORCH_CHECK(!pw || pw->numel() == cout * K, "rowlin_bwd: gw size");
+        TORCH_CHECK(!pb || pb->numel() == cout, "rowlin_bwd: gbias size");
+        TORCH_CHECK(!px || px->numel() == N * K, "rowlin_bwd: gx size");
+        items[i] = ub200_rowlin_item{rl_f32(x[i], "x"), rl_f32(w[i], "w"), nullptr, nullptr, rl_f32(gy[i], "gy"),
+                                     pw ? const_cast<float *>(rl_f32(*pw, "gw")) : nullptr,
+                                     pb ? const_cast<float *>(rl_f32(*pb, "gbias")) : nullptr,
+                                     px ? const_cast<float *>(rl_f32(*px, "gx")) : nullptr, cout};
+    }
+    check_rc(ub200_rowlin_bwd(items.data(), (int)n, N, K, silu ? 1 : 0, cur_stream()), "rowlin_bwd");
+}
+
 }  // namespace
 
 TORCH_LIBRARY(unet_b200, m) {
@@ -354,4 +413,6 @@ TORCH_LIBRARY(unet_b200, m) {
     m.def("sumsq", &sumsq);
     m.def("adam_ema_step", &adam_ema_step);
     m.def("pack_dgrad_weights_batched", &pack_dgrad_weights_batched);
+    m.def("rowlin_fwd", &rowlin_fwd);
+    m.def("rowlin_bwd", &rowlin_bwd);
 }

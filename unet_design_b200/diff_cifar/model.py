@@ -79,7 +79,17 @@ class TimeEmbedding(nn.Module):
                 init.zeros_(module.bias)
 
     def forward(self, t):
-        return self.timembedding(t)
+        return time_embeddings([self], t)[0]
+
+
+def time_embeddings(modules, t):
+    """[m(t) for m in modules]: the embedding gathers, then both Linear layers of ALL modules as two batched launches
+    (Linear, then Swish + Linear) instead of four framework ops per module."""
+    embs = [m.timembedding[0](t) for m in modules]
+    l1 = [m.timembedding[1] for m in modules]
+    l2 = [m.timembedding[3] for m in modules]
+    h = ops.rowlin_batch(embs, [l.weight for l in l1], [l.bias for l in l1], silu=False)
+    return ops.rowlin_batch(h, [l.weight for l in l2], [l.bias for l in l2], silu=True)
 
 
 class DownSample(nn.Module):
@@ -195,12 +205,16 @@ class ResBlock(nn.Module):
                 init.zeros_(module.bias)
         init.xavier_uniform_(self.block2[-1].weight, gain=1e-5)
 
-    def forward_nhwc(self, x, temb):
+    def forward_nhwc(self, x, temb, row=None):
+        """`row` = temb_proj(temb) when the caller already computed it for all blocks at once (UNetWaveletEnc)."""
         gn1, conv1 = self.block1[0], self.block1[2]
         gn2, drop, conv2 = self.block2[0], self.block2[2], self.block2[3]
         a1 = ops.gn_act(x, gn1.weight, gn1.bias, gn1.num_groups, act="silu", eps=gn1.eps)
+        if row is None:
+            lin = self.temb_proj[1]
+            row = ops.rowlin_batch([temb], [lin.weight], [lin.bias], silu=True)[0]
         # h = conv1(a1) + bias + temb_proj(temb)[:, :, None, None]   (model.py:163-164), one kernel
-        h = ops.conv(a1, conv1.weight, conv1.bias, rowadd=self.temb_proj(temb).float().contiguous())
+        h = ops.conv(a1, conv1.weight, conv1.bias, rowadd=row)
         p = drop.p if self.training else 0.0
         a2 = ops.gn_act(h, gn2.weight, gn2.bias, gn2.num_groups, act="silu", eps=gn2.eps, dropout_p=p)
         if isinstance(self.shortcut, nn.Conv2d):
@@ -348,11 +362,32 @@ class UNetWaveletEnc(nn.Module):
                 views.append(view)
         return pyramid, views
 
+    @staticmethod
+    def _run(layer, h, rows):
+        if isinstance(layer, ResBlock):
+            return layer.forward_nhwc(h, None, row=rows[id(layer)])
+        return layer.forward_nhwc(h)
+
     def forward(self, x, t, n_levels_used=-1):
         if n_levels_used == -1:
             n_levels_used = self.n_levels
         first = self.n_levels - n_levels_used            # finest level in use
         x = x.float().contiguous()
+
+        # ---- time embeddings of every level in use and the temb projections of every ResBlock that will run: three
+        # batched launches (reference: one TimeEmbedding call per level, model.py:451/:459/:465, and one Swish + Linear
+        # per ResBlock, model.py:164)
+        levels = list(range(first, self.n_levels))
+        tembs = dict(zip(levels, time_embeddings([self.time_embedding_list[l] for l in levels], t)))
+        plan = []
+        if not self.dwt_encoder:
+            plan += [(layer, lv) for lv in levels for layer in self.downblocks[lv] if isinstance(layer, ResBlock)]
+        plan += [(layer, self.n_levels - 1) for layer in self.middleblocks if isinstance(layer, ResBlock)]
+        plan += [(layer, lv) for lv in reversed(levels) for layer in self.upblocks[lv] if isinstance(layer, ResBlock)]
+        projs = [layer.temb_proj[1] for layer, _ in plan]
+        rows = dict(zip((id(layer) for layer, _ in plan),
+                        ops.rowlin_batch([tembs[lv] for _, lv in plan], [p.weight for p in projs], [p.bias for p in projs],
+                                         silu=True)))
 
         # ---- encoder
         if self.dwt_encoder:
@@ -365,25 +400,22 @@ class UNetWaveletEnc(nn.Module):
                                                     dtype=torch.bfloat16, device=x.device))
             hs = [h]
             for level in range(first, self.n_levels):
-                temb = self.time_embedding_list[level](t)
                 for layer in self.downblocks[level]:
-                    h = layer.forward_nhwc(h, temb)
+                    h = self._run(layer, h, rows)
                     hs.append(h)
             fetch = lambda v: v
 
         # ---- middle
-        temb = self.time_embedding_list[self.n_levels - 1](t)
         for layer in self.middleblocks:
-            h = layer.forward_nhwc(h, temb)
+            h = self._run(layer, h, rows)
 
         # ---- decoder
         model_out_list = []
         for l in range(self.n_levels - 1, first - 1, -1):
-            temb = self.time_embedding_list[l](t)
             for layer in self.upblocks[l]:
                 if isinstance(layer, ResBlock):
                     h = torch.cat([h, fetch(hs.pop())], dim=3)
-                    h = layer.forward_nhwc(h, temb)
+                    h = self._run(layer, h, rows)
                 elif l != first:                         # UpSample; skipped on the finest level in use
                     if self.multi_res_loss:
                         model_out_list.append(self._tail(l, h))

@@ -500,6 +500,70 @@ def conv(a: torch.Tensor, w: torch.Tensor, bias=None, rowadd=None, a2=None, w2=N
     return _Conv.apply(a, w, bias, rowadd, a2, w2, residual, out_nchw)
 
 
+class _RowLinBatch(torch.autograd.Function):
+    """y_i = act(x_i) @ w_i^T + b_i for a list of items in ONE launch (act = SiLU or identity); backward = two launches.
+    The time-embedding path of the reference: TimeEmbedding's two Linear layers (diff_cifar/model.py:29-36) and every
+    ResBlock's Swish + Linear `temb_proj` (model.py:134-137).  Items may share their x; its gradient is the sum."""
+
+    @staticmethod
+    def forward(ctx, silu, n, *tensors):
+        xs, ws, bs = list(tensors[:n]), list(tensors[n:2 * n]), list(tensors[2 * n:3 * n])
+        xs = [x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous() for x in xs]
+        ys = [torch.empty((xs[i].shape[0], ws[i].shape[0]), dtype=torch.float32, device=xs[i].device) for i in range(n)]
+        _ops().rowlin_fwd(xs, [w.detach() for w in ws], [b.detach() if b is not None else None for b in bs], ys, bool(silu))
+        _count()
+        ctx.save_for_backward(*xs, *ws)
+        ctx.cfg = (bool(silu), n, [_key(w) for w in ws], [_key(b) for b in bs], [b is not None for b in bs])
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *gys):
+        silu, n, wkeys, bkeys, has_b = ctx.cfg
+        saved = ctx.saved_tensors
+        xs, ws = list(saved[:n]), list(saved[n:])
+        needs = ctx.needs_input_grad            # (silu, n, xs..., ws..., bs...)
+        gys = [g.contiguous() if g is not None else torch.zeros((xs[i].shape[0], ws[i].shape[0]), dtype=torch.float32,
+                                                                device=xs[i].device) for i, g in enumerate(gys)]
+        gws, gbs, gxs = [None] * n, [None] * n, [None] * n
+        ret_w, ret_b, ret_x = [None] * n, [None] * n, [None] * n
+        done = []
+        shared = {}                              # data_ptr of x -> its gradient buffer (one per distinct input)
+        for i in range(n):
+            if needs[2 + n + i]:
+                sink = _sink_of(wkeys[i])
+                if sink is not None:
+                    gws[i] = sink[0]
+                    done.append(sink)
+                else:
+                    gws[i] = ret_w[i] = torch.zeros_like(ws[i], memory_format=torch.contiguous_format)
+            if has_b[i] and needs[2 + 2 * n + i]:
+                sink = _sink_of(bkeys[i])
+                if sink is not None:
+                    gbs[i] = sink[0]
+                    done.append(sink)
+                else:
+                    gbs[i] = ret_b[i] = torch.zeros((ws[i].shape[0],), dtype=torch.float32, device=ws[i].device)
+            if needs[2 + i]:
+                key = xs[i].data_ptr()
+                if key not in shared:
+                    shared[key] = torch.empty_like(xs[i])
+                    ret_x[i] = shared[key]       # autograd sums the slots of one tensor: hand the total to the first slot only
+                gxs[i] = shared[key]
+        _ops().rowlin_bwd(xs, [w.detach() for w in ws], gys, gws, gbs, gxs, silu)
+        _count(2)
+        for sink in done:
+            if sink[1] is not None:
+                sink[1]()
+        return (None, None, *ret_x, *ret_w, *ret_b)
+
+
+def rowlin_batch(xs, ws, bs, silu: bool):
+    """[act(x_i) @ w_i^T + b_i for i]: fp32 [N, K] inputs (all the same N and K), fp32 nn.Linear weights [cout_i, K]."""
+    n = len(xs)
+    assert n > 0 and len(ws) == n and len(bs) == n
+    return list(_RowLinBatch.apply(silu, n, *xs, *ws, *bs))
+
+
 class _Split3(torch.autograd.Function):
     """Three channel-slice views of a fused q|k|v projection; backward gathers the three gradients into one
     buffer with strided copies (no zero-fill + add chain as plain slicing would record)."""
