@@ -260,6 +260,12 @@ def run_gpu_arm(args):
     # ---- device-resident inputs: W warm-up + K timed steps
     for i in range(max(args.warmup, 3)):
         step(dev_batches[i % 4])
+    if args.profile_step:            # ncu --profile-from-start off: exactly one (eager) step between start/stop
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step._body(dev_batches[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -355,6 +361,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--no-overlap", action="store_true", help="one gradient all-reduce after backward instead of bucketed overlap")
     ap.add_argument("--dump-kernels", action="store_true", help="write per-launch conv timings to gpurun_out/conv_launch_table.json")
+    ap.add_argument("--profile-step", action="store_true", help="bracket one eager step with cudaProfilerStart/Stop (for ncu)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-haar", action="store_true")
     args = ap.parse_args()

@@ -494,8 +494,11 @@ PixelTile pick_pixel_tile(int64_t N, int64_t H, int64_t W) {
             const int bn = 128 / (bw * bh);
             const double cost = (double)((W + bw - 1) / bw * bw) * (double)((H + bh - 1) / bh * bh) *
                                 (double)((N + bn - 1) / bn * bn);
-            // ties: prefer wide boxes (longer contiguous runs per TMA row)
-            if (cost < best_cost - 0.5 || (cost < best_cost + 0.5 && bw > best.BW)) { best_cost = cost; best = {bw, bh, bn}; }
+            // ties: prefer wide boxes (longer contiguous runs per TMA row), then tall ones (fewer samples per tile: the
+            // epilogue's per-sample addend table stays within kTblRows rows)
+            if (cost < best_cost - 0.5 || (cost < best_cost + 0.5 && (bw > best.BW || (bw == best.BW && bh > best.BH)))) {
+                best_cost = cost; best = {bw, bh, bn};
+            }
         }
     return best;
 }

@@ -53,25 +53,33 @@ __device__ __forceinline__ void fma_slice(const float (*As)[kTile + kPad], const
     }
 }
 
-// 64 rows x 16 columns of a row-major matrix (leading dimension ld, contiguous along the 16) -> S[col][row]
-// (transposed); rows >= rows_valid and columns >= cols_valid read as zero.  ACT applies SiLU on the way.
-template <bool ACT>
-__device__ __forceinline__ void load_transposed(float (*S)[kTile + kPad], const float *src, int64_t ld, int row0, int rows_valid,
-                                                int col0, int cols_valid) {
+// Operand fetches for one 16-deep slice, split into the global read (issued one slice ahead, so the L2 latency is
+// covered by the FMAs of the current slice) and the shared-memory store.
+// "T": 64 rows x 16 columns of a row-major matrix (contiguous along the 16), stored transposed as S[col][row];
+// "D": 16 rows x 64 columns (contiguous along the 64), stored as S[row][col].
+// Rows >= rows_valid and columns >= cols_valid read as zero.  ACT applies SiLU at the shared-memory store (not at the
+// fetch, which would make the prefetched value a dependency of the current slice).
+__device__ __forceinline__ float4 fetch_T(const float *src, int64_t ld, int row0, int rows_valid, int col0, int cols_valid) {
     const int r = threadIdx.x >> 2, c4 = (threadIdx.x & 3) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row0 + r < rows_valid && col0 + c4 < cols_valid) v = *reinterpret_cast<const float4 *>(src + (int64_t)(row0 + r) * ld + col0 + c4);
+    if (row0 + r < rows_valid && col0 + c4 < cols_valid) v = __ldg(reinterpret_cast<const float4 *>(src + (int64_t)(row0 + r) * ld + col0 + c4));
+    return v;
+}
+template <bool ACT>
+__device__ __forceinline__ void put_T(float (*S)[kTile + kPad], float4 v) {
+    const int r = threadIdx.x >> 2, c4 = (threadIdx.x & 3) * 4;
     if (ACT) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
     S[c4][r] = v.x; S[c4 + 1][r] = v.y; S[c4 + 2][r] = v.z; S[c4 + 3][r] = v.w;
 }
-
-// 16 rows x 64 columns (contiguous along the 64) -> S[row][col]
-template <bool ACT>
-__device__ __forceinline__ void load_direct(float (*S)[kTile + kPad], const float *src, int64_t ld, int row0, int rows_valid,
-                                            int col0, int cols_valid) {
+__device__ __forceinline__ float4 fetch_D(const float *src, int64_t ld, int row0, int rows_valid, int col0, int cols_valid) {
     const int r = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row0 + r < rows_valid && col0 + c4 < cols_valid) v = *reinterpret_cast<const float4 *>(src + (int64_t)(row0 + r) * ld + col0 + c4);
+    if (row0 + r < rows_valid && col0 + c4 < cols_valid) v = __ldg(reinterpret_cast<const float4 *>(src + (int64_t)(row0 + r) * ld + col0 + c4));
+    return v;
+}
+template <bool ACT>
+__device__ __forceinline__ void put_D(float (*S)[kTile + kPad], float4 v) {
+    const int r = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;
     if (ACT) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
     *reinterpret_cast<float4 *>(&S[r][c4]) = v;
 }
@@ -85,18 +93,22 @@ __device__ __forceinline__ int find_item(const Batch &b, int tile) {
 // y[n, c] = bias[c] + sum_k act(x[n, k]) w[c, k].   grid: (cout tiles of all items, batch tiles)
 template <bool ACT>
 __global__ void __launch_bounds__(kThreads) rowlin_fwd_kernel(const __grid_constant__ Batch b) {
-    __shared__ __align__(16) float As[kSlice][kTile + kPad], Bs[kSlice][kTile + kPad];
+    __shared__ __align__(16) float As[2][kSlice][kTile + kPad], Bs[2][kSlice][kTile + kPad];
     const int ii = find_item(b, blockIdx.x);
     const Item &it = b.it[ii];
     const int c0 = (blockIdx.x - it.tile0) * kTile, n0 = blockIdx.y * kTile;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < b.K; k0 += kSlice) {
-        load_transposed<ACT>(As, it.x, b.K, n0, b.N, k0, b.K);
-        load_transposed<false>(Bs, it.w, b.K, c0, it.cout, k0, b.K);
+    const int ns = (b.K + kSlice - 1) / kSlice;
+    float4 ra = fetch_T(it.x, b.K, n0, b.N, 0, b.K), rb = fetch_T(it.w, b.K, c0, it.cout, 0, b.K);
+    for (int s = 0; s < ns; ++s) {
+        put_T<ACT>(As[s & 1], ra); put_T<false>(Bs[s & 1], rb);
         __syncthreads();
-        fma_slice(As, Bs, ty, tx, acc);
-        __syncthreads();
+        if (s + 1 < ns) {
+            ra = fetch_T(it.x, b.K, n0, b.N, (s + 1) * kSlice, b.K);
+            rb = fetch_T(it.w, b.K, c0, it.cout, (s + 1) * kSlice, b.K);
+        }
+        fma_slice(As[s & 1], Bs[s & 1], ty, tx, acc);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -113,25 +125,29 @@ __global__ void __launch_bounds__(kThreads) rowlin_fwd_kernel(const __grid_const
 // gw[c, k] += sum_n gy[n, c] act(x[n, k]);  gb[c] += sum_n gy[n, c].   grid: (cout tiles of all items, K tiles)
 template <bool ACT>
 __global__ void __launch_bounds__(kThreads) rowlin_wgrad_kernel(const __grid_constant__ Batch b) {
-    __shared__ __align__(16) float As[kSlice][kTile + kPad], Bs[kSlice][kTile + kPad];
+    __shared__ __align__(16) float As[2][kSlice][kTile + kPad], Bs[2][kSlice][kTile + kPad];
     const int ii = find_item(b, blockIdx.x);
     const Item &it = b.it[ii];
     const int c0 = (blockIdx.x - it.tile0) * kTile, k0 = blockIdx.y * kTile;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     float acc[4][4] = {};
     float colsum[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int n0 = 0; n0 < b.N; n0 += kSlice) {
-        load_direct<false>(As, it.gy, it.cout, n0, b.N, c0, it.cout);
-        load_direct<ACT>(Bs, it.x, b.K, n0, b.N, k0, b.K);
+    const int ns = (b.N + kSlice - 1) / kSlice;
+    float4 ra = fetch_D(it.gy, it.cout, 0, b.N, c0, it.cout), rb = fetch_D(it.x, b.K, 0, b.N, k0, b.K);
+    for (int s = 0; s < ns; ++s) {
+        put_D<false>(As[s & 1], ra); put_D<ACT>(Bs[s & 1], rb);
         __syncthreads();
-        fma_slice(As, Bs, ty, tx, acc);
+        if (s + 1 < ns) {
+            ra = fetch_D(it.gy, it.cout, (s + 1) * kSlice, b.N, c0, it.cout);
+            rb = fetch_D(it.x, b.K, (s + 1) * kSlice, b.N, k0, b.K);
+        }
+        fma_slice(As[s & 1], Bs[s & 1], ty, tx, acc);
         if (tx == 0 && blockIdx.y == 0) {
 #pragma unroll
             for (int kk = 0; kk < kSlice; ++kk)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) colsum[i] += As[kk][ty * 4 + i];
+                for (int i = 0; i < 4; ++i) colsum[i] += As[s & 1][kk][ty * 4 + i];
         }
-        __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -148,24 +164,27 @@ __global__ void __launch_bounds__(kThreads) rowlin_wgrad_kernel(const __grid_con
     }
 }
 
-// gx[n, k] (+)= act'(x[n, k]) * sum over the group's items, sum_c gy[n, c] w[c, k].   grid: (K tiles, batch tiles, groups)
+// gx[n, k] += act'(x[n, k]) * sum_c gy[n, c] w[c, k] for ONE item per CTA (fp32 atomics: the items that share an input
+// run in parallel; gx is zeroed by the host function first).   grid: (K tiles, batch tiles, items)
 template <bool ACT>
 __global__ void __launch_bounds__(kThreads) rowlin_xgrad_kernel(const __grid_constant__ Batch b) {
-    __shared__ __align__(16) float As[kSlice][kTile + kPad], Bs[kSlice][kTile + kPad];
-    const Group &g = b.gr[blockIdx.z];
+    __shared__ __align__(16) float As[2][kSlice][kTile + kPad], Bs[2][kSlice][kTile + kPad];
+    const Item &it = b.it[blockIdx.z];
+    if (it.group < 0) return;
+    const Group &g = b.gr[it.group];
     const int k0 = blockIdx.x * kTile, n0 = blockIdx.y * kTile;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     float acc[4][4] = {};
-    for (int ii = 0; ii < b.n_items; ++ii) {
-        const Item &it = b.it[ii];
-        if (it.group != (int)blockIdx.z) continue;
-        for (int c0 = 0; c0 < it.cout; c0 += kSlice) {
-            load_transposed<false>(As, it.gy, it.cout, n0, b.N, c0, it.cout);
-            load_direct<false>(Bs, it.w, b.K, c0, it.cout, k0, b.K);
-            __syncthreads();
-            fma_slice(As, Bs, ty, tx, acc);
-            __syncthreads();
+    const int ns = (it.cout + kSlice - 1) / kSlice;
+    float4 ra = fetch_T(it.gy, it.cout, n0, b.N, 0, it.cout), rb = fetch_D(it.w, b.K, 0, it.cout, k0, b.K);
+    for (int s = 0; s < ns; ++s) {
+        put_T<false>(As[s & 1], ra); put_D<false>(Bs[s & 1], rb);
+        __syncthreads();
+        if (s + 1 < ns) {
+            ra = fetch_T(it.gy, it.cout, n0, b.N, (s + 1) * kSlice, it.cout);
+            rb = fetch_D(it.w, b.K, (s + 1) * kSlice, it.cout, k0, b.K);
         }
+        fma_slice(As[s & 1], Bs[s & 1], ty, tx, acc);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -178,7 +197,7 @@ __global__ void __launch_bounds__(kThreads) rowlin_xgrad_kernel(const __grid_con
             const int64_t o = (int64_t)n * b.K + k;
             float v = acc[i][j];
             if (ACT) v *= dsilu_f(__ldg(g.x + o));
-            g.gx[o] = g.accumulate ? g.gx[o] + v : v;
+            atomicAdd(g.gx + o, v);
         }
     }
 }
@@ -261,7 +280,12 @@ int ub200_rowlin_bwd(const ub200_rowlin_item *items, int n_items, int64_t N, int
             UB_LAUNCH_CHECK();
         }
         if (b.n_groups > 0) {
-            dim3 grid((unsigned)((K + kTile - 1) / kTile), (unsigned)((N + kTile - 1) / kTile), (unsigned)b.n_groups);
+            for (int g = 0; g < b.n_groups; ++g)
+                if (!b.gr[g].accumulate) {
+                    cudaError_t e = cudaMemsetAsync(b.gr[g].gx, 0, (size_t)N * K * sizeof(float), s);
+                    if (e != cudaSuccess) return (int)e;
+                }
+            dim3 grid((unsigned)((K + kTile - 1) / kTile), (unsigned)((N + kTile - 1) / kTile), (unsigned)n);
             if (silu) rowlin_xgrad_kernel<true><<<grid, kThreads, 0, s>>>(b);
             else rowlin_xgrad_kernel<false><<<grid, kThreads, 0, s>>>(b);
             UB_LAUNCH_CHECK();
