@@ -291,6 +291,12 @@ def run_gpu_arm(args):
     e2e_s = time.perf_counter() - t0
     barrier()
 
+    phases = None
+    if world > 1 and not args.no_graph:
+        ph = step.timed_phases(dev_batches[0])
+        tp = torch.tensor(ph, device=dev, dtype=torch.float64)
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        phases = {"fwd_bwd_graph_ms": float(tp[0]), "grad_allreduce_ms": float(tp[1]), "clip_adam_ema_ms": float(tp[2])}
     if world > 1:
         t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -343,6 +349,7 @@ def run_gpu_arm(args):
             "e2e": {"value": imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": BATCH_PER_GPU * 3 * 32 * 32 * 4,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,
+            "dp_phases": phases,
             "roofline": roofline, "haar_roofline": haar, "cpu_baseline": cpu,
         }
     if world > 1:

@@ -158,7 +158,9 @@ int ub200_gn_act_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int
  * slab in distributed shared memory, so x (and gy) are read from HBM once.  forward = statistics + apply
  * (stats [N,G,2] is an OUTPUT here, kept for the backward); backward = both backward passes.  When the
  * slab does not fit one cluster (8 CTAs x ~200 KB) they run the multi-pass kernels instead: same results
- * either way.  stats == NULL ("no normalisation") is only valid for the backward. */
+ * either way.  stats == NULL ("no normalisation") is only valid for the backward.  gadd (backward, nullable):
+ * a second gradient of x, NHWC bf16 -- the ResBlock input also feeds the shortcut / residual branch
+ * (diff_cifar/model.py:167), and summing the two gradients here saves a separate pass over the tensor. */
 int ub200_gn_act_fused_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t HW, int64_t C, int G,
                                      float *stats, float eps, const float *gamma, const float *beta,
                                      const float *scale, const float *shift, int act,
@@ -171,6 +173,7 @@ int ub200_gn_act_fused_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *
                                      float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
                                      void *gx, int64_t ld_gx,
                                      float *dgamma, float *dbeta, float *dscale, float *dshift,
+                                     const void *gadd, int64_t ld_gadd,   /* nullable: gx = backward(gy) + gadd */
                                      float *ws, void *stream);
 
 /* ------------------------------------------------------------------------------------------

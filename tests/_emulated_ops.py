@@ -125,7 +125,7 @@ class EmulatedOps:
         return _bf(torch.from_numpy(np.ascontiguousarray(gx)).permute(0, 2, 3, 1)).contiguous()
 
     def gn_act_bwd(self, gy, x, G, stats, eps, gamma, beta, scale, shift, act, p, seed, off, off_dev, gx, accumulate,
-                   dgamma, dbeta, dscale, dshift):
+                   dgamma, dbeta, dscale, dshift, gadd=None):
         with torch.enable_grad():
             xr = x.float().requires_grad_(True)
             leaves = [xr]
@@ -142,6 +142,8 @@ class EmulatedOps:
             grads = torch.autograd.grad(y, leaves, gy.float())
         g_iter = iter(grads)
         dx = next(g_iter)
+        if gadd is not None:
+            dx = dx + gadd.float()
         gx.copy_(_bf(gx.float() + dx) if accumulate else _bf(dx))
         for src, dst in ((ga, dgamma), (be, dbeta), (sc, dscale), (sf, dshift)):
             if src is not None:

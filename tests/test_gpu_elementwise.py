@@ -233,3 +233,29 @@ def test_rowlin_batch_matches_torch(ops, N, K, couts, silu):
         assert (g is None) == (w_ is None)
         if g is not None:
             assert rel_err(g, w_) < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(4, 8, 8, 128), (3, 32, 32, 256), (1, 128, 128, 64), (2, 16, 16, 512)])
+def test_gn_act_fork_sums_both_gradients_in_the_kernel(ops, shape):
+    """gn_act_fork returns (act(GN(x)), x); the gradient of the second output is added inside the backward kernel
+    (single-CTA slab, cluster slab and multi-pass fallback shapes) and must equal autograd's separate add."""
+    torch.manual_seed(12)
+    c = shape[3]
+    x0 = torch.randn(*shape, device="cuda").to(torch.bfloat16)
+    gamma = (1 + 0.1 * torch.randn(c, device="cuda")).requires_grad_(True)
+    beta = (0.1 * torch.randn(c, device="cuda")).requires_grad_(True)
+    g1 = torch.randn(*shape, device="cuda").to(torch.bfloat16)
+    g2 = torch.randn(*shape, device="cuda").to(torch.bfloat16)
+    xa = x0.clone().requires_grad_(True)
+    a, xf = ops.gn_act_fork(xa, gamma, beta, 32)
+    torch.autograd.backward([a, xf], [g1, g2])
+    got, gg, gb = xa.grad.float(), gamma.grad.clone(), beta.grad.clone()
+    gamma.grad = beta.grad = None
+    xb = x0.clone().requires_grad_(True)
+    y = ops.gn_act(xb, gamma, beta, 32)
+    y.backward(g1)
+    want = xb.grad.float() + g2.float()
+    assert rel_err(a, y) < 1e-3          # the multi-pass fallback sums its statistics with fp32 atomics: order varies
+    assert rel_err(got, want) < BF16
+    assert rel_err(gg, gamma.grad) < 1e-4 and rel_err(gb, beta.grad) < 1e-4

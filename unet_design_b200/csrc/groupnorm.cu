@@ -530,7 +530,8 @@ __global__ void __launch_bounds__(kFusedThreads, 3) gn_fused_bwd_kernel(
     const float *__restrict__ stats, float eps, const float *__restrict__ gamma, const float *__restrict__ beta,
     const float *__restrict__ scale, const float *__restrict__ shift, float p_drop, uint64_t seed, uint64_t offset,
     const uint64_t *__restrict__ off_dev, __nv_bfloat16 *__restrict__ gx, int64_t ld_gx, float *__restrict__ dgamma,
-    float *__restrict__ dbeta, float *__restrict__ dscale, float *__restrict__ dshift) {
+    float *__restrict__ dbeta, float *__restrict__ dscale, float *__restrict__ dshift,
+    const __nv_bfloat16 *__restrict__ gadd, int64_t ld_gadd) {
     extern __shared__ __align__(128) uint8_t fsm[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -651,27 +652,63 @@ __global__ void __launch_bounds__(kFusedThreads, 3) gn_fused_bwd_kernel(
         R[u] = -rstd * m1 - mean * Qc[u];
     }
     __nv_bfloat16 *ob = gx + (n * sh.HW + p0) * ld_gx + 8 * q;
-    auto fin = [&](int p, const uint4 &xv) {
+    // gadd: a second gradient of x (the ResBlock's shortcut / residual branch), summed here instead of by a separate add
+    const __nv_bfloat16 *ab = gadd ? gadd + (n * sh.HW + p0) * ld_gadd + 8 * q : nullptr;
+    auto fin = [&](int p, const uint4 &xv, const uint4 &av) {
         float f[8], d[8];
         unpack8(xv, f);
         unpack8(ds[p * sh.chunks + q], d);
 #pragma unroll
         for (int u = 0; u < 8; ++u) d[u] = fmaf(d[u], P[u], fmaf(f[u], Qc[u], R[u]));
+        if (ab) {
+            float a[8];
+            unpack8(av, a);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d[u] += a[u];
+        }
         *reinterpret_cast<uint4 *>(ob + (int64_t)p * ld_gx) = pack8(d);
     };
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
     if (XSLAB) {
-#pragma unroll 2
-        for (int p = r; p < npx; p += step) fin(p, xs[p * sh.chunks + q]);
+        for (int p = r; p < npx; p += 2 * step) {
+            uint4 a0 = zero4, a1 = zero4;
+            if (ab) {
+                a0 = ld_stream_u4(reinterpret_cast<const uint4 *>(ab + (int64_t)p * ld_gadd));
+                if (p + step < npx) a1 = ld_stream_u4(reinterpret_cast<const uint4 *>(ab + (int64_t)(p + step) * ld_gadd));
+            }
+            fin(p, xs[p * sh.chunks + q], a0);
+            if (p + step < npx) fin(p + step, xs[(p + step) * sh.chunks + q], a1);
+        }
     } else {
         for (int p = r; p < npx; p += 4 * step) {                          // four L2 reads in flight per thread
-            uint4 t[4];
+            uint4 t[4], a[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (p + j * step < npx) t[j] = *reinterpret_cast<const uint4 *>(xb + (int64_t)(p + j * step) * ld_x);
+                if (p + j * step < npx) {
+                    t[j] = *reinterpret_cast<const uint4 *>(xb + (int64_t)(p + j * step) * ld_x);
+                    a[j] = ab ? ld_stream_u4(reinterpret_cast<const uint4 *>(ab + (int64_t)(p + j * step) * ld_gadd)) : zero4;
+                }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (p + j * step < npx) fin(p + j * step, t[j]);
+                if (p + j * step < npx) fin(p + j * step, t[j], a[j]);
         }
+    }
+}
+
+// gx += gadd (the multi-pass fallback of the fused backward's second-gradient input)
+__global__ void __launch_bounds__(256) add_rows_kernel(__nv_bfloat16 *__restrict__ gx, int64_t ld_gx,
+                                                      const __nv_bfloat16 *__restrict__ gadd, int64_t ld_gadd, int64_t pixels,
+                                                      int chunks) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels * chunks; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / chunks;
+        const int q = (int)(i - p * chunks);
+        float a[8], b[8];
+        uint4 *dst = reinterpret_cast<uint4 *>(gx + p * ld_gx + 8 * q);
+        unpack8(*dst, a);
+        unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(gadd + p * ld_gadd + 8 * q)), b);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] += b[u];
+        *dst = pack8(a);
     }
 }
 
@@ -890,7 +927,8 @@ int ub200_gn_act_fused_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *
                                      const float *beta, const float *scale, const float *shift, int act,
                                      float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
                                      void *gx, int64_t ld_gx, float *dgamma, float *dbeta, float *dscale, float *dshift,
-                                     float *ws, void *stream) {
+                                     const void *gadd, int64_t ld_gadd, float *ws, void *stream) {
+    UB_REQUIRE(!gadd || (ld_gadd % 8 == 0 && ld_gadd >= C && ub::aligned16(gadd)), UB200_E_UNSUPPORTED);
     UB_REQUIRE(gy && x && gx && ws && N > 0 && HW > 0 && C > 0 && G > 0 && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
     UB_REQUIRE(act == UB200_ACT_NONE || act == UB200_ACT_SILU || act == UB200_ACT_GELU, UB200_E_BADARG);
     FusedShape sh; size_t smem = 0;
@@ -899,15 +937,24 @@ int ub200_gn_act_fused_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *
     const size_t extra = (size_t)(4 * C + ((2 * G + 3) & ~3));
     const bool xslab = fits && plan_fused(N, HW, C, G, 2, extra, sh, smem, 1);
     const bool ok = xslab || (fits && plan_fused(N, HW, C, G, 1, extra, sh, smem));
-    if (!ok)
-        return ub200_gn_act_bwd_nhwc_bf16(gy, ld_gy, x, ld_x, N, HW, C, G, stats, eps, gamma, beta, scale, shift, act,
-                                          dropout_p, seed, offset, offset_dev, gx, ld_gx, 0, dgamma, dbeta, dscale, dshift,
-                                          ws, stream);
+    if (!ok) {
+        int rc = ub200_gn_act_bwd_nhwc_bf16(gy, ld_gy, x, ld_x, N, HW, C, G, stats, eps, gamma, beta, scale, shift, act,
+                                            dropout_p, seed, offset, offset_dev, gx, ld_gx, 0, dgamma, dbeta, dscale, dshift,
+                                            ws, stream);
+        if (rc || !gadd) return rc;
+        UB_REQUIRE(C % 8 == 0 && ld_gx % 8 == 0 && ub::aligned16(gx), UB200_E_UNSUPPORTED);
+        add_rows_kernel<<<148 * 8, 256, 0, ub::as_stream(stream)>>>(reinterpret_cast<__nv_bfloat16 *>(gx), ld_gx,
+                                                                    reinterpret_cast<const __nv_bfloat16 *>(gadd), ld_gadd,
+                                                                    N * HW, (int)(C / 8));
+        UB_LAUNCH_CHECK();
+        return UB200_OK;
+    }
     const bool drop = dropout_p > 0.f;
 #define BWD_ARGS                                                                                                      \
     (int)(N * sh.cs), sh.cs, smem, ub::as_stream(stream), reinterpret_cast<const __nv_bfloat16 *>(gy), ld_gy,         \
         reinterpret_cast<const __nv_bfloat16 *>(x), ld_x, sh, stats, eps, gamma, beta, scale, shift, dropout_p, seed, \
-        offset, offset_dev, reinterpret_cast<__nv_bfloat16 *>(gx), ld_gx, dgamma, dbeta, dscale, dshift
+        offset, offset_dev, reinterpret_cast<__nv_bfloat16 *>(gx), ld_gx, dgamma, dbeta, dscale, dshift,                 \
+        reinterpret_cast<const __nv_bfloat16 *>(gadd), ld_gadd
     if (xslab) return DISPATCH_FUSED(FUSED_BWD_X, act, drop, BWD_ARGS);
     return DISPATCH_FUSED(FUSED_BWD_S, act, drop, BWD_ARGS);
 #undef BWD_ARGS

@@ -209,9 +209,16 @@ void gn_act_bwd(const Tensor &gy, const Tensor &x, int64_t G, const c10::optiona
                 const c10::optional<Tensor> &gamma, const c10::optional<Tensor> &beta, const c10::optional<Tensor> &scale,
                 const c10::optional<Tensor> &shift, int64_t act, double dropout_p, int64_t seed, int64_t offset,
                 const c10::optional<Tensor> &offset_dev, const Tensor &gx, bool accumulate, const c10::optional<Tensor> &dgamma, const c10::optional<Tensor> &dbeta,
-                const c10::optional<Tensor> &dscale, const c10::optional<Tensor> &dshift) {
+                const c10::optional<Tensor> &dscale, const c10::optional<Tensor> &dshift, const c10::optional<Tensor> &gadd) {
     UB_GUARD(x);
     const Nhwc g = nhwc(gy, "gy"), i = nhwc(x, "x"), o = nhwc(gx, "gx");
+    const void *gap = nullptr;
+    int64_t ld_ga = 0;
+    if (gadd.has_value()) {
+        const Nhwc ga = nhwc(*gadd, "gadd");
+        TORCH_CHECK(ga.N == i.N && ga.H == i.H && ga.W == i.W && ga.C == i.C, "gn_act_bwd: gadd shape mismatch");
+        gap = ga.ptr; ld_ga = ga.ld;
+    }
     TORCH_CHECK(g.N == i.N && g.H == i.H && g.W == i.W && g.C == i.C && o.N == i.N && o.H == i.H && o.W == i.W && o.C == i.C,
                 "gn_act_bwd: shape mismatch");
     Tensor ws = at::empty({(int64_t)ub200_gn_act_bwd_ws_floats(i.N, i.C, (int)G)}, x.options().dtype(at::kFloat));
@@ -221,7 +228,7 @@ void gn_act_bwd(const Tensor &gy, const Tensor &x, int64_t G, const c10::optiona
                                               (float)eps, f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
                                               f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed,
                                               (uint64_t)offset, i64_opt(offset_dev), o.ptr, o.ld, mut(dgamma, "dgamma"),
-                                              mut(dbeta, "dbeta"), mut(dscale, "dscale"), mut(dshift, "dshift"),
+                                              mut(dbeta, "dbeta"), mut(dscale, "dscale"), mut(dshift, "dshift"), gap, ld_ga,
                                               ws.data_ptr<float>(), cur_stream()),
              "gn_act_bwd");
 }

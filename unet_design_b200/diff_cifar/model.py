@@ -209,7 +209,8 @@ class ResBlock(nn.Module):
         """`row` = temb_proj(temb) when the caller already computed it for all blocks at once (UNetWaveletEnc)."""
         gn1, conv1 = self.block1[0], self.block1[2]
         gn2, drop, conv2 = self.block2[0], self.block2[2], self.block2[3]
-        a1 = ops.gn_act(x, gn1.weight, gn1.bias, gn1.num_groups, act="silu", eps=gn1.eps)
+        # x also feeds the shortcut / residual branch below: its two gradients are summed in the GroupNorm backward
+        a1, x = ops.gn_act_fork(x, gn1.weight, gn1.bias, gn1.num_groups, act="silu", eps=gn1.eps)
         if row is None:
             lin = self.temb_proj[1]
             row = ops.rowlin_batch([temb], [lin.weight], [lin.bias], silu=True)[0]

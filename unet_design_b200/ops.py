@@ -254,7 +254,7 @@ def dwtblock_nhwc(x: torch.Tensor, J: int, out: torch.Tensor, chmap: Optional[to
 # --------------------------------------------------------------------------------------------------
 class _GnAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, shift, G, eps, act, p_drop, addend):
+    def forward(ctx, x, gamma, beta, scale, shift, G, eps, act, p_drop, addend, fork=False):
         x = _dense_nhwc(x)
         n, h, w, c = x.shape
         stats = None
@@ -274,13 +274,21 @@ class _GnAct(torch.autograd.Function):
         ctx.keys = (_key(gamma), _key(beta))
         ctx.save_for_backward(x, stats, gamma, beta, scale, shift)
         ctx.cfg = (G, eps, act, p_drop, seed, off, dev)
+        ctx.fork = bool(fork)
+        if fork:
+            # second output: x itself, for the branch that by-passes the normalisation (ResBlock shortcut / residual).
+            # Its gradient comes back to THIS node, where the backward kernel adds it to the GroupNorm gradient.
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, gx2=None):
         x, stats, gamma, beta, scale, shift = ctx.saved_tensors
         G, eps, act, p_drop, seed, off, dev = ctx.cfg
+        if gy is None:                 # only the by-pass branch carried a gradient
+            gy = torch.zeros(x.shape, dtype=torch.bfloat16, device=x.device)
         gy = _dense_nhwc(gy)
+        gadd = _dense_nhwc(gx2.to(torch.bfloat16)) if gx2 is not None else None
         gx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
         sg, sb = _sink_of(ctx.keys[0]), _sink_of(ctx.keys[1])
         dgamma = (sg[0] if sg else torch.zeros_like(gamma)) if gamma is not None else None
@@ -288,13 +296,13 @@ class _GnAct(torch.autograd.Function):
         dscale = torch.empty_like(scale) if scale is not None else None
         dshift = torch.empty_like(shift) if shift is not None else None
         _ops().gn_act_bwd(gy, x, G, stats, eps, gamma, beta, scale, shift, act, p_drop, seed, off, dev, gx, False,
-                          dgamma, dbeta, dscale, dshift)
+                          dgamma, dbeta, dscale, dshift, gadd)
         _count(1)
         for sink in (sg, sb):
             if sink and sink[1] is not None:
                 sink[1]()
         return (gx, None if sg else dgamma, None if sb else dbeta, dscale, dshift, None, None, None, None,
-                (gy if ctx.has_addend else None))
+                (gy if ctx.has_addend else None), None)
 
 
 def gn_act(x, gamma, beta, groups: int, act: str = "silu", eps: float = 1e-5, dropout_p: float = 0.0,
@@ -302,6 +310,12 @@ def gn_act(x, gamma, beta, groups: int, act: str = "silu", eps: float = 1e-5, dr
     """addend + dropout(act(GroupNorm(x) * (1 + scale) + shift)); NHWC bf16 in and out.
     `groups = 0` skips the normalisation (gamma / beta still apply if given)."""
     return _GnAct.apply(x, gamma, beta, scale, shift, groups, eps, _ACT[act], float(dropout_p), addend)
+
+
+def gn_act_fork(x, gamma, beta, groups: int, act: str = "silu", eps: float = 1e-5):
+    """(act(GroupNorm(x)), x): the second output is x for a branch that skips the normalisation; both gradients are
+    summed inside the GroupNorm backward kernel instead of by a separate add over the tensor."""
+    return _GnAct.apply(x, gamma, beta, None, None, groups, eps, _ACT[act], 0.0, None, True)
 
 
 class _DwtBlockNhwc(torch.autograd.Function):
@@ -577,6 +591,8 @@ class _Split3(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gq, gk, gv):
         c = ctx.shape[-1] // 3
+        if gq is not None and gk is not None and gv is not None:
+            return torch.cat([gq, gk, gv], dim=-1)          # one vectorised launch instead of three strided copies
         ref = next(g for g in (gq, gk, gv) if g is not None)
         out = torch.empty(ctx.shape, dtype=ref.dtype, device=ref.device)
         for i, g in enumerate((gq, gk, gv)):

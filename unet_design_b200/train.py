@@ -236,6 +236,9 @@ class DDPMTrainStep:
                 self._finish_allreduce()
             else:                      # one all-reduce of the whole arena after backward
                 dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM, group=self.pg)
+        self._update()
+
+    def _update(self):
         self.sumsq.zero_()
         ops.sumsq_(self.arena.g, self.sumsq)
         # gradients hold the SUM over ranks: the mean (what DataParallel / DDP produce) is a grad_scale of 1/world
@@ -263,6 +266,23 @@ class DDPMTrainStep:
         if self.world > 1:             # the collective and the optimiser tail stay outside the graph (3 launches)
             self._reduce_and_update(False)
         return self._static_loss
+
+    def timed_phases(self, x0: torch.Tensor, reps: int = 5):
+        """Device time (ms, averaged) of the three phases of a data-parallel step: forward+backward graph, gradient
+        all-reduce, clip+Adam+EMA tail.  Diagnostic only (bench.py reports it next to the step time)."""
+        assert self.use_graph and self.world > 1 and self._graph is not None
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(reps)]
+        for r in range(reps):
+            self._static_x0.copy_(x0, non_blocking=True)
+            ev[r][0].record()
+            self._graph.replay()
+            ev[r][1].record()
+            dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM, group=self.pg)
+            ev[r][2].record()
+            self._update()
+            ev[r][3].record()
+        torch.cuda.synchronize(self.device)
+        return [sum(e[i].elapsed_time(e[i + 1]) for e in ev) / reps for i in range(3)]
 
     def _capture(self, x0: torch.Tensor):
         """One CUDA graph for the whole step on a single GPU; forward + backward only when data-parallel (NCCL work
