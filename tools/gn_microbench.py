@@ -38,7 +38,7 @@ def main():
         dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
         stats = torch.empty(n, 32, 2, device="cuda")
         fwd = lambda: ops.gn_act_fwd(x, 32, stats, 1e-5, gamma, beta, None, None, 1, 0.0, 0, 0, None, None, y, True)
-        bwd = lambda: ops.gn_act_bwd(gy, x, 32, stats, 1e-5, gamma, beta, None, None, 1, 0.0, 0, 0, None, gx, False, dg, db, None, None)
+        bwd = lambda: ops.gn_act_bwd(gy, x, 32, stats, 1e-5, gamma, beta, None, None, 1, 0.0, 0, 0, None, gx, False, dg, db, None, None, None)
         tf, tb = timeit(fwd), timeit(bwd)
         mb = x.numel() * 2 / 1e6
         row = {"shape": [n, h, w, c], "fwd_us": round(tf, 1), "bwd_us": round(tb, 1), "fwd_GBs_2pass": round(2 * mb / tf * 1e3, 0),

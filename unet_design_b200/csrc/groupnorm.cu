@@ -447,26 +447,18 @@ __global__ void __launch_bounds__(kFusedThreads) gn_fused_fwd_kernel(
     }
     __syncthreads();
     if (threadIdx.x < 32) fetch_slab(tc::smem_u32(xs), x + (n * sh.HW + p0) * ld_x, ld_x, sh.C, npx, bar);
-    // per-channel affine parameters travel while the slab is in flight
-    float ga[8], be[8];
     const bool active = r < sh.rows;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int c = 8 * q + u;
-        const float g0 = (active && gamma) ? __ldg(gamma + c) : 1.f, b0 = (active && beta) ? __ldg(beta + c) : 0.f;
-        const float sc = (active && scale) ? 1.f + __ldg(scale + n * sh.C + c) : 1.f;
-        const float sf = (active && shift) ? __ldg(shift + n * sh.C + c) : 0.f;
-        ga[u] = g0 * sc; be[u] = fmaf(b0, sc, sf);                         // y = act(xhat*ga + be)
-    }
     if (DROP && off_dev) offset += __ldg(off_dev);
     tc::mbar_wait_a(bar, 0);
     float v[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) v[u] = 0.f;
+    const int step = sh.rows * sh.chunks;                                   // slab entries between a thread's pixels
     if (active) {
-        for (int p = r; p < npx; p += sh.rows) {
+        const uint4 *xp = xs + r * sh.chunks + q;
+        for (int p = r; p < npx; p += sh.rows, xp += step) {
             float f[8];
-            unpack8(xs[p * sh.chunks + q], f);
+            unpack8(*xp, f);
 #pragma unroll
             for (int u = 0; u < 8; ++u) { v[u] += f[u]; v[8 + u] = fmaf(f[u], f[u], v[8 + u]); }
         }
@@ -486,38 +478,55 @@ __global__ void __launch_bounds__(kFusedThreads) gn_fused_fwd_kernel(
         if (rank == 0) stats_out[n * 2 * sh.G + i] = acc;                   // raw sums: what the backward consumes
     }
     cluster.sync();                                                         // peers are done reading our cta_gs
-    if (!active) return;
+    // y = act(x * A[c] + B[c]): the per-channel coefficients are computed ONCE per CTA (one channel per thread, one
+    // integer division each) into the `chan` table instead of eight channels redundantly in every thread
     const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
-    float A[8], B[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int g = (8 * q + u) / sh.cpg;
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        const int g = c / sh.cpg;
         const float mean = tot_gs[2 * g] * inv_cnt;
         const float var = fmaxf(tot_gs[2 * g + 1] * inv_cnt - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
-        A[u] = rstd * ga[u];
-        B[u] = fmaf(-mean, A[u], be[u]);
+        const float g0 = gamma ? __ldg(gamma + c) : 1.f, b0 = beta ? __ldg(beta + c) : 0.f;
+        const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f;
+        const float sf = shift ? __ldg(shift + n * sh.C + c) : 0.f;
+        const float a = rstd * g0 * sc;
+        chan[c] = a;
+        chan[sh.C + c] = fmaf(-mean, a, fmaf(b0, sc, sf));
     }
-    __nv_bfloat16 *yb = y + (n * sh.HW + p0) * ld_y + 8 * q;
-    const __nv_bfloat16 *ab = addend ? addend + (n * sh.HW + p0) * ld_add + 8 * q : nullptr;
+    __syncthreads();
+    if (!active) return;
+    float A[8], B[8];
+    {
+        const float4 a0 = *reinterpret_cast<const float4 *>(chan + 8 * q), a1 = *reinterpret_cast<const float4 *>(chan + 8 * q + 4);
+        const float4 b0 = *reinterpret_cast<const float4 *>(chan + sh.C + 8 * q), b1 = *reinterpret_cast<const float4 *>(chan + sh.C + 8 * q + 4);
+        A[0] = a0.x; A[1] = a0.y; A[2] = a0.z; A[3] = a0.w; A[4] = a1.x; A[5] = a1.y; A[6] = a1.z; A[7] = a1.w;
+        B[0] = b0.x; B[1] = b0.y; B[2] = b0.z; B[3] = b0.w; B[4] = b1.x; B[5] = b1.y; B[6] = b1.z; B[7] = b1.w;
+    }
+    __nv_bfloat16 *yp = y + (n * sh.HW + p0 + r) * ld_y + 8 * q;
+    const __nv_bfloat16 *ap = addend ? addend + (n * sh.HW + p0 + r) * ld_add + 8 * q : nullptr;
+    const int64_t ystep = (int64_t)sh.rows * ld_y, astep = (int64_t)sh.rows * ld_add;
+    const uint4 *xp = xs + r * sh.chunks + q;
+    int64_t elem = (n * sh.HW + p0 + r) * sh.C + 8 * q;                     // dropout counter index
+    const int64_t estep = (int64_t)sh.rows * sh.C;
 #pragma unroll 2
-    for (int p = r; p < npx; p += sh.rows) {
+    for (int p = r; p < npx; p += sh.rows, xp += step, yp += ystep, elem += estep) {
         float f[8];
-        unpack8(xs[p * sh.chunks + q], f);
+        unpack8(*xp, f);
         float m[8];
-        if (DROP) dropout_mask8(seed, offset, (n * sh.HW + p0 + p) * sh.C + 8 * q, p_drop, m);
+        if (DROP) dropout_mask8(seed, offset, elem, p_drop, m);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             f[u] = act_fwd<ACT>(fmaf(f[u], A[u], B[u]));
             if (DROP) f[u] *= m[u];
         }
-        if (ab) {
+        if (ap) {
             float r8[8];
-            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(ab + (int64_t)p * ld_add)), r8);
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(ap)), r8);
+            ap += astep;
 #pragma unroll
             for (int u = 0; u < 8; ++u) f[u] += r8[u];
         }
-        *reinterpret_cast<uint4 *>(yb + (int64_t)p * ld_y) = pack8(f);
+        *reinterpret_cast<uint4 *>(yp) = pack8(f);
     }
 }
 
@@ -560,27 +569,44 @@ __global__ void __launch_bounds__(kFusedThreads, 3) gn_fused_bwd_kernel(
     }
     const __nv_bfloat16 *xb = x + (n * sh.HW + p0) * ld_x + 8 * q;
     const int step = sh.rows;
+    const int sstep = sh.rows * sh.chunks;                                 // slab entries between a thread's pixels
+    const int64_t xstep = (int64_t)step * ld_x;
     uint4 xa = make_uint4(0, 0, 0, 0), xc = xa;
     if (!XSLAB && active) {                                                // first two pixels travel with the bulk copy
         if (r < npx) xa = *reinterpret_cast<const uint4 *>(xb + (int64_t)r * ld_x);
         if (r + step < npx) xc = *reinterpret_cast<const uint4 *>(xb + (int64_t)(r + step) * ld_x);
     }
     const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
+    // z = x * A[c] + B[c]: per-channel coefficients computed once per CTA (one channel per thread) into the tot_q area,
+    // which is not needed before the cluster reduction
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        float mean, rstd;
+        mean_rstd(stats, n, sh.G, c / sh.cpg, inv_cnt, eps, mean, rstd);
+        const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
+        const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f, sf = shift ? __ldg(shift + n * sh.C + c) : 0.f;
+        const float a = rstd * ga * sc;
+        tot_q[c] = a;
+        tot_q[sh.C + c] = (be - mean * rstd * ga) * sc + sf;
+    }
+    __syncthreads();
     Coef k;
     if (active) {
-        Shape s2; s2.HW = sh.HW; s2.C = sh.C; s2.G = sh.G; s2.cpg = sh.cpg; s2.chunks = sh.chunks; s2.rows = sh.rows; s2.pix_per_cta = 0;
-        k = make_coef(s2, n, q, stats, gamma, beta, scale, shift, eps);
+        const float4 a0 = *reinterpret_cast<const float4 *>(tot_q + 8 * q), a1 = *reinterpret_cast<const float4 *>(tot_q + 8 * q + 4);
+        const float4 b0 = *reinterpret_cast<const float4 *>(tot_q + sh.C + 8 * q), b1 = *reinterpret_cast<const float4 *>(tot_q + sh.C + 8 * q + 4);
+        k.A[0] = a0.x; k.A[1] = a0.y; k.A[2] = a0.z; k.A[3] = a0.w; k.A[4] = a1.x; k.A[5] = a1.y; k.A[6] = a1.z; k.A[7] = a1.w;
+        k.B[0] = b0.x; k.B[1] = b0.y; k.B[2] = b0.z; k.B[3] = b0.w; k.B[4] = b1.x; k.B[5] = b1.y; k.B[6] = b1.z; k.B[7] = b1.w;
     }
     if (DROP && off_dev) offset += __ldg(off_dev);
     tc::mbar_wait_a(bar, 0);
     float v[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) v[u] = 0.f;
-    auto one = [&](int p, const uint4 &xv) {
+    const int64_t ebase = (n * sh.HW + p0) * sh.C + 8 * q;                  // dropout counter index of pixel 0
+    auto one = [&](int p, uint4 *dp, const uint4 &xv) {
         float f[8], g[8], m[8];
         unpack8(xv, f);
-        unpack8(ds[p * sh.chunks + q], g);
-        if (DROP) dropout_mask8(seed, offset, (n * sh.HW + p0 + p) * sh.C + 8 * q, p_drop, m);
+        unpack8(*dp, g);
+        if (DROP) dropout_mask8(seed, offset, ebase + (int64_t)p * sh.C, p_drop, m);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
@@ -588,19 +614,22 @@ __global__ void __launch_bounds__(kFusedThreads, 3) gn_fused_bwd_kernel(
             v[u] += dz; v[8 + u] = fmaf(dz, f[u], v[8 + u]);
             g[u] = dz;
         }
-        ds[p * sh.chunks + q] = pack8(g);
+        *dp = pack8(g);
     };
     if (active) {
+        uint4 *dp = ds + r * sh.chunks + q;
         if (XSLAB) {
+            const uint4 *xp = xs + r * sh.chunks + q;
 #pragma unroll 2
-            for (int p = r; p < npx; p += step) one(p, xs[p * sh.chunks + q]);
+            for (int p = r; p < npx; p += step, dp += sstep, xp += sstep) one(p, dp, *xp);
         } else {
-            for (int p = r; p < npx; p += 2 * step) {                      // two pixels per turn, the next two in flight
+            const __nv_bfloat16 *xn = xb + (int64_t)(r + 2 * step) * ld_x;  // next pair to prefetch
+            for (int p = r; p < npx; p += 2 * step, dp += 2 * sstep, xn += 2 * xstep) {   // two pixels per turn, the next two in flight
                 uint4 na = make_uint4(0, 0, 0, 0), nc = na;
-                if (p + 2 * step < npx) na = *reinterpret_cast<const uint4 *>(xb + (int64_t)(p + 2 * step) * ld_x);
-                if (p + 3 * step < npx) nc = *reinterpret_cast<const uint4 *>(xb + (int64_t)(p + 3 * step) * ld_x);
-                one(p, xa);
-                if (p + step < npx) one(p + step, xc);
+                if (p + 2 * step < npx) na = *reinterpret_cast<const uint4 *>(xn);
+                if (p + 3 * step < npx) nc = *reinterpret_cast<const uint4 *>(xn + xstep);
+                one(p, dp, xa);
+                if (p + step < npx) one(p + step, dp + sstep, xc);
                 xa = na; xc = nc;
             }
         }
@@ -638,59 +667,77 @@ __global__ void __launch_bounds__(kFusedThreads, 3) gn_fused_bwd_kernel(
         sg[i] = acc;
     }
     __syncthreads();
-    if (!active) return;
-    float P[8], Qc[8], R[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int c = 8 * q + u, g = c / sh.cpg;
+    // dx = dz * P[c] + x * Qc[c] + R[c]: tables again, one channel per thread (tot_q and cta_q are free now)
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        const int g = c / sh.cpg;
         float mean, rstd;
         mean_rstd(stats, n, sh.G, g, inv_cnt, eps, mean, rstd);
         const float m1 = sg[2 * g] * inv_cnt, m2 = sg[2 * g + 1] * inv_cnt;
         const float gs = (gamma ? __ldg(gamma + c) : 1.f) * (scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f);
-        P[u] = rstd * gs;
-        Qc[u] = -rstd * rstd * m2;
-        R[u] = -rstd * m1 - mean * Qc[u];
+        const float qc = -rstd * rstd * m2;
+        tot_q[c] = rstd * gs;
+        tot_q[sh.C + c] = qc;
+        cta_q[c] = -rstd * m1 - mean * qc;
     }
-    __nv_bfloat16 *ob = gx + (n * sh.HW + p0) * ld_gx + 8 * q;
+    __syncthreads();
+    if (!active) return;
+    float P[8], Qc[8], R[8];
+    {
+        const float4 *tp = reinterpret_cast<const float4 *>(tot_q + 8 * q), *tq = reinterpret_cast<const float4 *>(tot_q + sh.C + 8 * q);
+        const float4 *tr = reinterpret_cast<const float4 *>(cta_q + 8 * q);
+        const float4 p0v = tp[0], p1v = tp[1], q0v = tq[0], q1v = tq[1], r0v = tr[0], r1v = tr[1];
+        P[0] = p0v.x; P[1] = p0v.y; P[2] = p0v.z; P[3] = p0v.w; P[4] = p1v.x; P[5] = p1v.y; P[6] = p1v.z; P[7] = p1v.w;
+        Qc[0] = q0v.x; Qc[1] = q0v.y; Qc[2] = q0v.z; Qc[3] = q0v.w; Qc[4] = q1v.x; Qc[5] = q1v.y; Qc[6] = q1v.z; Qc[7] = q1v.w;
+        R[0] = r0v.x; R[1] = r0v.y; R[2] = r0v.z; R[3] = r0v.w; R[4] = r1v.x; R[5] = r1v.y; R[6] = r1v.z; R[7] = r1v.w;
+    }
     // gadd: a second gradient of x (the ResBlock's shortcut / residual branch), summed here instead of by a separate add
-    const __nv_bfloat16 *ab = gadd ? gadd + (n * sh.HW + p0) * ld_gadd + 8 * q : nullptr;
-    auto fin = [&](int p, const uint4 &xv, const uint4 &av) {
+    const bool has_add = gadd != nullptr;
+    auto fin = [&](const uint4 *dp, __nv_bfloat16 *op, const uint4 &xv, const uint4 &av) {
         float f[8], d[8];
         unpack8(xv, f);
-        unpack8(ds[p * sh.chunks + q], d);
+        unpack8(*dp, d);
 #pragma unroll
         for (int u = 0; u < 8; ++u) d[u] = fmaf(d[u], P[u], fmaf(f[u], Qc[u], R[u]));
-        if (ab) {
+        if (has_add) {
             float a[8];
             unpack8(av, a);
 #pragma unroll
             for (int u = 0; u < 8; ++u) d[u] += a[u];
         }
-        *reinterpret_cast<uint4 *>(ob + (int64_t)p * ld_gx) = pack8(d);
+        *reinterpret_cast<uint4 *>(op) = pack8(d);
     };
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    const uint4 *dp = ds + r * sh.chunks + q;
+    __nv_bfloat16 *op = gx + (n * sh.HW + p0 + r) * ld_gx + 8 * q;
+    const __nv_bfloat16 *ap = has_add ? gadd + (n * sh.HW + p0 + r) * ld_gadd + 8 * q : nullptr;
+    const int64_t ostep = (int64_t)step * ld_gx, astep = (int64_t)step * ld_gadd;
     if (XSLAB) {
-        for (int p = r; p < npx; p += 2 * step) {
+        const uint4 *xp = xs + r * sh.chunks + q;
+        for (int p = r; p < npx; p += 2 * step, dp += 2 * sstep, xp += 2 * sstep, op += 2 * ostep) {
+            const bool two = p + step < npx;
             uint4 a0 = zero4, a1 = zero4;
-            if (ab) {
-                a0 = ld_stream_u4(reinterpret_cast<const uint4 *>(ab + (int64_t)p * ld_gadd));
-                if (p + step < npx) a1 = ld_stream_u4(reinterpret_cast<const uint4 *>(ab + (int64_t)(p + step) * ld_gadd));
+            if (has_add) {
+                a0 = ld_stream_u4(reinterpret_cast<const uint4 *>(ap));
+                if (two) a1 = ld_stream_u4(reinterpret_cast<const uint4 *>(ap + astep));
+                ap += 2 * astep;
             }
-            fin(p, xs[p * sh.chunks + q], a0);
-            if (p + step < npx) fin(p + step, xs[(p + step) * sh.chunks + q], a1);
+            fin(dp, op, *xp, a0);
+            if (two) fin(dp + sstep, op + ostep, xp[sstep], a1);
         }
     } else {
-        for (int p = r; p < npx; p += 4 * step) {                          // four L2 reads in flight per thread
+        const __nv_bfloat16 *xp = xb + (int64_t)r * ld_x;
+        for (int p = r; p < npx; p += 4 * step, dp += 4 * sstep, xp += 4 * xstep, op += 4 * ostep) {   // four L2 reads in flight
             uint4 t[4], a[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (p + j * step < npx) {
-                    t[j] = *reinterpret_cast<const uint4 *>(xb + (int64_t)(p + j * step) * ld_x);
-                    a[j] = ab ? ld_stream_u4(reinterpret_cast<const uint4 *>(ab + (int64_t)(p + j * step) * ld_gadd)) : zero4;
+                    t[j] = *reinterpret_cast<const uint4 *>(xp + j * xstep);
+                    a[j] = has_add ? ld_stream_u4(reinterpret_cast<const uint4 *>(ap + j * astep)) : zero4;
                 }
+            if (has_add) ap += 4 * astep;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (p + j * step < npx) fin(p + j * step, t[j], a[j]);
+                if (p + j * step < npx) fin(dp + j * sstep, op + j * ostep, t[j], a[j]);
         }
     }
 }
