@@ -339,6 +339,33 @@ __global__ void __launch_bounds__(256) dwtblock_nhwc_bf16(const float *__restric
     }
 }
 
+// J = 0 (channel tiling of an image that is already at the target resolution: how the Multi-ResNet decoder fetches its
+// skip tensors from the cached Haar pyramid): grid (row-chunk blocks, image row, sample), no 64-bit div/mod per item.
+__global__ void __launch_bounds__(256) dwtblock_nhwc_bf16_j0(const float *__restrict__ x, int C, int H, int W, int out_channels,
+                                                            const int *__restrict__ chmap, __nv_bfloat16 *__restrict__ out,
+                                                            int64_t ld) {
+    const int chunks = out_channels >> 3;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= W * chunks) return;
+    const int q = idx % chunks, j = idx / chunks;
+    const int i = blockIdx.y;
+    const int64_t n = blockIdx.z;
+    int c[8];
+    if (chmap) {
+        const int4 a = __ldg(reinterpret_cast<const int4 *>(chmap + 8 * q)), b = __ldg(reinterpret_cast<const int4 *>(chmap + 8 * q) + 1);
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+    } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[u] = (8 * q + u) % C;
+    }
+    const int64_t plane = (int64_t)H * W;
+    const float *src = x + n * C * plane + (int64_t)i * W + j;
+    float f[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f[u] = __ldg(src + c[u] * plane);
+    *reinterpret_cast<uint4 *>(out + ((n * H + i) * (int64_t)W + j) * ld + 8 * q) = pack8(f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // DWTBlock on NHWC bf16 activations (pdearena / wmh: the head conv is learned, so the block sits inside the
 // network and has a backward).  J in {0, 1}; fp32 arithmetic, bf16 storage.  One work item = one 16-byte channel
@@ -528,6 +555,15 @@ int ub200_dwtblock_fwd_nhwc_bf16(const float *x, int64_t N, int64_t C, int64_t H
                    ub::aligned16(out_bf16) && H < (1 << 30) && W < (1 << 30),
                UB200_E_UNSUPPORTED);
     Ext e = make_ext(H, W);
+    if (J == 0 && H <= 65535 && N <= 65535 && W * (out_channels / 8) < (1 << 30)) {
+        const int per_row = (int)(W * (out_channels / 8));
+        const int threads = per_row >= 256 ? 256 : ((per_row + 31) / 32) * 32;
+        dim3 grid((unsigned)((per_row + threads - 1) / threads), (unsigned)H, (unsigned)N);
+        dwtblock_nhwc_bf16_j0<<<grid, threads, 0, ub::as_stream(stream)>>>(x, (int)C, (int)H, (int)W, (int)out_channels, chmap,
+                                                                          reinterpret_cast<__nv_bfloat16 *>(out_bf16), ld_out);
+        UB_LAUNCH_CHECK();
+        return UB200_OK;
+    }
     int grid = ub::grid_for(N * (int64_t)e.h[J] * e.w[J] * (out_channels / 8), 256, 8);
     dwtblock_nhwc_bf16<<<grid, 256, 0, ub::as_stream(stream)>>>(x, N, (int)C, e, J, (int)out_channels,
                                                                1.0f / (float)(1 << J), chmap,

@@ -131,8 +131,8 @@ class UpSample(nn.Module):
         init.xavier_uniform_(self.main.weight)
         init.zeros_(self.main.bias)
 
-    def forward_nhwc(self, x, temb=None):
-        return ops.conv(ops.upsample2x(x), self.main.weight, self.main.bias)
+    def forward_nhwc(self, x, temb=None, out=None):
+        return ops.conv(ops.upsample2x(x), self.main.weight, self.main.bias, out=out)
 
     def forward(self, x, temb):
         return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x), temb))
@@ -154,7 +154,7 @@ class AttnBlock(nn.Module):
             init.zeros_(module.bias)
         init.xavier_uniform_(self.proj.weight, gain=1e-5)
 
-    def forward_nhwc(self, x):
+    def forward_nhwc(self, x, out=None):
         n, h, w, c = x.shape
         y = ops.gn_act(x, self.group_norm.weight, self.group_norm.bias, 32, act="none", eps=self.group_norm.eps)
         # q, k, v projections as ONE 1x1 conv on the tensor cores (weights concatenated on the fly: the
@@ -165,7 +165,7 @@ class AttnBlock(nn.Module):
         q, k, v = ops.split3(qkv)
         o = F.scaled_dot_product_attention(q, k, v, scale=int(c) ** (-0.5))
         # x + proj(o): the residual add rides in the conv epilogue
-        return ops.conv(o.reshape(n, h, w, c), self.proj.weight, self.proj.bias, residual=x)
+        return ops.conv(o.reshape(n, h, w, c), self.proj.weight, self.proj.bias, residual=x, out=out)
 
     def forward(self, x):
         return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x)))
@@ -205,8 +205,9 @@ class ResBlock(nn.Module):
                 init.zeros_(module.bias)
         init.xavier_uniform_(self.block2[-1].weight, gain=1e-5)
 
-    def forward_nhwc(self, x, temb, row=None):
-        """`row` = temb_proj(temb) when the caller already computed it for all blocks at once (UNetWaveletEnc)."""
+    def forward_nhwc(self, x, temb, row=None, out=None):
+        """`row` = temb_proj(temb) when the caller already computed it for all blocks at once (UNetWaveletEnc);
+        `out` = where the block's result goes (a channel slice of the next block's concat buffer)."""
         gn1, conv1 = self.block1[0], self.block1[2]
         gn2, drop, conv2 = self.block2[0], self.block2[2], self.block2[3]
         # x also feeds the shortcut / residual branch below: its two gradients are summed in the GroupNorm backward
@@ -218,13 +219,15 @@ class ResBlock(nn.Module):
         h = ops.conv(a1, conv1.weight, conv1.bias, rowadd=row)
         p = drop.p if self.training else 0.0
         a2 = ops.gn_act(h, gn2.weight, gn2.bias, gn2.num_groups, act="silu", eps=gn2.eps, dropout_p=p)
+        has_attn = isinstance(self.attn, AttnBlock)
+        out2 = None if has_attn else out
         if isinstance(self.shortcut, nn.Conv2d):
             # conv2(a2) + shortcut(x): the 1x1 conv rides along as extra K slices of the same GEMM
-            h = ops.conv(a2, conv2.weight, conv2.bias + self.shortcut.bias, a2=x, w2=self.shortcut.weight)
+            h = ops.conv(a2, conv2.weight, conv2.bias + self.shortcut.bias, a2=x, w2=self.shortcut.weight, out=out2)
         else:
-            h = ops.conv(a2, conv2.weight, conv2.bias, residual=x)
-        if isinstance(self.attn, AttnBlock):
-            h = self.attn.forward_nhwc(h)
+            h = ops.conv(a2, conv2.weight, conv2.bias, residual=x, out=out2)
+        if has_attn:
+            h = self.attn.forward_nhwc(h, out=out)
         return h
 
     def forward(self, x, temb):
@@ -334,7 +337,7 @@ class UNetWaveletEnc(nn.Module):
         a = ops.gn_act(h, gn.weight, gn.bias, gn.num_groups, act="silu", eps=gn.eps)
         return ops.conv(a, conv.weight, conv.bias, out_nchw=True)      # fp32 NCHW [N,3,H,W] straight from TMEM
 
-    def _materialise(self, pyramid, view: _PyramidView) -> torch.Tensor:
+    def _materialise(self, pyramid, view: _PyramidView, out=None) -> torch.Tensor:
         base = pyramid[view.level]
         n, _, h, w = base.shape
         key = (tuple(view.chmap), base.device)
@@ -342,7 +345,8 @@ class UNetWaveletEnc(nn.Module):
         if cm is None:
             cm = torch.tensor(view.chmap, dtype=torch.int32, device=base.device)
             self._chmap_cache[key] = cm
-        out = torch.empty((n, h, w, len(view.chmap)), dtype=torch.bfloat16, device=base.device)
+        if out is None:
+            out = torch.empty((n, h, w, len(view.chmap)), dtype=torch.bfloat16, device=base.device)
         return ops.dwtblock_nhwc(base, 0, out, cm)
 
     def _encode_haar(self, x, first):
@@ -364,9 +368,11 @@ class UNetWaveletEnc(nn.Module):
         return pyramid, views
 
     @staticmethod
-    def _run(layer, h, rows):
+    def _run(layer, h, rows, out=None):
         if isinstance(layer, ResBlock):
-            return layer.forward_nhwc(h, None, row=rows[id(layer)])
+            return layer.forward_nhwc(h, None, row=rows[id(layer)], out=out)
+        if out is not None:
+            return layer.forward_nhwc(h, out=out)
         return layer.forward_nhwc(h)
 
     def forward(self, x, t, n_levels_used=-1):
@@ -406,21 +412,34 @@ class UNetWaveletEnc(nn.Module):
                     hs.append(h)
             fetch = lambda v: v
 
-        # ---- middle
-        for layer in self.middleblocks:
-            h = self._run(layer, h, rows)
-
-        # ---- decoder
-        model_out_list = []
+        # ---- middle + decoder as one layer list.  In the Haar-encoder arm every decoder ResBlock reads
+        # cat(h, skip) (reference model.py:462) where the skip is a gradient-free channel tile of the image pyramid: the
+        # producer of h writes straight into the first channels of the concat buffer and the tile kernel fills the rest,
+        # so no concat copy is made (the residual-encoder arm keeps torch.cat: its skips carry gradients).
+        layers = [(layer, None) for layer in self.middleblocks]
         for l in range(self.n_levels - 1, first - 1, -1):
-            for layer in self.upblocks[l]:
-                if isinstance(layer, ResBlock):
-                    h = torch.cat([h, fetch(hs.pop())], dim=3)
-                    h = self._run(layer, h, rows)
-                elif l != first:                         # UpSample; skipped on the finest level in use
-                    if self.multi_res_loss:
-                        model_out_list.append(self._tail(l, h))
-                    h = layer.forward_nhwc(h)
+            layers += [(layer, l) for layer in self.upblocks[l] if isinstance(layer, ResBlock) or l != first]
+        model_out_list = []
+        full = None                                       # concat buffer whose first channels already hold h
+        for i, (layer, l) in enumerate(layers):
+            if l is not None and isinstance(layer, ResBlock):
+                skip = hs.pop()
+                if full is not None:
+                    self._materialise(pyramid, skip, out=ops.channel_slice_alias(full, h.shape[3], full.shape[3]))
+                    h, full = ops.cat_view(h, full), None
+                else:
+                    h = torch.cat([h, fetch(skip)], dim=3)
+            elif l is not None and self.multi_res_loss:    # an UpSample: the coarse output leaves before it
+                model_out_list.append(self._tail(l, h))
+            out = None
+            nxt = layers[i + 1] if i + 1 < len(layers) else None
+            if self.dwt_encoder and nxt is not None and nxt[1] is not None and isinstance(nxt[0], ResBlock):
+                up = not isinstance(layer, ResBlock)
+                c_out = h.shape[3] if up else layer.out_ch
+                hh, ww = (2 * h.shape[1], 2 * h.shape[2]) if up else (h.shape[1], h.shape[2])
+                full = torch.empty((h.shape[0], hh, ww, c_out + len(hs[-1].chmap)), dtype=torch.bfloat16, device=h.device)
+                out = ops.channel_slice_alias(full, 0, c_out)
+            h = self._run(layer, h, rows, out)
         model_out_list.append(self._tail(first, h))
         assert len(hs) == 0
 

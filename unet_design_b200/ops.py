@@ -390,7 +390,7 @@ class _Conv(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, a, w, bias, rowadd, a2, w2, residual, out_nchw):
+    def forward(ctx, a, w, bias, rowadd, a2, w2, residual, out_nchw, out_box=None):
         o = _ops()
         a = _dense_nhwc(a)
         n, h, wd, cin = a.shape
@@ -407,6 +407,13 @@ class _Conv(torch.autograd.Function):
         if out_nchw:
             out = torch.empty((n, cout, h, wd), dtype=torch.float32, device=a.device)
             o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, None, out)
+        elif out_box is not None:
+            # the caller owns the destination: an NHWC view (pixel stride > Cout) inside a wider buffer, e.g. the first
+            # channels of a decoder concat buffer.  Passed in a list so autograd does not treat it as an input.
+            dst = out_box[0]
+            assert dst.shape == (n, h, wd, cout) and dst.dtype == torch.bfloat16
+            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, dst, None)
+            out = dst.view_as(dst)
         else:
             out = torch.empty((n, h, wd, cout), dtype=torch.bfloat16, device=a.device)
             o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, out, None)
@@ -505,13 +512,43 @@ class _Conv(torch.autograd.Function):
                     gw2 = dw2[:cout].permute(0, 3, 1, 2)
         if has_res and needs[6]:
             gres = g_valid
-        return ga, gw, gbias, growadd, ga2, gw2, gres, None
+        return ga, gw, gbias, growadd, ga2, gw2, gres, None, None
 
 
 def conv(a: torch.Tensor, w: torch.Tensor, bias=None, rowadd=None, a2=None, w2=None, residual=None,
-         out_nchw: bool = False) -> torch.Tensor:
-    """Fused stride-1 same-padding convolution (k = 1 or 3).  `a` NHWC bf16 with C % 16 == 0."""
-    return _Conv.apply(a, w, bias, rowadd, a2, w2, residual, out_nchw)
+         out_nchw: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused stride-1 same-padding convolution (k = 1 or 3).  `a` NHWC bf16 with C % 16 == 0.
+    `out`: optional destination, an NHWC bf16 view [N,H,W,Cout] (may be a channel slice of a wider buffer)."""
+    return _Conv.apply(a, w, bias, rowadd, a2, w2, residual, out_nchw, [out] if out is not None else None)
+
+
+class _CatView(torch.autograd.Function):
+    """`full` already holds `head` in its first channels (the producer wrote there) and a gradient-free tensor in the
+    rest: returns `full` as the concatenation without copying; backward hands the head's channel slice back."""
+
+    @staticmethod
+    def forward(ctx, head, box):
+        full = box[0]
+        assert head.data_ptr() == full.data_ptr() and head.shape[:3] == full.shape[:3]
+        ctx.c = head.shape[3]
+        return full.view_as(full)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[..., :ctx.c], None
+
+
+def cat_view(head: torch.Tensor, full: torch.Tensor) -> torch.Tensor:
+    return _CatView.apply(head, [full])
+
+
+def channel_slice_alias(full: torch.Tensor, c0: int, c1: int) -> torch.Tensor:
+    """Channels [c0, c1) of an NHWC buffer as an independent tensor object over the same storage (not an autograd view:
+    kernels fill disjoint channel ranges of one concat buffer, which view + in-place tracking would reject)."""
+    n, h, w, _ = full.shape
+    t = torch.empty(0, dtype=full.dtype, device=full.device)
+    t.set_(full.untyped_storage(), full.storage_offset() + c0, (n, h, w, c1 - c0), full.stride())
+    return t
 
 
 class _RowLinBatch(torch.autograd.Function):
