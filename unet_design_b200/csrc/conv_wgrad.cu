@@ -12,9 +12,15 @@
 // in the packed [Cout, k, k, Cin] layout (= the channels_last memory of the torch weight).
 //
 // Replaces the wgrad half of nn.Conv2d backward at the sites listed in conv_fprop.cu.
+#include <cooperative_groups.h>
+
+#include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 #include "tc_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 using namespace ub;
@@ -208,6 +214,86 @@ __global__ void __launch_bounds__(256) chansum_kernel(const __nv_bfloat16 *__res
     }
 }
 
+// Single-launch variant: one thread-block cluster per sample (no atomics, no zero-fill of per_sample): every CTA sums its
+// pixel range, rank 0 combines the cluster through DSMEM and writes per_sample[n, :]; the cluster that finishes LAST
+// (device counter) then adds sum_n per_sample[n, :] to total in a fixed order.  Replaces memset + chansum + colsum.
+__device__ unsigned int g_chansum_done[64];
+
+__global__ void __launch_bounds__(256) chansum_cluster_kernel(const __nv_bfloat16 *__restrict__ x, int64_t ld, int64_t HW, int C,
+                                                             int chunks, int rows, int64_t pix_per_cta, int cs, int N,
+                                                             float *__restrict__ per_sample, float *__restrict__ total,
+                                                             int slot) {
+    extern __shared__ float csm[];                 // part [256][8], then chan [C]
+    float *part = csm, *chan = csm + 256 * 8;
+    __shared__ bool last;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int64_t n = blockIdx.x / cs;
+    const int q = threadIdx.x % chunks, r = threadIdx.x / chunks;
+    float s[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] = 0.f;
+    if (r < rows) {
+        const int64_t p0 = (int64_t)rank * pix_per_cta;
+        int64_t p1 = p0 + pix_per_cta;
+        if (p1 > HW) p1 = HW;
+        const int64_t step = (int64_t)rows * ld;
+        const __nv_bfloat16 *xp = x + (n * HW + p0 + r) * ld + 8 * q;
+        int64_t pp = p0 + r;
+        for (; pp + 3 * rows < p1; pp += 4 * rows, xp += 4 * step) {          // four 16-byte loads in flight per thread
+            const uint4 a = ld_stream_u4(reinterpret_cast<const uint4 *>(xp));
+            const uint4 b = ld_stream_u4(reinterpret_cast<const uint4 *>(xp + step));
+            const uint4 c = ld_stream_u4(reinterpret_cast<const uint4 *>(xp + 2 * step));
+            const uint4 d = ld_stream_u4(reinterpret_cast<const uint4 *>(xp + 3 * step));
+            float f[8], g[8], h[8], k[8];
+            unpack8(a, f); unpack8(b, g); unpack8(c, h); unpack8(d, k);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[u] += (f[u] + g[u]) + (h[u] + k[u]);
+        }
+        for (; pp < p1; pp += rows, xp += step) {
+            float f[8];
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(xp)), f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[u] += f[u];
+        }
+    }
+    {
+        float4 *dst = reinterpret_cast<float4 *>(part + (size_t)threadIdx.x * 8);
+        dst[0] = make_float4(s[0], s[1], s[2], s[3]); dst[1] = make_float4(s[4], s[5], s[6], s[7]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int rr = 0; rr < rows; ++rr) acc += part[(size_t)(rr * chunks + (c >> 3)) * 8 + (c & 7)];
+        chan[c] = acc;
+    }
+    cluster.sync();
+    if (rank == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float acc = 0.f;
+            for (int rk = 0; rk < cs; ++rk) acc += cluster.map_shared_rank(chan, rk)[c];
+            per_sample[n * C + c] = acc;
+        }
+    }
+    cluster.sync();                                // peers stay alive until rank 0 has read their sums
+    if (rank != 0 || !total) return;
+    __threadfence();                               // per_sample[n, :] visible before the counter moves
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&g_chansum_done[slot], 1u);
+        last = prev == (unsigned int)(N - 1);
+        if (last) g_chansum_done[slot] = 0u;       // ready for the next launch (graph replay included)
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int64_t m = 0; m < N; ++m) acc += __ldcg(per_sample + m * C + c);
+        total[c] += acc;
+    }
+}
+
 __global__ void __launch_bounds__(256) colsum_rows_kernel(const float *__restrict__ per_sample, int64_t N, int C,
                                                          float *__restrict__ total) {
     // 32 channels x 8 row-lanes per CTA; rows strided by 8, combined through shared memory
@@ -339,9 +425,43 @@ int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, in
     UB_REQUIRE(x && per_sample && N > 0 && HW > 0 && C > 0, UB200_E_BADARG);
     UB_REQUIRE(C % 8 == 0 && C <= 2048 && ld % 8 == 0 && ld >= C && ub::aligned16(x) && N <= 65535, UB200_E_UNSUPPORTED);
     cudaStream_t s = ub::as_stream(stream);
+    const int chunks = (int)(C / 8), rows = 256 / chunks;
+    static const bool use_cluster = [] { const char *e = getenv("UB200_CHANSUM_CLUSTER"); return !(e && e[0] == '0'); }();
+    if (use_cluster) {
+        // cluster size: enough CTAs to fill the machine, at least 4 passes of the CTA's threads per CTA
+        int cs = 1;
+        while (cs < 8 && N * cs < 2 * ub::kSMs && HW / (2 * cs) >= 4 * rows) cs *= 2;
+        while (cs < 8 && HW * C * 2 / cs > 256 * 1024 && HW / (2 * cs) >= 4 * rows) cs *= 2;
+        static std::atomic<unsigned> next_slot{0};
+        const int slot = (int)(next_slot.fetch_add(1) % 64u);
+        const int64_t ppc = (HW + cs - 1) / cs;
+        if ((int64_t)(cs - 1) * ppc < HW) {           // no empty CTA in the cluster
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(N * cs), 1, 1);
+            cfg.blockDim = dim3(256, 1, 1);
+            cfg.dynamicSmemBytes = (256 * 8 + C) * sizeof(float);
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            // the in-kernel "last cluster adds the column sums" tail is a serial latency chain (one CTA, N dependent
+            // rounds of L2 reads): measured slower than a second small launch, so total goes through colsum_rows_kernel
+            static const bool tail = [] { const char *e = getenv("UB200_CHANSUM_TAIL"); return e && e[0] == '1'; }();
+            cudaError_t e = cudaLaunchKernelEx(&cfg, chansum_cluster_kernel, reinterpret_cast<const __nv_bfloat16 *>(x), ld, HW,
+                                               (int)C, chunks, rows, ppc, cs, (int)N, per_sample,
+                                               tail ? total : static_cast<float *>(nullptr), slot);
+            if (e != cudaSuccess) return (int)e;
+            UB_LAUNCH_CHECK();
+            if (total && !tail) {
+                colsum_rows_kernel<<<(unsigned)((C + 31) / 32), 256, 0, s>>>(per_sample, N, (int)C, total);
+                UB_LAUNCH_CHECK();
+            }
+            return UB200_OK;
+        }
+    }
     cudaError_t e = cudaMemsetAsync(per_sample, 0, sizeof(float) * N * C, s);
     if (e != cudaSuccess) return (int)e;
-    const int chunks = (int)(C / 8), rows = 256 / chunks;
     int64_t splits = (148 * 8 + N - 1) / N;
     const int64_t max_splits = (HW + rows - 1) / rows;
     if (splits > max_splits) splits = max_splits;

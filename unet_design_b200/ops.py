@@ -62,6 +62,40 @@ def clear_registry() -> None:
     _Registry.packed.clear()
 
 
+class _Side:
+    """Weight-gradient launches of SMALL layers on a second stream.  A wgrad only feeds the optimiser, so it need not sit
+    on the backward critical path; at the coarse levels every kernel covers a fraction of the 148 SMs and is bound by
+    launch-to-launch latency, so running the wgrad next to the following dgrad / GroupNorm kernels hides it.  The caller
+    (train.DDPMTrainStep) enables this and joins the stream after backward; operands are kept alive until the join."""
+    enabled = False
+    max_pixels = 128 * 8 * 8
+    stream = None
+    keep = []
+
+
+def enable_side_wgrad(flag: bool, max_pixels: int = 128 * 8 * 8) -> None:
+    _Side.enabled, _Side.max_pixels = bool(flag), int(max_pixels)
+
+
+def join_side_stream() -> None:
+    if _Side.stream is not None and _Side.keep:
+        torch.cuda.current_stream(_Side.keep[0].device).wait_stream(_Side.stream)
+    _Side.keep.clear()
+
+
+def _wgrad(o, g, a, k, dst) -> None:
+    n, h, w, _ = a.shape
+    if _Side.enabled and a.is_cuda and n * h * w <= _Side.max_pixels:
+        if _Side.stream is None:
+            _Side.stream = torch.cuda.Stream(device=a.device)
+        _Side.stream.wait_stream(torch.cuda.current_stream(a.device))
+        with torch.cuda.stream(_Side.stream):
+            o.conv_wgrad(g, a, k, dst)
+        _Side.keep += [g, a]
+    else:
+        o.conv_wgrad(g, a, k, dst)
+
+
 def _sink_of(key):
     return _Registry.sinks.get(key) if key is not None else None
 
@@ -463,7 +497,7 @@ class _Conv(torch.autograd.Function):
         if needs[1]:
             sink = _sink_of(kw) if cpad == cout else None
             if sink is not None:                        # accumulate straight into the gradient arena
-                o.conv_wgrad(g_full, a, k, sink[0])
+                _wgrad(o, g_full, a, k, sink[0])
                 _count()
                 if sink[1] is not None:
                     sink[1]()
@@ -481,7 +515,7 @@ class _Conv(torch.autograd.Function):
                 else:
                     tot = torch.zeros((cout,), dtype=torch.float32, device=g.device) if has_bias else None
                 o.chansum(g_valid, per, tot)
-                _count(3)
+                _count(2 if tot is not None else 1)
                 growadd, gbias = (per if has_rowadd else None), (None if bsink is not None else tot)
                 if bsink is not None and bsink[1] is not None:
                     bsink[1]()
@@ -489,7 +523,7 @@ class _Conv(torch.autograd.Function):
                 per = torch.empty((n, cpad), dtype=torch.float32, device=g.device)
                 tot = torch.zeros((cpad,), dtype=torch.float32, device=g.device) if has_bias else None
                 o.chansum(g_full, per, tot)
-                _count(3)
+                _count(2 if tot is not None else 1)
                 growadd = per[:, :cout].contiguous() if has_rowadd else None
                 gbias = tot[:cout] if has_bias else None
         if a2 is not None:
@@ -501,7 +535,7 @@ class _Conv(torch.autograd.Function):
             if needs[5]:
                 sink2 = _sink_of(kw2) if cpad == cout else None
                 if sink2 is not None:
-                    o.conv_wgrad(g_full, a2, 1, sink2[0])
+                    _wgrad(o, g_full, a2, 1, sink2[0])
                     _count()
                     if sink2[1] is not None:
                         sink2[1]()

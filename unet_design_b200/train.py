@@ -23,6 +23,8 @@ What is B200-first about it (reference file:line in parentheses):
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional
 
 import torch
@@ -145,6 +147,9 @@ class DDPMTrainStep:
         for p, off in zip(self.arena.params, self.arena.offsets):
             ops.register_grad_sink(p, p.grad, None)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        if self.device.type == "cuda":
+            ops.enable_side_wgrad(os.environ.get("UB200_SIDE_WGRAD", "1") != "0",
+                                  int(os.environ.get("UB200_SIDE_WGRAD_PIXELS", str(128 * 8 * 8))))
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)       # 1-based after the first bump
         self.steps_done = 0
         self.use_graph = use_cuda_graph and self.device.type == "cuda"
@@ -228,6 +233,7 @@ class DDPMTrainStep:
         with _Tf32Matmul():
             loss, _ = self.trainer(x0)
             loss.backward()
+        ops.join_side_stream()          # small-layer weight gradients ran on a second stream (ops._Side)
         return loss.detach()
 
     def _reduce_and_update(self, overlapped: bool):
