@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "unet_b200.h"
 
@@ -31,6 +32,24 @@ inline int grid_for(int64_t work, int threads, int per_sm, int waves = 4) {
     int64_t cap = (int64_t)kSMs * per_sm * waves;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
+}
+
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor in the stream is still draining: its CTAs become resident as SMs free up and run their prologue
+// (barrier init, TMEM allocation, descriptor prefetch), then block in pdl_wait() until the predecessor has completed and
+// its memory is visible.  pdl_wait() must precede the first read of upstream data AND the first global write (the
+// predecessor may still be reading a buffer this kernel overwrites).  pdl_trigger() lets the NEXT kernel do the same.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// launch attribute for the kernels above; UB200_PDL=0 switches it off (A/B)
+inline bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("UB200_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+inline void pdl_attr(cudaLaunchAttribute &a) {
+    a.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    a.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
 }
 
 // Streaming (read-once / write-once) 128-bit accesses: keep them out of L1.

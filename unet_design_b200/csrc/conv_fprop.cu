@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
     // control flow and the producer / MMA loops below keep their state in uniform registers
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int num_kb = p.kb_main + p.kb_extra;
+    pdl_trigger();                     // the next kernel in the stream may set itself up behind this one
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_a);
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
     if (p.cluster > 1) cluster_sync_all();   // the peer multicasts into our smem and arrives on our barriers
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_wait();                        // everything above overlapped the previous kernel's tail; its data is needed now
     const int kCluster = p.cluster;
     const int crank = kCluster > 1 ? (int)cluster_ctarank() : 0;
     const int cluster_id = blockIdx.x / kCluster, num_clusters = gridDim.x / kCluster;
@@ -526,10 +528,11 @@ int launch_fprop(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    pdl_attr(attr[1]);
+    cfg.attrs = attr; cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BK, FAST, RES, TBL>, ta, tw, ta2, tw2, tout, p);
     if (e != cudaSuccess) return (int)e;
     UB_LAUNCH_CHECK();

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
 
     // shuffled warp index: provably warp-uniform, so the role branches are uniform control flow (see conv_fprop.cu)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    pdl_trigger();
 
     // blockIdx.x -> (ci tile, ky group, co tile); blockIdx.y -> pixel split
     int t = blockIdx.x;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_wait();
 
     const uint32_t g_chunk_bytes = kPix * p.cw_g * 2, a_chunk_bytes = kPix * p.cw_a * 2;
 
@@ -230,6 +232,8 @@ __global__ void __launch_bounds__(256) chansum_cluster_kernel(const __nv_bfloat1
     const int rank = (int)cluster.block_rank();
     const int64_t n = blockIdx.x / cs;
     const int q = threadIdx.x % chunks, r = threadIdx.x / chunks;
+    pdl_trigger();
+    pdl_wait();
     float s[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) s[u] = 0.f;
@@ -298,6 +302,8 @@ __global__ void __launch_bounds__(256) colsum_rows_kernel(const float *__restric
                                                          float *__restrict__ total) {
     // 32 channels x 8 row-lanes per CTA; rows strided by 8, combined through shared memory
     __shared__ float part[8][33];
+    pdl_trigger();
+    pdl_wait();
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     float s = 0.f;
@@ -414,8 +420,16 @@ int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a
     });
     if (attr_err != cudaSuccess) return (int)attr_err;
     const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
-    dim3 grid((unsigned)out_tiles, (unsigned)splits, 1);
-    conv_wgrad_kernel<<<grid, kThreads, smem, ub::as_stream(stream)>>>(tg, ta, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)out_tiles, (unsigned)splits, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ub::as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    ub::pdl_attr(attr[0]);
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, tg, ta, p);
+    if (le != cudaSuccess) return (int)le;
     UB_LAUNCH_CHECK();
     return UB200_OK;
 }
@@ -441,10 +455,11 @@ int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, in
             cfg.blockDim = dim3(256, 1, 1);
             cfg.dynamicSmemBytes = (256 * 8 + C) * sizeof(float);
             cfg.stream = s;
-            cudaLaunchAttribute attr[1];
+            cudaLaunchAttribute attr[2];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
+            ub::pdl_attr(attr[1]);
+            cfg.attrs = attr; cfg.numAttrs = 2;
             // the in-kernel "last cluster adds the column sums" tail is a serial latency chain (one CTA, N dependent
             // rounds of L2 reads): measured slower than a second small launch, so total goes through colsum_rows_kernel
             static const bool tail = [] { const char *e = getenv("UB200_CHANSUM_TAIL"); return e && e[0] == '1'; }();
@@ -454,7 +469,15 @@ int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, in
             if (e != cudaSuccess) return (int)e;
             UB_LAUNCH_CHECK();
             if (total && !tail) {
-                colsum_rows_kernel<<<(unsigned)((C + 31) / 32), 256, 0, s>>>(per_sample, N, (int)C, total);
+                cudaLaunchConfig_t c2{};
+                c2.gridDim = dim3((unsigned)((C + 31) / 32), 1, 1);
+                c2.blockDim = dim3(256, 1, 1);
+                c2.stream = s;
+                cudaLaunchAttribute a2[1];
+                ub::pdl_attr(a2[0]);
+                c2.attrs = a2; c2.numAttrs = 1;
+                e = cudaLaunchKernelEx(&c2, colsum_rows_kernel, (const float *)per_sample, N, (int)C, total);
+                if (e != cudaSuccess) return (int)e;
                 UB_LAUNCH_CHECK();
             }
             return UB200_OK;

@@ -445,7 +445,9 @@ __global__ void __launch_bounds__(kFusedThreads) gn_fused_fwd_kernel(
         tc::fence_barrier_init();
         tc::mbar_arrive_expect_tx_a(bar, (uint32_t)npx * (uint32_t)sh.C * 2u);
     }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();
     if (threadIdx.x < 32) fetch_slab(tc::smem_u32(xs), x + (n * sh.HW + p0) * ld_x, ld_x, sh.C, npx, bar);
     const bool active = r < sh.rows;
     if (DROP && off_dev) offset += __ldg(off_dev);
@@ -562,7 +564,9 @@ __global__ void __launch_bounds__(kFusedThreads, 3) gn_fused_bwd_kernel(
         tc::fence_barrier_init();
         tc::mbar_arrive_expect_tx_a(bar, (XSLAB ? 2u : 1u) * (uint32_t)npx * (uint32_t)sh.C * 2u);
     }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();
     if (threadIdx.x < 32) {
         fetch_slab(tc::smem_u32(ds), gy + (n * sh.HW + p0) * ld_gy, ld_gy, sh.C, npx, bar);
         if (XSLAB) fetch_slab(tc::smem_u32(xs), x + (n * sh.HW + p0) * ld_x, ld_x, sh.C, npx, bar);
@@ -819,10 +823,11 @@ int launch_cluster(K kernel, int grid, int cs, size_t smem, cudaStream_t s, Args
     cfg.blockDim = dim3(kFusedThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    pdl_attr(attr[1]);
+    cfg.attrs = attr; cfg.numAttrs = 2;
     e = cudaLaunchKernelEx(&cfg, kernel, args...);
     return e == cudaSuccess ? (int)cudaPeekAtLastError() : (int)e;
 }
