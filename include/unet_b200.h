@@ -207,6 +207,8 @@ typedef struct ub200_conv_args {
     int64_t N, H, W, Cout;
     float *gn_partial;                               /* optional [N, G, 2] sum / sumsq of the output  */
     int gn_groups;                                   /*   (next layer's GroupNorm statistics) or 0    */
+    const float *bias2;                              /* [Cout] or NULL: a second bias (the fused 1x1  */
+                                                     /*   shortcut's, diff_cifar/model.py:167)        */
 } ub200_conv_args;
 
 int ub200_conv_fprop(const ub200_conv_args *args, void *stream);
@@ -224,6 +226,8 @@ int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a
  * not NULL, total[C] += sum_n per_sample[n,c] (the conv bias gradient; accumulates). */
 int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, int64_t C,
                             float *per_sample, float *total, void *stream);
+/* total[C] += sum_n rows[n, c]: the second pass alone (a second bias that shares the same gradient). */
+int ub200_colsum_rows_f32(const float *rows, int64_t N, int64_t C, float *total, void *stream);
 
 /* fp32 weight (element (co,ci,ky,kx) at w[co*s_co + ci*s_ci + ky*s_ky + kx*s_kx], so both the
  * contiguous torch layout and channels_last work) -> packed bf16 [rows_pad,k,k,cols]:

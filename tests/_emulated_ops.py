@@ -155,7 +155,7 @@ class EmulatedOps:
                         dst.copy_(val)
 
     # ---- conv
-    def conv_fprop(self, a, w, k, cout, a2, w2, bias, rowadd, residual, out, out_nchw):
+    def conv_fprop(self, a, w, k, cout, a2, w2, bias, rowadd, residual, out, out_nchw, bias2=None):
         n, h, wd, cin = a.shape
         cpad = (cout + 15) // 16 * 16
         wt = w.float().reshape(cpad, k, k, cin)[:cout].permute(0, 3, 1, 2)
@@ -165,6 +165,8 @@ class EmulatedOps:
             y = y + F.conv2d(a2.float().permute(0, 3, 1, 2), w2t)
         if bias is not None:
             y = y + bias[None, :, None, None]
+        if bias2 is not None:
+            y = y + bias2[None, :, None, None]
         if rowadd is not None:
             y = y + rowadd[:, :, None, None]
         if residual is not None:
@@ -185,11 +187,13 @@ class EmulatedOps:
         else:
             dw.view(cout, k, k, cin).add_(gw.permute(0, 2, 3, 1))
 
-    def chansum(self, x, per_sample, total):
+    def chansum(self, x, per_sample, total, total2=None):
         s = x.float().sum(dim=(1, 2))
         per_sample.copy_(s)
         if total is not None:
             total.add_(s.sum(0))
+        if total2 is not None:
+            total2.add_(s.sum(0))
 
     def pack_conv_weight(self, w, transpose_flip, out):
         cout, cin, k, _ = w.shape

@@ -129,9 +129,11 @@ def test_chansum(ops):
     per = torch.full((4, 256), 7.0, device="cuda")     # overwritten
     tot = torch.zeros(256, device="cuda")
     from unet_design_b200._lib import ops as raw
-    raw().chansum(x, per, tot)
+    tot2 = torch.full((256,), -1.0, device="cuda")
+    raw().chansum(x, per, tot, tot2)
     assert rel_err(per, x.float().sum(dim=(1, 2))) < 1e-5
     assert rel_err(tot, x.float().sum(dim=(0, 1, 2))) < 1e-5
+    assert rel_err(tot2 + 1.0, x.float().sum(dim=(0, 1, 2))) < 1e-5      # total2 accumulates too
 
 
 def test_adam_ema_clip_matches_torch(ops):

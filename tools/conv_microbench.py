@@ -24,13 +24,13 @@ for (n, h, w, cin, cout, k) in shapes:
     wp = ops.pack_weight(wt)
     out = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
     for _ in range(5):
-        o.conv_fprop(a, wp, k, cout, None, None, None, None, None, out, None)
+        o.conv_fprop(a, wp, k, cout, None, None, None, None, None, out, None, None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 20
     g = torch.cuda.CUDAGraph()                      # replayed graph: no host launch latency between the kernels
     with torch.cuda.graph(g):
         for _ in range(reps):
-            o.conv_fprop(a, wp, k, cout, None, None, None, None, None, out, None)
+            o.conv_fprop(a, wp, k, cout, None, None, None, None, None, out, None, None)
     g.replay()
     torch.cuda.synchronize()
     e0.record()

@@ -40,7 +40,7 @@ struct FpropParams {
     uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, tbl_bytes;
     int cluster_tiles;                // (channel tile, pixel-tile group) units walked by one cluster
     int cluster;                      // CTAs per cluster: 1, or 2 with weight multicast
-    const float *bias, *rowadd;
+    const float *bias, *bias2, *rowadd;
     const __nv_bfloat16 *residual; int64_t ld_res;
     int has_out;                      // bf16 NHWC output through the TMA store
     float *out_nchw;
@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                         float v = 0.f;
                         if (co < p.Cout) {
                             if (p.bias) v = __ldg(p.bias + co);
+                            if (p.bias2) v += __ldg(p.bias2 + co);
                             if (p.rowadd && ns < p.N) v += __ldg(p.rowadd + (int64_t)ns * p.Cout + co);
                         }
                         tb[i] = v;
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         const int wi = r % p.BW, hi = (r / p.BW) % p.BH, ni = r / (p.BW * p.BH);
         const bool issuer = (warp == 2 && lane == 0);
         const int64_t hw = (int64_t)p.H * p.W;
-        const bool use_tbl = (p.bias || p.rowadd) && p.BNI <= kTblRows;
+        const bool use_tbl = (p.bias || p.bias2 || p.rowadd) && p.BNI <= kTblRows;
         uint32_t local = 0, chunk_ctr = 0;
         for (int ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters, ++local) {
             const int nt = ct % p.n_tiles, co0 = nt * p.BN;
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                         float v = 0.f;
                         if (co < p.Cout) {
                             if (p.bias) v = __ldg(p.bias + co);
+                            if (p.bias2) v += __ldg(p.bias2 + co);
                             if (p.rowadd && n0 + sidx < p.N) v += __ldg(p.rowadd + (int64_t)(n0 + sidx) * p.Cout + co);
                         }
                         tbl[i] = v;
@@ -421,6 +423,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                                 if (p.bias) {
 #pragma unroll
                                     for (int i = 0; i < 16; ++i) if (i < nv) vv[i] += __ldg(p.bias + co + i);
+                                }
+                                if (p.bias2) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) if (i < nv) vv[i] += __ldg(p.bias2 + co + i);
                                 }
                                 if (p.rowadd) {
 #pragma unroll
@@ -590,7 +596,7 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     p.num_tiles = m_units * p.n_tiles;
     p.cluster_tiles = ((m_units + kCluster - 1) / kCluster) * p.n_tiles;
     static const int env_fast = [] { const char *e = getenv("UB200_FPROP_FAST_EPI"); return e ? atoi(e) : 1; }();
-    const bool has_tbl = (a->bias || a->rowadd);
+    const bool has_tbl = (a->bias || a->bias2 || a->rowadd);
     const bool fast = env_fast && bk == 64 && a->out && !a->out_f32_nchw && a->Cout % 64 == 0 && p.BN % 64 == 0 &&
                       (!has_tbl || p.BNI <= kTblRows);
     // generic: [BNI][BN]; fast: [2 tile parities][msub][BNI][BN]
@@ -610,7 +616,7 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     if (stages < 2) stages = 2;
     p.stages = stages;
     p.tmem_cols = pow2_at_least(2u * (uint32_t)(p.msub * p.BN), 32);
-    p.bias = a->bias; p.rowadd = a->rowadd;
+    p.bias = a->bias; p.bias2 = a->bias2; p.rowadd = a->rowadd;
     p.residual = reinterpret_cast<const __nv_bfloat16 *>(a->residual); p.ld_res = a->ld_res;
     p.has_out = a->out != nullptr;
     p.out_nchw = a->out_f32_nchw;

@@ -502,6 +502,21 @@ int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, in
     return UB200_OK;
 }
 
+int ub200_colsum_rows_f32(const float *rows, int64_t N, int64_t C, float *total, void *stream) {
+    UB_REQUIRE(rows && total && N > 0 && C > 0 && C < (1 << 24), UB200_E_BADARG);
+    cudaLaunchConfig_t c2{};
+    c2.gridDim = dim3((unsigned)((C + 31) / 32), 1, 1);
+    c2.blockDim = dim3(256, 1, 1);
+    c2.stream = ub::as_stream(stream);
+    cudaLaunchAttribute a2[1];
+    ub::pdl_attr(a2[0]);
+    c2.attrs = a2; c2.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&c2, colsum_rows_kernel, rows, N, (int)C, total);
+    if (e != cudaSuccess) return (int)e;
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
 int ub200_pack_conv_weight(const float *w, int64_t Cout, int64_t Cin, int ksize, int64_t s_co, int64_t s_ci,
                            int64_t s_ky, int64_t s_kx, int transpose_flip, void *out_bf16, void *stream) {
     UB_REQUIRE(w && out_bf16 && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3), UB200_E_BADARG);

@@ -238,7 +238,7 @@ void gn_act_bwd(const Tensor &gy, const Tensor &x, int64_t G, const c10::optiona
 void conv_fprop(const Tensor &a, const Tensor &w, int64_t ksize, int64_t Cout, const c10::optional<Tensor> &a2,
                 const c10::optional<Tensor> &w2, const c10::optional<Tensor> &bias, const c10::optional<Tensor> &rowadd,
                 const c10::optional<Tensor> &residual, const c10::optional<Tensor> &out,
-                const c10::optional<Tensor> &out_nchw) {
+                const c10::optional<Tensor> &out_nchw, const c10::optional<Tensor> &bias2) {
     UB_GUARD(a);
     const Nhwc A = nhwc(a, "a");
     ub200_conv_args args{};
@@ -256,6 +256,7 @@ void conv_fprop(const Tensor &a, const Tensor &w, int64_t ksize, int64_t Cout, c
         args.a2 = A2.ptr; args.ld_a2 = A2.ld; args.Cin2 = A2.C; args.w2 = w2->data_ptr();
     }
     if (bias.has_value()) { TORCH_CHECK(bias->numel() == Cout, "conv_fprop: bias size"); args.bias = f32(*bias, "bias"); }
+    if (bias2.has_value()) { TORCH_CHECK(bias2->numel() == Cout, "conv_fprop: bias2 size"); args.bias2 = f32(*bias2, "bias2"); }
     if (rowadd.has_value()) { TORCH_CHECK(rowadd->numel() == A.N * Cout, "conv_fprop: rowadd size"); args.rowadd = f32(*rowadd, "rowadd"); }
     if (residual.has_value()) {
         const Nhwc R = nhwc(*residual, "residual");
@@ -286,13 +287,16 @@ void conv_wgrad(const Tensor &gout, const Tensor &a, int64_t ksize, const Tensor
              "conv_wgrad");
 }
 
-void chansum(const Tensor &x, const Tensor &per_sample, const c10::optional<Tensor> &total) {
+void chansum(const Tensor &x, const Tensor &per_sample, const c10::optional<Tensor> &total,
+             const c10::optional<Tensor> &total2) {
     UB_GUARD(x);
     const Nhwc X = nhwc(x, "x");
     TORCH_CHECK(per_sample.numel() == X.N * X.C, "chansum: per_sample must hold N*C floats");
     float *ps = f32_mut(per_sample, "per_sample");
     float *tt = total.has_value() ? f32_mut(*total, "total") : nullptr;
     check_rc(ub200_chansum_nhwc_bf16(X.ptr, X.ld, X.N, X.H * X.W, X.C, ps, tt, cur_stream()), "chansum");
+    if (total2.has_value())      // a second bias with the same gradient (conv bias + fused shortcut bias)
+        check_rc(ub200_colsum_rows_f32(ps, X.N, X.C, f32_mut(*total2, "total2"), cur_stream()), "colsum_rows");
 }
 
 // w: fp32 [Cout,Cin,k,k] with any dense strides (contiguous or channels_last)

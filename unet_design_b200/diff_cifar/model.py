@@ -223,7 +223,7 @@ class ResBlock(nn.Module):
         out2 = None if has_attn else out
         if isinstance(self.shortcut, nn.Conv2d):
             # conv2(a2) + shortcut(x): the 1x1 conv rides along as extra K slices of the same GEMM
-            h = ops.conv(a2, conv2.weight, conv2.bias + self.shortcut.bias, a2=x, w2=self.shortcut.weight, out=out2)
+            h = ops.conv(a2, conv2.weight, conv2.bias, a2=x, w2=self.shortcut.weight, out=out2, bias2=self.shortcut.bias)
         else:
             h = ops.conv(a2, conv2.weight, conv2.bias, residual=x, out=out2)
         if has_attn:

@@ -425,7 +425,7 @@ class _Conv(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, a, w, bias, rowadd, a2, w2, residual, out_nchw, out_box=None):
+    def forward(ctx, a, w, bias, rowadd, a2, w2, residual, out_nchw, out_box=None, bias2=None):
         o = _ops()
         a = _dense_nhwc(a)
         n, h, wd, cin = a.shape
@@ -441,21 +441,23 @@ class _Conv(torch.autograd.Function):
         res = _dense_nhwc(residual) if residual is not None else None
         if out_nchw:
             out = torch.empty((n, cout, h, wd), dtype=torch.float32, device=a.device)
-            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, None, out)
+            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, None, out, bias2)
         elif out_box is not None:
             # the caller owns the destination: an NHWC view (pixel stride > Cout) inside a wider buffer, e.g. the first
             # channels of a decoder concat buffer.  Passed in a list so autograd does not treat it as an input.
             dst = out_box[0]
             assert dst.shape == (n, h, wd, cout) and dst.dtype == torch.bfloat16
-            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, dst, None)
+            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, dst, None, bias2)
             out = dst.view_as(dst)
         else:
             out = torch.empty((n, h, wd, cout), dtype=torch.bfloat16, device=a.device)
-            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, out, None)
+            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, out, None, bias2)
         _count()
         ctx.save_for_backward(a, w, a2d, w2)
         ctx.flags = (bias is not None, rowadd is not None, residual is not None, out_nchw)
         ctx.keys = (_key(w), _key(bias), _key(w2))
+        ctx.bias2_key = _key(bias2) if bias2 is not None else None
+        ctx.has_bias2 = bias2 is not None
         return out
 
     @staticmethod
@@ -478,7 +480,8 @@ class _Conv(torch.autograd.Function):
                 gp[..., :cout].copy_(g_valid)
                 g_full = gp
         needs = ctx.needs_input_grad
-        ga = gw = gbias = growadd = ga2 = gw2 = gres = None
+        ga = gw = gbias = growadd = ga2 = gw2 = gres = gbias2 = None
+        want_b2 = ctx.has_bias2 and needs[9]
         kw, kb, kw2 = ctx.keys
         pk, pk2 = _Registry.packed.get(kw), _Registry.packed.get(kw2)
         if needs[0]:
@@ -493,7 +496,7 @@ class _Conv(torch.autograd.Function):
                     w_t = w
                 wtp = pack_weight(w_t, transpose_flip=True)
             ga = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=a.device)
-            o.conv_fprop(g_full, wtp, k, cin, None, None, None, None, None, ga, None)
+            o.conv_fprop(g_full, wtp, k, cin, None, None, None, None, None, ga, None, None)
             _count()
         if needs[1]:
             sink = _sink_of(kw) if cpad == cout else None
@@ -507,7 +510,7 @@ class _Conv(torch.autograd.Function):
                 o.conv_wgrad(g_full, a, k, dw)
                 _count(2)
                 gw = dw[:cout].permute(0, 3, 1, 2)      # [Cout,Cin,k,k] view with channels_last strides
-        if (has_bias and needs[2]) or (has_rowadd and needs[3]):
+        if (has_bias and needs[2]) or (has_rowadd and needs[3]) or want_b2:
             bsink = _sink_of(kb) if (has_bias and needs[2] and cout % 8 == 0) else None
             if cout % 8 == 0:
                 per = torch.empty((n, cout), dtype=torch.float32, device=g.device)
@@ -515,23 +518,30 @@ class _Conv(torch.autograd.Function):
                     tot = bsink[0]
                 else:
                     tot = torch.zeros((cout,), dtype=torch.float32, device=g.device) if has_bias else None
-                o.chansum(g_valid, per, tot)
-                _count(2 if tot is not None else 1)
+                tot2 = b2sink = None
+                if want_b2:                 # the second bias receives the same column sums
+                    b2sink = _sink_of(ctx.bias2_key)
+                    tot2 = b2sink[0] if b2sink is not None else torch.zeros((cout,), dtype=torch.float32, device=g.device)
+                o.chansum(g_valid, per, tot, tot2)
+                _count(1 + (tot is not None) + (tot2 is not None))
                 growadd, gbias = (per if has_rowadd else None), (None if bsink is not None else tot)
-                if bsink is not None and bsink[1] is not None:
-                    bsink[1]()
+                gbias2 = None if b2sink is not None else tot2
+                for sk in (bsink, b2sink):
+                    if sk is not None and sk[1] is not None:
+                        sk[1]()
             else:
                 per = torch.empty((n, cpad), dtype=torch.float32, device=g.device)
                 tot = torch.zeros((cpad,), dtype=torch.float32, device=g.device) if has_bias else None
-                o.chansum(g_full, per, tot)
+                o.chansum(g_full, per, tot, None)
                 _count(2 if tot is not None else 1)
                 growadd = per[:, :cout].contiguous() if has_rowadd else None
                 gbias = tot[:cout] if has_bias else None
+                gbias2 = tot[:cout].clone() if want_b2 else None
         if a2 is not None:
             if needs[4]:
                 w2tp = pk2[1] if (pk2 is not None and cpad == cout) else pack_weight(w2, transpose_flip=True)
                 ga2 = torch.empty(a2.shape, dtype=torch.bfloat16, device=a.device)
-                o.conv_fprop(g_full, w2tp, 1, a2.shape[3], None, None, None, None, None, ga2, None)
+                o.conv_fprop(g_full, w2tp, 1, a2.shape[3], None, None, None, None, None, ga2, None, None)
                 _count()
             if needs[5]:
                 sink2 = _sink_of(kw2) if cpad == cout else None
@@ -547,14 +557,14 @@ class _Conv(torch.autograd.Function):
                     gw2 = dw2[:cout].permute(0, 3, 1, 2)
         if has_res and needs[6]:
             gres = g_valid
-        return ga, gw, gbias, growadd, ga2, gw2, gres, None, None
+        return ga, gw, gbias, growadd, ga2, gw2, gres, None, None, gbias2
 
 
 def conv(a: torch.Tensor, w: torch.Tensor, bias=None, rowadd=None, a2=None, w2=None, residual=None,
-         out_nchw: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out_nchw: bool = False, out: Optional[torch.Tensor] = None, bias2=None) -> torch.Tensor:
     """Fused stride-1 same-padding convolution (k = 1 or 3).  `a` NHWC bf16 with C % 16 == 0.
     `out`: optional destination, an NHWC bf16 view [N,H,W,Cout] (may be a channel slice of a wider buffer)."""
-    return _Conv.apply(a, w, bias, rowadd, a2, w2, residual, out_nchw, [out] if out is not None else None)
+    return _Conv.apply(a, w, bias, rowadd, a2, w2, residual, out_nchw, [out] if out is not None else None, bias2)
 
 
 class _CatView(torch.autograd.Function):
