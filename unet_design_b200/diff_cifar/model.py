@@ -154,14 +154,25 @@ class AttnBlock(nn.Module):
             init.zeros_(module.bias)
         init.xavier_uniform_(self.proj.weight, gain=1e-5)
 
+    def fused_param_groups(self):
+        """Parameters a training arena should lay out contiguously (train.FlatArena): q|k|v weights, q|k|v biases."""
+        return ([self.proj_q.weight, self.proj_k.weight, self.proj_v.weight],
+                [self.proj_q.bias, self.proj_k.bias, self.proj_v.bias])
+
     def forward_nhwc(self, x, out=None):
         n, h, w, c = x.shape
         y = ops.gn_act(x, self.group_norm.weight, self.group_norm.bias, 32, act="none", eps=self.group_norm.eps)
         # q, k, v projections as ONE 1x1 conv on the tensor cores (weights concatenated on the fly: the
         # state_dict keeps the reference's three separate convs); softmax(QK^T/sqrt(C))V on PyTorch SDPA
-        wqkv = torch.cat([self.proj_q.weight, self.proj_k.weight, self.proj_v.weight], dim=0)
-        bqkv = torch.cat([self.proj_q.bias, self.proj_k.bias, self.proj_v.bias], dim=0)
-        qkv = ops.conv(y, wqkv, bqkv).reshape(n, 1, h * w, 3 * c)
+        if ops.fused_conv_registered(self.proj_q.weight):
+            # under train.DDPMTrainStep the three weights (and biases) are neighbours in the parameter arena: their
+            # concatenation, its packed operands and its gradient are views -- nothing is copied or re-packed
+            qkv = ops.fused_conv1x1(y, *self.fused_param_groups())
+        else:
+            wqkv = torch.cat([self.proj_q.weight, self.proj_k.weight, self.proj_v.weight], dim=0)
+            bqkv = torch.cat([self.proj_q.bias, self.proj_k.bias, self.proj_v.bias], dim=0)
+            qkv = ops.conv(y, wqkv, bqkv)
+        qkv = qkv.reshape(n, 1, h * w, 3 * c)
         q, k, v = ops.split3(qkv)
         o = F.scaled_dot_product_attention(q, k, v, scale=int(c) ** (-0.5))
         # x + proj(o): the residual add rides in the conv epilogue

@@ -11,6 +11,8 @@ from __future__ import annotations
 import math
 from typing import Optional
 
+import weakref
+
 import torch
 
 from ._lib import ops as _ops
@@ -47,19 +49,47 @@ def _count(n: int = 1) -> None:
 class _Registry:
     sinks = {}      # id(param) -> (grad view in the arena, on_ready callback or None)
     packed = {}     # id(param) -> (fprop/wgrad operand, dgrad operand)  bf16, flat
+    fused = {}      # id(first weight of a fused group) -> dict (see register_fused_conv)
+    owner = {}      # id -> weakref of the tensor that registered it: a recycled id must not inherit stale entries
+
+
+def _own(t: torch.Tensor) -> int:
+    k = id(t)
+    ref = _Registry.owner.get(k)
+    if ref is not None and ref() is not t:          # the id was recycled by a new tensor: drop what the old one left
+        _Registry.sinks.pop(k, None); _Registry.packed.pop(k, None); _Registry.fused.pop(k, None)
+    _Registry.owner[k] = weakref.ref(t)
+    return k
+
+
+def _valid(t: torch.Tensor) -> bool:
+    ref = _Registry.owner.get(id(t))
+    return ref is not None and ref() is t
 
 
 def register_grad_sink(param: torch.Tensor, grad_view: torch.Tensor, on_ready=None) -> None:
-    _Registry.sinks[id(param)] = (grad_view, on_ready)
+    _Registry.sinks[_own(param)] = (grad_view, on_ready)
 
 
 def register_packed_weight(param: torch.Tensor, fwd: torch.Tensor, bwd: torch.Tensor) -> None:
-    _Registry.packed[id(param)] = (fwd, bwd)
+    _Registry.packed[_own(param)] = (fwd, bwd)
+
+
+def register_fused_conv(first_weight: torch.Tensor, packed_fwd, packed_bwd, w_sink, bias, b_sink) -> None:
+    """Several 1x1 convs of one input (AttnBlock q/k/v) whose parameters lie next to each other in the training arena:
+    their concatenation is then a plain view -- packed operands, the fp32 bias and both gradient sinks of the fused conv."""
+    _Registry.fused[_own(first_weight)] = dict(fwd=packed_fwd, bwd=packed_bwd, w_sink=w_sink, bias=bias, b_sink=b_sink)
+
+
+def fused_conv_registered(first_weight: torch.Tensor) -> bool:
+    return id(first_weight) in _Registry.fused and _valid(first_weight)
 
 
 def clear_registry() -> None:
     _Registry.sinks.clear()
     _Registry.packed.clear()
+    _Registry.fused.clear()
+    _Registry.owner.clear()
 
 
 class _Side:
@@ -102,7 +132,12 @@ def _sink_of(key):
 
 
 def _key(t):
-    return id(t) if isinstance(t, torch.nn.Parameter) else None
+    """Registry key of a parameter; None for anything else (and for a parameter whose id is a recycled one)."""
+    if not isinstance(t, torch.nn.Parameter):
+        return None
+    k = id(t)
+    ref = _Registry.owner.get(k)
+    return k if (ref is None or ref() is t) else None
 
 
 def _dense_nhwc(t: torch.Tensor) -> torch.Tensor:
@@ -565,6 +600,46 @@ def conv(a: torch.Tensor, w: torch.Tensor, bias=None, rowadd=None, a2=None, w2=N
     """Fused stride-1 same-padding convolution (k = 1 or 3).  `a` NHWC bf16 with C % 16 == 0.
     `out`: optional destination, an NHWC bf16 view [N,H,W,Cout] (may be a channel slice of a wider buffer)."""
     return _Conv.apply(a, w, bias, rowadd, a2, w2, residual, out_nchw, [out] if out is not None else None, bias2)
+
+
+class _FusedConv1x1(torch.autograd.Function):
+    """out[..., :] = conv1x1(a, cat(w_i)) + cat(b_i) with the concatenations taken as views of the training arena
+    (register_fused_conv): no weight / bias concat in forward, no split + accumulate of the gradients in backward."""
+
+    @staticmethod
+    def forward(ctx, a, *params):
+        reg = _Registry.fused[id(params[0])]
+        a = _dense_nhwc(a)
+        n, h, wd, cin = a.shape
+        cout = reg["bias"].numel()
+        out = torch.empty((n, h, wd, cout), dtype=torch.bfloat16, device=a.device)
+        _ops().conv_fprop(a, reg["fwd"], 1, cout, None, None, reg["bias"], None, None, out, None, None)
+        _count()
+        ctx.save_for_backward(a)
+        ctx.reg, ctx.nparams = reg, len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        o = _ops()
+        (a,), reg = ctx.saved_tensors, ctx.reg
+        n, h, wd, cin = a.shape
+        g = _dense_nhwc(g)
+        cout = g.shape[3]
+        ga = None
+        if ctx.needs_input_grad[0]:
+            ga = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=a.device)
+            o.conv_fprop(g, reg["bwd"], 1, cin, None, None, None, None, None, ga, None, None)
+            _count()
+        _wgrad(o, g, a, 1, reg["w_sink"])
+        per = torch.empty((n, cout), dtype=torch.float32, device=g.device)
+        o.chansum(g, per, reg["b_sink"], None)
+        _count(3)
+        return (ga,) + (None,) * ctx.nparams
+
+
+def fused_conv1x1(a: torch.Tensor, weights, biases) -> torch.Tensor:
+    return _FusedConv1x1.apply(a, *weights, *biases)
 
 
 class _CatView(torch.autograd.Function):

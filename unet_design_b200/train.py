@@ -55,6 +55,26 @@ class FlatArena:
         params = [p for p in model.parameters() if p.requires_grad]
         assert params, "model has no trainable parameters"
         dev = params[0].device
+        # modules may ask for some parameters to be neighbours (AttnBlock: q|k|v weights, q|k|v biases), so that their
+        # concatenation is a view of the arena; members of a group are emitted together at the first member's position
+        groups, member_of = [], {}
+        for m in model.modules():
+            if hasattr(m, "fused_param_groups"):
+                gw, gb = m.fused_param_groups()
+                if all(p.requires_grad and p.numel() % 4 == 0 for p in list(gw) + list(gb)):
+                    groups.append((list(gw), list(gb)))
+                    for grp in (gw, gb):
+                        for p in grp:
+                            member_of[id(p)] = grp
+        ordered, seen = [], set()
+        for p in params:
+            if id(p) in seen:
+                continue
+            for q in member_of.get(id(p), [p]):
+                ordered.append(q)
+                seen.add(id(q))
+        params = ordered
+        self.fused_groups = groups
         self.params = params
         sizes = [(p.numel() + 3) // 4 * 4 for p in params]          # keep every slice 16-byte aligned
         self.offsets = [0]
@@ -107,10 +127,25 @@ class PackedWeights:
                 rows.append([off, doff, cout, cin, k])
                 self.entries.append((p, off, n_fwd, doff, n_bwd))
                 doff += (n_bwd + 7) // 8 * 8                    # keep every operand 16-byte aligned
+        # fused 1x1 groups (q|k|v): one more dgrad operand for the concatenated weight, everything else is a view
+        off_of = {id(p): off for p, off in zip(arena.params, arena.offsets)}
+        fused = []
+        for gw, gb in getattr(arena, "fused_groups", []):
+            cout, cin = sum(w.shape[0] for w in gw), gw[0].shape[1]
+            if gw[0].dim() == 4 and gw[0].shape[2] == 1 and cin % 16 == 0 and cout % 16 == 0:
+                off, boff = off_of[id(gw[0])], off_of[id(gb[0])]
+                rows.append([off, doff, cout, cin, 1])
+                fused.append((gw[0], off, boff, cout, cin, doff))
+                doff += (cin * cout + 7) // 8 * 8
         self.dgrad = torch.empty(max(doff, 8), dtype=torch.bfloat16, device=dev)
         self.table = torch.tensor(rows, dtype=torch.int64, device=dev) if rows else None
         for p, off, n_fwd, d0, n_bwd in self.entries:
             ops.register_packed_weight(p, self.shadow[off:off + n_fwd], self.dgrad[d0:d0 + n_bwd])
+        for first, off, boff, cout, cin, d0 in fused:
+            n = cout * cin
+            ops.register_fused_conv(first, self.shadow[off:off + n], self.dgrad[d0:d0 + n],
+                                    arena.g[off:off + n].view(cout, 1, 1, cin).permute(0, 3, 1, 2),
+                                    arena.p[boff:boff + cout], arena.g[boff:boff + cout])
         self.refresh_from_master()
 
     def refresh_dgrad(self):
