@@ -241,3 +241,39 @@ class GaussianDiffusionTrainer(nn.Module):  # diffusion.py:17-91
     def forward(self, x_0, n_levels_used=-1, n_downsample=0):
         t = torch.randint(self.T, size=(x_0.shape[0],), device=x_0.device)
         return self.loss_from(x_0, t, torch.randn_like(x_0), n_levels_used, n_downsample)
+
+
+class GaussianDiffusionSampler(nn.Module):  # diffusion.py:94-222 (mean_type 'epsilon' / 'xstart' / 'xprev')
+    def __init__(self, model, beta_1, beta_T, T, mean_type="epsilon", var_type="fixedlarge", multi_res_loss=False):
+        super().__init__()
+        self.model, self.T, self.mean_type, self.var_type, self.multi_res_loss = model, T, mean_type, var_type, multi_res_loss
+        betas = torch.linspace(beta_1, beta_T, T).double()
+        alphas = 1.0 - betas
+        abar = torch.cumprod(alphas, dim=0)
+        abar_prev = torch.cat([torch.ones(1, dtype=torch.float64), abar[:-1]])
+        self.betas = betas
+        self.recip = (1.0 / abar).sqrt()
+        self.recipm1 = (1.0 / abar - 1.0).sqrt()
+        self.post_var = betas * (1.0 - abar_prev) / (1.0 - abar)
+        self.post_logvar = torch.log(torch.cat([self.post_var[1:2], self.post_var[1:]]))
+        self.c1 = abar_prev.sqrt() * betas / (1.0 - abar)
+        self.c2 = alphas.sqrt() * (1.0 - abar_prev) / (1.0 - abar)
+
+    @torch.no_grad()
+    def forward(self, x_T, n_levels_used, noises):
+        """`noises[i]` is the draw of loop iteration i (time step T-1-i); the last iteration (t = 0) adds none."""
+        x = x_T
+        logvar = {"fixedlarge": torch.log(torch.cat([self.post_var[1:2], self.betas[1:]])),
+                  "fixedsmall": self.post_logvar}[self.var_type]
+        for i, ts in enumerate(reversed(range(self.T))):
+            t = torch.full((x.shape[0],), ts, dtype=torch.long)
+            out = self.model(x, t, n_levels_used=n_levels_used)
+            out = out[-1] if self.multi_res_loss else out
+            if self.mean_type == "xprev":
+                mean = out
+            else:
+                x0 = out if self.mean_type == "xstart" else self.recip[ts].float() * x - self.recipm1[ts].float() * out
+                mean = self.c1[ts].float() * x0 + self.c2[ts].float() * x
+            noise = noises[i] if ts > 0 else torch.zeros_like(x)
+            x = mean + torch.exp(0.5 * logvar[ts].float()) * noise
+        return torch.clip(x, -1, 1)

@@ -84,6 +84,18 @@ def check_cifar_model(ns, trainer_cls, tag, device, tol_out, tol_grad):
     _check_grads(net, g["gparams"], tol_grad, loose=("attn.proj_q.bias", "time_embedding"))
 
 
+def check_cifar_sampler(ns, make_sampler, device, tol):
+    """DDPM Algorithm 2 against the reference's own sampler (tools/make_golden.py::cifar_sampler_golden), replaying
+    the reference loop's Gaussian draws.  `make_sampler(net, T, var_type)` builds the implementation under test."""
+    cases = load("cifar_sampler.pt")
+    for var_type, g in cases.items():
+        net = apply_det_init(ns.UNetWaveletEnc(**g["cfg"])).to(device).eval()
+        sampler = make_sampler(net, g["cfg"]["T"], var_type)
+        x0 = sampler(g["x_T"].to(device), -1, [n.to(device) for n in g["noises"]])
+        assert x0.shape == g["x_0"].shape and float(x0.abs().max()) <= 1.0
+        assert rel_err(x0, g["x_0"]) < tol, (var_type, rel_err(x0, g["x_0"]))
+
+
 def check_pdearena_blocks(base_ns, unet_ns, device, tol):
     blocks = load("pdearena_blocks.pt")
     ctors = {"conv": lambda: base_ns.ConvBlock(32, 48),

@@ -74,3 +74,21 @@ def test_mnist_blocks(emulated_ops):
 def test_mnist_unet_wavelet(emulated_ops, tag):
     from unet_design_b200.diff_mnist.unet import get_unet_wavelet
     gc.check_mnist_unet(get_unet_wavelet, tag, "cpu", 3 * TOL, 0.12)   # 4 levels deep through 1-channel bottlenecks
+
+
+def test_cifar_sampler(emulated_ops):
+    """Drop-in GaussianDiffusionSampler (DDPM Algorithm 2, diffusion.py:94-222) against the reference's sampler."""
+    from unet_design_b200.diff_cifar import model
+    from unet_design_b200.diff_cifar.diffusion import GaussianDiffusionSampler
+
+    def make(net, T, vt):
+        return GaussianDiffusionSampler(net, 1e-4, 0.02, T, img_size=16, mean_type="epsilon", var_type=vt)
+
+    gc.check_cifar_sampler(model, make, "cpu", 3 * TOL)
+    with pytest.raises(AssertionError):          # the reference's default mean_type is rejected by its own assert
+        GaussianDiffusionSampler(None, 1e-4, 0.02, 4)
+    # buffer surface of the reference class
+    sd = make(torch.nn.Identity(), 6, "fixedlarge").state_dict()
+    assert set(sd) == {"betas", "sqrt_recip_alphas_bar", "sqrt_recipm1_alphas_bar", "posterior_var",
+                       "posterior_log_var_clipped", "posterior_mean_coef1", "posterior_mean_coef2"}
+    assert all(v.dtype == torch.float64 for v in sd.values())

@@ -89,3 +89,33 @@ def test_mnist_blocks_golden():
 def test_mnist_unet_wavelet_golden(tag):
     from unet_design_b200.diff_mnist.unet import get_unet_wavelet
     gc.check_mnist_unet(get_unet_wavelet, tag, "cuda", 3 * TOL, 0.12)   # 4 levels deep through 1-channel bottlenecks
+
+
+@pytest.mark.gpu
+def test_cifar_sampler_gpu_matches_reference_and_graph_matches_eager():
+    """DDPM Algorithm 2 on the sm_100a kernels: (1) replaying the reference loop's noise, against the golden produced by
+    the reference's own sampler; (2) the CUDA-graph loop (time index on the device, T replays) against the eager loop,
+    with the noise term switched off so both are deterministic."""
+    from unet_design_b200.diff_cifar import model
+    from unet_design_b200.diff_cifar.diffusion import GaussianDiffusionSampler
+
+    def make(net, T, vt):
+        return GaussianDiffusionSampler(net, 1e-4, 0.02, T, img_size=16, mean_type="epsilon", var_type=vt)
+
+    gc.check_cifar_sampler(model, make, "cuda", 3 * TOL)
+    g = gc.load("cifar_sampler.pt")["fixedlarge"]
+    net = gc.apply_det_init(model.UNetWaveletEnc(**g["cfg"])).cuda().eval()
+    sampler = make(net, g["cfg"]["T"], "fixedsmall").cuda()
+    x_T = g["x_T"].cuda()
+    zeros = [torch.zeros_like(x_T) for _ in g["noises"]]
+    eager = sampler(x_T, -1, zeros)
+    real = torch.randn_like
+    torch.randn_like = lambda t: torch.zeros_like(t)       # the graphed step draws through randn_like: silence it
+    try:
+        graphed = sampler(x_T, -1)
+        again = sampler(x_T, -1)                            # second call replays the cached graph
+    finally:
+        torch.randn_like = real
+    assert rel_err(graphed, eager) < 1e-2 and rel_err(again, eager) < 1e-2
+    noisy = sampler(x_T, -1)                                # real noise: finite, clipped
+    assert torch.isfinite(noisy).all() and float(noisy.abs().max()) <= 1.0

@@ -34,3 +34,8 @@ def test_model_and_loss_match_reference(tag):
     net = torch_ref.UNetWaveletEnc(**g["cfg"])
     trainer = torch_ref.GaussianDiffusionTrainer(net, 1e-4, 0.02, g["cfg"]["T"], g["cfg"]["multi_res_loss"])
     assert float((trainer.q_sample(g["x0"], g["t"], g["noise"]) - g["x_t"]).abs().max()) < 1e-6
+
+
+def test_cifar_sampler_oracle_matches_reference():
+    gc.check_cifar_sampler(torch_ref, lambda net, T, vt: torch_ref.GaussianDiffusionSampler(net, 1e-4, 0.02, T, "epsilon", vt),
+                           "cpu", 1e-5)

@@ -111,6 +111,35 @@ def cifar_goldens():
                     "gparams": small_grads(net, also=("upblocks.0.0.block1.2.weight",))}, f"{OUT}/cifar_{tag}.pt")
 
 
+def cifar_sampler_golden():
+    """DDPM Algorithm 2 (diffusion.py:94-222) through the reference's own sampler on a small Multi-ResNet, with the
+    loop's `torch.randn_like` draws recorded so that the oracle and the CUDA path can replay them."""
+    m = load_reference_module("ref_cifar_model", f"{REF}/diff_cifar/model.py")
+    d = load_reference_module("ref_cifar_diffusion", f"{REF}/diff_cifar/diffusion.py")
+    cases = {}
+    for var_type in ("fixedlarge", "fixedsmall"):
+        cfg = dict(T=6, ch=64, ch_mult=[1, 1], attn=[1], num_res_blocks=1, dropout=0.0, dwt_encoder=True, multi_res_loss=False)
+        net = apply_det_init(m.UNetWaveletEnc(**cfg)).eval()
+        sampler = d.GaussianDiffusionSampler(net, 1e-4, 0.02, 6, img_size=16, mean_type="epsilon", var_type=var_type)
+        torch.manual_seed(3)
+        x_T = torch.randn(2, 3, 16, 16)
+        noises, real = [], torch.randn_like
+
+        def recording(x):
+            n = real(x)
+            noises.append(n)
+            return n
+
+        torch.randn_like = recording
+        try:
+            with torch.no_grad():
+                x_0 = sampler(x_T, n_levels_used=-1)
+        finally:
+            torch.randn_like = real
+        cases[var_type] = {"cfg": cfg, "x_T": x_T, "noises": noises, "x_0": x_0}
+    torch.save(cases, f"{OUT}/cifar_sampler.pt")
+
+
 def pdearena_wmh_goldens():
     sys.modules["pytorch_wavelets"] = pw
     sys.path.insert(0, f"{REF}/pdearena")
@@ -233,7 +262,11 @@ def state_dict_keys():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "sampler":      # only the sampler fixture (the others are unchanged)
+        cifar_sampler_golden()
+        raise SystemExit(0)
     cifar_goldens()
+    cifar_sampler_golden()
     pdearena_wmh_goldens()
     mnist_goldens()
     state_dict_keys()
