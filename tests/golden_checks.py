@@ -90,7 +90,7 @@ def check_cifar_sampler(ns, make_sampler, device, tol):
     cases = load("cifar_sampler.pt")
     for var_type, g in cases.items():
         net = apply_det_init(ns.UNetWaveletEnc(**g["cfg"])).to(device).eval()
-        sampler = make_sampler(net, g["cfg"]["T"], var_type)
+        sampler = make_sampler(net, g["cfg"]["T"], var_type).to(device)
         x0 = sampler(g["x_T"].to(device), -1, [n.to(device) for n in g["noises"]])
         assert x0.shape == g["x_0"].shape and float(x0.abs().max()) <= 1.0
         assert rel_err(x0, g["x_0"]) < tol, (var_type, rel_err(x0, g["x_0"]))
