@@ -99,6 +99,7 @@ class _Side:
     -0.1 ms/step with the <= 8x8 layers only, -0.15 ms with all layers).  The caller (train.DDPMTrainStep) enables this and
     joins the stream after backward; operands are kept alive until the join."""
     enabled = False
+    chansum = True
     max_pixels = 1 << 30
     stream = None
     keep = []
@@ -125,6 +126,27 @@ def _wgrad(o, g, a, k, dst) -> None:
         _Side.keep += [g, a]
     else:
         o.conv_wgrad(g, a, k, dst)
+
+
+def _chansum(o, g, per, tot, tot2, side_ok: bool) -> None:
+    """Bias / time-row column sums of a conv's output gradient.  Like the wgrad they only feed the optimiser (and, for
+    `per`, the batched time-embedding backward, which waits for the side stream): off the critical path when both
+    destinations are arena sinks or fresh buffers nobody reads before the join."""
+    if side_ok and _Side.enabled and _Side.chansum and g.is_cuda:
+        if _Side.stream is None:
+            _Side.stream = torch.cuda.Stream(device=g.device)
+        _Side.stream.wait_stream(torch.cuda.current_stream(g.device))
+        with torch.cuda.stream(_Side.stream):
+            o.chansum(g, per, tot, tot2)
+        _Side.keep += [g, per]
+    else:
+        o.chansum(g, per, tot, tot2)
+
+
+def wait_side_stream(device) -> None:
+    """The current stream waits for everything queued on the side stream so far (consumers of its results)."""
+    if _Side.stream is not None and _Side.keep:
+        torch.cuda.current_stream(device).wait_stream(_Side.stream)
 
 
 def _sink_of(key):
@@ -557,7 +579,10 @@ class _Conv(torch.autograd.Function):
                 if want_b2:                 # the second bias receives the same column sums
                     b2sink = _sink_of(ctx.bias2_key)
                     tot2 = b2sink[0] if b2sink is not None else torch.zeros((cout,), dtype=torch.float32, device=g.device)
-                o.chansum(g_valid, per, tot, tot2)
+                # on the side stream only if nothing on the main stream reads the results before the join: sinks, or
+                # `per` (consumed by the batched time-embedding backward, which waits for the side stream itself)
+                side_ok = (bsink is not None or tot is None) and (b2sink is not None or tot2 is None)
+                _chansum(o, g_valid, per, tot, tot2, side_ok)
                 _count(1 + (tot is not None) + (tot2 is not None))
                 growadd, gbias = (per if has_rowadd else None), (None if bsink is not None else tot)
                 gbias2 = None if b2sink is not None else tot2
@@ -633,7 +658,7 @@ class _FusedConv1x1(torch.autograd.Function):
             _count()
         _wgrad(o, g, a, 1, reg["w_sink"])
         per = torch.empty((n, cout), dtype=torch.float32, device=g.device)
-        o.chansum(g, per, reg["b_sink"], None)
+        _chansum(o, g, per, reg["b_sink"], None, True)
         _count(3)
         return (ga,) + (None,) * ctx.nparams
 
@@ -691,6 +716,8 @@ class _RowLinBatch(torch.autograd.Function):
     def backward(ctx, *gys):
         silu, n, wkeys, bkeys, has_b = ctx.cfg
         saved = ctx.saved_tensors
+        if saved[0].is_cuda:
+            wait_side_stream(saved[0].device)      # the row gradients are channel sums that may have run there
         xs, ws = list(saved[:n]), list(saved[n:])
         needs = ctx.needs_input_grad            # (silu, n, xs..., ws..., bs...)
         gys = [g.contiguous() if g is not None else torch.zeros((xs[i].shape[0], ws[i].shape[0]), dtype=torch.float32,

@@ -185,6 +185,7 @@ class DDPMTrainStep:
         if self.device.type == "cuda":
             ops.enable_side_wgrad(os.environ.get("UB200_SIDE_WGRAD", "1") != "0",
                                   int(os.environ.get("UB200_SIDE_WGRAD_PIXELS", str(1 << 30))))
+            ops._Side.chansum = os.environ.get("UB200_SIDE_CHANSUM", "1") != "0"
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)       # 1-based after the first bump
         self.steps_done = 0
         self.use_graph = use_cuda_graph and self.device.type == "cuda"
