@@ -21,6 +21,8 @@ AttnBlock (2.2% of the FLOPs, out of scope per SURVEY.md §2.1) runs on PyTorch'
 """
 from __future__ import annotations
 
+import contextlib
+import os
 import math
 from typing import List
 
@@ -265,6 +267,16 @@ class DTWBlock(nn.Module):
         return ops.dwtblock(x.float(), self.J, self.out_channels)
 
 
+_SKIP_STREAMS = {}
+
+
+def _skip_stream(device):
+    st = _SKIP_STREAMS.get(device)
+    if st is None:
+        st = _SKIP_STREAMS[device] = torch.cuda.Stream(device=device)
+    return st
+
+
 class _PyramidView:
     """A DTWBlock-chain output that was never materialised: pyramid level + channel map."""
 
@@ -431,25 +443,41 @@ class UNetWaveletEnc(nn.Module):
         for l in range(self.n_levels - 1, first - 1, -1):
             layers += [(layer, l) for layer in self.upblocks[l] if isinstance(layer, ResBlock) or l != first]
         model_out_list = []
-        full = None                                       # concat buffer whose first channels already hold h
+        # Haar arm: all concat buffers are allocated up front and their skip halves (channel tiles of the pyramid, a
+        # function of x alone) are written on a second stream while the main stream runs the time embeddings and the
+        # middle blocks; the main stream joins before the first decoder block.
+        fulls, side = {}, None
+        if self.dwt_encoder:
+            c, k = h.shape[3], len(hs)
+            for i, (layer, l) in enumerate(layers):
+                if l is not None and isinstance(layer, ResBlock):
+                    k -= 1
+                    skip = hs[k]
+                    _, _, sh_, sw_ = pyramid[skip.level].shape
+                    if i > 0:                              # the producer is layers[i-1]: it writes channels [0, c)
+                        fulls[i] = (torch.empty((h.shape[0], sh_, sw_, c + len(skip.chmap)), dtype=torch.bfloat16,
+                                                device=h.device), c, skip)
+                if isinstance(layer, ResBlock):
+                    c = layer.out_ch
+            if fulls and h.is_cuda and os.environ.get("UB200_SKIP_STREAM", "1") != "0":
+                side = _skip_stream(h.device)
+                side.wait_stream(torch.cuda.current_stream(h.device))
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                for full, c0, skip in fulls.values():
+                    self._materialise(pyramid, skip, out=ops.channel_slice_alias(full, c0, full.shape[3]))
         for i, (layer, l) in enumerate(layers):
             if l is not None and isinstance(layer, ResBlock):
                 skip = hs.pop()
-                if full is not None:
-                    self._materialise(pyramid, skip, out=ops.channel_slice_alias(full, h.shape[3], full.shape[3]))
-                    h, full = ops.cat_view(h, full), None
+                if i in fulls:
+                    if side is not None:
+                        torch.cuda.current_stream(h.device).wait_stream(side)
+                        side = None
+                    h = ops.cat_view(h, fulls[i][0])
                 else:
                     h = torch.cat([h, fetch(skip)], dim=3)
             elif l is not None and self.multi_res_loss:    # an UpSample: the coarse output leaves before it
                 model_out_list.append(self._tail(l, h))
-            out = None
-            nxt = layers[i + 1] if i + 1 < len(layers) else None
-            if self.dwt_encoder and nxt is not None and nxt[1] is not None and isinstance(nxt[0], ResBlock):
-                up = not isinstance(layer, ResBlock)
-                c_out = h.shape[3] if up else layer.out_ch
-                hh, ww = (2 * h.shape[1], 2 * h.shape[2]) if up else (h.shape[1], h.shape[2])
-                full = torch.empty((h.shape[0], hh, ww, c_out + len(hs[-1].chmap)), dtype=torch.bfloat16, device=h.device)
-                out = ops.channel_slice_alias(full, 0, c_out)
+            out = ops.channel_slice_alias(fulls[i + 1][0], 0, fulls[i + 1][1]) if (i + 1) in fulls else None
             h = self._run(layer, h, rows, out)
         model_out_list.append(self._tail(first, h))
         assert len(hs) == 0
