@@ -183,9 +183,13 @@ class DDPMTrainStep:
             ops.register_grad_sink(p, p.grad, None)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         if self.device.type == "cuda":
-            ops.enable_side_wgrad(os.environ.get("UB200_SIDE_WGRAD", "1") != "0",
+            # second stream for the kernels that only feed the optimiser (ops._Side).  Not with the eager bucketed
+            # all-reduce: its hooks launch a bucket's collective as soon as autograd has passed the parameters, which
+            # would race with a weight gradient still queued on the side stream.
+            eager_overlap = self.world > 1 and overlap_allreduce and not use_cuda_graph
+            ops.enable_side_wgrad(os.environ.get("UB200_SIDE_WGRAD", "1") != "0" and not eager_overlap,
                                   int(os.environ.get("UB200_SIDE_WGRAD_PIXELS", str(1 << 30))))
-            ops._Side.chansum = os.environ.get("UB200_SIDE_CHANSUM", "1") != "0"
+            ops._Side.chansum = os.environ.get("UB200_SIDE_CHANSUM", "1") != "0" and not eager_overlap
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)       # 1-based after the first bump
         self.steps_done = 0
         self.use_graph = use_cuda_graph and self.device.type == "cuda"
