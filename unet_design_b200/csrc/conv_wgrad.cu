@@ -385,6 +385,10 @@ int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a
     if (splits > p.pix_tiles) splits = p.pix_tiles;
     if (splits < 1) splits = 1;
     p.tiles_per_split = (p.pix_tiles + splits - 1) / splits;
+    // every split pays the full epilogue (3 x 128 x 128 fp32 atomics): keep at least this many 64-pixel stages per split
+    // (6 measured marginally best on config 2: 7.07 -> 7.04 ms/step; 12 is worse)
+    static const int min_tiles = [] { const char *e = getenv("UB200_WGRAD_MIN_TILES"); return e ? atoi(e) : 6; }();
+    if (p.tiles_per_split < min_tiles) p.tiles_per_split = min_tiles < p.pix_tiles ? min_tiles : p.pix_tiles;
     splits = (p.pix_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
     const int ncols_max = (int)(Cin < 128 ? Cin : 128);
     p.g_stage_bytes = kPix * 128 * 2;                       // room for a full 128-channel G tile
