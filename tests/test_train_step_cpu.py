@@ -144,3 +144,32 @@ def test_data_parallel_buckets_world2_gloo(emulated_ops):
     assert torch.equal(g0, g1)                               # both ranks hold the same reduced gradient
     assert abs(0.5 * (l0 + l1) - float(loss)) < 1e-2 * abs(float(loss))
     assert rel_err(g0, g_full) < 3e-2                        # bf16 activations: batch split changes rounding only
+
+
+def test_arena_lays_out_fused_groups_contiguously(emulated_ops):
+    """AttnBlock asks for q|k|v weights (and biases) to be neighbours in the parameter arena: their concatenation is then
+    a view (no concat / split kernels).  The reorder must not change any value, and the EMA state_dict keeps the
+    reference's per-parameter keys."""
+    from unet_design_b200 import ops
+    from unet_design_b200.diff_cifar.model import AttnBlock, UNetWaveletEnc
+    from unet_design_b200.train import DDPMTrainStep
+
+    torch.manual_seed(0)
+    net = UNetWaveletEnc(**CFG)
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    step = DDPMTrainStep(net, T=CFG["T"], use_cuda_graph=False)
+    after = net.state_dict()
+    assert set(before) == set(after) and all(torch.equal(before[k], after[k]) for k in before)
+    attn = [m for m in net.modules() if isinstance(m, AttnBlock)]
+    assert attn
+    off = {id(p): o for p, o in zip(step.arena.params, step.arena.offsets)}
+    for a in attn:
+        for grp in a.fused_param_groups():
+            pos = [off[id(p)] for p in grp]
+            assert pos == [pos[0] + i * grp[0].numel() for i in range(3)]          # back to back, in q, k, v order
+            flat = step.arena.p[pos[0]:pos[0] + 3 * grp[0].numel()]
+            want = torch.cat([p.detach().permute(0, 2, 3, 1).reshape(-1) if p.dim() == 4 else p.detach().reshape(-1) for p in grp])
+            assert torch.equal(flat, want)
+        assert ops.fused_conv_registered(a.proj_q.weight)
+    ema = step.ema_state_dict()
+    assert set(ema) == set(before) and all(torch.equal(ema[k], before[k]) for k in before)
