@@ -14,7 +14,6 @@
 // Replaces the wgrad half of nn.Conv2d backward at the sites listed in conv_fprop.cu.
 #include <cooperative_groups.h>
 
-#include <atomic>
 #include <cstdlib>
 #include <mutex>
 
@@ -216,18 +215,16 @@ __global__ void __launch_bounds__(256) chansum_kernel(const __nv_bfloat16 *__res
     }
 }
 
-// Single-launch variant: one thread-block cluster per sample (no atomics, no zero-fill of per_sample): every CTA sums its
-// pixel range, rank 0 combines the cluster through DSMEM and writes per_sample[n, :]; the cluster that finishes LAST
-// (device counter) then adds sum_n per_sample[n, :] to total in a fixed order.  Replaces memset + chansum + colsum.
-__device__ unsigned int g_chansum_done[64];
+// One thread-block cluster per sample (no atomics, no zero-fill of per_sample): every CTA sums its pixel range, rank 0
+// combines the cluster through DSMEM and writes per_sample[n, :].  The column sums over n (bias gradient) stay a second,
+// tiny launch: doing them in the last-finishing cluster (device counter) was measured SLOWER (+0.3 ms/step), one CTA
+// walking N rows is a serial chain of L2 round trips.
 
 __global__ void __launch_bounds__(256) chansum_cluster_kernel(const __nv_bfloat16 *__restrict__ x, int64_t ld, int64_t HW, int C,
-                                                             int chunks, int rows, int64_t pix_per_cta, int cs, int N,
-                                                             float *__restrict__ per_sample, float *__restrict__ total,
-                                                             int slot) {
+                                                             int chunks, int rows, int64_t pix_per_cta, int cs,
+                                                             float *__restrict__ per_sample) {
     extern __shared__ float csm[];                 // part [256][8], then chan [C]
     float *part = csm, *chan = csm + 256 * 8;
-    __shared__ bool last;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int64_t n = blockIdx.x / cs;
@@ -280,22 +277,6 @@ __global__ void __launch_bounds__(256) chansum_cluster_kernel(const __nv_bfloat1
         }
     }
     cluster.sync();                                // peers stay alive until rank 0 has read their sums
-    if (rank != 0 || !total) return;
-    __threadfence();                               // per_sample[n, :] visible before the counter moves
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(&g_chansum_done[slot], 1u);
-        last = prev == (unsigned int)(N - 1);
-        if (last) g_chansum_done[slot] = 0u;       // ready for the next launch (graph replay included)
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float acc = 0.f;
-        for (int64_t m = 0; m < N; ++m) acc += __ldcg(per_sample + m * C + c);
-        total[c] += acc;
-    }
 }
 
 __global__ void __launch_bounds__(256) colsum_rows_kernel(const float *__restrict__ per_sample, int64_t N, int C,
@@ -450,8 +431,6 @@ int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, in
         int cs = 1;
         while (cs < 8 && N * cs < 2 * ub::kSMs && HW / (2 * cs) >= 4 * rows) cs *= 2;
         while (cs < 8 && HW * C * 2 / cs > 256 * 1024 && HW / (2 * cs) >= 4 * rows) cs *= 2;
-        static std::atomic<unsigned> next_slot{0};
-        const int slot = (int)(next_slot.fetch_add(1) % 64u);
         const int64_t ppc = (HW + cs - 1) / cs;
         if ((int64_t)(cs - 1) * ppc < HW) {           // no empty CTA in the cluster
             cudaLaunchConfig_t cfg{};
@@ -464,15 +443,11 @@ int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, in
             attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             ub::pdl_attr(attr[1]);
             cfg.attrs = attr; cfg.numAttrs = 2;
-            // the in-kernel "last cluster adds the column sums" tail is a serial latency chain (one CTA, N dependent
-            // rounds of L2 reads): measured slower than a second small launch, so total goes through colsum_rows_kernel
-            static const bool tail = [] { const char *e = getenv("UB200_CHANSUM_TAIL"); return e && e[0] == '1'; }();
             cudaError_t e = cudaLaunchKernelEx(&cfg, chansum_cluster_kernel, reinterpret_cast<const __nv_bfloat16 *>(x), ld, HW,
-                                               (int)C, chunks, rows, ppc, cs, (int)N, per_sample,
-                                               tail ? total : static_cast<float *>(nullptr), slot);
+                                               (int)C, chunks, rows, ppc, cs, per_sample);
             if (e != cudaSuccess) return (int)e;
             UB_LAUNCH_CHECK();
-            if (total && !tail) {
+            if (total) {
                 cudaLaunchConfig_t c2{};
                 c2.gridDim = dim3((unsigned)((C + 31) / 32), 1, 1);
                 c2.blockDim = dim3(256, 1, 1);
