@@ -119,3 +119,32 @@ def test_cifar_sampler_gpu_matches_reference_and_graph_matches_eager():
     assert rel_err(graphed, eager) < 1e-2 and rel_err(again, eager) < 1e-2
     noisy = sampler(x_T, -1)                                # real noise: finite, clipped
     assert torch.isfinite(noisy).all() and float(noisy.abs().max()) <= 1.0
+
+
+@pytest.mark.gpu
+def test_train_step_cuda_graph_tracks_eager():
+    """DDPMTrainStep (noise draw, forward, backward on two streams, clip + Adam + EMA) as ONE CUDA graph against the same
+    step launched eagerly: same initial weights, same fixed batch, 30 steps each.  The random draws differ between the two
+    modes, so the check is statistical: both runs learn (loss falls well below its start), stay finite, end at similar
+    loss and similar weights; and the graph's warm-up steps must not count (step counter == 30, not 33)."""
+    from unet_design_b200.diff_cifar.model import UNetWaveletEnc
+    from unet_design_b200.train import DDPMTrainStep
+
+    cfg = dict(T=50, ch=64, ch_mult=[1, 2], attn=[1], num_res_blocks=1, dropout=0.1, dwt_encoder=True)
+    torch.manual_seed(0)
+    x0 = torch.randn(16, 3, 16, 16, device="cuda").clamp(-1, 1)
+    results = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(1)
+        net = apply_det_init(UNetWaveletEnc(**cfg)).cuda()
+        step = DDPMTrainStep(net, T=cfg["T"], lr=2e-3, warmup=1, use_cuda_graph=(mode == "graph"))
+        torch.manual_seed(2)
+        losses = [float(step(x0)) for _ in range(30)]
+        assert all(l == l and l < 1e3 for l in losses), (mode, losses)
+        results[mode] = (losses, step.arena.p.clone(), int(step.step_dev))
+    (le, pe, se), (lg, pg, sg) = results["eager"], results["graph"]
+    assert se == 30 and sg == 30
+    first, last_e, last_g = sum(le[:3]) / 3, sum(le[-5:]) / 5, sum(lg[-5:]) / 5
+    assert last_e < 0.8 * first and last_g < 0.8 * first, (first, last_e, last_g)
+    assert abs(last_e - last_g) < 0.35 * max(last_e, last_g), (last_e, last_g)
+    assert rel_err(pg, pe) < 0.2            # weights moved the same way (different noise draws, same data and init)

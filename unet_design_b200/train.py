@@ -335,13 +335,22 @@ class DDPMTrainStep:
         captured into a graph dead-locked on this stack, so the gradient all-reduce is issued right after the replay)."""
         self._static_x0 = x0.clone()
         whole = self.world == 1
+        # The warm-up runs real steps (allocator, tensor maps, cuBLAS handles): snapshot every piece of training state
+        # they touch and put it back, so that the first replay is step 1 of the run exactly as in eager mode.
+        state = [self.arena.p, self.m, self.v, self.ema, self.step_dev, self.packed.shadow, self.packed.dgrad,
+                 ops.dropout_device_counter(self.device)]
+        saved = [t.clone() for t in state]
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):           # warm-up on a side stream: allocator, tensor maps, cuBLAS handles
+        with torch.cuda.stream(side):           # warm-up on a side stream
             for _ in range(3):
                 self._fwd_bwd(self._static_x0, False)
                 self._reduce_and_update(False)
         torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        for t, keep in zip(state, saved):
+            t.copy_(keep)
+        del saved
         torch.cuda.synchronize(self.device)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
