@@ -52,6 +52,17 @@ inline void pdl_attr(cudaLaunchAttribute &a) {
     a.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
 }
 
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute (the kernel must call pdl_trigger / pdl_wait)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    pdl_attr(attr[0]);
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Streaming (read-once / write-once) 128-bit accesses: keep them out of L1.
 __device__ __forceinline__ float4 ld_stream(const float4 *p) {
     float4 r;

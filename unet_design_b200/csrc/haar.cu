@@ -344,6 +344,8 @@ __global__ void __launch_bounds__(256) dwtblock_nhwc_bf16(const float *__restric
 __global__ void __launch_bounds__(256) dwtblock_nhwc_bf16_j0(const float *__restrict__ x, int C, int H, int W, int out_channels,
                                                             const int *__restrict__ chmap, __nv_bfloat16 *__restrict__ out,
                                                             int64_t ld) {
+    pdl_trigger();
+    pdl_wait();
     const int chunks = out_channels >> 3;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= W * chunks) return;
@@ -559,8 +561,9 @@ int ub200_dwtblock_fwd_nhwc_bf16(const float *x, int64_t N, int64_t C, int64_t H
         const int per_row = (int)(W * (out_channels / 8));
         const int threads = per_row >= 256 ? 256 : ((per_row + 31) / 32) * 32;
         dim3 grid((unsigned)((per_row + threads - 1) / threads), (unsigned)H, (unsigned)N);
-        dwtblock_nhwc_bf16_j0<<<grid, threads, 0, ub::as_stream(stream)>>>(x, (int)C, (int)H, (int)W, (int)out_channels, chmap,
-                                                                          reinterpret_cast<__nv_bfloat16 *>(out_bf16), ld_out);
+        cudaError_t le = ub::launch_pdl(dwtblock_nhwc_bf16_j0, grid, dim3(threads), 0, ub::as_stream(stream), x, (int)C, (int)H, (int)W,
+                                        (int)out_channels, chmap, reinterpret_cast<__nv_bfloat16 *>(out_bf16), ld_out);
+        if (le != cudaSuccess) return (int)le;
         UB_LAUNCH_CHECK();
         return UB200_OK;
     }

@@ -93,6 +93,8 @@ __device__ __forceinline__ int find_item(const Batch &b, int tile) {
 // y[n, c] = bias[c] + sum_k act(x[n, k]) w[c, k].   grid: (cout tiles of all items, batch tiles)
 template <bool ACT>
 __global__ void __launch_bounds__(kThreads) rowlin_fwd_kernel(const __grid_constant__ Batch b) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float As[2][kSlice][kTile + kPad], Bs[2][kSlice][kTile + kPad];
     const int ii = find_item(b, blockIdx.x);
     const Item &it = b.it[ii];
@@ -125,6 +127,8 @@ __global__ void __launch_bounds__(kThreads) rowlin_fwd_kernel(const __grid_const
 // gw[c, k] += sum_n gy[n, c] act(x[n, k]);  gb[c] += sum_n gy[n, c].   grid: (cout tiles of all items, K tiles)
 template <bool ACT>
 __global__ void __launch_bounds__(kThreads) rowlin_wgrad_kernel(const __grid_constant__ Batch b) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float As[2][kSlice][kTile + kPad], Bs[2][kSlice][kTile + kPad];
     const int ii = find_item(b, blockIdx.x);
     const Item &it = b.it[ii];
@@ -168,6 +172,8 @@ __global__ void __launch_bounds__(kThreads) rowlin_wgrad_kernel(const __grid_con
 // run in parallel; gx is zeroed by the host function first).   grid: (K tiles, batch tiles, items)
 template <bool ACT>
 __global__ void __launch_bounds__(kThreads) rowlin_xgrad_kernel(const __grid_constant__ Batch b) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float As[2][kSlice][kTile + kPad], Bs[2][kSlice][kTile + kPad];
     const Item &it = b.it[blockIdx.z];
     if (it.group < 0) return;
@@ -232,8 +238,9 @@ int ub200_rowlin_fwd(const ub200_rowlin_item *items, int n_items, int64_t N, int
         if (rc) return rc;
         for (int i = 0; i < n; ++i) UB_REQUIRE(items[i0 + i].y, UB200_E_BADARG);
         dim3 grid((unsigned)b.tiles_total, (unsigned)((N + kTile - 1) / kTile), 1);
-        if (silu) rowlin_fwd_kernel<true><<<grid, kThreads, 0, s>>>(b);
-        else rowlin_fwd_kernel<false><<<grid, kThreads, 0, s>>>(b);
+        cudaError_t le = silu ? launch_pdl(rowlin_fwd_kernel<true>, grid, dim3(kThreads), 0, s, b)
+                              : launch_pdl(rowlin_fwd_kernel<false>, grid, dim3(kThreads), 0, s, b);
+        if (le != cudaSuccess) return (int)le;
         UB_LAUNCH_CHECK();
     }
     return UB200_OK;
@@ -275,8 +282,9 @@ int ub200_rowlin_bwd(const ub200_rowlin_item *items, int n_items, int64_t N, int
         }
         if (any_w) {
             dim3 grid((unsigned)b.tiles_total, (unsigned)((K + kTile - 1) / kTile), 1);
-            if (silu) rowlin_wgrad_kernel<true><<<grid, kThreads, 0, s>>>(b);
-            else rowlin_wgrad_kernel<false><<<grid, kThreads, 0, s>>>(b);
+            cudaError_t le = silu ? launch_pdl(rowlin_wgrad_kernel<true>, grid, dim3(kThreads), 0, s, b)
+                                  : launch_pdl(rowlin_wgrad_kernel<false>, grid, dim3(kThreads), 0, s, b);
+            if (le != cudaSuccess) return (int)le;
             UB_LAUNCH_CHECK();
         }
         if (b.n_groups > 0) {
@@ -286,8 +294,9 @@ int ub200_rowlin_bwd(const ub200_rowlin_item *items, int n_items, int64_t N, int
                     if (e != cudaSuccess) return (int)e;
                 }
             dim3 grid((unsigned)((K + kTile - 1) / kTile), (unsigned)((N + kTile - 1) / kTile), (unsigned)n);
-            if (silu) rowlin_xgrad_kernel<true><<<grid, kThreads, 0, s>>>(b);
-            else rowlin_xgrad_kernel<false><<<grid, kThreads, 0, s>>>(b);
+            cudaError_t le = silu ? launch_pdl(rowlin_xgrad_kernel<true>, grid, dim3(kThreads), 0, s, b)
+                                  : launch_pdl(rowlin_xgrad_kernel<false>, grid, dim3(kThreads), 0, s, b);
+            if (le != cudaSuccess) return (int)le;
             UB_LAUNCH_CHECK();
         }
     }

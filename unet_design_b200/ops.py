@@ -747,7 +747,20 @@ class _RowLinBatch(torch.autograd.Function):
                     shared[key] = torch.empty_like(xs[i])
                     ret_x[i] = shared[key]       # autograd sums the slots of one tensor: hand the total to the first slot only
                 gxs[i] = shared[key]
-        _ops().rowlin_bwd(xs, [w.detach() for w in ws], gys, gws, gbs, gxs, silu)
+        wd = [w.detach() for w in ws]
+        none = [None] * n
+        if _Side.enabled and _Side.chansum and xs[0].is_cuda and any(g is not None for g in gws + gbs) \
+                and any(g is not None for g in gxs):
+            # weight / bias gradients only feed the optimiser: second stream; the input gradient stays on this one
+            if _Side.stream is None:
+                _Side.stream = torch.cuda.Stream(device=xs[0].device)
+            _Side.stream.wait_stream(torch.cuda.current_stream(xs[0].device))
+            with torch.cuda.stream(_Side.stream):
+                _ops().rowlin_bwd(xs, wd, gys, gws, gbs, none, silu)
+            _Side.keep += list(xs) + list(gys)
+            _ops().rowlin_bwd(xs, wd, gys, none, none, gxs, silu)
+        else:
+            _ops().rowlin_bwd(xs, wd, gys, gws, gbs, gxs, silu)
         _count(2)
         for sink in done:
             if sink[1] is not None:
