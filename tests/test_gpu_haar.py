@@ -125,3 +125,20 @@ def test_full_size_properties(ops):
     lhs = ops.haar_dwt2d(x + 2 * z, 1)[0]
     rhs = yl + 2 * ops.haar_dwt2d(z, 1)[0]
     assert float((lhs - rhs).abs().max()) < 2e-5
+
+
+@pytest.mark.gpu
+def test_multires_helpers_on_gpu():
+    """§8 a4 call sites (per-step data / mask / PDE target down-sampling) on the fused Haar kernel, against the numpy oracle."""
+    import numpy as np
+    from oracle import haar_np
+    from unet_design_b200 import multires
+    torch.manual_seed(0)
+    x = torch.randn(3, 2, 25, 18)
+    for J in (1, 2):
+        got = multires.downsample(x.cuda(), J).cpu()
+        assert np.array_equal(got.numpy(), haar_np.dwtblock(x.numpy(), J, 2))          # bit-exact, like the other Haar paths
+    xb, yb = torch.randn(2, 3, 4, 16, 16), torch.randn(2, 1, 4, 16, 16)
+    gx, ys = multires.dwt_downsample(xb.cuda(), yb.cuda(), 1, n_levels=3, multi_res_loss=True)
+    assert gx.shape == (2, 3, 4, 8, 8) and [t.shape[-1] for t in ys] == [4, 8]
+    assert np.array_equal(ys[0].cpu().numpy().reshape(2, 4, 4, 4), haar_np.dwtblock(yb.flatten(0, 1).numpy(), 2, 4))
