@@ -256,6 +256,14 @@ int ub200_adam_ema_step_f32(float *p, const float *g, float *m, float *v, float 
                             float lr, float beta1, float beta2, float eps, float ema_decay,
                             int64_t step_host, int64_t warmup_steps, const int64_t *step_dev,
                             void *shadow_bf16, void *stream);
+/* Same with decoupled weight decay, p *= 1 - lr_eff * weight_decay before the Adam update: torch.optim.AdamW as
+ * pdearena's PDEModel configures it (pdearena/pdearena/models/pdemodel.py, lr 2e-4, weight_decay 1e-5).
+ * weight_decay = 0 is ub200_adam_ema_step_f32 exactly. */
+int ub200_adamw_ema_step_f32(float *p, const float *g, float *m, float *v, float *ema, int64_t n,
+                             const float *sumsq, float max_norm, float grad_scale,
+                             float lr, float beta1, float beta2, float eps, float weight_decay, float ema_decay,
+                             int64_t step_host, int64_t warmup_steps, const int64_t *step_dev,
+                             void *shadow_bf16, void *stream);
 
 /* shadow_bf16 (nullable, n bf16 elements) receives bf16(p) from the optimiser kernel: conv weights keep
  * the [Cout,kh,kw,Cin] order in the arena, so their shadow slice IS the packed fprop / wgrad operand.

@@ -245,7 +245,7 @@ class EmulatedOps:
             dgrad_arena[dst:dst + buf.numel()] = buf.reshape(-1)
 
     def adam_ema_step(self, p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, b1, b2, eps, decay, step,
-                      warmup_steps=0, step_dev=None, shadow=None):
+                      warmup_steps=0, step_dev=None, shadow=None, weight_decay=0.0):
         if step_dev is not None:
             step = int(step_dev)
         if warmup_steps > 0:
@@ -258,6 +258,7 @@ class EmulatedOps:
         m.mul_(b1).add_(gg, alpha=1 - b1)
         v.mul_(b2).addcmul_(gg, gg, value=1 - b2)
         bc1, bc2 = 1 - b1 ** step, math.sqrt(1 - b2 ** step)
+        p.mul_(1 - lr * weight_decay)
         p.sub_((lr / bc1) * m / (v.sqrt() / bc2 + eps))
         if ema is not None:
             ema.mul_(decay).add_(p, alpha=1 - decay)

@@ -173,3 +173,78 @@ def test_arena_lays_out_fused_groups_contiguously(emulated_ops):
         assert ops.fused_conv_registered(a.proj_q.weight)
     ema = step.ema_state_dict()
     assert set(ema) == set(before) and all(torch.equal(ema[k], before[k]) for k in before)
+
+
+def test_checkpoint_round_trip_resumes_identically(emulated_ops):
+    """state_dict() / load_state_dict() of the training step (diff_cifar/main.py:443-453 saves net_model, ema_model,
+    optim, sched, step): 2 steps + save, then A continues and B is rebuilt from the checkpoint; both take the same 3rd step."""
+    state = _init_state()
+    torch.manual_seed(0)
+    x0s = [torch.randn(4, 3, 16, 16) for _ in range(3)]
+    net, step = _make(state)
+    for i, x0 in enumerate(x0s[:2]):
+        torch.manual_seed(20 + i)
+        step(x0)
+    ckpt = step.state_dict()
+    ckpt = {k: (v.copy() if isinstance(v, dict) else v) for k, v in ckpt.items()}
+    torch.manual_seed(22)
+    la = float(step(x0s[2]))
+    net_b, step_b = _make(_init_state())                 # fresh model + step, then restore
+    step_b.load_state_dict(ckpt)
+    assert int(step_b.step_dev) == 2 and step_b.steps_done == 2
+    torch.manual_seed(22)
+    lb = float(step_b(x0s[2]))
+    assert la == lb
+    assert torch.equal(step.arena.p, step_b.arena.p) and torch.equal(step.m, step_b.m) and torch.equal(step.v, step_b.v)
+    assert torch.equal(step.ema, step_b.ema) and torch.equal(step.packed.shadow, step_b.packed.shadow)
+
+
+def test_model_load_after_step_construction_refreshes_operands(emulated_ops):
+    """`net_model.load_state_dict(...)` AFTER the step was built (the reference restores after constructing everything,
+    main.py:219-221): the bf16 operands the kernels read follow the new masters, and an untrained EMA follows too."""
+    state = _init_state()
+    net, step = _make(state)
+    other = {k: (v + 0.25 if v.dtype.is_floating_point else v) for k, v in state.items()}
+    net.load_state_dict(other)
+    assert torch.equal(step.packed.shadow.float(), step.arena.p.to(torch.bfloat16).float())
+    assert torch.equal(step.ema, step.arena.p)
+    names = {id(p): n for n, p in net.named_parameters()}
+    for p in step.arena.params:
+        assert torch.equal(p.detach(), other[names[id(p)]])
+
+
+def test_generic_train_step_adamw_matches_torch(emulated_ops):
+    """TrainStep(model, loss_fn) with decoupled weight decay on a pdearena ResidualBlock against torch.optim.AdamW."""
+    from unet_design_b200.pdearena.modules.twod_unet import ResidualBlock
+    from unet_design_b200.train import TrainStep
+    import copy
+    torch.manual_seed(3)
+    blk = ResidualBlock(16, 32, activation="gelu", norm=True, n_groups=1)
+    ref = copy.deepcopy(blk)
+    x, y = torch.randn(2, 16, 8, 8), torch.randn(2, 32, 8, 8)
+
+    def loss_fn(xb, yb):
+        return torch.nn.functional.mse_loss(blk(xb), yb)
+
+    step = TrainStep(blk, loss_fn, lr=1e-2, weight_decay=0.1, use_cuda_graph=False)
+    opt = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=0.1)
+    for _ in range(3):
+        step(x, y)
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(ref(x), y).backward()
+        opt.step()
+    for (n, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+        assert rel_err(p, q) < 2e-2, n
+
+
+def test_bucket_overlap_is_not_armed_while_a_second_stream_carries_weight_gradients(emulated_ops, monkeypatch):
+    """with ops._Side enabled (graph mode), an eager `_body` must fall back to one post-backward all-reduce."""
+    from unet_design_b200 import ops
+    state = _init_state()
+    net, step = _make(state)
+    step.world, step.overlap = 2, True
+    armed = []
+    monkeypatch.setattr(step, "_arm_buckets", lambda: armed.append(1))
+    monkeypatch.setattr(ops._Side, "enabled", True)
+    step._fwd_bwd((torch.randn(2, 3, 16, 16),), {}, True)
+    assert not armed and step._overlapped is False

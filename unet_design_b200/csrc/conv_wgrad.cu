@@ -35,6 +35,11 @@ struct WgradParams {
     int cw_g, cw_a;                     // channel chunk width (elements) of the G and A boxes
     int stages;
     uint32_t g_stage_bytes, a_tap_bytes, tmem_cols;
+    // halo mode (3x3, 128-byte channel chunks, BW % 16 == 0): the three kx taps of a stage are ONE TMA box of
+    // (BW + 2) x BH x BNI pixels; tap kx of pixel (x, y) is row y * (BW + 2) + x + kx of that box, so each 16-pixel
+    // MMA slab is a run of 16 consecutive 128-byte rows starting at an arbitrary row (not an 8-row swizzle atom)
+    int halo, bo_mode;
+    uint32_t a_chunk_stride, a_halo_bytes;
     float *dw;
 };
 
@@ -43,7 +48,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                                                              const WgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t stage_bytes = p.g_stage_bytes + p.ntaps * p.a_tap_bytes;
+    const uint32_t stage_bytes = p.g_stage_bytes + (p.halo ? p.a_halo_bytes : p.ntaps * p.a_tap_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
     uint64_t *empty = full + p.stages;
     uint64_t *tmem_full = empty + p.stages;
@@ -86,7 +91,9 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
         // ===================== TMA producer: warp-uniform loop, lane 0 issues (no div/mod per stage) =====================
         {
             const bool leader = lane == 0;
-            const uint32_t tx_bytes = chunks_g * g_chunk_bytes + p.ntaps * chunks_a * a_chunk_bytes;
+            const uint32_t halo_box_bytes = (uint32_t)((p.BW + 2) * p.BH * p.BNI) * 128u;
+            const uint32_t tx_bytes = chunks_g * g_chunk_bytes +
+                                      (p.halo ? chunks_a * halo_box_bytes : p.ntaps * chunks_a * a_chunk_bytes);
             const uint32_t base = smem_u32(smem), full0 = smem_u32(full), empty0 = smem_u32(empty);
             // first pixel tile of this split, then advance (x fastest, then y, then image group) incrementally
             int pt = pt0;
@@ -102,11 +109,16 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                 if (leader) mbar_arrive_expect_tx_a(fb, tx_bytes);
                 for (int c = 0; c < chunks_g; ++c)
                     if (leader) tma_load_4d_a(sg + c * g_chunk_bytes, &tm_g, fb, co0 + c * p.cw_g, x0, y0, n0);
-                for (int tp = 0; tp < p.ntaps; ++tp) {
-                    const int kx = p.ksize == 3 ? tp - 1 : 0;
-                    const uint32_t sa = sg + p.g_stage_bytes + tp * p.a_tap_bytes;
+                if (p.halo) {
                     for (int c = 0; c < chunks_a; ++c)
-                        if (leader) tma_load_4d_a(sa + c * a_chunk_bytes, &tm_a, fb, ci0 + c * p.cw_a, x0 + kx, y0 + ky, n0);
+                        if (leader) tma_load_4d_a(sg + p.g_stage_bytes + c * p.a_chunk_stride, &tm_a, fb, ci0 + c * 64, x0 - 1, y0 + ky, n0);
+                } else {
+                    for (int tp = 0; tp < p.ntaps; ++tp) {
+                        const int kx = p.ksize == 3 ? tp - 1 : 0;
+                        const uint32_t sa = sg + p.g_stage_bytes + tp * p.a_tap_bytes;
+                        for (int c = 0; c < chunks_a; ++c)
+                            if (leader) tma_load_4d_a(sa + c * a_chunk_bytes, &tm_a, fb, ci0 + c * p.cw_a, x0 + kx, y0 + ky, n0);
+                    }
                 }
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
                 if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
@@ -124,11 +136,29 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
             const uint64_t da0 = make_smem_desc(base + p.g_stage_bytes, a_chunk_bytes, 8 * row_a, swz_a);
             const uint32_t kstep_g = (16 * row_g) >> 4, kstep_a = (16 * row_a) >> 4, tap_step = p.a_tap_bytes >> 4;
             const uint32_t stage_step = stage_bytes >> 4;
+            // halo mode: first box row of each 16-pixel slab (tap kx adds kx rows); rows are 128 bytes = 8 descriptor units
+            uint32_t slab_row[kPix / 16];
+#pragma unroll
+            for (int k = 0; k < kPix / 16; ++k) slab_row[k] = (uint32_t)(((16 * k) / p.BW) * (p.BW + 2) + (16 * k) % p.BW);
+            const uint64_t dh0 = make_smem_desc(base + p.g_stage_bytes, p.a_chunk_stride, 1024, 2u);
             int s = 0; uint32_t ph = 0, accum = 0;
             for (int it = 0; it < iters; ++it) {
                 mbar_wait_a(full0 + 8u * s, ph);
                 tc_fence_after();
                 const uint64_t dg = dg0 + (uint64_t)(s * stage_step), da = da0 + (uint64_t)(s * stage_step);
+                if (p.halo) {
+                    const uint64_t dh = dh0 + (uint64_t)(s * stage_step);
+                    for (int tp = 0; tp < 3; ++tp) {
+#pragma unroll
+                        for (int k = 0; k < kPix / 16; ++k) {
+                            const uint32_t row = slab_row[k] + (uint32_t)tp;
+                            // swizzle phase of a start address that is not 1024-byte aligned (descriptor bits 49..51)
+                            const uint32_t bo = p.bo_mode == 0 ? 0u : p.bo_mode == 1 ? (row & 7u) : ((8u - (row & 7u)) & 7u);
+                            const uint64_t db = (dh + (uint64_t)(row * 8u)) | ((uint64_t)bo << 49);
+                            if (leader) umma_bf16(tmem_base + tp * 128, dg + k * kstep_g, db, idesc, (accum | (uint32_t)k) != 0 ? 1u : 0u);
+                        }
+                    }
+                } else
                 for (int tp = 0; tp < p.ntaps; ++tp) {
                     if (leader) {
 #pragma unroll
@@ -374,7 +404,13 @@ int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a
     const int ncols_max = (int)(Cin < 128 ? Cin : 128);
     p.g_stage_bytes = kPix * 128 * 2;                       // room for a full 128-channel G tile
     p.a_tap_bytes = (uint32_t)((kPix * ncols_max * 2 + 1023) & ~1023);
-    const uint32_t stage = p.g_stage_bytes + p.ntaps * p.a_tap_bytes;
+    static const int env_halo = [] { const char *e = getenv("UB200_WGRAD_HALO"); return e ? atoi(e) : 1; }();
+    static const int env_bo = [] { const char *e = getenv("UB200_WGRAD_BO"); return e ? atoi(e) : 0; }();
+    p.halo = (env_halo && ksize == 3 && p.cw_a == 64 && p.BW % 16 == 0) ? 1 : 0;
+    p.bo_mode = env_bo;
+    p.a_chunk_stride = (uint32_t)(((p.BW + 2) * p.BH * p.BNI * 128 + 1023) & ~1023);
+    p.a_halo_bytes = (uint32_t)((ncols_max + 63) / 64) * p.a_chunk_stride;
+    const uint32_t stage = p.g_stage_bytes + (p.halo ? p.a_halo_bytes : p.ntaps * p.a_tap_bytes);
     int stages = (int)((200u * 1024u) / stage);
     if (stages > 6) stages = 6;
     if (stages > p.tiles_per_split) stages = p.tiles_per_split;
@@ -394,7 +430,7 @@ int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a
     {
         const int64_t dims[4] = {Cin, W, H, N};
         const int64_t str[3] = {ld_a, ld_a * W, ld_a * W * H};
-        const int box[4] = {p.cw_a, p.BW, p.BH, p.BNI};
+        const int box[4] = {p.cw_a, p.halo ? p.BW + 2 : p.BW, p.BH, p.BNI};
         int rc = encode_bf16_tensor_map(&ta, a, 4, dims, str, box);
         if (rc) return rc;
     }

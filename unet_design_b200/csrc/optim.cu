@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float *__restrict__ g,
 
 struct AdamArgs {
     float max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, bc1, bc2;
+    float weight_decay;             // decoupled (torch.optim.AdamW): p *= 1 - lr * weight_decay before the Adam update
     long long warmup;               // > 0: lr *= min(step - 1, warmup) / warmup   (LambdaLR of diff_cifar/main.py:90-91)
     const long long *step_dev;      // device-resident 1-based step (CUDA-graph replays); NULL = host value baked in
 };
@@ -45,7 +46,8 @@ __device__ __forceinline__ void adam1(float &p, float g, float &m, float &v, flo
     g *= clip;
     m = a.beta1 * m + (1.f - a.beta1) * g;
     v = a.beta2 * v + (1.f - a.beta2) * g * g;
-    // torch.optim.Adam: p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+    // torch.optim.Adam: p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps); AdamW decays p first
+    p *= 1.f - a.lr * a.weight_decay;
     p -= (a.lr / a.bc1) * m / (sqrtf(v) / a.bc2 + a.eps);
     if (ema) *ema = a.ema_decay * *ema + (1.f - a.ema_decay) * p;
 }
@@ -128,10 +130,18 @@ int ub200_adam_ema_step_f32(float *p, const float *g, float *m, float *v, float 
                             float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
                             float ema_decay, int64_t step_host, int64_t warmup_steps, const int64_t *step_dev,
                             void *shadow_bf16, void *stream) {
+    return ub200_adamw_ema_step_f32(p, g, m, v, ema, n, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, 0.f, ema_decay,
+                                    step_host, warmup_steps, step_dev, shadow_bf16, stream);
+}
+
+int ub200_adamw_ema_step_f32(float *p, const float *g, float *m, float *v, float *ema, int64_t n, const float *sumsq,
+                             float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, float ema_decay, int64_t step_host, int64_t warmup_steps,
+                             const int64_t *step_dev, void *shadow_bf16, void *stream) {
     UB_REQUIRE(p && g && m && v && n > 0 && (step_dev || step_host >= 1), UB200_E_BADARG);
     UB_REQUIRE(ub::aligned16(p) && ub::aligned16(g) && ub::aligned16(m) && ub::aligned16(v) && (!ema || ub::aligned16(ema)),
                UB200_E_UNSUPPORTED);
-    AdamArgs a{max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, 1.f, 1.f, (long long)warmup_steps,
+    AdamArgs a{max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, 1.f, 1.f, weight_decay, (long long)warmup_steps,
                reinterpret_cast<const long long *>(step_dev)};
     if (!step_dev) {
         a.bc1 = (float)(1.0 - pow((double)beta1, (double)step_host));

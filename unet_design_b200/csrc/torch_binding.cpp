@@ -320,14 +320,14 @@ void sumsq(const Tensor &g, const Tensor &acc) {
 void adam_ema_step(const Tensor &p, const Tensor &g, const Tensor &m, const Tensor &v, const c10::optional<Tensor> &ema,
                    const c10::optional<Tensor> &sumsq_t, double max_norm, double grad_scale, double lr, double beta1,
                    double beta2, double eps, double ema_decay, int64_t step, int64_t warmup_steps,
-                   const c10::optional<Tensor> &step_dev, const c10::optional<Tensor> &shadow) {
+                   const c10::optional<Tensor> &step_dev, const c10::optional<Tensor> &shadow, double weight_decay) {
     UB_GUARD(p);
     const int64_t n = p.numel();
     TORCH_CHECK(g.numel() == n && m.numel() == n && v.numel() == n && (!ema.has_value() || ema->numel() == n), "adam_ema_step: size mismatch");
-    check_rc(ub200_adam_ema_step_f32(f32_mut(p, "p"), f32(g, "g"), f32_mut(m, "m"), f32_mut(v, "v"),
+    check_rc(ub200_adamw_ema_step_f32(f32_mut(p, "p"), f32(g, "g"), f32_mut(m, "m"), f32_mut(v, "v"),
                                      ema.has_value() ? f32_mut(*ema, "ema") : nullptr, n, f32_opt(sumsq_t, "sumsq"),
                                      (float)max_norm, (float)grad_scale, (float)lr, (float)beta1, (float)beta2, (float)eps,
-                                     (float)ema_decay, step, warmup_steps,
+                                     (float)weight_decay, (float)ema_decay, step, warmup_steps,
                                      reinterpret_cast<const int64_t *>(i64_opt(step_dev)), bf16_opt(shadow, n), cur_stream()),
              "adam_ema_step");
 }

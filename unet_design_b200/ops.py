@@ -813,9 +813,10 @@ def sumsq_(g: torch.Tensor, acc: torch.Tensor) -> None:
 
 
 def adam_ema_step_(p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, step,
-                   warmup_steps: int = 0, step_dev=None, shadow=None) -> None:
+                   warmup_steps: int = 0, step_dev=None, shadow=None, weight_decay: float = 0.0) -> None:
+    """Global-norm clip + Adam (AdamW when `weight_decay` > 0: decoupled decay) + EMA + bf16 shadow over flat arenas."""
     _ops().adam_ema_step(p, g, m, v, ema, sumsq, max_norm, grad_scale, lr, beta1, beta2, eps, ema_decay, step,
-                         warmup_steps, step_dev, shadow)
+                         warmup_steps, step_dev, shadow, weight_decay)
     _count()
 
 

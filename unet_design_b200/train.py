@@ -20,6 +20,9 @@ What is B200-first about it (reference file:line in parentheses):
   optimiser tail (default; ~0.4 ms of NVLink time per step); (b) eager (`use_cuda_graph=False`): arena buckets
   all-reduced by NCCL from post-accumulate hooks on a side stream as backward produces them, overlapping the
   rest of backward.
+
+`TrainStep(model, loss_fn)` is the model-agnostic form (any of the reference's families); `DDPMTrainStep` binds it to the
+diff_cifar loss.  `state_dict()` / `load_state_dict()` cover what diff_cifar/main.py:443-453 checkpoints.
 """
 from __future__ import annotations
 
@@ -157,16 +160,28 @@ class PackedWeights:
         self.refresh_dgrad()
 
 
-class DDPMTrainStep:
-    def __init__(self, model: nn.Module, T: int = 1000, beta_1: float = 1e-4, beta_T: float = 0.02, lr: float = 2e-4,
-                 warmup: int = 5000, grad_clip: float = 1.0, ema_decay: float = 0.9999, multi_res_loss: bool = False,
-                 betas=(0.9, 0.999), eps: float = 1e-8, use_cuda_graph: bool = True, process_group=None,
-                 bucket_mb: float = 16.0, overlap_allreduce: bool = True):
+class TrainStep:
+    """Model-agnostic fast training step: flat arenas, packed bf16 weight shadow, gradient sinks, the fused
+    clip + Adam(W) + EMA tail and (optionally) the whole step as one CUDA graph, data-parallel over `process_group`.
+
+        step = TrainStep(model, loss_fn, lr=2e-4, weight_decay=1e-5)      # pdearena: AdamW
+        loss = step(x, y)                                                # tensors already on the device
+
+    `loss_fn(*tensors, **static)` runs the model and returns a scalar loss (or a tuple whose first element is the loss).
+    Tensor arguments are copied into static buffers when the step is a CUDA graph; keyword arguments must be hashable
+    Python values (e.g. `n_levels_used`): graphs are captured per (tensor shapes, keyword values).
+    Serves every model family of the reference: diff_cifar through `DDPMTrainStep` below, diff_mnist / pdearena /
+    wmh through a loss closure (bench.py `--config`)."""
+
+    def __init__(self, model: nn.Module, loss_fn, lr: float = 2e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, warmup: int = 0, grad_clip: float = 0.0, ema_decay: Optional[float] = None,
+                 use_cuda_graph: bool = True, process_group=None, bucket_mb: float = 16.0,
+                 overlap_allreduce: bool = True):
         self.model = model
+        self.loss_fn = loss_fn
         self.device = next(model.parameters()).device
-        self.trainer = GaussianDiffusionTrainer(model, beta_1, beta_T, T, multi_res_loss, False, self.device).to(self.device)
         self.lr, self.warmup, self.grad_clip, self.ema_decay = lr, warmup, grad_clip, ema_decay
-        self.betas, self.eps = betas, eps
+        self.betas, self.eps, self.weight_decay = betas, eps, weight_decay
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (process_group is not None or
                                                               (dist.is_available() and dist.is_initialized())) else 1
@@ -177,7 +192,7 @@ class DDPMTrainStep:
         n = self.arena.p.numel()
         self.m = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.v = torch.zeros(n, dtype=torch.float32, device=self.device)
-        self.ema = self.arena.p.clone()
+        self.ema = self.arena.p.clone() if ema_decay is not None else None
         self.packed = PackedWeights(self.arena)
         for p, off in zip(self.arena.params, self.arena.offsets):
             ops.register_grad_sink(p, p.grad, None)
@@ -193,15 +208,22 @@ class DDPMTrainStep:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)       # 1-based after the first bump
         self.steps_done = 0
         self.use_graph = use_cuda_graph and self.device.type == "cuda"
-        self._graph = None
-        self._static_x0 = None
-        self._static_loss = None
+        self._graphs = {}              # (tensor shapes / dtypes, static kwargs) -> (graph, static inputs, static loss)
         self._buckets: List[tuple] = []
         self._comm_stream = None
         self._hooks_live = False
         self.overlap = overlap_allreduce
         if self.world > 1 and self.overlap:
             self._build_buckets(int(bucket_mb * (1 << 20) / 4))
+        # `model.load_state_dict(...)` after this point writes the fp32 masters in place (they are arena views); the
+        # bf16 operands forward / backward actually read must follow, and before any training the EMA is by definition
+        # a copy of the (now loaded) weights -- diff_cifar/main.py:217-221 deep-copies, then restores both models.
+        model.register_load_state_dict_post_hook(lambda _m, _incompatible: self._after_model_load())
+
+    def _after_model_load(self):
+        self.packed.refresh_from_master()
+        if self.ema is not None and self.steps_done == 0:
+            self.ema.copy_(self.arena.p)
 
     # ------------------------------------------------------------------ data parallel
     def _build_buckets(self, bucket_elems: int):
@@ -264,16 +286,25 @@ class DDPMTrainStep:
             torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
 
     # ------------------------------------------------------------------ one step
-    def _fwd_bwd(self, x0: torch.Tensor, overlap: bool) -> torch.Tensor:
+    def _loss(self, inputs, static) -> torch.Tensor:
+        out = self.loss_fn(*inputs, **static)
+        return out[0] if isinstance(out, (tuple, list)) else out
+
+    def _fwd_bwd(self, inputs, static, overlap: bool) -> torch.Tensor:
         self.arena.g.zero_()
         self.step_dev.add_(1)
+        # a bucket must not be all-reduced while weight-gradient kernels into it are still queued on the second stream
+        # (ops._Side): the bucketed overlap is only armed when that stream is off
+        overlap = overlap and not ops._Side.enabled
         self._hooks_live = overlap
         if overlap:
             self._arm_buckets()
         with _Tf32Matmul():
-            loss, _ = self.trainer(x0)
+            loss = self._loss(inputs, static)
             loss.backward()
-        ops.join_side_stream()          # small-layer weight gradients ran on a second stream (ops._Side)
+        self._hooks_live = False
+        ops.join_side_stream()          # weight gradients ran on a second stream (ops._Side)
+        self._overlapped = overlap
         return loss.detach()
 
     def _reduce_and_update(self, overlapped: bool):
@@ -285,43 +316,51 @@ class DDPMTrainStep:
         self._update()
 
     def _update(self):
-        self.sumsq.zero_()
-        ops.sumsq_(self.arena.g, self.sumsq)
+        if self.grad_clip > 0:
+            self.sumsq.zero_()
+            ops.sumsq_(self.arena.g, self.sumsq)
         # gradients hold the SUM over ranks: the mean (what DataParallel / DDP produce) is a grad_scale of 1/world
-        ops.adam_ema_step_(self.arena.p, self.arena.g, self.m, self.v, self.ema, self.sumsq, self.grad_clip,
-                           1.0 / self.world, self.lr, self.betas[0], self.betas[1], self.eps, self.ema_decay, 1,
-                           self.warmup, self.step_dev, self.packed.shadow)
+        ops.adam_ema_step_(self.arena.p, self.arena.g, self.m, self.v, self.ema,
+                           self.sumsq if self.grad_clip > 0 else None, self.grad_clip,
+                           1.0 / self.world, self.lr, self.betas[0], self.betas[1], self.eps,
+                           self.ema_decay if self.ema_decay is not None else 0.0, 1,
+                           self.warmup, self.step_dev, self.packed.shadow, self.weight_decay)
         self.packed.refresh_dgrad()                 # one launch: dgrad operands of every conv from the bf16 shadow
         ops.advance_dropout_state(self.device)
 
-    def _body(self, x0: torch.Tensor) -> torch.Tensor:
-        """Eager step; with several ranks the bucketed all-reduce overlaps backward."""
-        overlap = self.world > 1 and self.overlap
-        loss = self._fwd_bwd(x0, overlap)
-        self._reduce_and_update(overlap)
+    def _body(self, *inputs, **static) -> torch.Tensor:
+        """Eager step; with several ranks the bucketed all-reduce overlaps backward (when no second stream is in use)."""
+        loss = self._fwd_bwd(inputs, static, self.world > 1 and self.overlap)
+        self._reduce_and_update(self._overlapped)
         return loss
 
-    def __call__(self, x0: torch.Tensor) -> torch.Tensor:
+    def __call__(self, *inputs, **static) -> torch.Tensor:
         self.steps_done += 1
         if not self.use_graph:
-            return self._body(x0)
-        if self._graph is None:
-            self._capture(x0)
-        self._static_x0.copy_(x0, non_blocking=True)
-        self._graph.replay()
+            return self._body(*inputs, **static)
+        key = (tuple((tuple(t.shape), t.dtype) for t in inputs), tuple(sorted(static.items())))
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = self._capture(key, inputs, static)
+        graph, static_in, static_loss = entry
+        for dst, src in zip(static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
         if self.world > 1:             # the collective and the optimiser tail stay outside the graph (3 launches)
             self._reduce_and_update(False)
-        return self._static_loss
+        return static_loss
 
-    def timed_phases(self, x0: torch.Tensor, reps: int = 5):
+    def timed_phases(self, *inputs, reps: int = 5, **static):
         """Device time (ms, averaged) of the three phases of a data-parallel step: forward+backward graph, gradient
         all-reduce, clip+Adam+EMA tail.  Diagnostic only (bench.py reports it next to the step time)."""
-        assert self.use_graph and self.world > 1 and self._graph is not None
+        assert self.use_graph and self.world > 1 and self._graphs
+        graph, static_in, _ = next(iter(self._graphs.values()))
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(reps)]
         for r in range(reps):
-            self._static_x0.copy_(x0, non_blocking=True)
+            for dst, src in zip(static_in, inputs):
+                dst.copy_(src, non_blocking=True)
             ev[r][0].record()
-            self._graph.replay()
+            graph.replay()
             ev[r][1].record()
             dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM, group=self.pg)
             ev[r][2].record()
@@ -330,21 +369,25 @@ class DDPMTrainStep:
         torch.cuda.synchronize(self.device)
         return [sum(e[i].elapsed_time(e[i + 1]) for e in ev) / reps for i in range(3)]
 
-    def _capture(self, x0: torch.Tensor):
+    def _training_state(self):
+        state = [self.arena.p, self.m, self.v, self.step_dev, self.packed.shadow, self.packed.dgrad,
+                 ops.dropout_device_counter(self.device)]
+        return state + ([self.ema] if self.ema is not None else [])
+
+    def _capture(self, key, inputs, static):
         """One CUDA graph for the whole step on a single GPU; forward + backward only when data-parallel (NCCL work
         captured into a graph dead-locked on this stack, so the gradient all-reduce is issued right after the replay)."""
-        self._static_x0 = x0.clone()
+        static_in = [t.clone() for t in inputs]
         whole = self.world == 1
         # The warm-up runs real steps (allocator, tensor maps, cuBLAS handles): snapshot every piece of training state
         # they touch and put it back, so that the first replay is step 1 of the run exactly as in eager mode.
-        state = [self.arena.p, self.m, self.v, self.ema, self.step_dev, self.packed.shadow, self.packed.dgrad,
-                 ops.dropout_device_counter(self.device)]
+        state = self._training_state()
         saved = [t.clone() for t in state]
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):           # warm-up on a side stream
             for _ in range(3):
-                self._fwd_bwd(self._static_x0, False)
+                self._fwd_bwd(static_in, static, False)
                 self._reduce_and_update(False)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
@@ -352,23 +395,82 @@ class DDPMTrainStep:
             t.copy_(keep)
         del saved
         torch.cuda.synchronize(self.device)
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._static_loss = self._fwd_bwd(self._static_x0, False)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = self._fwd_bwd(static_in, static, False)
             if whole:
                 self._reduce_and_update(False)
-
-    def step_from_host(self, x0_pinned: torch.Tensor) -> float:
-        """The end-to-end call a user makes: batch in pinned host memory in, loss (a Python float) out."""
-        x0 = x0_pinned.to(self.device, non_blocking=True)
-        loss = self(x0)
-        return float(loss.cpu())
+        entry = (graph, static_in, static_loss)
+        self._graphs[key] = entry
+        return entry
 
     # ------------------------------------------------------------------ checkpoint surface
+    def _named(self):
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        return [(names[id(p)], p, off) for p, off in zip(self.arena.params, self.arena.offsets)]
+
     def ema_state_dict(self):
         """`state_dict` of the EMA model (the reference keeps a deep copy, main.py:207-219)."""
+        assert self.ema is not None, "this step keeps no EMA (ema_decay=None)"
         sd = {k: v.clone() for k, v in self.model.state_dict().items()}
-        names = {id(p): n for n, p in self.model.named_parameters()}
-        for p, off in zip(self.arena.params, self.arena.offsets):
-            sd[names[id(p)]] = FlatArena._view(self.ema, p, off).clone()
+        for name, p, off in self._named():
+            sd[name] = FlatArena._view(self.ema, p, off).clone()
         return sd
+
+    def load_ema_state_dict(self, sd):
+        """Restore the EMA weights from a model-shaped state_dict (`ema_model.load_state_dict` at main.py:221)."""
+        assert self.ema is not None
+        for name, p, off in self._named():
+            FlatArena._view(self.ema, p, off).copy_(sd[name])
+
+    def state_dict(self):
+        """Everything a resumed run needs beyond the model weights: Adam moments per parameter name (the layout of
+        `torch.optim.Adam.state_dict()['state']`: exp_avg / exp_avg_sq), the step counter (bias correction, LambdaLR
+        warm-up), the EMA weights and the dropout RNG counters.  diff_cifar/main.py:443-453 saves net_model,
+        ema_model, sched, optim and step."""
+        opt = {name: {"exp_avg": FlatArena._view(self.m, p, off).clone(), "exp_avg_sq": FlatArena._view(self.v, p, off).clone()}
+               for name, p, off in self._named()}
+        return {"model": {k: v.clone() for k, v in self.model.state_dict().items()},
+                "ema": self.ema_state_dict() if self.ema is not None else None,
+                "optim": opt, "step": int(self.step_dev), "steps_done": self.steps_done,
+                "dropout": {"seed": ops._DropoutState.seed, "host_offset": ops._DropoutState.host_offset,
+                            "dev_offset": int(ops.dropout_device_counter(self.device))}}
+
+    def load_state_dict(self, sd):
+        self.steps_done = int(sd["steps_done"])          # before the model load: a resumed EMA is not re-initialised
+        self.model.load_state_dict(sd["model"])          # post-hook refreshes the bf16 operands
+        for name, p, off in self._named():
+            FlatArena._view(self.m, p, off).copy_(sd["optim"][name]["exp_avg"])
+            FlatArena._view(self.v, p, off).copy_(sd["optim"][name]["exp_avg_sq"])
+        if self.ema is not None and sd.get("ema") is not None:
+            self.load_ema_state_dict(sd["ema"])
+        self.step_dev.fill_(int(sd["step"]))
+        d = sd["dropout"]
+        ops._DropoutState.seed, ops._DropoutState.host_offset = int(d["seed"]), int(d["host_offset"])
+        ops.dropout_device_counter(self.device).fill_(int(d["dev_offset"]))
+        self.packed.refresh_from_master()
+
+
+class DDPMTrainStep(TrainStep):
+    """The diff_cifar training step (main.py:397-429): DDPM Algorithm 1 loss + clip 1.0 + Adam + LambdaLR warm-up + EMA.
+    `step(x0, n_levels_used=..., n_downsample=...)` serves the staged (sequential-resolution) loop of main.py:397-423:
+    one CUDA graph per (batch shape, level count)."""
+
+    def __init__(self, model: nn.Module, T: int = 1000, beta_1: float = 1e-4, beta_T: float = 0.02, lr: float = 2e-4,
+                 warmup: int = 5000, grad_clip: float = 1.0, ema_decay: float = 0.9999, multi_res_loss: bool = False,
+                 betas=(0.9, 0.999), eps: float = 1e-8, use_cuda_graph: bool = True, process_group=None,
+                 bucket_mb: float = 16.0, overlap_allreduce: bool = True, sequ_train_algo: bool = False):
+        dev = next(model.parameters()).device
+        self.trainer = GaussianDiffusionTrainer(model, beta_1, beta_T, T, multi_res_loss, sequ_train_algo, dev).to(dev)
+        super().__init__(model, self._ddpm_loss, lr=lr, betas=betas, eps=eps, warmup=warmup, grad_clip=grad_clip,
+                         ema_decay=ema_decay, use_cuda_graph=use_cuda_graph, process_group=process_group,
+                         bucket_mb=bucket_mb, overlap_allreduce=overlap_allreduce)
+
+    def _ddpm_loss(self, x0, n_levels_used: int = -1, n_downsample: int = 0):
+        return self.trainer(x0, n_levels_used, n_downsample)
+
+    def step_from_host(self, x0_pinned: torch.Tensor, **static) -> float:
+        """The end-to-end call a user makes: batch in pinned host memory in, loss (a Python float) out."""
+        x0 = x0_pinned.to(self.device, non_blocking=True)
+        loss = self(x0, **static)
+        return float(loss.cpu())
