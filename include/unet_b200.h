@@ -61,6 +61,18 @@ int ub200_haar_dwt2d_fwd(const float *x, int64_t planes, int64_t H, int64_t W,
 int ub200_haar_idwt2d(const float *ll, const float *highs, int64_t planes, int64_t h2, int64_t w2,
                       int64_t Hout, int64_t Wout, float *out, void *stream);
 
+/* J analysis levels in ONE pass over x (DWTForward(J=2|3): the call sites above construct it with J > 1 for the
+ * multi-resolution targets, diff_cifar/diffusion.py:63-64): x [planes,H,W] -> ll [planes,H/2^J,W/2^J] and
+ * highs[j] [planes,3,H/2^(j+1),W/2^(j+1)], j = 0 the finest (`highs` is a HOST array of J device pointers).
+ * Algorithmic traffic 2*E*4 bytes instead of E*4*sum_j 2*4^-j level by level.  Supported when
+ * H % 2^J == 0, W % 8 == 0 and all pointers are 16-byte aligned; returns UB200_E_UNSUPPORTED otherwise
+ * (the caller then goes level by level through ub200_haar_dwt2d_fwd; results are bit-identical). */
+int ub200_haar_dwt2d_multi_fwd(const float *x, int64_t planes, int64_t H, int64_t W, int J,
+                               float *ll, float *const *highs, void *stream);
+/* Its inverse (and adjoint): ll + highs[0..J) -> out [planes,H,W], same support conditions. */
+int ub200_haar_idwt2d_multi(const float *ll, const float *const *highs, int64_t planes, int64_t H, int64_t W,
+                            int J, float *out, void *stream);
+
 /* DTWBlock / DWTBlock forward (diff_cifar/model.py:270-323; diff_mnist/mnist_diff/models.py:29-82;
  * twod_unetbase.py:173-193; wmh/model.py:72-95), fused:  out[n,k] = LL_J(x[n, k mod C]) / 2^J,
  * k < out_channels, J in [0,3] (J = 0 is the channel tile alone).  x [N,C,H,W] f32 ->
@@ -118,6 +130,7 @@ int ub200_upsample2x_bwd_nhwc_bf16(const void *gout, int64_t ld_g, int64_t N, in
 #define UB200_ACT_NONE 0
 #define UB200_ACT_SILU 1
 #define UB200_ACT_GELU 2   /* exact erf form (pdearena/pdearena/modules/activations.py:3-9) */
+#define UB200_ACT_RELU 3   /* nn.ReLU of the same registry (the `Unetbase` docstring lists gelu / relu / silu) */
 
 /* stats[n,g] = (sum, sum of squares) over the (C/G)*HW slab of sample n; float [N,G,2], zeroed
  * here.  Consumers derive mean / rstd; the conv epilogue can accumulate the same layout
@@ -209,6 +222,11 @@ typedef struct ub200_conv_args {
     int gn_groups;                                   /*   (next layer's GroupNorm statistics) or 0    */
     const float *bias2;                              /* [Cout] or NULL: a second bias (the fused 1x1  */
                                                      /*   shortcut's, diff_cifar/model.py:167)        */
+    int stride;                                      /* 0 / 1: stride 1.  2: nn.Conv2d(.., 3, stride=2, padding=1) of the      */
+                                                     /*   down-sampling arms (diff_cifar/model.py:52, layers.py:238,           */
+                                                     /*   twod_unet.py Downsample): H, W are the INPUT extents, out / residual */
+                                                     /*   / a2 have ceil(H/2) x ceil(W/2) pixels; the TMA traversal stride     */
+                                                     /*   fetches every second pixel, so no full-resolution conv is computed   */
 } ub200_conv_args;
 
 int ub200_conv_fprop(const ub200_conv_args *args, void *stream);
@@ -220,6 +238,11 @@ int ub200_conv_fprop(const ub200_conv_args *args, void *stream);
 int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a,
                      int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize,
                      float *dw, void *stream);
+/* Same for a convolution of stride 1 or 2 (padding k/2): H, W are the extents of `a`; gout has ceil(H/stride) x
+ * ceil(W/stride) pixels and dW[co,ky,kx,ci] += sum gout[n,y,x,co] * a[n, stride*y+ky-p, stride*x+kx-p, ci]. */
+int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int64_t ld_a,
+                             int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, int stride,
+                             float *dw, void *stream);
 
 /* Channel sums of an NHWC bf16 tensor: per_sample[N,C] = sum_p x[n,p,c] (overwritten; the
  * time-embedding / scale-shift gradient, and the workspace of the second pass) and, when total is

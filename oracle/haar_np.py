@@ -22,12 +22,26 @@ import numpy as np
 
 S = np.float32(1.0 / np.sqrt(2.0))
 
+# The ONE unpinned convention of this path: where mode='zero' puts the single zero that makes an odd
+# extent even.  Upstream pytorch_wavelets appends it at the END; the reference only pins the output extent ceil(n/2)
+# (wmh/model.py:146-155: 25 -> 13).  Flip here and set UB200_HAAR_PAD_AT_START=1 for the kernels (csrc/haar.cu
+# `pad_at_start()`) to move it to the start; only odd extents (config 5's 25 -> 13, odd sweep entries) change.
+PAD_AT_END = True
+
 
 def _pad_even(x: np.ndarray) -> np.ndarray:
     h, w = x.shape[-2:]
     if h % 2 or w % 2:
-        x = np.pad(x, [(0, 0)] * (x.ndim - 2) + [(0, h % 2), (0, w % 2)])
+        pad_h, pad_w = ((0, h % 2), (0, w % 2)) if PAD_AT_END else ((h % 2, 0), (w % 2, 0))
+        x = np.pad(x, [(0, 0)] * (x.ndim - 2) + [pad_h, pad_w])
     return x
+
+
+def _crop(x: np.ndarray, h: int, w: int) -> np.ndarray:
+    """Undo the zero extension: drop the row / column that was added (end or start)."""
+    if PAD_AT_END:
+        return x[..., :h, :w]
+    return x[..., x.shape[-2] - h:, x.shape[-1] - w:]
 
 
 def dwt2_level(x: np.ndarray):
@@ -67,10 +81,7 @@ def idwt2(yl: np.ndarray, highs) -> np.ndarray:
     """Synthesis from (Yl, [Yh_1..Yh_J]); an empty list returns Yl (the reference's only use)."""
     ll = np.asarray(yl, dtype=np.float32)
     for band in highs[::-1]:
-        if ll.shape[-2] > band.shape[-2]:
-            ll = ll[..., :-1, :]
-        if ll.shape[-1] > band.shape[-1]:
-            ll = ll[..., :-1]
+        ll = _crop(ll, min(ll.shape[-2], band.shape[-2]), min(ll.shape[-1], band.shape[-1]))
         ll = idwt2_level(ll, band[:, :, 0], band[:, :, 1], band[:, :, 2])
     return ll
 
@@ -112,5 +123,5 @@ def dwtblock_bwd(grad_out: np.ndarray, in_shape, J: int) -> np.ndarray:
         ext.append(((ext[-1][0] + 1) // 2, (ext[-1][1] + 1) // 2))
     for lvl in range(J, 0, -1):
         z = np.zeros_like(cur)
-        cur = idwt2_level(cur, z, z, z)[..., : ext[lvl - 1][0], : ext[lvl - 1][1]]
+        cur = _crop(idwt2_level(cur, z, z, z), ext[lvl - 1][0], ext[lvl - 1][1])
     return cur

@@ -40,6 +40,16 @@ class EmulatedOps:
             out = haar_np.idwt2_level(ll.numpy(), h[:, :, 0], h[:, :, 1], h[:, :, 2])
         return torch.from_numpy(np.ascontiguousarray(out[..., :hout, :wout]))
 
+    def haar_dwt2d_multi(self, x, J):
+        h, w = x.shape[-2:]
+        if J not in (2, 3) or h % (1 << J) or w % 8:
+            return []
+        yl, yh = haar_np.dwt2(x.numpy(), J)
+        return [torch.from_numpy(np.ascontiguousarray(yl))] + [torch.from_numpy(np.ascontiguousarray(b)) for b in yh]
+
+    def haar_idwt2d_multi(self, ll, highs):
+        return torch.from_numpy(np.ascontiguousarray(haar_np.idwt2(ll.numpy(), [h.numpy() for h in highs])))
+
     def dwtblock_fwd(self, x, J, out_channels):
         return torch.from_numpy(haar_np.dwtblock(x.numpy(), J, out_channels))
 
@@ -84,6 +94,8 @@ class EmulatedOps:
             return z * torch.sigmoid(z)
         if act == 2:
             return F.gelu(z)
+        if act == 3:
+            return F.relu(z)
         return z
 
     def _gn_forward_fp32(self, x, G, stats, eps, gamma, beta, scale, shift, act, p, seed, off):
@@ -155,11 +167,11 @@ class EmulatedOps:
                         dst.copy_(val)
 
     # ---- conv
-    def conv_fprop(self, a, w, k, cout, a2, w2, bias, rowadd, residual, out, out_nchw, bias2=None):
+    def conv_fprop(self, a, w, k, cout, a2, w2, bias, rowadd, residual, out, out_nchw, bias2=None, stride=1):
         n, h, wd, cin = a.shape
         cpad = (cout + 15) // 16 * 16
         wt = w.float().reshape(cpad, k, k, cin)[:cout].permute(0, 3, 1, 2)
-        y = F.conv2d(a.float().permute(0, 3, 1, 2), wt, padding=k // 2)
+        y = F.conv2d(a.float().permute(0, 3, 1, 2), wt, padding=k // 2, stride=stride)
         if a2 is not None:
             w2t = w2.float().reshape(cpad, a2.shape[3])[:cout, :, None, None]
             y = y + F.conv2d(a2.float().permute(0, 3, 1, 2), w2t)
@@ -176,12 +188,12 @@ class EmulatedOps:
         if out_nchw is not None:
             out_nchw.copy_(y)
 
-    def conv_wgrad(self, gout, a, k, dw):
+    def conv_wgrad(self, gout, a, k, dw, stride=1):
         n, h, wd, cin = a.shape
         cout = gout.shape[3]
         xg = a.float().permute(0, 3, 1, 2)
         gg = gout.float().permute(0, 3, 1, 2)
-        gw = torch.nn.grad.conv2d_weight(xg, (cout, cin, k, k), gg, padding=k // 2)     # [Cout,Cin,k,k]
+        gw = torch.nn.grad.conv2d_weight(xg, (cout, cin, k, k), gg, padding=k // 2, stride=stride)     # [Cout,Cin,k,k]
         if dw.dim() == 4 and tuple(dw.shape) == (cout, cin, k, k):      # a [Cout,Cin,k,k] view with channels_last strides
             dw.add_(gw)
         else:

@@ -8,6 +8,12 @@ import torch
 from conftest import GOLDEN, rel_err
 from det_init import apply_det_init
 
+# Gradient tolerances of the two fixtures that are ill-conditioned in bf16 by construction (measured on the REFERENCE
+# classes with every layer output rounded to bf16, tools: see the round-2 notes in profiles/README.md):
+#   unetbase_relu     ReLU + MaxPool are not smooth: one rounding flips a sign / an argmax, 4 levels down to 2x3 pixels
+#   unetmod_1x1_attn  twod_unet.AttentionBlock takes its softmax over the QUERY axis; the rounded reference itself shows
+#                     2.2 % output / 11 % gradient error against its fp32 self
+CONTAINER_GRAD_TOL = {"unetbase_relu": 0.35, "unetmod_1x1_attn": 0.2}
 ZERO_IN_EXACT_ARITHMETIC = ("proj_k.bias",)      # softmax is invariant to a key bias: gradient is round-off only
 
 
@@ -117,6 +123,8 @@ def check_pdearena_blocks(base_ns, unet_ns, device, tol):
 def check_unetbase_g(cls, fixture, device, tol_out, tol_grad):
     g = load(fixture)
     net = apply_det_init(cls(**g["cfg"])).to(device)
+    if "keys" in g:                                   # state_dict surface recorded from the reference class
+        assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == g["keys"]
     x = g["x"].float().to(device)
     out = net(x)
     outs = out if isinstance(out, list) else [out]
@@ -177,3 +185,18 @@ def check_mnist_unet(get_unet_wavelet, tag, device, tol_out, tol_grad):
     out2 = out2 if isinstance(out2, list) else [out2]
     for a, b in zip(out2, g["out_2lvl"]):
         assert a.shape == b.shape and rel_err(a, b) < tol_out
+
+
+def check_mnist_unetmodel(get_unet, device, tol_out, tol_grad):
+    """diff_mnist `UNetModel` through `get_unet` (torch_ddpm/ddpm/models/unet/unet.py:14-311, models/utils.py:5-53)."""
+    g = load("mnist_unetmodel.pt")
+    net = apply_det_init(get_unet(**g["cfg"])).to(device)
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == g["keys"]
+    x, t = g["x"].to(device), g["t"].to(device)
+    out = net(x, t)
+    assert out.shape == g["out"].shape and rel_err(out, g["out"]) < tol_out, rel_err(out, g["out"])
+    (out * g["gy"].to(device)).sum().backward()
+    _check_grads(net, g["gparams"], tol_grad)
+    with torch.no_grad():
+        out2 = net(x[..., ::4, ::4].contiguous(), t, n_levels_used=2)
+    assert out2.shape == g["out_2lvl"].shape and rel_err(out2, g["out_2lvl"]) < tol_out

@@ -92,3 +92,17 @@ def test_cifar_sampler(emulated_ops):
     assert set(sd) == {"betas", "sqrt_recip_alphas_bar", "sqrt_recipm1_alphas_bar", "posterior_var",
                        "posterior_log_var_clipped", "posterior_mean_coef1", "posterior_mean_coef2"}
     assert all(v.dtype == torch.float64 for v in sd.values())
+
+
+@pytest.mark.parametrize("tag", ["unetbase", "unetbase_relu", "unetmod", "unetmod_1x1_attn"])
+def test_pdearena_unetbase_and_modern_unet(emulated_ops, tag):
+    """The remaining pdearena containers north_star names: `Unetbase` (twod_unetbase.py:60-141) and `twod_unet.Unet`."""
+    from unet_design_b200.pdearena.modules.twod_unet import Unet
+    from unet_design_b200.pdearena.modules.twod_unetbase import Unetbase
+    gc.check_unetbase_g(Unetbase if tag.startswith("unetbase") else Unet, f"pdearena_{tag}.pt", "cpu", 3 * TOL,
+                        gc.CONTAINER_GRAD_TOL.get(tag, 8e-2))
+
+
+def test_mnist_unetmodel_get_unet(emulated_ops):
+    from unet_design_b200.diff_mnist.unet import get_unet
+    gc.check_mnist_unetmodel(get_unet, "cpu", 3 * TOL, 0.12)

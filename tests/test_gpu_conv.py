@@ -139,3 +139,31 @@ def test_linearity_at_full_config_size(ops):
     assert rel_err(ysum, y1.float() + y2.float()) < 2e-2
     ref = F.conv2d(a1[:2].float().permute(0, 3, 1, 2), wt, padding=1).permute(0, 2, 3, 1)
     assert rel_err(y1[:2], ref) < TOL
+
+
+STRIDED = [(2, 32, 32, 128, 128, 3), (2, 16, 16, 64, 64, 3), (3, 8, 8, 256, 256, 3), (2, 25, 13, 32, 48, 3), (1, 128, 128, 64, 64, 3),
+           (2, 7, 9, 16, 32, 3), (4, 4, 4, 128, 128, 3), (2, 32, 32, 64, 64, 1)]
+
+
+@pytest.mark.parametrize("case", STRIDED)
+def test_stride2_fprop_dgrad_wgrad(ops, case):
+    """nn.Conv2d(C, C, 3, stride=2, padding=1) of the down-sampling arms (diff_cifar/model.py:52, layers.py:238,
+    twod_unet.py Downsample) through the TMA traversal stride, forward and all gradients, incl. odd extents."""
+    n, h, w, cin, cout, k = case
+    a, wt = _mk(*case)
+    a = a.requires_grad_(True)
+    wt = wt.requires_grad_(True)
+    bias = torch.zeros(cout, device="cuda", requires_grad=True)
+    y = ops.conv(a, wt, bias, stride=2)
+    ar = a.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.detach().clone().requires_grad_(True)
+    br = torch.zeros(cout, device="cuda", requires_grad=True)
+    yr = F.conv2d(ar, wr, br, stride=2, padding=k // 2)
+    assert y.shape == yr.permute(0, 2, 3, 1).shape == (n, (h + 1) // 2, (w + 1) // 2, cout)
+    assert rel_err(y, yr.permute(0, 2, 3, 1)) < TOL
+    g = torch.randn_like(y)
+    y.backward(g)
+    yr.backward(g.float().permute(0, 3, 1, 2))
+    assert rel_err(a.grad, ar.grad.permute(0, 2, 3, 1)) < TOL
+    assert rel_err(wt.grad, wr.grad) < TOL
+    assert rel_err(bias.grad, br.grad) < TOL

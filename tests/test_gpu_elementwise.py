@@ -51,13 +51,13 @@ def _gn_ref(x, G, gamma, beta, scale, shift, act, eps=1e-5):
     xn = F.group_norm(x.float().permute(0, 3, 1, 2), G, gamma, beta, eps)
     if scale is not None:
         xn = xn * (1 + scale[:, :, None, None]) + shift[:, :, None, None]
-    y = {"silu": F.silu, "gelu": F.gelu, "none": lambda t: t}[act](xn)
+    y = {"silu": F.silu, "gelu": F.gelu, "relu": F.relu, "none": lambda t: t}[act](xn)
     return y.permute(0, 2, 3, 1)
 
 
 @pytest.mark.parametrize("shape,G", [((4, 8, 8, 128), 32), ((2, 32, 32, 384), 32), ((3, 4, 4, 512), 32), ((2, 16, 16, 64), 32),
                                      ((2, 16, 16, 64), 1), ((2, 25, 13, 16), 1), ((3, 32, 32, 128), 32), ((2, 32, 32, 256), 32), ((2, 31, 33, 48), 3), ((1, 128, 128, 64), 1), ((2, 8, 8, 1024), 1)])
-@pytest.mark.parametrize("act", ["silu", "gelu", "none"])
+@pytest.mark.parametrize("act", ["silu", "gelu", "relu", "none"])
 @pytest.mark.parametrize("scale_shift", [False, True])
 def test_gn_act_forward_backward(ops, shape, G, act, scale_shift):
     if scale_shift and (act != "silu" or shape[3] > 128):

@@ -142,3 +142,84 @@ def test_multires_helpers_on_gpu():
     gx, ys = multires.dwt_downsample(xb.cuda(), yb.cuda(), 1, n_levels=3, multi_res_loss=True)
     assert gx.shape == (2, 3, 4, 8, 8) and [t.shape[-1] for t in ys] == [4, 8]
     assert np.array_equal(ys[0].cpu().numpy().reshape(2, 4, 4, 4), haar_np.dwtblock(yb.flatten(0, 1).numpy(), 2, 4))
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 32, 32), (4, 16, 64, 64), (1, 2, 96, 192), (2, 5, 8, 8), (1, 3, 200, 200), (3, 2, 16, 24)])
+@pytest.mark.parametrize("J", [2, 3])
+def test_fused_multilevel_is_bit_exact_and_one_launch(ops, shape, J):
+    """ub200_haar_dwt2d_multi_fwd / ub200_haar_idwt2d_multi: all J levels in one pass, bit-identical to the numpy oracle
+    (and therefore to the level-by-level kernels); backward of each is the other (adjoint identity)."""
+    torch.manual_seed(4)
+    x = torch.randn(*shape)
+    h, w = shape[-2:]
+    eligible = h % (1 << J) == 0 and w % 8 == 0
+    before = ops.launches()
+    yl, yh = ops.haar_dwt2d(x.cuda(), J)
+    assert ops.launches() - before == (1 if eligible else J)
+    ref_l, ref_h = haar_np.dwt2(x.numpy(), J)
+    np.testing.assert_array_equal(yl.cpu().numpy(), ref_l)
+    for a, b in zip(yh, ref_h):
+        np.testing.assert_array_equal(a.cpu().numpy(), b)
+    before = ops.launches()
+    rec = ops.haar_idwt2d(yl, yh)
+    assert ops.launches() - before == (1 if eligible else J)
+    np.testing.assert_array_equal(rec.cpu().numpy(), haar_np.idwt2(ref_l, ref_h))
+    assert rel_err(rec[..., :h, :w], x) < 1e-6
+    # autograd through the fused pair: <DWT x, g> == <x, DWT^T g>
+    xg = x.cuda().requires_grad_(True)
+    yl, yh = ops.haar_dwt2d(xg, J)
+    gl, gh = torch.randn_like(yl), [torch.randn_like(b) for b in yh]
+    loss = (yl * gl).sum() + sum((b * g).sum() for b, g in zip(yh, gh))
+    loss.backward()
+    want = ops.haar_idwt2d(gl, gh)[..., :h, :w]
+    assert rel_err(xg.grad, want) < 1e-6
+
+
+def test_dwtblock_deeper_than_three_levels_composes(ops):
+    """DWTForward accepts any J; the fused kernel holds 3 levels, deeper blocks compose."""
+    torch.manual_seed(5)
+    for shape, J in (((2, 3, 64, 64), 4), ((1, 2, 100, 36), 5), ((1, 3, 32, 32), 5)):
+        x = torch.randn(*shape)
+        xg = x.cuda().requires_grad_(True)
+        y = ops.dwtblock(xg, J, 7)
+        ref = haar_np.dwtblock(x.numpy(), J, 7)
+        assert y.shape == ref.shape
+        assert rel_err(y, torch.from_numpy(ref)) < 1e-6
+        g = torch.randn_like(y)
+        y.backward(g)
+        assert rel_err(xg.grad, torch.from_numpy(haar_np.dwtblock_bwd(g.cpu().numpy(), shape, J))) < 1e-6
+
+
+def test_pad_at_start_switch_matches_flipped_oracle():
+    """The one unpinned convention, flipped in one place on each side: UB200_HAAR_PAD_AT_START=1 (kernels, read once per
+    process, hence the subprocess) against oracle.haar_np.PAD_AT_END = False, on odd extents, bit-exact."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from oracle import haar_np
+from unet_design_b200 import ops
+haar_np.PAD_AT_END = False
+torch.manual_seed(0)
+for shape in [(2, 2, 25, 13), (1, 5, 7, 9), (1, 3, 200, 6), (2, 3, 8, 8)]:
+    x = torch.randn(*shape)
+    for J in (1, 2, 3):
+        yl, yh = ops.haar_dwt2d(x.cuda(), J)
+        rl, rh = haar_np.dwt2(x.numpy(), J)
+        assert np.array_equal(yl.cpu().numpy(), rl), (shape, J)
+        assert all(np.array_equal(a.cpu().numpy(), b) for a, b in zip(yh, rh)), (shape, J)
+        xg = x.cuda().requires_grad_(True)
+        y = ops.dwtblock(xg, J, 6)
+        assert np.array_equal(y.detach().cpu().numpy(), haar_np.dwtblock(x.numpy(), J, 6)), (shape, J)
+        g = torch.randn_like(y)
+        y.backward(g)
+        assert np.allclose(xg.grad.cpu().numpy(), haar_np.dwtblock_bwd(g.cpu().numpy(), shape, J), atol=1e-6), (shape, J)
+    a = x.cuda().permute(0, 2, 3, 1).to(torch.bfloat16) if shape[1] % 8 == 0 else None
+print("pad-at-start ok")
+""" % root
+    env = dict(os.environ, UB200_HAAR_PAD_AT_START="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "pad-at-start ok" in r.stdout, r.stdout + r.stderr

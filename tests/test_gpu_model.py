@@ -50,6 +50,20 @@ def test_wmh_unetbase_g_odd_extents_golden(tag):
     gc.check_unetbase_g(Unetbase_G, f"wmh_unetbase_g_{tag}.pt", "cuda", 3 * TOL, 8e-2)
 
 
+@pytest.mark.parametrize("tag", ["unetbase", "unetbase_relu", "unetmod", "unetmod_1x1_attn"])
+def test_pdearena_unetbase_and_modern_unet_golden(tag):
+    """`Unetbase` (twod_unetbase.py:60-141) and `twod_unet.Unet` (twod_unet.py:389-548) against the reference classes."""
+    from unet_design_b200.pdearena.modules.twod_unet import Unet
+    from unet_design_b200.pdearena.modules.twod_unetbase import Unetbase
+    gc.check_unetbase_g(Unetbase if tag.startswith("unetbase") else Unet, f"pdearena_{tag}.pt", "cuda", 3 * TOL,
+                        gc.CONTAINER_GRAD_TOL.get(tag, 8e-2))
+
+
+def test_mnist_unetmodel_get_unet_golden():
+    from unet_design_b200.diff_mnist.unet import get_unet
+    gc.check_mnist_unetmodel(get_unet, "cuda", 3 * TOL, 0.12)
+
+
 def test_config2_architecture_against_oracle():
     """BASELINE config 2 architecture (ch=128, ch_mult=[1,2,2,2], attn=[1], 2 res blocks, Haar encoder) on a small
     batch: loss and every parameter gradient against oracle/torch_ref.py run on the GPU in fp32 (TF32 off)."""
@@ -70,14 +84,23 @@ def test_config2_architecture_against_oracle():
     lr.backward(); lo.backward()
     assert abs(float(lo.detach()) - float(lr.detach())) < 2e-2 * abs(float(lr.detach()))
     pr = dict(ref.named_parameters())
-    worst, name = 0.0, None
-    for n, p in net.named_parameters():
-        if p.grad is None or n.endswith("proj_k.bias"):
-            continue
-        e = rel_err(p.grad, pr[n].grad, floor=1e-5)
-        if e > worst:
-            worst, name = e, n
-    assert worst < 0.1, (worst, name)
+    errs = {n: rel_err(p.grad, pr[n].grad, floor=1e-5) for n, p in net.named_parameters()
+            if p.grad is not None and not n.endswith("proj_k.bias")}
+    worst = max(errs, key=errs.get)
+    ranked = sorted(errs.values())
+    conv_w = [e for n, e in errs.items() if n.endswith(("block1.2.weight", "block2.3.weight", "main.weight", "shortcut.weight"))]
+    report = {"loss_rel": abs(float(lo.detach()) - float(lr.detach())) / abs(float(lr.detach())),
+              "grad_worst": errs[worst], "grad_worst_name": worst, "grad_median": ranked[len(ranked) // 2],
+              "grad_p90": ranked[int(0.9 * len(ranked))], "conv_weight_grad_worst": max(conv_w), "n_params": len(errs)}
+    print("config2 parity:", report)
+    import json
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/config2_parity.json", "w") as f:
+        json.dump(report, f, indent=1)
+    # north_star bound (<= 1e-2) holds per block (tests above); through the 30-conv network bf16 noise compounds
+    assert report["grad_median"] < 3e-2 and report["conv_weight_grad_worst"] < 6e-2, report
+    assert errs[worst] < 0.1, (errs[worst], worst)
 
 
 def test_mnist_blocks_golden():

@@ -122,3 +122,26 @@ def test_c_restatement_matches_numpy(shape):
                                 ctypes.c_int64(w), ctypes.c_int(J), ctypes.c_int64(out_ch),
                                 got.ctypes.data_as(fp), scratch.ctypes.data_as(fp))
         np.testing.assert_array_equal(got, want)
+
+
+def test_odd_extent_pad_side_is_one_switch(monkeypatch):
+    """The unpinned convention: PAD_AT_END moves the single zero of an odd extent.  Even extents do not
+    depend on it; odd ones keep the output extent ceil(n/2), perfect reconstruction and the adjoint identity either way."""
+    rng = np.random.default_rng(0)
+    even, odd = rng.standard_normal((2, 3, 8, 12)).astype(np.float32), rng.standard_normal((2, 3, 25, 13)).astype(np.float32)
+    ref_even, ref_odd = haar_np.dwt2(even, 2), haar_np.dwt2(odd, 2)
+    monkeypatch.setattr(haar_np, "PAD_AT_END", False)
+    yl, yh = haar_np.dwt2(even, 2)
+    np.testing.assert_array_equal(yl, ref_even[0])
+    yl, yh = haar_np.dwt2(odd, 2)
+    assert yl.shape == ref_odd[0].shape == (2, 3, 7, 4) and not np.array_equal(yl, ref_odd[0])
+    rec = haar_np.idwt2(yl, yh)
+    np.testing.assert_allclose(haar_np._crop(rec, 25, 13), odd, atol=2e-6)
+    # first row of the level-1 LL now sees the zero row: LL[0, j] = (0 + 0 + x[0, 2j-1] + x[0, 2j]) / 2
+    ll1 = haar_np.dwt2_level(odd)[0]
+    np.testing.assert_allclose(ll1[..., 0, 1], (odd[..., 0, 1] + odd[..., 0, 2]) / 2, atol=1e-6)
+    # adjoint of the block (what the kernels' backward computes) under the flipped convention
+    g = rng.standard_normal((2, 6, 13, 7)).astype(np.float32)
+    lhs = float((haar_np.dwtblock(odd, 1, 6).astype(np.float64) * g).sum())
+    rhs = float((odd.astype(np.float64) * haar_np.dwtblock_bwd(g, odd.shape, 1)).sum())
+    assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))

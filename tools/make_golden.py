@@ -242,6 +242,51 @@ def mnist_goldens():
                     "keys": {k: tuple(v.shape) for k, v in net.state_dict().items()}}, f"{OUT}/mnist_unet_wavelet_{tag}.pt")
 
 
+def containers_r2_goldens():
+    """Round-2 additions: the remaining container classes north_star names -- pdearena `Unetbase`
+    (twod_unetbase.py:60-141), `twod_unet.Unet` ("Unetmod", twod_unet.py:389-548) and diff_mnist `UNetModel` through
+    `get_unet` (torch_ddpm/ddpm/models/unet/unet.py:14-311, models/utils.py:5-53) -- plus a ReLU ConvBlock."""
+    sys.modules["pytorch_wavelets"] = pw
+    sys.path.insert(0, f"{REF}/pdearena")
+    # twod_unet.py imports .fourier (torch.fft only) -- importable as is
+    import pdearena.modules.twod_unet as ref_unet          # noqa: E402
+    import pdearena.modules.twod_unetbase as ref_base      # noqa: E402
+    common = dict(n_input_scalar_components=1, n_input_vector_components=1, n_output_scalar_components=1,
+                  n_output_vector_components=1, time_history=2, time_future=1)
+    for tag, ctor, cfg in (("unetbase", ref_base.Unetbase, dict(hidden_channels=16, activation="gelu", **common)),
+                           ("unetbase_relu", ref_base.Unetbase, dict(hidden_channels=16, activation="relu", **common)),
+                           ("unetmod", ref_unet.Unet, dict(hidden_channels=16, activation="gelu", norm=True, **common)),
+                           ("unetmod_1x1_attn", ref_unet.Unet, dict(hidden_channels=16, activation="silu", norm=True,
+                                                                    ch_mults=(1, 2), is_attn=(False, True), mid_attn=True,
+                                                                    n_blocks=1, use1x1=True, **common))):
+        net = apply_det_init(ctor(**cfg))
+        torch.manual_seed(0)
+        x = torch.randn(2, 2, 3, 32, 48) if "attn" not in tag else torch.randn(2, 2, 3, 16, 16)
+        out = net(x)
+        gy = torch.randn_like(out)
+        (out * gy).sum().backward()
+        torch.save({"cfg": cfg, "x": x, "out": [out.detach()], "gy": [gy], "out_2lvl": None,
+                    "gparams": small_grads(net, also=("final.weight",)),
+                    "keys": {k: tuple(v.shape) for k, v in net.state_dict().items()}}, f"{OUT}/pdearena_{tag}.pt")
+
+    load_reference_module("_mpl_stub_probe", f"{REF}/diff_cifar/model.py")     # installs the matplotlib stub
+    sys.path.insert(0, f"{REF}/diff_mnist")
+    import torch_ddpm.ddpm.models.utils as ref_utils               # noqa: E402
+    cfg = dict(image_size=32, image_channels=1, num_channels=32, dropout=0.0, num_res_blocks=1)
+    net = apply_det_init(ref_utils.get_unet(**cfg))
+    torch.manual_seed(0)
+    x = torch.randn(2, 1, 32, 32)
+    t = torch.randint(30, (2, 1))
+    out = net(x, t)
+    gy = torch.randn_like(out)
+    (out * gy).sum().backward()
+    with torch.no_grad():
+        out2 = net(x[..., ::4, ::4].contiguous(), t, n_levels_used=2)
+    torch.save({"cfg": cfg, "x": x, "t": t, "out": out.detach(), "gy": gy, "out_2lvl": out2,
+                "gparams": small_grads(net, also=("output_blocks.0.0.in_layers.2.weight",)),
+                "keys": {k: tuple(v.shape) for k, v in net.state_dict().items()}}, f"{OUT}/mnist_unetmodel.pt")
+
+
 def state_dict_keys():
     """Key names and shapes of the reference's state_dicts (the checkpoint compatibility surface)."""
     m = load_reference_module("ref_cifar_model", f"{REF}/diff_cifar/model.py")
@@ -265,10 +310,14 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "sampler":      # only the sampler fixture (the others are unchanged)
         cifar_sampler_golden()
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "r2":           # only the round-2 container fixtures
+        containers_r2_goldens()
+        raise SystemExit(0)
     cifar_goldens()
     cifar_sampler_golden()
     pdearena_wmh_goldens()
     mnist_goldens()
+    containers_r2_goldens()
     state_dict_keys()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -40,6 +40,7 @@ struct FpropParams {
     uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, tbl_bytes;
     int cluster_tiles;                // (channel tile, pixel-tile group) units walked by one cluster
     int cluster;                      // CTAs per cluster: 1, or 2 with weight multicast
+    int S;                            // convolution stride (1 or 2): input pixel = S * output pixel + tap offset
     const float *bias, *bias2, *rowadd;
     const __nv_bfloat16 *residual; int64_t ld_res;
     int has_out;                      // bf16 NHWC output through the TMA store
@@ -152,8 +153,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                             mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
                             if (leader) {
                                 mbar_arrive_expect_tx_a(fb, tx_bytes);
-                                tma_load_4d_a(sa, &tm_a, fb, c, xa + dx, ya + dy, na);
-                                if (p.msub == 2) tma_load_4d_a(sa + 128 * BK * 2, &tm_a, fb, c, xb + dx, yb + dy, nb);
+                                tma_load_4d_a(sa, &tm_a, fb, c, p.S * xa + dx, p.S * ya + dy, na);
+                                if (p.msub == 2) tma_load_4d_a(sa + 128 * BK * 2, &tm_a, fb, c, p.S * xb + dx, p.S * yb + dy, nb);
                                 if (kCluster > 1) tma_load_2d_mcast_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w, fb, wk, co0, (uint16_t)0x3);
                                 else tma_load_2d_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w, fb, wk, co0);
                             }
@@ -564,11 +565,15 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     UB_REQUIRE(a->N < (1 << 24) && a->H < (1 << 15) && a->W < (1 << 15) && a->Cin <= 16384 && a->Cout <= 16384,
                UB200_E_UNSUPPORTED);
     UB_REQUIRE(!a->gn_partial, UB200_E_UNSUPPORTED);   // epilogue statistics: not in this build yet
+    const int S = a->stride == 0 ? 1 : a->stride;
+    UB_REQUIRE(S == 1 || S == 2, UB200_E_UNSUPPORTED);
+    // a->H, a->W are the INPUT extents; with padding k/2 the output extents are ceil(H / S), ceil(W / S)
+    const int64_t Ho = (a->H + S - 1) / S, Wo = (a->W + S - 1) / S;
 
     const int64_t cout_pad = (a->Cout + 15) / 16 * 16;
     FpropParams p{};
-    p.N = (int)a->N; p.H = (int)a->H; p.W = (int)a->W; p.Cout = (int)a->Cout;
-    const PixelTile pt = pick_pixel_tile(a->N, a->H, a->W);
+    p.N = (int)a->N; p.H = (int)Ho; p.W = (int)Wo; p.Cout = (int)a->Cout; p.S = S;
+    const PixelTile pt = pick_pixel_tile(a->N, Ho, Wo);
     p.BW = pt.BW; p.BH = pt.BH; p.BNI = pt.BNI;
     p.tiles_w = (p.W + p.BW - 1) / p.BW;
     p.tiles_h = (p.H + p.BH - 1) / p.BH;
@@ -627,7 +632,8 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
         const int64_t dims[4] = {a->Cin, a->W, a->H, a->N};
         const int64_t str[3] = {a->ld_a, a->ld_a * a->W, a->ld_a * a->W * a->H};
         const int box[4] = {bk, p.BW, p.BH, p.BNI};
-        int rc = encode_bf16_tensor_map(&ta, a->a, 4, dims, str, box);
+        const int es[4] = {1, S, S, 1};
+        int rc = encode_bf16_tensor_map(&ta, a->a, 4, dims, str, box, es);
         if (rc) return rc;
         const int64_t wd[2] = {(int64_t)p.taps * a->Cin, cout_pad};
         const int64_t ws[1] = {(int64_t)p.taps * a->Cin};
@@ -636,8 +642,8 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
         if (rc) return rc;
     }
     if (extra) {
-        const int64_t dims[4] = {a->Cin2, a->W, a->H, a->N};
-        const int64_t str[3] = {a->ld_a2, a->ld_a2 * a->W, a->ld_a2 * a->W * a->H};
+        const int64_t dims[4] = {a->Cin2, Wo, Ho, a->N};          // the 1x1 term lives at the output resolution
+        const int64_t str[3] = {a->ld_a2, a->ld_a2 * Wo, a->ld_a2 * Wo * Ho};
         const int box[4] = {bk, p.BW, p.BH, p.BNI};
         int rc = encode_bf16_tensor_map(&ta2, a->a2, 4, dims, str, box);
         if (rc) return rc;
@@ -650,8 +656,8 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
         ta2 = ta; tw2 = tw;
     }
     if (a->out) {
-        const int64_t dims[4] = {a->Cout, a->W, a->H, a->N};
-        const int64_t str[3] = {a->ld_out, a->ld_out * a->W, a->ld_out * a->W * a->H};
+        const int64_t dims[4] = {a->Cout, Wo, Ho, a->N};
+        const int64_t str[3] = {a->ld_out, a->ld_out * Wo, a->ld_out * Wo * Ho};
         const int box[4] = {64, p.BW, p.BH, p.BNI};
         int rc = encode_bf16_tensor_map(&tout, a->out, 4, dims, str, box);
         if (rc) return rc;

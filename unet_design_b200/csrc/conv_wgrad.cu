@@ -39,6 +39,7 @@ struct WgradParams {
     // (BW + 2) x BH x BNI pixels; tap kx of pixel (x, y) is row y * (BW + 2) + x + kx of that box, so each 16-pixel
     // MMA slab is a run of 16 consecutive 128-byte rows starting at an arbitrary row (not an 8-row swizzle atom)
     int halo, bo_mode;
+    int S;                              // conv stride: A pixel = S * G pixel + tap offset (TMA traversal stride S)
     uint32_t a_chunk_stride, a_halo_bytes;
     float *dw;
 };
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                         const int kx = p.ksize == 3 ? tp - 1 : 0;
                         const uint32_t sa = sg + p.g_stage_bytes + tp * p.a_tap_bytes;
                         for (int c = 0; c < chunks_a; ++c)
-                            if (leader) tma_load_4d_a(sa + c * a_chunk_bytes, &tm_a, fb, ci0 + c * p.cw_a, x0 + kx, y0 + ky, n0);
+                            if (leader) tma_load_4d_a(sa + c * a_chunk_bytes, &tm_a, fb, ci0 + c * p.cw_a, p.S * x0 + kx, p.S * y0 + ky, n0);
                     }
                 }
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -371,7 +372,14 @@ extern "C" {
 
 int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a, int64_t N, int64_t H, int64_t W,
                      int64_t Cin, int64_t Cout, int ksize, float *dw, void *stream) {
-    UB_REQUIRE(gout && a && dw && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, UB200_E_BADARG);
+    return ub200_conv_wgrad_strided(gout, ld_g, a, ld_a, N, H, W, Cin, Cout, ksize, 1, dw, stream);
+}
+
+int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int64_t ld_a, int64_t N, int64_t Hin, int64_t Win,
+                             int64_t Cin, int64_t Cout, int ksize, int stride, float *dw, void *stream) {
+    UB_REQUIRE(gout && a && dw && N > 0 && Hin > 0 && Win > 0 && Cin > 0 && Cout > 0, UB200_E_BADARG);
+    UB_REQUIRE(stride == 1 || stride == 2, UB200_E_UNSUPPORTED);
+    const int64_t H = (Hin + stride - 1) / stride, W = (Win + stride - 1) / stride;      // extents of gout: the pixel tiling
     UB_REQUIRE(ksize == 1 || ksize == 3, UB200_E_UNSUPPORTED);
     WgradParams p{};
     p.cw_g = chunk_width(Cout); p.cw_a = chunk_width(Cin);
@@ -406,7 +414,8 @@ int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a
     p.a_tap_bytes = (uint32_t)((kPix * ncols_max * 2 + 1023) & ~1023);
     static const int env_halo = [] { const char *e = getenv("UB200_WGRAD_HALO"); return e ? atoi(e) : 1; }();
     static const int env_bo = [] { const char *e = getenv("UB200_WGRAD_BO"); return e ? atoi(e) : 0; }();
-    p.halo = (env_halo && ksize == 3 && p.cw_a == 64 && p.BW % 16 == 0) ? 1 : 0;
+    p.S = stride;
+    p.halo = (env_halo && stride == 1 && ksize == 3 && p.cw_a == 64 && p.BW % 16 == 0) ? 1 : 0;
     p.bo_mode = env_bo;
     p.a_chunk_stride = (uint32_t)(((p.BW + 2) * p.BH * p.BNI * 128 + 1023) & ~1023);
     p.a_halo_bytes = (uint32_t)((ncols_max + 63) / 64) * p.a_chunk_stride;
@@ -428,10 +437,11 @@ int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a
         if (rc) return rc;
     }
     {
-        const int64_t dims[4] = {Cin, W, H, N};
-        const int64_t str[3] = {ld_a, ld_a * W, ld_a * W * H};
+        const int64_t dims[4] = {Cin, Win, Hin, N};
+        const int64_t str[3] = {ld_a, ld_a * Win, ld_a * Win * Hin};
         const int box[4] = {p.cw_a, p.halo ? p.BW + 2 : p.BW, p.BH, p.BNI};
-        int rc = encode_bf16_tensor_map(&ta, a, 4, dims, str, box);
+        const int es[4] = {1, stride, stride, 1};
+        int rc = encode_bf16_tensor_map(&ta, a, 4, dims, str, box, es);
         if (rc) return rc;
     }
     static std::once_flag once;

@@ -59,6 +59,7 @@ template <int ACT>
 __device__ __forceinline__ float act_fwd(float z) {
     if constexpr (ACT == UB200_ACT_SILU) return z * fast_sigmoid(z);
     else if constexpr (ACT == UB200_ACT_GELU) return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f));
+    else if constexpr (ACT == UB200_ACT_RELU) return fmaxf(z, 0.f);
     else return z;
 }
 template <int ACT>
@@ -68,6 +69,8 @@ __device__ __forceinline__ float act_bwd(float z) {   // d act / d z
         return fmaf(z, fmaf(-s, s, s), s);          // s + z*s*(1-s)
     } else if constexpr (ACT == UB200_ACT_GELU) {
         return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+    } else if constexpr (ACT == UB200_ACT_RELU) {
+        return z > 0.f ? 1.0f : 0.f;               // torch: relu'(0) = 0
     } else return 1.0f;
 }
 
@@ -842,10 +845,12 @@ int make_shape(int64_t N, int64_t HW, int64_t C, int G, Shape &sh, dim3 &grid) {
         if (drop) {                                                                                  \
             if (act == UB200_ACT_SILU) KERNEL<UB200_ACT_SILU, true> __VA_ARGS__;                     \
             else if (act == UB200_ACT_GELU) KERNEL<UB200_ACT_GELU, true> __VA_ARGS__;                \
+            else if (act == UB200_ACT_RELU) KERNEL<UB200_ACT_RELU, true> __VA_ARGS__;                \
             else KERNEL<UB200_ACT_NONE, true> __VA_ARGS__;                                           \
         } else {                                                                                     \
             if (act == UB200_ACT_SILU) KERNEL<UB200_ACT_SILU, false> __VA_ARGS__;                    \
             else if (act == UB200_ACT_GELU) KERNEL<UB200_ACT_GELU, false> __VA_ARGS__;               \
+            else if (act == UB200_ACT_RELU) KERNEL<UB200_ACT_RELU, false> __VA_ARGS__;               \
             else KERNEL<UB200_ACT_NONE, false> __VA_ARGS__;                                          \
         }                                                                                            \
     } while (0)
@@ -874,7 +879,7 @@ int ub200_gn_act_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t H
                                int act, float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
                                const void *addend, int64_t ld_add, void *y, int64_t ld_y, void *stream) {
     UB_REQUIRE(x && y && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
-    UB_REQUIRE(act == UB200_ACT_NONE || act == UB200_ACT_SILU || act == UB200_ACT_GELU, UB200_E_BADARG);
+    UB_REQUIRE(act >= UB200_ACT_NONE && act <= UB200_ACT_RELU, UB200_E_BADARG);
     Shape sh; dim3 grid;
     int rc = make_shape(N, HW, C, G, sh, grid);
     if (rc) return rc;
@@ -903,7 +908,7 @@ int ub200_gn_act_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int
                                uint64_t offset, const uint64_t *offset_dev, void *gx, int64_t ld_gx, int accumulate, float *dgamma, float *dbeta,
                                float *dscale, float *dshift, float *ws, void *stream) {
     UB_REQUIRE(gy && x && gx && ws && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
-    UB_REQUIRE(act == UB200_ACT_NONE || act == UB200_ACT_SILU || act == UB200_ACT_GELU, UB200_E_BADARG);
+    UB_REQUIRE(act >= UB200_ACT_NONE && act <= UB200_ACT_RELU, UB200_E_BADARG);
     Shape sh; dim3 grid;
     int rc = make_shape(N, HW, C, G, sh, grid);
     if (rc) return rc;
@@ -930,9 +935,11 @@ int ub200_gn_act_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int
 #define DISPATCH_FUSED(KERNEL, act, drop, ...)                                                                  \
     ((drop) ? ((act) == UB200_ACT_SILU   ? launch_cluster(KERNEL(UB200_ACT_SILU, true), __VA_ARGS__)            \
                : (act) == UB200_ACT_GELU ? launch_cluster(KERNEL(UB200_ACT_GELU, true), __VA_ARGS__)            \
+               : (act) == UB200_ACT_RELU ? launch_cluster(KERNEL(UB200_ACT_RELU, true), __VA_ARGS__)            \
                                          : launch_cluster(KERNEL(UB200_ACT_NONE, true), __VA_ARGS__))           \
             : ((act) == UB200_ACT_SILU   ? launch_cluster(KERNEL(UB200_ACT_SILU, false), __VA_ARGS__)           \
                : (act) == UB200_ACT_GELU ? launch_cluster(KERNEL(UB200_ACT_GELU, false), __VA_ARGS__)           \
+               : (act) == UB200_ACT_RELU ? launch_cluster(KERNEL(UB200_ACT_RELU, false), __VA_ARGS__)           \
                                          : launch_cluster(KERNEL(UB200_ACT_NONE, false), __VA_ARGS__)))
 #define FUSED_FWD(A, D) gn_fused_fwd_kernel<A, D>
 #define FUSED_BWD_X(A, D) gn_fused_bwd_kernel<A, D, true>
@@ -944,7 +951,7 @@ int ub200_gn_act_fused_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int
                                      const uint64_t *offset_dev, const void *addend, int64_t ld_add, void *y,
                                      int64_t ld_y, void *stream) {
     UB_REQUIRE(x && y && stats && N > 0 && HW > 0 && C > 0 && G > 0 && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
-    UB_REQUIRE(act == UB200_ACT_NONE || act == UB200_ACT_SILU || act == UB200_ACT_GELU, UB200_E_BADARG);
+    UB_REQUIRE(act >= UB200_ACT_NONE && act <= UB200_ACT_RELU, UB200_E_BADARG);
     FusedShape sh; size_t smem = 0;
     const size_t gpad = (size_t)((2 * G + 3) & ~3);
     const bool ok = ld_x % 8 == 0 && ld_y % 8 == 0 && ld_x >= C && ld_y >= C && ub::aligned16(x) && ub::aligned16(y) &&
@@ -971,7 +978,7 @@ int ub200_gn_act_fused_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *
                                      const void *gadd, int64_t ld_gadd, float *ws, void *stream) {
     UB_REQUIRE(!gadd || (ld_gadd % 8 == 0 && ld_gadd >= C && ub::aligned16(gadd)), UB200_E_UNSUPPORTED);
     UB_REQUIRE(gy && x && gx && ws && N > 0 && HW > 0 && C > 0 && G > 0 && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
-    UB_REQUIRE(act == UB200_ACT_NONE || act == UB200_ACT_SILU || act == UB200_ACT_GELU, UB200_E_BADARG);
+    UB_REQUIRE(act >= UB200_ACT_NONE && act <= UB200_ACT_RELU, UB200_E_BADARG);
     FusedShape sh; size_t smem = 0;
     const bool fits = ld_x % 8 == 0 && ld_gy % 8 == 0 && ld_gx % 8 == 0 && ld_x >= C && ld_gy >= C && ld_gx >= C &&
                       ub::aligned16(x) && ub::aligned16(gy) && ub::aligned16(gx);

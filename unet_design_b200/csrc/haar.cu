@@ -22,6 +22,16 @@ __device__ __forceinline__ float sub2(float a, float b) { return __fsub_rn(mul_s
 
 struct Bands { float ll, lh, hl, hh; };
 
+// mode='zero' extends an odd extent by ONE zero.  Upstream pytorch_wavelets appends it at the END (right / bottom); the
+// reference itself only pins the output extent ceil(n/2) (wmh/model.py:146-155), so the side is the one unpinned
+// convention of this path.  It lives in this one switch (and `PAD_AT_END` in oracle/haar_np.py):
+// UB200_HAAR_PAD_AT_START=1 puts the zero at the start instead.  `odd_shift(n, ps)` is the number of leading zeros.
+inline int pad_at_start() {
+    static const int v = [] { const char *e = getenv("UB200_HAAR_PAD_AT_START"); return (e && e[0] == '1') ? 1 : 0; }();
+    return v;
+}
+__host__ __device__ __forceinline__ int odd_shift(int n, int ps) { return (ps && (n & 1)) ? 1 : 0; }
+
 __device__ __forceinline__ Bands analyse(float a, float b, float c, float d) {
     float lo_t = add2(a, b), hi_t = sub2(a, b);
     float lo_b = add2(c, d), hi_b = sub2(c, d);
@@ -70,8 +80,9 @@ __global__ void __launch_bounds__(256) haar_dwt_vec4(const float *__restrict__ x
 // Any extents (odd H / W, tiny planes): one output coefficient per work item, zero extension.
 template <bool HIGHS>
 __global__ void __launch_bounds__(256) haar_dwt_any(const float *__restrict__ x, int64_t planes, int H, int W,
-                                                   float *__restrict__ ll, float *__restrict__ highs) {
+                                                   float *__restrict__ ll, float *__restrict__ highs, int ps) {
     const int h2 = (H + 1) >> 1, w2 = (W + 1) >> 1;
+    const int sy = odd_shift(H, ps), sx = odd_shift(W, ps);
     const int64_t items = planes * h2 * w2;
     const int64_t band = (int64_t)h2 * w2;
     for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
@@ -80,11 +91,12 @@ __global__ void __launch_bounds__(256) haar_dwt_any(const float *__restrict__ x,
         const int i = (int)(t % h2);
         const int64_t p = t / h2;
         const float *src = x + p * (int64_t)H * W;
-        const bool r1 = 2 * i + 1 < H, c1 = 2 * j + 1 < W;
-        float a = __ldg(src + (int64_t)(2 * i) * W + 2 * j);
-        float b = c1 ? __ldg(src + (int64_t)(2 * i) * W + 2 * j + 1) : 0.f;
-        float c = r1 ? __ldg(src + (int64_t)(2 * i + 1) * W + 2 * j) : 0.f;
-        float d = (r1 && c1) ? __ldg(src + (int64_t)(2 * i + 1) * W + 2 * j + 1) : 0.f;
+        const int y0 = 2 * i - sy, x0 = 2 * j - sx;
+        const bool r0 = y0 >= 0, r1 = y0 + 1 < H, c0 = x0 >= 0, c1 = x0 + 1 < W;
+        float a = (r0 && c0) ? __ldg(src + (int64_t)y0 * W + x0) : 0.f;
+        float b = (r0 && c1) ? __ldg(src + (int64_t)y0 * W + x0 + 1) : 0.f;
+        float c = (r1 && c0) ? __ldg(src + (int64_t)(y0 + 1) * W + x0) : 0.f;
+        float d = (r1 && c1) ? __ldg(src + (int64_t)(y0 + 1) * W + x0 + 1) : 0.f;
         Bands q = analyse(a, b, c, d);
         ll[it] = q.ll;
         if (HIGHS) {
@@ -143,7 +155,8 @@ __global__ void __launch_bounds__(256) haar_idwt_vec4(const float *__restrict__ 
 template <bool HIGHS>
 __global__ void __launch_bounds__(256) haar_idwt_any(const float *__restrict__ ll, const float *__restrict__ highs,
                                                     int64_t planes, int h2, int w2, int Hout, int Wout,
-                                                    float *__restrict__ out) {
+                                                    float *__restrict__ out, int ps) {
+    const int sy = odd_shift(Hout, ps), sx = odd_shift(Wout, ps);
     const int64_t items = planes * h2 * w2;
     const int64_t band = (int64_t)h2 * w2;
     for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
@@ -159,11 +172,167 @@ __global__ void __launch_bounds__(256) haar_idwt_any(const float *__restrict__ l
         float o00, o01, o10, o11;
         synth(__ldg(ll + it), vlh, vhl, vhh, o00, o01, o10, o11);
         float *dst = out + p * (int64_t)Hout * Wout;
-        const bool r1 = 2 * i + 1 < Hout, c1 = 2 * j + 1 < Wout;
-        dst[(int64_t)(2 * i) * Wout + 2 * j] = o00;
-        if (c1) dst[(int64_t)(2 * i) * Wout + 2 * j + 1] = o01;
-        if (r1) dst[(int64_t)(2 * i + 1) * Wout + 2 * j] = o10;
-        if (r1 && c1) dst[(int64_t)(2 * i + 1) * Wout + 2 * j + 1] = o11;
+        const int y0 = 2 * i - sy, x0 = 2 * j - sx;          // the crop drops the row / column of the zero extension
+        const bool r0 = y0 >= 0, r1 = y0 + 1 < Hout, c0 = x0 >= 0, c1 = x0 + 1 < Wout;
+        if (r0 && c0) dst[(int64_t)y0 * Wout + x0] = o00;
+        if (r0 && c1) dst[(int64_t)y0 * Wout + x0 + 1] = o01;
+        if (r1 && c0) dst[(int64_t)(y0 + 1) * Wout + x0] = o10;
+        if (r1 && c1) dst[(int64_t)(y0 + 1) * Wout + x0 + 1] = o11;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused J-level analysis / synthesis (J = 2 or 3): the input crosses HBM once (2*E*b bytes for all bands of all
+// levels, instead of E*b*sum_j 2*4^-j level by level).  One thread owns a strip of 2^J rows x 4 columns: level 1 and 2
+// are in-register, level 3 pairs neighbouring lanes with one warp shuffle per coefficient (the butterfly's last
+// stage).  Loads and stores are contiguous across the lanes of a warp at every level.  Same per-level arithmetic
+// as the single-level kernels, so results are bit-identical to the level-by-level path and to the oracle.
+// Requires H % 2^J == 0, W % 8 == 0 and 16-byte aligned pointers; otherwise the caller goes level by level.
+// ---------------------------------------------------------------------------------------------
+template <int J>
+__global__ void __launch_bounds__(256) haar_dwt_multi(const float *__restrict__ x, int64_t planes, int H, int W,
+                                                     float *__restrict__ ll, float *__restrict__ h1,
+                                                     float *__restrict__ h2, float *__restrict__ h3) {
+    constexpr int R = 1 << J;                       // input rows per strip
+    const int wq = W >> 2, strips = H / R;
+    const int64_t items = planes * strips * wq;     // even: wq is even
+    const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2, H3 = H >> 3, W3 = W >> 3;
+    const int64_t b1 = (int64_t)H1 * W1, b2 = (int64_t)H2 * W2, b3 = (int64_t)H3 * W3;
+    const int lane = threadIdx.x & 31;
+    for (int64_t it0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x - lane; it0 < items; it0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t it = it0 + lane;
+        const bool live = it < items;               // pairs of lanes are live together
+        const int jq = (int)(it % wq);
+        const int64_t t = it / wq;
+        const int sidx = (int)(t % strips);
+        const int64_t p = t / strips;
+        float l1[R / 2][2];                         // level-1 LL of the strip
+        if (live) {
+            const float *src = x + (p * H + (int64_t)sidx * R) * W + 4 * jq;
+            float *hp = h1 + p * 3 * b1 + ((int64_t)sidx * (R / 2)) * W1 + 2 * jq;
+#pragma unroll
+            for (int r = 0; r < R / 2; ++r) {
+                const float4 a = ld_stream(reinterpret_cast<const float4 *>(src + (int64_t)(2 * r) * W));
+                const float4 b = ld_stream(reinterpret_cast<const float4 *>(src + (int64_t)(2 * r + 1) * W));
+                const Bands q0 = analyse(a.x, a.y, b.x, b.y), q1 = analyse(a.z, a.w, b.z, b.w);
+                l1[r][0] = q0.ll; l1[r][1] = q1.ll;
+                float *hr = hp + (int64_t)r * W1;
+                *reinterpret_cast<float2 *>(hr) = make_float2(q0.lh, q1.lh);
+                *reinterpret_cast<float2 *>(hr + b1) = make_float2(q0.hl, q1.hl);
+                *reinterpret_cast<float2 *>(hr + 2 * b1) = make_float2(q0.hh, q1.hh);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R / 2; ++r) l1[r][0] = l1[r][1] = 0.f;
+        }
+        float l2[R / 4];
+#pragma unroll
+        for (int r = 0; r < R / 4; ++r) {
+            const Bands q = analyse(l1[2 * r][0], l1[2 * r][1], l1[2 * r + 1][0], l1[2 * r + 1][1]);
+            l2[r] = q.ll;
+            if (live) {
+                float *hr = h2 + p * 3 * b2 + ((int64_t)sidx * (R / 4) + r) * W2 + jq;
+                hr[0] = q.lh; hr[b2] = q.hl; hr[2 * b2] = q.hh;
+            }
+        }
+        if constexpr (J == 2) {
+            if (live) ll[(p * H2 + sidx) * (int64_t)W2 + jq] = l2[0];
+        } else {
+            const float o0 = __shfl_xor_sync(0xffffffffu, l2[0], 1), o1 = __shfl_xor_sync(0xffffffffu, l2[1], 1);
+            if (live && !(jq & 1)) {
+                const Bands q = analyse(l2[0], o0, l2[1], o1);
+                const int64_t o = (int64_t)sidx * W3 + (jq >> 1);
+                ll[p * b3 + o] = q.ll;
+                float *hr = h3 + p * 3 * b3 + o;
+                hr[0] = q.lh; hr[b3] = q.hl; hr[2 * b3] = q.hh;
+            }
+        }
+    }
+}
+
+template <int J>
+__global__ void __launch_bounds__(256) haar_idwt_multi(const float *__restrict__ ll, const float *__restrict__ h1,
+                                                      const float *__restrict__ h2, const float *__restrict__ h3,
+                                                      int64_t planes, int H, int W, float *__restrict__ out) {
+    constexpr int R = 1 << J;
+    const int wq = W >> 2, strips = H / R;
+    const int64_t items = planes * strips * wq;
+    const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2, H3 = H >> 3, W3 = W >> 3;
+    const int64_t b1 = (int64_t)H1 * W1, b2 = (int64_t)H2 * W2, b3 = (int64_t)H3 * W3;
+    const int lane = threadIdx.x & 31;
+    for (int64_t it0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x - lane; it0 < items; it0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t it = it0 + lane;
+        const bool live = it < items;
+        const int jq = (int)(it % wq);
+        const int64_t t = it / wq;
+        const int sidx = (int)(t % strips);
+        const int64_t p = t / strips;
+        float l2[R / 4];
+        if constexpr (J == 2) {
+            l2[0] = live ? __ldg(ll + (p * H2 + sidx) * (int64_t)W2 + jq) : 0.f;
+        } else {
+            // even lane reconstructs the 2x2 level-2 block of the pair and hands the odd column to its neighbour
+            float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
+            if (live && !(jq & 1)) {
+                const int64_t o = (int64_t)sidx * W3 + (jq >> 1);
+                const float *hr = h3 + p * 3 * b3 + o;
+                synth(__ldg(ll + p * b3 + o), __ldg(hr), __ldg(hr + b3), __ldg(hr + 2 * b3), o00, o01, o10, o11);
+            }
+            const float n0 = __shfl_xor_sync(0xffffffffu, o01, 1), n1 = __shfl_xor_sync(0xffffffffu, o11, 1);
+            l2[0] = (jq & 1) ? n0 : o00;
+            l2[1] = (jq & 1) ? n1 : o10;
+        }
+        if (!live) continue;
+        float l1[R / 2][2];
+#pragma unroll
+        for (int r = 0; r < R / 4; ++r) {
+            const float *hr = h2 + p * 3 * b2 + ((int64_t)sidx * (R / 4) + r) * W2 + jq;
+            synth(l2[r], __ldg(hr), __ldg(hr + b2), __ldg(hr + 2 * b2), l1[2 * r][0], l1[2 * r][1], l1[2 * r + 1][0], l1[2 * r + 1][1]);
+        }
+        float *dst = out + (p * H + (int64_t)sidx * R) * W + 4 * jq;
+        const float *hp = h1 + p * 3 * b1 + ((int64_t)sidx * (R / 2)) * W1 + 2 * jq;
+#pragma unroll
+        for (int r = 0; r < R / 2; ++r) {
+            const float *hr = hp + (int64_t)r * W1;
+            const float2 vlh = *reinterpret_cast<const float2 *>(hr), vhl = *reinterpret_cast<const float2 *>(hr + b1),
+                         vhh = *reinterpret_cast<const float2 *>(hr + 2 * b1);
+            float4 top, bot;
+            synth(l1[r][0], vlh.x, vhl.x, vhh.x, top.x, top.y, bot.x, bot.y);
+            synth(l1[r][1], vlh.y, vhl.y, vhh.y, top.z, top.w, bot.z, bot.w);
+            st_stream(reinterpret_cast<float4 *>(dst + (int64_t)(2 * r) * W), top);
+            st_stream(reinterpret_cast<float4 *>(dst + (int64_t)(2 * r + 1) * W), bot);
+        }
+    }
+}
+
+// One synthesis level, w2 % 2 == 0, Wout == 2*w2, aligned: one work item = 2 coefficient columns -> one float4 per output
+// row, so that a warp's stores are 512 contiguous bytes (the 4-column variant writes half a 32-byte sector per lane).
+template <bool HIGHS>
+__global__ void __launch_bounds__(256) haar_idwt_vec2(const float *__restrict__ ll, const float *__restrict__ highs,
+                                                     int64_t planes, int h2, int w2, int Hout, float *__restrict__ out) {
+    const int wq = w2 >> 1, W = 2 * w2;
+    const int64_t items = planes * h2 * wq;
+    const int64_t band = (int64_t)h2 * w2;
+    for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int jq = (int)(it % wq);
+        const int64_t t = it / wq;
+        const int i = (int)(t % h2);
+        const int64_t p = t / h2;
+        const int64_t o = (p * h2 + i) * (int64_t)w2 + 2 * jq;
+        const float2 a = *reinterpret_cast<const float2 *>(ll + o);
+        float2 b = make_float2(0.f, 0.f), c = b, d = b;
+        if (HIGHS) {
+            const float *hp = highs + p * 3 * band + (int64_t)i * w2 + 2 * jq;
+            b = *reinterpret_cast<const float2 *>(hp);
+            c = *reinterpret_cast<const float2 *>(hp + band);
+            d = *reinterpret_cast<const float2 *>(hp + 2 * band);
+        }
+        float4 top, bot;
+        synth(a.x, b.x, c.x, d.x, top.x, top.y, bot.x, bot.y);
+        synth(a.y, b.y, c.y, d.y, top.z, top.w, bot.z, bot.w);
+        float *dst = out + (p * Hout + 2 * i) * (int64_t)W + 4 * jq;
+        st_stream(reinterpret_cast<float4 *>(dst), top);
+        if (2 * i + 1 < Hout) st_stream(reinterpret_cast<float4 *>(dst + W), bot);
     }
 }
 
@@ -171,16 +340,17 @@ __global__ void __launch_bounds__(256) haar_idwt_any(const float *__restrict__ l
 // DTWBlock: LL_J / 2^J + channel tile.  Level extents are carried so that the zero extension of an
 // odd intermediate level is reproduced exactly (ll_at returns 0 outside a level's extent).
 // ---------------------------------------------------------------------------------------------
-struct Ext { int h[4], w[4]; };   // extent of level 0..3 (level 0 = input)
+struct Ext { int h[4], w[4]; int ps; };   // extent of level 0..3 (level 0 = input); ps: odd extents padded at the start
 
 template <int L>
 __device__ __forceinline__ float ll_at(const float *__restrict__ src, const Ext &e, int y, int x) {
-    if (y >= e.h[L] || x >= e.w[L]) return 0.f;
+    if (y < 0 || x < 0 || y >= e.h[L] || x >= e.w[L]) return 0.f;
     if constexpr (L == 0) {
         return __ldg(src + (int64_t)y * e.w[0] + x);
     } else {
-        return analyse_ll(ll_at<L - 1>(src, e, 2 * y, 2 * x), ll_at<L - 1>(src, e, 2 * y, 2 * x + 1),
-                          ll_at<L - 1>(src, e, 2 * y + 1, 2 * x), ll_at<L - 1>(src, e, 2 * y + 1, 2 * x + 1));
+        const int y0 = 2 * y - odd_shift(e.h[L - 1], e.ps), x0 = 2 * x - odd_shift(e.w[L - 1], e.ps);
+        return analyse_ll(ll_at<L - 1>(src, e, y0, x0), ll_at<L - 1>(src, e, y0, x0 + 1),
+                          ll_at<L - 1>(src, e, y0 + 1, x0), ll_at<L - 1>(src, e, y0 + 1, x0 + 1));
     }
 }
 
@@ -195,6 +365,7 @@ __device__ __forceinline__ float ll_dyn(const float *src, const Ext &e, int J, i
 
 inline Ext make_ext(int64_t H, int64_t W) {
     Ext e;
+    e.ps = pad_at_start();
     e.h[0] = (int)H; e.w[0] = (int)W;
     for (int l = 1; l < 4; ++l) { e.h[l] = (e.h[l - 1] + 1) / 2; e.w[l] = (e.w[l - 1] + 1) / 2; }
     return e;
@@ -274,9 +445,11 @@ __global__ void __launch_bounds__(256) dwtblock_bwd_any(const float *__restrict_
         t /= H;
         const int c = (int)(t % C);
         const int64_t n = t / C;
+        int yo = y, xo = xw;                                // coefficient that covers this pixel, level by level
+        for (int l = 0; l < J; ++l) { yo = (yo + odd_shift(e.h[l], e.ps)) >> 1; xo = (xo + odd_shift(e.w[l], e.ps)) >> 1; }
         float acc = 0.f;
         for (int k = c; k < out_channels; k += C)
-            acc = __fadd_rn(acc, __ldg(g + (n * out_channels + k) * plane_o + (int64_t)(y >> J) * wo + (xw >> J)));
+            acc = __fadd_rn(acc, __ldg(g + (n * out_channels + k) * plane_o + (int64_t)yo * wo + xo));
         acc *= scale;                                     // exact power of two
         for (int l = 0; l < J; ++l) acc = mul_s(mul_s(acc));   // synthesis with zero high bands, per level
         gx[it] = acc;
@@ -375,8 +548,9 @@ __global__ void __launch_bounds__(256) dwtblock_nhwc_bf16_j0(const float *__rest
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dwtblock_nhwc_fwd(const __nv_bfloat16 *__restrict__ x, int64_t ld_x, int64_t N,
                                                         int H, int W, int C, int J, __nv_bfloat16 *__restrict__ out,
-                                                        int64_t ld_o, int Cout) {
+                                                        int64_t ld_o, int Cout, int ps) {
     const int ho = J ? (H + 1) >> 1 : H, wo = J ? (W + 1) >> 1 : W, chunks = C >> 3;
+    const int sy = odd_shift(H, ps), sx = odd_shift(W, ps);
     const int64_t items = N * ho * (int64_t)wo * chunks;
     for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
         const int q = (int)(it % chunks);
@@ -390,12 +564,13 @@ __global__ void __launch_bounds__(256) dwtblock_nhwc_fwd(const __nv_bfloat16 *__
             unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(x + pix * ld_x + 8 * q)), f);
         } else {
             float a[8], b[8], c[8], d[8];
-            const bool r1 = 2 * i + 1 < H, c1 = 2 * j + 1 < W;
-            const __nv_bfloat16 *p00 = x + ((n * H + 2 * i) * (int64_t)W + 2 * j) * ld_x + 8 * q;
+            const int y0 = 2 * i - sy, x0 = 2 * j - sx;
+            const bool r0 = y0 >= 0, r1 = y0 + 1 < H, c0 = x0 >= 0, c1 = x0 + 1 < W;
+            const __nv_bfloat16 *p00 = x + ((n * H + y0) * (int64_t)W + x0) * ld_x + 8 * q;
             const uint4 z = make_uint4(0, 0, 0, 0);
-            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(p00)), a);
-            unpack8(c1 ? ld_stream_u4(reinterpret_cast<const uint4 *>(p00 + ld_x)) : z, b);
-            unpack8(r1 ? ld_stream_u4(reinterpret_cast<const uint4 *>(p00 + (int64_t)W * ld_x)) : z, c);
+            unpack8((r0 && c0) ? ld_stream_u4(reinterpret_cast<const uint4 *>(p00)) : z, a);
+            unpack8((r0 && c1) ? ld_stream_u4(reinterpret_cast<const uint4 *>(p00 + ld_x)) : z, b);
+            unpack8((r1 && c0) ? ld_stream_u4(reinterpret_cast<const uint4 *>(p00 + (int64_t)W * ld_x)) : z, c);
             unpack8((r1 && c1) ? ld_stream_u4(reinterpret_cast<const uint4 *>(p00 + (int64_t)W * ld_x + ld_x)) : z, d);
 #pragma unroll
             for (int u = 0; u < 8; ++u) f[u] = analyse_ll(a[u], b[u], c[u], d[u]) * 0.5f;
@@ -407,8 +582,9 @@ __global__ void __launch_bounds__(256) dwtblock_nhwc_fwd(const __nv_bfloat16 *__
 
 __global__ void __launch_bounds__(256) dwtblock_nhwc_bwd(const __nv_bfloat16 *__restrict__ g, int64_t ld_g, int64_t N,
                                                         int H, int W, int C, int J, int Cout,
-                                                        __nv_bfloat16 *__restrict__ gx, int64_t ld_gx) {
+                                                        __nv_bfloat16 *__restrict__ gx, int64_t ld_gx, int ps) {
     const int wo = J ? (W + 1) >> 1 : W, ho = J ? (H + 1) >> 1 : H, chunks = C >> 3;
+    const int sy = J ? odd_shift(H, ps) : 0, sx = J ? odd_shift(W, ps) : 0;
     const int64_t items = N * H * (int64_t)W * chunks;
     for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
         const int q = (int)(it % chunks);
@@ -417,7 +593,7 @@ __global__ void __launch_bounds__(256) dwtblock_nhwc_bwd(const __nv_bfloat16 *__
         int64_t t = pix / W;
         const int y = (int)(t % H);
         const int64_t n = t / H;
-        const int64_t opix = (n * ho + (y >> J)) * wo + (xw >> J);
+        const int64_t opix = (n * ho + ((y + sy) >> J)) * wo + ((xw + sx) >> J);
         float acc[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc[u] = 0.f;
@@ -449,7 +625,7 @@ int ub200_dwtblock_nhwc_bf16_fwd(const void *x, int64_t ld_x, int64_t N, int64_t
     int grid = ub::grid_for(N * ho * wo * (C / 8), 256, 8);
     dwtblock_nhwc_fwd<<<grid, 256, 0, ub::as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16 *>(x), ld_x, N, (int)H, (int)W,
                                                               (int)C, J, reinterpret_cast<__nv_bfloat16 *>(out), ld_out,
-                                                              (int)out_channels);
+                                                              (int)out_channels, pad_at_start());
     UB_LAUNCH_CHECK();
     return UB200_OK;
 }
@@ -463,7 +639,7 @@ int ub200_dwtblock_nhwc_bf16_bwd(const void *gout, int64_t ld_g, int64_t N, int6
     int grid = ub::grid_for(N * H * W * (C / 8), 256, 8);
     dwtblock_nhwc_bwd<<<grid, 256, 0, ub::as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16 *>(gout), ld_g, N, (int)H,
                                                               (int)W, (int)C, J, (int)out_channels,
-                                                              reinterpret_cast<__nv_bfloat16 *>(gx), ld_gx);
+                                                              reinterpret_cast<__nv_bfloat16 *>(gx), ld_gx, pad_at_start());
     UB_LAUNCH_CHECK();
     return UB200_OK;
 }
@@ -473,15 +649,17 @@ int ub200_haar_dwt2d_fwd(const float *x, int64_t planes, int64_t H, int64_t W, f
     UB_REQUIRE(H < (1 << 30) && W < (1 << 30), UB200_E_UNSUPPORTED);
     cudaStream_t s = ub::as_stream(stream);
     const int64_t h2 = (H + 1) / 2, w2 = (W + 1) / 2;
-    const bool fast = (W % 8 == 0) && ub::aligned16(x) && ub::aligned16(ll) && (!highs || ub::aligned16(highs));
+    const int ps = pad_at_start();
+    const bool fast = (W % 8 == 0) && ub::aligned16(x) && ub::aligned16(ll) && (!highs || ub::aligned16(highs)) &&
+                      !(ps && (H & 1));
     if (fast) {
         int grid = ub::grid_for(planes * h2 * (w2 / 4), 256, 8);
         if (highs) haar_dwt_vec4<true><<<grid, 256, 0, s>>>(x, planes, (int)H, (int)W, ll, highs);
         else haar_dwt_vec4<false><<<grid, 256, 0, s>>>(x, planes, (int)H, (int)W, ll, highs);
     } else {
         int grid = ub::grid_for(planes * h2 * w2, 256, 8);
-        if (highs) haar_dwt_any<true><<<grid, 256, 0, s>>>(x, planes, (int)H, (int)W, ll, highs);
-        else haar_dwt_any<false><<<grid, 256, 0, s>>>(x, planes, (int)H, (int)W, ll, highs);
+        if (highs) haar_dwt_any<true><<<grid, 256, 0, s>>>(x, planes, (int)H, (int)W, ll, highs, ps);
+        else haar_dwt_any<false><<<grid, 256, 0, s>>>(x, planes, (int)H, (int)W, ll, highs, ps);
     }
     UB_LAUNCH_CHECK();
     return UB200_OK;
@@ -493,17 +671,53 @@ int ub200_haar_idwt2d(const float *ll, const float *highs, int64_t planes, int64
     UB_REQUIRE((Hout == 2 * h2 || Hout == 2 * h2 - 1) && (Wout == 2 * w2 || Wout == 2 * w2 - 1), UB200_E_BADARG);
     UB_REQUIRE(Hout < (1 << 30) && Wout < (1 << 30), UB200_E_UNSUPPORTED);
     cudaStream_t s = ub::as_stream(stream);
+    const int ps = pad_at_start();
     const bool fast = (w2 % 4 == 0) && Wout == 2 * w2 && ub::aligned16(ll) && ub::aligned16(out) &&
-                      (!highs || ub::aligned16(highs));
-    if (fast) {
+                      (!highs || ub::aligned16(highs)) && !(ps && (Hout & 1));
+    static const bool vec2 = [] { const char *e = getenv("UB200_IDWT_VEC2"); return !(e && e[0] == '0'); }();
+    if (fast && vec2) {
+        int grid = ub::grid_for(planes * h2 * (w2 / 2), 256, 8);
+        if (highs) haar_idwt_vec2<true><<<grid, 256, 0, s>>>(ll, highs, planes, (int)h2, (int)w2, (int)Hout, out);
+        else haar_idwt_vec2<false><<<grid, 256, 0, s>>>(ll, highs, planes, (int)h2, (int)w2, (int)Hout, out);
+    } else if (fast) {
         int grid = ub::grid_for(planes * h2 * (w2 / 4), 256, 8);
         if (highs) haar_idwt_vec4<true><<<grid, 256, 0, s>>>(ll, highs, planes, (int)h2, (int)w2, (int)Hout, out);
         else haar_idwt_vec4<false><<<grid, 256, 0, s>>>(ll, highs, planes, (int)h2, (int)w2, (int)Hout, out);
     } else {
         int grid = ub::grid_for(planes * h2 * w2, 256, 8);
-        if (highs) haar_idwt_any<true><<<grid, 256, 0, s>>>(ll, highs, planes, (int)h2, (int)w2, (int)Hout, (int)Wout, out);
-        else haar_idwt_any<false><<<grid, 256, 0, s>>>(ll, highs, planes, (int)h2, (int)w2, (int)Hout, (int)Wout, out);
+        if (highs) haar_idwt_any<true><<<grid, 256, 0, s>>>(ll, highs, planes, (int)h2, (int)w2, (int)Hout, (int)Wout, out, ps);
+        else haar_idwt_any<false><<<grid, 256, 0, s>>>(ll, highs, planes, (int)h2, (int)w2, (int)Hout, (int)Wout, out, ps);
     }
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+int ub200_haar_dwt2d_multi_fwd(const float *x, int64_t planes, int64_t H, int64_t W, int J, float *ll,
+                               float *const *highs, void *stream) {
+    UB_REQUIRE(x && ll && highs && planes > 0 && H > 0 && W > 0, UB200_E_BADARG);
+    UB_REQUIRE((J == 2 || J == 3) && H % (1 << J) == 0 && W % 8 == 0 && H < (1 << 30) && W < (1 << 30), UB200_E_UNSUPPORTED);
+    bool al = ub::aligned16(x) && ub::aligned16(ll);
+    for (int j = 0; j < J; ++j) { UB_REQUIRE(highs[j], UB200_E_BADARG); al = al && ub::aligned16(highs[j]); }
+    UB_REQUIRE(al, UB200_E_UNSUPPORTED);
+    cudaStream_t s = ub::as_stream(stream);
+    const int grid = ub::grid_for(planes * (H >> J) * (W / 4), 256, 8);
+    if (J == 2) haar_dwt_multi<2><<<grid, 256, 0, s>>>(x, planes, (int)H, (int)W, ll, highs[0], highs[1], nullptr);
+    else haar_dwt_multi<3><<<grid, 256, 0, s>>>(x, planes, (int)H, (int)W, ll, highs[0], highs[1], highs[2]);
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+int ub200_haar_idwt2d_multi(const float *ll, const float *const *highs, int64_t planes, int64_t H, int64_t W, int J,
+                            float *out, void *stream) {
+    UB_REQUIRE(ll && out && highs && planes > 0 && H > 0 && W > 0, UB200_E_BADARG);
+    UB_REQUIRE((J == 2 || J == 3) && H % (1 << J) == 0 && W % 8 == 0 && H < (1 << 30) && W < (1 << 30), UB200_E_UNSUPPORTED);
+    bool al = ub::aligned16(out) && ub::aligned16(ll);
+    for (int j = 0; j < J; ++j) { UB_REQUIRE(highs[j], UB200_E_BADARG); al = al && ub::aligned16(highs[j]); }
+    UB_REQUIRE(al, UB200_E_UNSUPPORTED);
+    cudaStream_t s = ub::as_stream(stream);
+    const int grid = ub::grid_for(planes * (H >> J) * (W / 4), 256, 8);
+    if (J == 2) haar_idwt_multi<2><<<grid, 256, 0, s>>>(ll, highs[0], highs[1], nullptr, planes, (int)H, (int)W, out);
+    else haar_idwt_multi<3><<<grid, 256, 0, s>>>(ll, highs[0], highs[1], highs[2], planes, (int)H, (int)W, out);
     UB_LAUNCH_CHECK();
     return UB200_OK;
 }
@@ -518,7 +732,7 @@ int ub200_dwtblock_fwd(const float *x, int64_t N, int64_t C, int64_t H, int64_t 
     if (J == 0 && al && (H * W) % 4 == 0) {
         int grid = ub::grid_for(N * C * (H * W / 4), 256, 8);
         tile_vec4<<<grid, 256, 0, s>>>(x, N, (int)C, H * W / 4, (int)out_channels, out);
-    } else if (J == 1 && al && W % 8 == 0) {
+    } else if (J == 1 && al && W % 8 == 0 && !(pad_at_start() && (H & 1))) {
         int grid = ub::grid_for(N * C * ((H + 1) / 2) * (W / 8), 256, 8);
         dwtblock_j1_vec4<<<grid, 256, 0, s>>>(x, N, (int)C, (int)H, (int)W, (int)out_channels, out);
     } else {

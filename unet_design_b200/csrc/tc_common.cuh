@@ -257,8 +257,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // bf16 tensor of rank 2..4; dims / strides innermost first (strides in ELEMENTS, stride[0] == 1 is
 // implied and not passed), box per dim, swizzle span = box[0] * 2 bytes (32 / 64 / 128).
 // Returns 0 or a UB200_E_* / CUresult-derived code.
+// `elem_strides` (optional, per dim): TMA traversal stride; box[i] then counts elements actually loaded along dim i
+// (the driver's bounding box is box[i] * elem_strides[i]) -- how the stride-2 convolutions fetch every second pixel.
 int encode_bf16_tensor_map(CUtensorMap *out, const void *base, int rank, const int64_t *dims,
-                           const int64_t *strides_elems, const int *box);
+                           const int64_t *strides_elems, const int *box, const int *elem_strides = nullptr);
 
 }  // namespace tc
 }  // namespace ub

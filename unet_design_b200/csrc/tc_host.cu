@@ -31,7 +31,7 @@ EncodeTiledFn resolve_encoder() {
 }
 
 struct Key {
-    uint64_t v[14];
+    uint64_t v[18];
     bool operator==(const Key &o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
 };
 struct KeyHash {
@@ -48,7 +48,7 @@ std::unordered_map<Key, CUtensorMap, KeyHash> g_cache;
 }  // namespace
 
 int encode_bf16_tensor_map(CUtensorMap *out, const void *base, int rank, const int64_t *dims,
-                           const int64_t *strides_elems, const int *box) {
+                           const int64_t *strides_elems, const int *box, const int *elem_strides) {
     if (!out || !base || rank < 2 || rank > 4) return UB200_E_BADARG;
     Key key{};
     key.v[0] = reinterpret_cast<uint64_t>(base);
@@ -57,6 +57,7 @@ int encode_bf16_tensor_map(CUtensorMap *out, const void *base, int rank, const i
         key.v[2 + i] = (uint64_t)dims[i];
         key.v[6 + i] = (uint64_t)box[i];
         if (i + 1 < rank) key.v[10 + i] = (uint64_t)strides_elems[i];
+        key.v[14 + i] = (uint64_t)(elem_strides ? elem_strides[i] : 1);
     }
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -68,10 +69,11 @@ int encode_bf16_tensor_map(CUtensorMap *out, const void *base, int rank, const i
     cuuint64_t gdim[4], gstr[3];
     cuuint32_t gbox[4], estr[4];
     for (int i = 0; i < rank; ++i) {
-        if (dims[i] <= 0 || box[i] <= 0 || box[i] > 256) return UB200_E_UNSUPPORTED;
+        const int es = elem_strides ? elem_strides[i] : 1;
+        if (dims[i] <= 0 || box[i] <= 0 || es < 1 || es > 8 || box[i] * es > 256) return UB200_E_UNSUPPORTED;
         gdim[i] = (cuuint64_t)dims[i];
-        gbox[i] = (cuuint32_t)box[i];
-        estr[i] = 1;
+        gbox[i] = (cuuint32_t)(box[i] * es);      // bounding box; ceil(gbox / es) = box elements are loaded
+        estr[i] = (cuuint32_t)es;
         if (i + 1 < rank) {
             if (strides_elems[i] <= 0 || (strides_elems[i] * 2) % 16 != 0) return UB200_E_UNSUPPORTED;
             gstr[i] = (cuuint64_t)strides_elems[i] * 2;

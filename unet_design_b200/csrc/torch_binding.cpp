@@ -62,6 +62,46 @@ const uint64_t *i64_opt(const c10::optional<Tensor> &t) {
 }
 
 // ---------------------------------------------------------------- Haar
+
+// J-level fused analysis; returns {ll, highs_1 (finest), ..., highs_J}; empty vector if the shape is not eligible
+std::vector<Tensor> haar_dwt2d_multi(const Tensor &x, int64_t J) {
+    TORCH_CHECK(x.dim() == 4, "haar_dwt2d_multi: expected [N,C,H,W]");
+    UB_GUARD(x);
+    const float *xp = f32(x, "x");
+    const int64_t N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3);
+    if (!(J == 2 || J == 3) || H % (1 << J) != 0 || W % 8 != 0) return {};
+    std::vector<Tensor> out;
+    out.push_back(at::empty({N, C, H >> J, W >> J}, x.options()));
+    float *hp[3] = {nullptr, nullptr, nullptr};
+    for (int64_t j = 1; j <= J; ++j) {
+        out.push_back(at::empty({N, C, 3, H >> j, W >> j}, x.options()));
+        hp[j - 1] = out.back().data_ptr<float>();
+    }
+    const int rc = ub200_haar_dwt2d_multi_fwd(xp, N * C, H, W, (int)J, out[0].data_ptr<float>(), hp, cur_stream());
+    if (rc == UB200_E_UNSUPPORTED) return {};
+    check_rc(rc, "haar_dwt2d_multi_fwd");
+    return out;
+}
+
+// fused synthesis of J levels; highs finest first; returns an undefined tensor if not eligible
+Tensor haar_idwt2d_multi(const Tensor &ll, const std::vector<Tensor> &highs) {
+    UB_GUARD(ll);
+    const int64_t J = (int64_t)highs.size();
+    TORCH_CHECK(ll.dim() == 4 && (J == 2 || J == 3), "haar_idwt2d_multi: expected ll [N,C,h,w] and 2 or 3 levels");
+    const int64_t N = ll.size(0), C = ll.size(1), H = ll.size(2) << J, W = ll.size(3) << J;
+    const float *hp[3] = {nullptr, nullptr, nullptr};
+    for (int64_t j = 1; j <= J; ++j) {
+        const Tensor &h = highs[j - 1];
+        TORCH_CHECK(h.dim() == 5 && h.size(0) == N && h.size(1) == C && h.size(2) == 3 && h.size(3) == (H >> j) && h.size(4) == (W >> j),
+                    "haar_idwt2d_multi: band shape mismatch at level ", j);
+        hp[j - 1] = f32(h, "highs");
+    }
+    Tensor out = at::empty({N, C, H, W}, ll.options());
+    const int rc = ub200_haar_idwt2d_multi(f32(ll, "ll"), hp, N * C, H, W, (int)J, out.data_ptr<float>(), cur_stream());
+    if (rc == UB200_E_UNSUPPORTED) return Tensor();
+    check_rc(rc, "haar_idwt2d_multi");
+    return out;
+}
 std::tuple<Tensor, Tensor> haar_dwt2d_fwd(const Tensor &x, bool want_highs) {
     TORCH_CHECK(x.dim() == 4, "haar_dwt2d_fwd: expected [N,C,H,W]");
     UB_GUARD(x);
@@ -238,10 +278,13 @@ void gn_act_bwd(const Tensor &gy, const Tensor &x, int64_t G, const c10::optiona
 void conv_fprop(const Tensor &a, const Tensor &w, int64_t ksize, int64_t Cout, const c10::optional<Tensor> &a2,
                 const c10::optional<Tensor> &w2, const c10::optional<Tensor> &bias, const c10::optional<Tensor> &rowadd,
                 const c10::optional<Tensor> &residual, const c10::optional<Tensor> &out,
-                const c10::optional<Tensor> &out_nchw, const c10::optional<Tensor> &bias2) {
+                const c10::optional<Tensor> &out_nchw, const c10::optional<Tensor> &bias2, int64_t stride) {
     UB_GUARD(a);
     const Nhwc A = nhwc(a, "a");
+    TORCH_CHECK(stride == 1 || stride == 2, "conv_fprop: stride must be 1 or 2");
+    const int64_t Ho = (A.H + stride - 1) / stride, Wo = (A.W + stride - 1) / stride;
     ub200_conv_args args{};
+    args.stride = (int)stride;
     args.a = A.ptr; args.ld_a = A.ld; args.Cin = A.C;
     TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kBFloat16 && w.is_contiguous(), "conv_fprop: w must be packed bf16");
     const int64_t cout_pad = (Cout + 15) / 16 * 16;
@@ -250,7 +293,7 @@ void conv_fprop(const Tensor &a, const Tensor &w, int64_t ksize, int64_t Cout, c
     args.w = w.data_ptr(); args.ksize = (int)ksize;
     if (a2.has_value()) {
         const Nhwc A2 = nhwc(*a2, "a2");
-        TORCH_CHECK(A2.N == A.N && A2.H == A.H && A2.W == A.W, "conv_fprop: a2 shape mismatch");
+        TORCH_CHECK(A2.N == A.N && A2.H == Ho && A2.W == Wo, "conv_fprop: a2 shape mismatch");
         TORCH_CHECK(w2.has_value() && w2->scalar_type() == at::kBFloat16 && w2->is_contiguous() && w2->numel() == cout_pad * A2.C,
                     "conv_fprop: w2 must be packed bf16 [Cout_pad, Cin2]");
         args.a2 = A2.ptr; args.ld_a2 = A2.ld; args.Cin2 = A2.C; args.w2 = w2->data_ptr();
@@ -260,31 +303,32 @@ void conv_fprop(const Tensor &a, const Tensor &w, int64_t ksize, int64_t Cout, c
     if (rowadd.has_value()) { TORCH_CHECK(rowadd->numel() == A.N * Cout, "conv_fprop: rowadd size"); args.rowadd = f32(*rowadd, "rowadd"); }
     if (residual.has_value()) {
         const Nhwc R = nhwc(*residual, "residual");
-        TORCH_CHECK(R.N == A.N && R.H == A.H && R.W == A.W && R.C == Cout, "conv_fprop: residual shape mismatch");
+        TORCH_CHECK(R.N == A.N && R.H == Ho && R.W == Wo && R.C == Cout, "conv_fprop: residual shape mismatch");
         args.residual = R.ptr; args.ld_res = R.ld;
     }
     if (out.has_value()) {
         const Nhwc O = nhwc(*out, "out");
-        TORCH_CHECK(O.N == A.N && O.H == A.H && O.W == A.W && O.C == Cout, "conv_fprop: out shape mismatch");
+        TORCH_CHECK(O.N == A.N && O.H == Ho && O.W == Wo && O.C == Cout, "conv_fprop: out shape mismatch");
         args.out = O.ptr; args.ld_out = O.ld;
     }
     if (out_nchw.has_value()) {
-        TORCH_CHECK(out_nchw->numel() == A.N * Cout * A.H * A.W, "conv_fprop: out_nchw size");
+        TORCH_CHECK(out_nchw->numel() == A.N * Cout * Ho * Wo, "conv_fprop: out_nchw size");
         args.out_f32_nchw = f32_mut(*out_nchw, "out_nchw");
     }
     args.N = A.N; args.H = A.H; args.W = A.W; args.Cout = Cout;
     check_rc(ub200_conv_fprop(&args, cur_stream()), "conv_fprop");
 }
 
-void conv_wgrad(const Tensor &gout, const Tensor &a, int64_t ksize, const Tensor &dw) {
+void conv_wgrad(const Tensor &gout, const Tensor &a, int64_t ksize, const Tensor &dw, int64_t stride) {
     UB_GUARD(a);
     const Nhwc G = nhwc(gout, "gout"), A = nhwc(a, "a");
-    TORCH_CHECK(G.N == A.N && G.H == A.H && G.W == A.W, "conv_wgrad: shape mismatch");
+    TORCH_CHECK(stride == 1 || stride == 2, "conv_wgrad: stride must be 1 or 2");
+    TORCH_CHECK(G.N == A.N && G.H == (A.H + stride - 1) / stride && G.W == (A.W + stride - 1) / stride, "conv_wgrad: shape mismatch");
     TORCH_CHECK(dw.is_cuda() && dw.scalar_type() == at::kFloat && dw.numel() == G.C * ksize * ksize * A.C, "conv_wgrad: dw size");
     // dw is the fp32 gradient in [Cout,k,k,Cin] memory order (channels_last view of [Cout,Cin,k,k] accepted)
     TORCH_CHECK(dw.is_contiguous() || dw.is_contiguous(at::MemoryFormat::ChannelsLast), "conv_wgrad: dw must be dense");
-    check_rc(ub200_conv_wgrad(G.ptr, G.ld, A.ptr, A.ld, A.N, A.H, A.W, A.C, G.C, (int)ksize, (float *)dw.data_ptr(), cur_stream()),
-             "conv_wgrad");
+    check_rc(ub200_conv_wgrad_strided(G.ptr, G.ld, A.ptr, A.ld, A.N, A.H, A.W, A.C, G.C, (int)ksize, (int)stride,
+                                      (float *)dw.data_ptr(), cur_stream()), "conv_wgrad");
 }
 
 void chansum(const Tensor &x, const Tensor &per_sample, const c10::optional<Tensor> &total,
@@ -417,8 +461,11 @@ TORCH_LIBRARY(unet_b200, m) {
     m.def("gn_stats", &gn_stats);
     m.def("gn_act_fwd", &gn_act_fwd);
     m.def("gn_act_bwd", &gn_act_bwd);
-    m.def("conv_fprop", &conv_fprop);
-    m.def("conv_wgrad", &conv_wgrad);
+    m.def("conv_fprop(Tensor a, Tensor w, int ksize, int Cout, Tensor? a2, Tensor? w2, Tensor? bias, Tensor? rowadd, "
+          "Tensor? residual, Tensor? out, Tensor? out_nchw, Tensor? bias2, int stride=1) -> ()", &conv_fprop);
+    m.def("conv_wgrad(Tensor gout, Tensor a, int ksize, Tensor dw, int stride=1) -> ()", &conv_wgrad);
+    m.def("haar_dwt2d_multi", &haar_dwt2d_multi);
+    m.def("haar_idwt2d_multi", &haar_idwt2d_multi);
     m.def("chansum", &chansum);
     m.def("pack_conv_weight", &pack_conv_weight);
     m.def("sumsq", &sumsq);

@@ -114,10 +114,11 @@ class DownSample(nn.Module):
 
     def forward_nhwc(self, x, temb=None):
         if self.type == "conv":
-            # stride-2 pad-1 conv == every second pixel of the stride-1 conv (baseline arm only)
-            return ops.conv(x, self.main.weight, self.main.bias)[:, ::2, ::2, :].contiguous()
+            return ops.conv(x, self.main.weight, self.main.bias, stride=2)     # TMA traversal stride 2 (model.py:52)
         n, h, w, c = x.shape
-        return x.reshape(n, h // 2, 2, w // 2, 2, c).float().mean(dim=(2, 4)).to(torch.bfloat16)
+        if h % 2 or w % 2:                            # AvgPool2d floors: drop the odd row / column first
+            x = x[:, : h - h % 2, : w - w % 2, :].contiguous()
+        return ops.dwtblock_act(x, 1, c)              # LL/2 == 2x2 average (model.py:54), fwd + adjoint kernels
 
     def forward(self, x, temb):
         return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x), temb))

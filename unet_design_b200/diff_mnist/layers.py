@@ -114,8 +114,8 @@ class Downsample(nn.Module):
 
     def forward_nhwc(self, x):
         assert x.shape[3] == self.channels
-        if self.use_conv:      # stride-2 pad-1 conv == every second pixel of the stride-1 conv (baseline arm only)
-            return ops.conv(x, self.op.weight, self.op.bias)[:, ::2, ::2, :].contiguous()
+        if self.use_conv:      # nn.Conv2d(C, C, 3, stride=2, padding=1) (layers.py:238): TMA traversal stride 2
+            return ops.conv(x, self.op.weight, self.op.bias, stride=2)
         n, h, w, c = x.shape
         if h % 2 or w % 2:
             x = x[:, : h - h % 2, : w - w % 2, :].contiguous()

@@ -253,3 +253,116 @@ class UNet_wavelet(nn.Module):
         if self.multi_res_loss:
             return model_out_list, norms
         return out.type(x.dtype), norms
+
+
+# --------------------------------------------------------------------------------------------------
+# The plain guided-diffusion U-Net of diff_mnist (torch_ddpm/ddpm/models/unet/unet.py:14-311) and its factory
+# (torch_ddpm/ddpm/models/utils.py:5-53).  Same constructor / forward signatures and state_dict keys
+# (`time_embed`, `input_blocks`, `middle_block`, `output_blocks`, `out`, `out_reduce_channels`).
+# --------------------------------------------------------------------------------------------------
+from .layers import conv_nd  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+
+class UNetModel(nn.Module):
+    def __init__(self, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout=0,
+                 channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False, num_heads=1,
+                 num_heads_upsample=-1, use_scale_shift_norm=False):
+        super().__init__()
+        if num_heads_upsample == -1:
+            num_heads_upsample = num_heads
+        self.locals = [in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions, dropout, channel_mult,
+                       conv_resample, dims, num_classes, use_checkpoint, num_heads, num_heads_upsample, use_scale_shift_norm]
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.num_res_blocks, self.attention_resolutions, self.dropout = num_res_blocks, attention_resolutions, dropout
+        self.channel_mult, self.conv_resample, self.num_classes = channel_mult, conv_resample, num_classes
+        self.use_checkpoint, self.num_heads, self.num_heads_upsample = use_checkpoint, num_heads, num_heads_upsample
+        self.n_levels = len(channel_mult)
+        time_embed_dim = model_channels * 4
+        self.time_embed = nn.Sequential(linear(model_channels, time_embed_dim), SiLU(), linear(time_embed_dim, time_embed_dim))
+        if self.num_classes is not None:
+            self.label_emb = nn.Embedding(num_classes, time_embed_dim)
+        ch = model_channels * channel_mult[0]
+        input_block_chans = [ch]
+        ds = 1
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(conv_nd(dims, in_channels, ch, 3, padding=1))])
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [ResBlock(ch, time_embed_dim, dropout, out_channels=mult * model_channels, dims=dims,
+                                   use_checkpoint=use_checkpoint, use_scale_shift_norm=use_scale_shift_norm)]
+                ch = mult * model_channels
+                if ds in attention_resolutions:
+                    layers.append(AttentionBlock(ch, use_checkpoint=use_checkpoint, num_heads=num_heads))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                input_block_chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, dims=dims)))
+                input_block_chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(
+            ResBlock(ch, time_embed_dim, dropout, dims=dims, use_checkpoint=use_checkpoint,
+                     use_scale_shift_norm=use_scale_shift_norm),
+            AttentionBlock(ch, use_checkpoint=use_checkpoint, num_heads=num_heads),
+            ResBlock(ch, time_embed_dim, dropout, dims=dims, use_checkpoint=use_checkpoint,
+                     use_scale_shift_norm=use_scale_shift_norm),
+        )
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                layers = [ResBlock(ch + input_block_chans.pop(), time_embed_dim, dropout, out_channels=model_channels * mult,
+                                   dims=dims, use_checkpoint=use_checkpoint, use_scale_shift_norm=use_scale_shift_norm)]
+                ch = model_channels * mult
+                if ds in attention_resolutions:
+                    layers.append(AttentionBlock(ch, use_checkpoint=use_checkpoint, num_heads=num_heads_upsample))
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch, conv_resample, dims=dims))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(normalization(ch), SiLU())
+        self.out_reduce_channels = _conv_param(nn.Conv2d(in_channels=ch, out_channels=out_channels, kernel_size=1, stride=1))
+
+    def forward(self, x, t, y=None, n_levels_used: int = -1):
+        if n_levels_used == -1:
+            n_levels_used = len(self.channel_mult)
+        timesteps = t.squeeze()
+        if timesteps.dim() == 0:
+            timesteps = timesteps[None]
+        assert (y is not None) == (self.num_classes is not None), \
+            "must specify y if and only if the model is class-conditional"
+        emb = self.time_embed(timestep_embedding(timesteps, self.model_channels))
+        if self.num_classes is not None:
+            assert y.shape == (x.shape[0],)
+            emb = emb + self.label_emb(y)
+        hs = []
+        cin = x.shape[1]
+        h = ops.to_nhwc(x.float(), (cin + 15) // 16 * 16)
+        # the reference's slicing of the block lists for a reduced level count (unet.py:233, :241)
+        for i, module in enumerate(self.input_blocks[:n_levels_used * (self.num_res_blocks + 1) + 1 - 1]):
+            if i == 0:
+                conv = module[0]
+                w = conv.weight
+                if h.shape[3] != cin:
+                    w = F.pad(w, (0, 0, 0, 0, 0, h.shape[3] - cin))
+                h = ops.conv(h, w, conv.bias)
+            else:
+                h = module.forward_nhwc(h, emb)
+            hs.append(h)
+        h = self.middle_block.forward_nhwc(h, emb)
+        for module in self.output_blocks[:n_levels_used * (self.num_res_blocks + 1) - 1]:
+            h = module.forward_nhwc(th.cat([h, hs.pop()], dim=3), emb)
+        gn = self.out[0]
+        a = ops.gn_act(h, gn.weight, gn.bias, gn.num_groups, act="silu", eps=gn.eps)
+        return ops.conv(a, self.out_reduce_channels.weight, self.out_reduce_channels.bias, out_nchw=True).type(x.dtype)
+
+
+def get_unet(image_size, image_channels, num_channels=32, dropout=0.0, num_res_blocks=2):
+    """torch_ddpm/ddpm/models/utils.py:5-53."""
+    channel_mult = {256: (1, 1, 2, 2, 4, 4), 64: (1, 2, 3, 4), 32: (2, 2, 2, 2), 28: (1, 2, 2), 16: (1, 2, 2, 2),
+                    8: (1, 2, 2), 4: (1, 2), 2: (1, 2), 1: (1,)}.get(image_size)
+    if channel_mult is None:
+        raise ValueError(f"unsupported image size: {image_size}")
+    attention_ds = [image_size // int(res) for res in "168".split(",")]
+    return UNetModel(in_channels=image_channels, model_channels=num_channels, out_channels=image_channels,
+                     num_res_blocks=num_res_blocks, attention_resolutions=tuple(attention_ds), dropout=dropout,
+                     channel_mult=channel_mult, num_classes=None, use_checkpoint=False, num_heads=4,
+                     num_heads_upsample=-1, use_scale_shift_norm=True)

@@ -17,8 +17,8 @@ import torch
 
 from ._lib import ops as _ops
 
-ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
-_ACT = {"none": ACT_NONE, "silu": ACT_SILU, "swish": ACT_SILU, "gelu": ACT_GELU}
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_RELU = 0, 1, 2, 3
+_ACT = {"none": ACT_NONE, "silu": ACT_SILU, "swish": ACT_SILU, "gelu": ACT_GELU, "relu": ACT_RELU}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -115,17 +115,17 @@ def join_side_stream() -> None:
     _Side.keep.clear()
 
 
-def _wgrad(o, g, a, k, dst) -> None:
+def _wgrad(o, g, a, k, dst, stride: int = 1) -> None:
     n, h, w, _ = a.shape
     if _Side.enabled and a.is_cuda and n * h * w <= _Side.max_pixels:
         if _Side.stream is None:
             _Side.stream = torch.cuda.Stream(device=a.device)
         _Side.stream.wait_stream(torch.cuda.current_stream(a.device))
         with torch.cuda.stream(_Side.stream):
-            o.conv_wgrad(g, a, k, dst)
+            o.conv_wgrad(g, a, k, dst, stride)
         _Side.keep += [g, a]
     else:
-        o.conv_wgrad(g, a, k, dst)
+        o.conv_wgrad(g, a, k, dst, stride)
 
 
 def _chansum(o, g, per, tot, tot2, side_ok: bool) -> None:
@@ -288,8 +288,50 @@ class _HaarIdwtLevel(torch.autograd.Function):
         return gll, (ghighs if ctx.has_highs else None), None, None
 
 
+class _HaarDwtMulti(torch.autograd.Function):
+    """J = 2 or 3 analysis levels in one pass over x (ub200_haar_dwt2d_multi_fwd); backward is the fused synthesis."""
+
+    @staticmethod
+    def forward(ctx, x, J):
+        outs = _ops().haar_dwt2d_multi(x.contiguous(), J)
+        _count()
+        ctx.J = J
+        ctx.shapes = [o.shape for o in outs]
+        ctx.opts = (x.dtype, x.device)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        gs = [g.contiguous() if g is not None else torch.zeros(shp, dtype=ctx.opts[0], device=ctx.opts[1])
+              for g, shp in zip(grads, ctx.shapes)]
+        _count()
+        return _ops().haar_idwt2d_multi(gs[0], gs[1:]), None
+
+
+class _HaarIdwtMulti(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ll, *highs):
+        ctx.J = len(highs)
+        _count()
+        return _ops().haar_idwt2d_multi(ll.contiguous(), [h.contiguous() for h in highs])
+
+    @staticmethod
+    def backward(ctx, g):
+        outs = _ops().haar_dwt2d_multi(g.contiguous(), ctx.J)
+        _count()
+        return tuple(outs)
+
+
+def _multi_ok(h: int, w: int, J: int) -> bool:
+    return J in (2, 3) and h % (1 << J) == 0 and w % 8 == 0
+
+
 def haar_dwt2d(x: torch.Tensor, J: int):
-    """`(Yl, [Yh_1..Yh_J])`, the contract of `pytorch_wavelets.DWTForward(J, mode='zero', wave='haar')`."""
+    """`(Yl, [Yh_1..Yh_J])`, the contract of `pytorch_wavelets.DWTForward(J, mode='zero', wave='haar')`.
+    J = 2 or 3 on extents divisible by 2^J (W by 8) runs as ONE kernel; anything else level by level."""
+    if _multi_ok(x.shape[-2], x.shape[-1], J) and x.dtype == torch.float32:
+        outs = _HaarDwtMulti.apply(x, J)
+        return outs[0], list(outs[1:])
     highs = []
     ll = x
     for _ in range(J):
@@ -300,6 +342,11 @@ def haar_dwt2d(x: torch.Tensor, J: int):
 
 def haar_idwt2d(yl: torch.Tensor, highs) -> torch.Tensor:
     """`pytorch_wavelets.DWTInverse(mode='zero', wave='haar')((Yl, Yh))`; identity for an empty list."""
+    J = len(highs)
+    if J in (2, 3) and all(h is not None for h in highs) and yl.dtype == torch.float32 \
+            and _multi_ok(yl.shape[-2] << J, yl.shape[-1] << J, J) \
+            and all(tuple(h.shape[-2:]) == (yl.shape[-2] << (J - 1 - j), yl.shape[-1] << (J - 1 - j)) for j, h in enumerate(highs)):
+        return _HaarIdwtMulti.apply(yl, *highs)
     ll = yl
     for band in highs[::-1]:
         if band is None:
@@ -329,7 +376,12 @@ class _DwtBlock(torch.autograd.Function):
 
 
 def dwtblock(x: torch.Tensor, J: int, out_channels: int) -> torch.Tensor:
-    """Fused DTWBlock / DWTBlock: LL_J(x)/2^J then channel tile, NCHW fp32 (diff_cifar/model.py:270-323)."""
+    """Fused DTWBlock / DWTBlock: LL_J(x)/2^J then channel tile, NCHW fp32 (diff_cifar/model.py:270-323).
+    The kernel fuses up to 3 levels; deeper transforms (DWTForward accepts any J) compose: LL_J/2^J = (LL_3/8) applied
+    repeatedly, the zero extension of odd extents composing level by level."""
+    while J > 3:
+        x = _DwtBlock.apply(x, 3, x.shape[1])
+        J -= 3
     return _DwtBlock.apply(x, J, out_channels)
 
 
@@ -482,10 +534,11 @@ class _Conv(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, a, w, bias, rowadd, a2, w2, residual, out_nchw, out_box=None, bias2=None):
+    def forward(ctx, a, w, bias, rowadd, a2, w2, residual, out_nchw, out_box=None, bias2=None, stride=1):
         o = _ops()
         a = _dense_nhwc(a)
-        n, h, wd, cin = a.shape
+        n, hin, win, cin = a.shape
+        h, wd = (hin + stride - 1) // stride, (win + stride - 1) // stride          # output extents (padding k // 2)
         cout, k = w.shape[0], w.shape[2]
         assert w.shape[1] == cin, f"conv: weight expects {w.shape[1]} input channels, activation has {cin}"
         pk = _Registry.packed.get(_key(w))
@@ -498,23 +551,24 @@ class _Conv(torch.autograd.Function):
         res = _dense_nhwc(residual) if residual is not None else None
         if out_nchw:
             out = torch.empty((n, cout, h, wd), dtype=torch.float32, device=a.device)
-            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, None, out, bias2)
+            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, None, out, bias2, stride)
         elif out_box is not None:
             # the caller owns the destination: an NHWC view (pixel stride > Cout) inside a wider buffer, e.g. the first
             # channels of a decoder concat buffer.  Passed in a list so autograd does not treat it as an input.
             dst = out_box[0]
             assert dst.shape == (n, h, wd, cout) and dst.dtype == torch.bfloat16
-            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, dst, None, bias2)
+            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, dst, None, bias2, stride)
             out = dst.view_as(dst)
         else:
             out = torch.empty((n, h, wd, cout), dtype=torch.bfloat16, device=a.device)
-            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, out, None, bias2)
+            o.conv_fprop(a, wp, k, cout, a2d, w2p, bias, rowadd, res, out, None, bias2, stride)
         _count()
         ctx.save_for_backward(a, w, a2d, w2)
         ctx.flags = (bias is not None, rowadd is not None, residual is not None, out_nchw)
         ctx.keys = (_key(w), _key(bias), _key(w2))
         ctx.bias2_key = _key(bias2) if bias2 is not None else None
         ctx.has_bias2 = bias2 is not None
+        ctx.stride = stride
         return out
 
     @staticmethod
@@ -522,7 +576,9 @@ class _Conv(torch.autograd.Function):
         o = _ops()
         a, w, a2, w2 = ctx.saved_tensors
         has_bias, has_rowadd, has_res, out_nchw = ctx.flags
-        n, h, wd, cin = a.shape
+        stride = ctx.stride
+        n, hin, win, cin = a.shape
+        h, wd = (hin + stride - 1) // stride, (win + stride - 1) // stride
         cout, k = w.shape[0], w.shape[2]
         cpad = _pad16(cout)
         if out_nchw:      # fp32 NCHW gradient of a narrow tail: pad the channel dim for the tensor cores
@@ -552,19 +608,25 @@ class _Conv(torch.autograd.Function):
                 else:
                     w_t = w
                 wtp = pack_weight(w_t, transpose_flip=True)
-            ga = torch.empty((n, h, wd, cin), dtype=torch.bfloat16, device=a.device)
-            o.conv_fprop(g_full, wtp, k, cin, None, None, None, None, None, ga, None, None)
+            ga = torch.empty((n, hin, win, cin), dtype=torch.bfloat16, device=a.device)
+            g_in = g_full
+            if stride != 1:
+                # transposed convolution: the output gradient zero-stuffed onto the input grid, then the stride-1 kernel
+                # (the down-sampling arms are one conv per level of the baseline U-Net, not on the Multi-ResNet path)
+                g_in = torch.zeros((n, hin, win, cpad), dtype=torch.bfloat16, device=a.device)
+                g_in[:, ::stride, ::stride, :].copy_(g_full)
+            o.conv_fprop(g_in, wtp, k, cin, None, None, None, None, None, ga, None, None, 1)
             _count()
         if needs[1]:
             sink = _sink_of(kw) if cpad == cout else None
             if sink is not None:                        # accumulate straight into the gradient arena
-                _wgrad(o, g_full, a, k, sink[0])
+                _wgrad(o, g_full, a, k, sink[0], stride)
                 _count()
                 if sink[1] is not None:
                     sink[1]()
             else:
                 dw = torch.zeros((cpad, k, k, cin), dtype=torch.float32, device=w.device)
-                o.conv_wgrad(g_full, a, k, dw)
+                o.conv_wgrad(g_full, a, k, dw, stride)
                 _count(2)
                 gw = dw[:cout].permute(0, 3, 1, 2)      # [Cout,Cin,k,k] view with channels_last strides
         if (has_bias and needs[2]) or (has_rowadd and needs[3]) or want_b2:
@@ -617,14 +679,15 @@ class _Conv(torch.autograd.Function):
                     gw2 = dw2[:cout].permute(0, 3, 1, 2)
         if has_res and needs[6]:
             gres = g_valid
-        return ga, gw, gbias, growadd, ga2, gw2, gres, None, None, gbias2
+        return ga, gw, gbias, growadd, ga2, gw2, gres, None, None, gbias2, None
 
 
 def conv(a: torch.Tensor, w: torch.Tensor, bias=None, rowadd=None, a2=None, w2=None, residual=None,
-         out_nchw: bool = False, out: Optional[torch.Tensor] = None, bias2=None) -> torch.Tensor:
-    """Fused stride-1 same-padding convolution (k = 1 or 3).  `a` NHWC bf16 with C % 16 == 0.
-    `out`: optional destination, an NHWC bf16 view [N,H,W,Cout] (may be a channel slice of a wider buffer)."""
-    return _Conv.apply(a, w, bias, rowadd, a2, w2, residual, out_nchw, [out] if out is not None else None, bias2)
+         out_nchw: bool = False, out: Optional[torch.Tensor] = None, bias2=None, stride: int = 1) -> torch.Tensor:
+    """Fused convolution, k = 1 or 3, padding k // 2, stride 1 or 2 (`nn.Conv2d(C, C, 3, stride=2, padding=1)` of the
+    down-sampling arms: the TMA traversal stride fetches every second pixel).  `a` NHWC bf16 with C % 16 == 0.
+    `out`: optional destination, an NHWC bf16 view [N,Ho,Wo,Cout] (may be a channel slice of a wider buffer)."""
+    return _Conv.apply(a, w, bias, rowadd, a2, w2, residual, out_nchw, [out] if out is not None else None, bias2, stride)
 
 
 class _FusedConv1x1(torch.autograd.Function):

@@ -7,8 +7,10 @@ Blocks are POST-norm: `act(GroupNorm(1, C)(conv3x3(x)))` twice; the residual add
 ride in the fused GroupNorm+activation kernel (`addend`).  Inside a model activations are NHWC bf16; public
 `forward`s keep the reference's NCHW fp32 (and [B, T, C, H, W] for the container).
 
-Not fused (raise NotImplementedError): `up_fct='conv'` (ConvTranspose2d), activations other than gelu / silu;
-the 2015-style `Unetbase` (MaxPool / ConvTranspose) is out of scope.
+`Unetbase` (:60-141, the 2015-style baseline: Down = MaxPool2d + ConvBlock, Up = ConvTranspose2d + cat + ConvBlock)
+keeps its class, signature and state_dict; its ConvBlocks run on the kernels, MaxPool2d / ConvTranspose2d stay on
+PyTorch's channels_last bf16 kernels (SURVEY.md §2.3 allows it; they are not on the Multi-ResNet path).
+Not fused (raise NotImplementedError): `up_fct='conv'` of the `_G` family, activations tanh / sigmoid.
 """
 from __future__ import annotations
 
@@ -58,6 +60,88 @@ class ConvBlock(nn.Module):
 
     def forward(self, x: torch.Tensor):
         return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x, _pad16(x.shape[1]))))
+
+
+def _as_nchw_view(x):
+    """NHWC bf16 tensor as its NCHW (channels_last) view, for the two PyTorch ops of the baseline `Unetbase`."""
+    return ops._dense_nhwc(x).permute(0, 3, 1, 2)
+
+
+def _from_nchw_view(y):
+    return y.permute(0, 2, 3, 1)              # channels_last NCHW -> dense NHWC (ops re-pack if a backend answered NCHW)
+
+
+class Down(nn.Module):
+    """twod_unetbase.py:35-45: MaxPool2d(2) then ConvBlock."""
+
+    def __init__(self, in_channels, out_channels, num_groups=1, norm: bool = True, activation="gelu") -> None:
+        super().__init__()
+        self.conv = ConvBlock(in_channels, out_channels, num_groups, norm, activation)
+        self.pool = nn.MaxPool2d(2)
+
+    def forward_nhwc(self, x):
+        return self.conv.forward_nhwc(_from_nchw_view(self.pool(_as_nchw_view(x))))
+
+    def forward(self, x: torch.Tensor):
+        return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x)))
+
+
+class Up(nn.Module):
+    """twod_unetbase.py:48-57: ConvTranspose2d(in, in/2, 2, stride 2), cat([skip, h]), ConvBlock."""
+
+    def __init__(self, in_channels, out_channels, num_groups=1, norm: bool = True, activation="gelu") -> None:
+        super().__init__()
+        self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+        self.conv = ConvBlock(in_channels, out_channels, num_groups, norm, activation)
+
+    def forward_nhwc(self, x1, x2):
+        h = F.conv_transpose2d(_as_nchw_view(x1), self.up.weight.to(torch.bfloat16), self.up.bias.to(torch.bfloat16), stride=2)
+        h = torch.cat([x2, _from_nchw_view(h)], dim=3)
+        return self.conv.forward_nhwc(h)
+
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor):
+        return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x1), ops.to_nhwc(x2)))
+
+
+class Unetbase(nn.Module):
+    """pdearena `Unetbase` (twod_unetbase.py:60-141): forward(x[B,T,C,H,W]) -> [B, time_future, C_out, H, W]."""
+
+    def __init__(self, n_input_scalar_components: int, n_input_vector_components: int, n_output_scalar_components: int,
+                 n_output_vector_components: int, time_history: int, time_future: int, hidden_channels: int,
+                 activation="gelu") -> None:
+        super().__init__()
+        self.n_input_scalar_components = n_input_scalar_components
+        self.n_input_vector_components = n_input_vector_components
+        self.n_output_scalar_components = n_output_scalar_components
+        self.n_output_vector_components = n_output_vector_components
+        self.time_history = time_history
+        self.time_future = time_future
+        self.hidden_channels = hidden_channels
+        self.activation = resolve(activation)
+        insize = time_history * (n_input_scalar_components + n_input_vector_components * 2)
+        n_channels = hidden_channels
+        self.image_proj = ConvBlock(insize, n_channels, activation=activation)
+        self.down = nn.ModuleList([Down(n_channels * m, n_channels * 2 * m, activation=activation) for m in (1, 2, 4, 8)])
+        self.up = nn.ModuleList([Up(n_channels * 2 * m, n_channels * m, activation=activation) for m in (8, 4, 2, 1)])
+        out_channels = time_future * (n_output_scalar_components + n_output_vector_components * 2)
+        self.final = _conv_param(nn.Conv2d(n_channels, out_channels, kernel_size=(3, 3), padding=(1, 1)))
+
+    def forward(self, x):
+        assert x.dim() == 5
+        orig_shape = x.shape
+        x = x.reshape(x.size(0), -1, *x.shape[3:])
+        h = self.image_proj.forward_nhwc(ops.to_nhwc(x.float(), _pad16(x.shape[1])))
+        x1 = self.down[0].forward_nhwc(h)
+        x2 = self.down[1].forward_nhwc(x1)
+        x3 = self.down[2].forward_nhwc(x2)
+        x4 = self.down[3].forward_nhwc(x3)
+        y = self.up[0].forward_nhwc(x4, x3)
+        y = self.up[1].forward_nhwc(y, x2)
+        y = self.up[2].forward_nhwc(y, x1)
+        y = self.up[3].forward_nhwc(y, h)
+        out = _conv(y, self.final, out_nchw=True)
+        return out.reshape(orig_shape[0], -1, (self.n_output_scalar_components + self.n_output_vector_components * 2),
+                           *orig_shape[3:])
 
 
 class FullResnetConvBlock(ConvBlock):
