@@ -113,25 +113,114 @@ def cpu_train_steps(batch: int, steps: int, warmup: int):
     return times, cores
 
 
+def reference_steps(name: str, batch: int, steps: int, warmup: int, dev="cpu", autocast=False, channels_last=False):
+    """Timed train steps of the reference algorithm (oracle/ restatement) for a non-headline config: CPU baseline, or
+    the GPU library (cuDNN) comparator when `dev` is a CUDA device.  Returns (seconds per step list, cores)."""
+    import bench_configs as bc
+    built = bc.build_reference(name, dev)
+    if built is None:
+        return None, os.cpu_count() or 1
+    model, opt, loss_fn = built
+    cores = os.cpu_count() or 1
+    if str(dev) == "cpu":
+        torch.set_num_threads(cores)
+    if channels_last:
+        model = model.to(memory_format=torch.channels_last)
+    torch.manual_seed(0)
+    shapes = {"c3": ((batch, 4, 3, 128, 128), (batch, 1, 3, 128, 128)), "c3u": ((batch, 4, 3, 128, 128), (batch, 1, 3, 128, 128)),
+              "c4": ((batch, 2, 3, 96, 192), (batch, 1, 3, 96, 192)), "c5": ((batch, 2, 200, 200), (batch, 1, 200, 200))}[name]
+    x = torch.randn(*shapes[0], device=dev)
+    y = torch.randn(*shapes[1], device=dev) if name != "c5" else (torch.rand(*shapes[1], device=dev) < 0.01).float()
+    times = []
+    for i in range(warmup + steps):
+        if str(dev) != "cpu":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            loss = loss_fn(x, y)
+        loss.backward()
+        opt.step()
+        if str(dev) != "cpu":
+            torch.cuda.synchronize()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times, cores
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 16
-    times, cores = cpu_train_steps(batch, args.steps, args.warmup)
+    if args.config == "c2":
+        batch, unit, workload, metric = BATCH_PER_GPU, "images/s", WORKLOAD, METRIC
+        times, cores = cpu_train_steps(batch, args.steps, args.warmup)
+        kind, src = "port", "oracle/torch_ref.py"
+    else:
+        import bench_configs as bc
+        workload, batch, unit, _ = bc.CONFIGS[args.config]
+        metric = f"{args.config}_train_{unit.replace('/', '_per_')}"
+        times, cores = reference_steps(args.config, batch, args.steps, args.warmup)
+        kind, src = "port", "oracle/torch_ref_pde.py"
+        if times is None:
+            print(json.dumps({"impl": "reference", "unavailable": f"no fp32 restatement of config {args.config} in oracle/ "
+                              "(its CPU number is quoted from profiles/r02_reference_cpu_probe.json)"}), flush=True)
+            return
     total = sum(times)
     value = batch * len(times) / total
-    sample = f"{len(times)} steps of batch {batch} (of the 128-per-GPU workload), fp32, PyTorch CPU, {cores} threads"
+    sample = f"{len(times)} steps of the full per-GPU batch {batch}, fp32, PyTorch CPU ({src}), {cores} threads"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference algorithm on host cores via oracle/torch_ref.py (the reference is "
-                   "pure Python and /root/reference does not travel to the GPU box)"},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload, "global_batch": batch, "note": "reference algorithm on host cores via the pinned oracle "
+                   "restatement (the reference is pure Python and /root/reference does not travel to the GPU box); one process, "
+                   "whatever --gpus says"},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
+
+
+def gpu_library_baseline(dev, steps=6, warmup=3):
+    """The secondary comparator SURVEY.md 8(d) names: the reference algorithm (oracle/torch_ref.py) on the SAME GPU through
+    PyTorch's library path -- cuDNN / cuBLAS / flash-attention, channels_last + bf16 autocast, and plain fp32 (TF32 on, the
+    PyTorch default for cuDNN) -- same step definition (loss, backward, clip, Adam, EMA), eager launches."""
+    from oracle import torch_ref
+    out = {}
+    for tag, autocast, cl in (("bf16_autocast_channels_last", True, True), ("fp32_tf32_convs", False, False)):
+        torch.manual_seed(1234)
+        net = torch_ref.UNetWaveletEnc(**CFG).to(dev)
+        if cl:
+            net = net.to(memory_format=torch.channels_last)
+        trainer = torch_ref.GaussianDiffusionTrainer(net, 1e-4, 0.02, CFG["T"]).to(dev)
+        params = [p for p in net.parameters() if p.requires_grad]
+        opt = torch.optim.Adam(params, lr=2e-4, fused=True)
+        ema = [p.detach().clone() for p in params]
+        x0 = torch.rand(BATCH_PER_GPU, *IMG, device=dev) * 2 - 1
+        ev = []
+        for i in range(warmup + steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                loss, _ = trainer(x0)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            torch._foreach_mul_(ema, 0.9999)
+            torch._foreach_add_(ema, [p.detach() for p in params], alpha=1e-4)
+            e1.record()
+            if i >= warmup:
+                ev.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+        out[tag] = {"ms_per_step": ms, "images_per_s": BATCH_PER_GPU / (ms * 1e-3)}
+        del net, trainer, opt, ema, params
+        torch.cuda.empty_cache()
+    out["what"] = ("oracle/torch_ref.py (the reference's model, pinned by goldens) on this GPU via cuDNN/cuBLAS/SDPA, eager, "
+                   f"batch {BATCH_PER_GPU}, {steps} timed steps; not the product path")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -194,12 +283,12 @@ class KernelTimer:
             rows.append({"kernel": name, "n_h_w_cin_cout_k_cin2": shape, "us": 1e3 * ms, "tflops": flops / (ms * 1e-3) / 1e12})
         return rows
 
-    def summary(self):
+    def summary(self, raw=False):
         torch.cuda.synchronize()
         out = {}
         for name, flops, e0, e1, _ in self.records:
             d = out.setdefault(name, {"launches": 0, "flops": 0.0, "ms": 0.0})
-            d["launches"] += 1; d["flops"] += flops; d["ms"] += self._ms(e0, e1)
+            d["launches"] += 1; d["flops"] += flops; d["ms"] += (e0.elapsed_time(e1) if raw else self._ms(e0, e1))
         return out
 
 
@@ -330,6 +419,7 @@ def run_gpu_arm(args):
     ops.enable_side_wgrad(False)      # the events below see only the current stream: time the wgrad launches on it
     step._body(dev_batches[0])
     ksum = timer.summary()
+    ksum_raw = timer.summary(raw=True)
     if args.dump_kernels and rank == 0:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(timer.table(), open(os.path.join(ROOT, "gpurun_out", "conv_launch_table.json"), "w"), indent=0)
@@ -342,9 +432,12 @@ def run_gpu_arm(args):
         fp = ksum.get("conv_fprop", {"flops": 0.0, "ms": 1.0, "launches": 0})
         wg = ksum.get("conv_wgrad", {"flops": 0.0, "ms": 1.0, "launches": 0})
         peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
-        ach = fp["flops"] / (fp["ms"] * 1e-3) / 1e12
+        raw_fp, raw_wg = ksum_raw.get("conv_fprop", fp), ksum_raw.get("conv_wgrad", wg)
+        ach = raw_fp["flops"] / (raw_fp["ms"] * 1e-3) / 1e12                 # no event-overhead subtraction
+        ach_adj = fp["flops"] / (fp["ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "conv_fprop_kernel (fprop + dgrad launches)", "achieved": ach, "peak": peak_tf,
-                    "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "unit": "TFLOP/s", "frac": ach / peak_tf, "frac_of_burst_peak": ach / peaks["bf16_tflops"],
+                    "achieved_event_overhead_adjusted": ach_adj,
                     # DRAM bytes of the largest launch (256->256 @ 32x32, batch 128, 111 us) in the ncu --set full capture
                     # profiles/r01_ncu_full_conv_fprop_final_raw.csv: 68.3 MB read + 26.8 MB written (67 + 67 MB
                     # algorithmic; part of the output is still in L2 when the kernel ends)
@@ -353,15 +446,19 @@ def run_gpu_arm(args):
                     "launches_per_step": fp["launches"],
                     "flops_per_step": fp["flops"], "ms_per_step": fp["ms"],
                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-                    "wgrad": {"achieved": wg["flops"] / (wg["ms"] * 1e-3) / 1e12, "launches_per_step": wg["launches"],
-                              "ms_per_step": wg["ms"], "frac": wg["flops"] / (wg["ms"] * 1e-3) / 1e12 / peak_tf},
+                    "wgrad": {"achieved": raw_wg["flops"] / (raw_wg["ms"] * 1e-3) / 1e12, "launches_per_step": wg["launches"],
+                              "ms_per_step": raw_wg["ms"], "frac": raw_wg["flops"] / (raw_wg["ms"] * 1e-3) / 1e12 / peak_tf,
+                              "frac_of_burst_peak": raw_wg["flops"] / (raw_wg["ms"] * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                              "achieved_event_overhead_adjusted": wg["flops"] / (wg["ms"] * 1e-3) / 1e12},
                     "conv_share_of_step": (fp["ms"] + wg["ms"]) / (ms / args.steps)}
         haar = haar_roofline(peaks) if not args.skip_haar else None
         cpu = None
         if not args.skip_cpu:
-            times, cores = cpu_train_steps(16, 2, 1)
-            cpu = {"value": 16 * len(times) / sum(times), "unit": "images/s", "cores": cores, "kind": "port",
-                   "sample": f"{len(times)} steps of batch 16 of the same model and optimiser, fp32 PyTorch CPU (oracle/torch_ref.py)"}
+            times, cores = cpu_train_steps(BATCH_PER_GPU, 4, 1)
+            cpu = {"value": BATCH_PER_GPU * len(times) / sum(times), "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": f"{len(times)} steps of the full per-GPU batch {BATCH_PER_GPU}, same model and optimiser, fp32 PyTorch "
+                             "CPU (oracle/torch_ref.py)"}
+        lib = gpu_library_baseline(dev) if not args.skip_lib else None
         line = {
             "metric": METRIC, "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -374,7 +471,137 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,
             "dp_phases": phases,
-            "roofline": roofline, "haar_roofline": haar, "cpu_baseline": cpu,
+            "roofline": roofline, "haar_roofline": haar, "cpu_baseline": cpu, "gpu_library_baseline": lib,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def run_gpu_arm_generic(args):
+    """BASELINE configs 1, 3, 4, 5 through the model-agnostic `TrainStep` (one CUDA graph per step, same timing rules)."""
+    import torch.distributed as dist
+    import bench_configs as bc
+    from unet_design_b200 import _lib, ops
+    from unet_design_b200.train import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback in the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = measured_peaks()
+    workload, batch, unit, gflop = bc.CONFIGS[args.config]
+    built = bc.build(args.config, dev, rank)
+    model = built["model"]
+    model.train()
+    step = TrainStep(model, built["loss_fn"], use_cuda_graph=not args.no_graph, overlap_allreduce=not args.no_overlap,
+                     **built["opt"])
+    host = [built["host_batch"]() for _ in range(4)]
+    devb = [tuple(t.to(dev) for t in hb) for hb in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    l0 = ops.launches()
+    step._body(*devb[0])
+    launches_per_step = ops.launches() - l0
+    for i in range(max(args.warmup, 3)):
+        step(*devb[i % 4])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(*devb[i % 4])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(loss)
+
+    def from_host(hb):
+        out = step(*[t.to(dev, non_blocking=True) for t in hb])
+        return float(out.cpu())
+
+    for i in range(3):
+        from_host(host[i % 4])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        from_host(host[i % 4])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+
+    timer = KernelTimer(_lib.ops())
+    _lib._ops = timer
+    ops.enable_side_wgrad(False)
+    step._body(*devb[0])
+    ksum = timer.summary(raw=True)
+    _lib._ops = timer._real
+    barrier()
+
+    line = None
+    if rank == 0:
+        n = batch * world * args.steps
+        peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        fl = sum(d["flops"] for d in ksum.values())
+        tms = sum(d["ms"] for d in ksum.values())
+        ach = fl / (tms * 1e-3) / 1e12
+        value = n / (ms * 1e-3)
+        roofline = {"bound": "tensor", "kernel": "conv_fprop_kernel + conv_wgrad_kernel (all conv launches of one step)",
+                    "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "frac_of_burst_peak": ach / peaks["bf16_tflops"], "traffic": None,
+                    "launches_per_step": sum(d["launches"] for d in ksum.values()), "flops_per_step": fl, "ms_per_step": tms,
+                    "conv_share_of_step": tms / (ms / args.steps),
+                    "whole_step_tflops": gflop * 1e9 * value / world / 1e12,
+                    "whole_step_frac": gflop * 1e9 * value / world / 1e12 / peak_tf,
+                    "peak_source": peaks["source"] + ", sustained figure; CUDA events around every conv launch of one eager step, raw"}
+        cpu = lib = None
+        if not args.skip_cpu:
+            small = {"c3": 2, "c3u": 2, "c4": 2, "c5": 4}.get(args.config)
+            if small:
+                times, cores = reference_steps(args.config, small, 2, 1)
+                cpu = {"value": small * len(times) / sum(times), "unit": unit, "cores": cores, "kind": "port",
+                       "sample": f"{len(times)} steps of batch {small} (of {batch}), fp32 PyTorch CPU (oracle/torch_ref_pde.py)"}
+            else:
+                probe = os.path.join(ROOT, "profiles", "r02_reference_cpu_probe.json")
+                ref = json.load(open(probe)).get(args.config) if os.path.exists(probe) else None
+                if ref:
+                    cpu = {"value": ref["value"], "unit": unit, "cores": ref["cores"], "kind": "reference",
+                           "sample": ref["sample"] + " -- measured in the build container by tools/ref_cpu_probe.py (the reference "
+                                     "cannot travel to the GPU box), NOT on this host"}
+        if not args.skip_lib and args.config != "c1":
+            lib = {}
+            for tag, ac, cl in (("bf16_autocast_channels_last", True, True), ("fp32_tf32_convs", False, False)):
+                times, _ = reference_steps(args.config, batch, 4, 2, dev=dev, autocast=ac, channels_last=cl)
+                lib[tag] = {"ms_per_step": 1e3 * sum(times) / len(times), "samples_per_s": batch * len(times) / sum(times)}
+            lib["what"] = "oracle/torch_ref_pde.py on this GPU via cuDNN (eager), full batch; not the product path"
+        line = {
+            "metric": f"{args.config}_train_{unit.replace('/', '_per_')}", "value": value, "unit": unit, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": batch * world, "parallelism": f"dp{world}",
+                       "cuda_graph": not args.no_graph, "l2_policy": "4 rotating input batches", "loss": loss_val},
+            "clocks": clocks,
+            "e2e": {"value": n / e2e_s, "unit": unit, "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host[0]),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "gpu_library_baseline": lib,
         }
     if world > 1:
         dist.barrier()
@@ -395,9 +622,14 @@ def main():
     ap.add_argument("--profile-step", action="store_true", help="bracket one eager step with cudaProfilerStart/Stop (for ncu)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-haar", action="store_true")
+    ap.add_argument("--skip-lib", action="store_true", help="skip the cuDNN / library comparator leg")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c3u", "c4", "c5"],
+                    help="BASELINE.json config (c2 = the headline diff_cifar Multi-ResNet; c3u = the residual U-Net arm of c3)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.config != "c2":
+        run_gpu_arm_generic(args)
     else:
         run_gpu_arm(args)
 

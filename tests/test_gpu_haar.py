@@ -199,7 +199,7 @@ def test_pad_at_start_switch_matches_flipped_oracle():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = r"""
 import numpy as np, torch, sys
-sys.path.insert(0, %r)
+sys.path.insert(0, "@ROOT@")
 from oracle import haar_np
 from unet_design_b200 import ops
 haar_np.PAD_AT_END = False
@@ -219,7 +219,7 @@ for shape in [(2, 2, 25, 13), (1, 5, 7, 9), (1, 3, 200, 6), (2, 3, 8, 8)]:
         assert np.allclose(xg.grad.cpu().numpy(), haar_np.dwtblock_bwd(g.cpu().numpy(), shape, J), atol=1e-6), (shape, J)
     a = x.cuda().permute(0, 2, 3, 1).to(torch.bfloat16) if shape[1] % 8 == 0 else None
 print("pad-at-start ok")
-""" % root
+""".replace("@ROOT@", root)
     env = dict(os.environ, UB200_HAAR_PAD_AT_START="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "pad-at-start ok" in r.stdout, r.stdout + r.stderr

@@ -82,7 +82,6 @@ def test_config2_architecture_against_oracle():
     lr, _ = torch_ref.GaussianDiffusionTrainer(ref, 1e-4, 0.02, 1000).cuda().loss_from(x0, t, noise)
     lo, _ = GaussianDiffusionTrainer(net, 1e-4, 0.02, 1000).cuda().loss_from(x0, t, noise)
     lr.backward(); lo.backward()
-    assert abs(float(lo.detach()) - float(lr.detach())) < 2e-2 * abs(float(lr.detach()))
     pr = dict(ref.named_parameters())
     errs = {n: rel_err(p.grad, pr[n].grad, floor=1e-5) for n, p in net.named_parameters()
             if p.grad is not None and not n.endswith("proj_k.bias")}
@@ -98,9 +97,11 @@ def test_config2_architecture_against_oracle():
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/config2_parity.json", "w") as f:
         json.dump(report, f, indent=1)
-    # north_star bound (<= 1e-2) holds per block (tests above); through the 30-conv network bf16 noise compounds
-    assert report["grad_median"] < 3e-2 and report["conv_weight_grad_worst"] < 6e-2, report
-    assert errs[worst] < 0.1, (errs[worst], worst)
+    # observed on B200 (round 2, gpurun_out/config2_parity.json): loss 1.8e-5, gradients median 3.2e-3, p90 8.8e-3, worst
+    # 1.7e-2 (attention key projection), worst conv weight 1.3e-2.  north_star's <= 1e-2 holds for 90 % of the parameters
+    # through the whole 30-conv network; the bounds below leave 2x head-room over the observed values.
+    assert report["loss_rel"] < 1e-3 and report["grad_median"] < 1e-2 and report["grad_p90"] < 2e-2, report
+    assert report["conv_weight_grad_worst"] < 3e-2 and errs[worst] < 4e-2, report
 
 
 def test_mnist_blocks_golden():
@@ -171,3 +172,21 @@ def test_train_step_cuda_graph_tracks_eager():
     assert last_e < 0.8 * first and last_g < 0.8 * first, (first, last_e, last_g)
     assert abs(last_e - last_g) < 0.35 * max(last_e, last_g), (last_e, last_g)
     assert rel_err(pg, pe) < 0.2            # weights moved the same way (different noise draws, same data and init)
+
+
+@pytest.mark.gpu
+def test_loss_curve_tracks_the_fp32_reference_algorithm():
+    """north_star "loss curves matched": a 150-step slice of tools/loss_curve.py (the committed 1k-step curves are
+    profiles/r02_loss_curve_*.json) on a reduced-width config-2 architecture: same init, data, t and noise in both arms;
+    the raw losses of the first steps agree to bf16 accuracy and the smoothed curves stay within 5 % of each other."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import loss_curve
+    cfg = dict(T=1000, ch=64, ch_mult=[1, 2, 2], attn=[1], num_res_blocks=1, dwt_encoder=True)
+    res = loss_curve.run_curves(steps=150, batch=32, dropout=0.0, cfg=cfg, lr=2e-4, warmup=50)
+    s = loss_curve.compare(res, window=25, marks=(50, 100, 150))
+    print("loss-curve slice:", s)
+    assert s["max_rel_diff_first_20_raw_steps"] < 2e-2, s
+    assert all(m["rel_diff"] < 5e-2 for m in s["marks"]), s
+    assert s["final_b200"] < 0.8 * res["losses"]["b200"][0]          # it actually trains

@@ -39,3 +39,14 @@ def test_model_and_loss_match_reference(tag):
 def test_cifar_sampler_oracle_matches_reference():
     gc.check_cifar_sampler(torch_ref, lambda net, T, vt: torch_ref.GaussianDiffusionSampler(net, 1e-4, 0.02, T, "epsilon", vt),
                            "cpu", 1e-5)
+
+
+@pytest.mark.parametrize("fixture,wmh", [("pdearena_unetbase_g_multiresnet.pt", False), ("pdearena_unetbase_g_unet.pt", False),
+                                         ("pdearena_unetbase_g_multiresnet_mrl.pt", False),
+                                         ("wmh_unetbase_g_multiresnet.pt", True), ("wmh_unetbase_g_unet.pt", True)])
+def test_pde_family_oracle_matches_reference(fixture, wmh):
+    """oracle/torch_ref_pde.py (pdearena / wmh `Unetbase_G`) against goldens recorded from the reference's own classes;
+    the wmh fixtures store bf16-rounded tensors, hence their looser bound."""
+    from oracle import torch_ref_pde
+    tol = 1e-2 if wmh else 5e-6
+    gc.check_unetbase_g(lambda **cfg: torch_ref_pde.from_reference_cfg(cfg, wmh=wmh), fixture, "cpu", tol, 50 * tol if not wmh else 3e-2)

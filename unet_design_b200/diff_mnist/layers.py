@@ -57,7 +57,7 @@ def normalization(channels):
 
 def timestep_embedding(timesteps, dim, max_period=10000):
     half = dim // 2
-    freqs = th.exp(-math.log(max_period) * th.arange(start=0, end=half, dtype=th.float32) / half).to(device=timesteps.device)
+    freqs = th.exp(-math.log(max_period) * th.arange(start=0, end=half, dtype=th.float32, device=timesteps.device) / half)   # built on the device: no H2D copy inside a CUDA-graph capture
     args = timesteps[:, None].float() * freqs[None]
     embedding = th.cat([th.cos(args), th.sin(args)], dim=-1)
     if dim % 2:

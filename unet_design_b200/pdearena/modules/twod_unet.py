@@ -46,7 +46,7 @@ class ResidualBlock(nn.Module):
         h = ops.conv(self._norm_act(x, self.norm1), self.conv1.weight, self.conv1.bias)
         a2 = self._norm_act(h, self.norm2)
         if isinstance(self.shortcut, nn.Conv2d):
-            return ops.conv(a2, self.conv2.weight, self.conv2.bias + self.shortcut.bias, a2=x, w2=self.shortcut.weight)
+            return ops.conv(a2, self.conv2.weight, self.conv2.bias, a2=x, w2=self.shortcut.weight, bias2=self.shortcut.bias)
         return ops.conv(a2, self.conv2.weight, self.conv2.bias, residual=x)
 
     def forward(self, x: torch.Tensor):
