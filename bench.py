@@ -402,7 +402,7 @@ def run_gpu_arm(args):
     barrier()
 
     phases = None
-    if world > 1 and not args.no_graph:
+    if world > 1 and not args.no_graph and not step._graph_has_tail:
         ph = step.timed_phases(dev_batches[0])
         tp = torch.tensor(ph, device=dev, dtype=torch.float64)
         dist.all_reduce(tp, op=dist.ReduceOp.MAX)
@@ -464,7 +464,7 @@ def run_gpu_arm(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}",
-                       "cuda_graph": not args.no_graph, "allreduce": ("none" if world == 1 else ("one NCCL all-reduce of the gradient arena after the forward+backward graph" if not args.no_graph else ("tail" if args.no_overlap else "bucketed, overlapped with backward"))), "l2_policy": "4 rotating input batches; activations+weights per step "
+                       "cuda_graph": not args.no_graph, "allreduce": ("none" if world == 1 else (("bucketed NCCL all-reduces captured inside the step graph, overlapped with backward" if step._graph_has_tail else "one NCCL all-reduce of the gradient arena after the forward+backward graph") if not args.no_graph else ("tail" if args.no_overlap else "bucketed, overlapped with backward"))), "l2_policy": "4 rotating input batches; activations+weights per step "
                        "(~3 GB) exceed the 126 MB L2", "loss": loss_val},
             "clocks": clocks,
             "e2e": {"value": imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": BATCH_PER_GPU * 3 * 32 * 32 * 4,

@@ -73,6 +73,16 @@ int ub200_haar_dwt2d_multi_fwd(const float *x, int64_t planes, int64_t H, int64_
 int ub200_haar_idwt2d_multi(const float *ll, const float *const *highs, int64_t planes, int64_t H, int64_t W,
                             int J, float *out, void *stream);
 
+/* Multi-resolution loss of the staged / multi-res training arms (diff_cifar/diffusion.py:52-91, diff_mnist/main.py:375-403,
+ * pdearena pdemodel.py:222-229), fused: with t_k = LL_k(noise) / 2^k, k = 0..J (J in 1..3; H % 2^J == 0, W % 8 == 0),
+ *     sums[k] += sum (outs[k] - t_k)^2            (fp32; the caller zeroes sums and divides by numel_k for the means)
+ *     grads[k] = (2 / numel_k) * (outs[k] - t_k)  (gradient of sum_k mean-squared-error; grads or grads[k] may be NULL)
+ * in ONE pass over the noise: the target pyramid never touches memory.  outs / grads: HOST arrays of J+1 device pointers,
+ * level 0 = full resolution [planes, H, W], level k = [planes, H/2^k, W/2^k].  UB200_E_UNSUPPORTED for other shapes
+ * (the caller then builds the targets level by level with ub200_dwtblock_fwd). */
+int ub200_multires_mse_f32(const float *noise, int64_t planes, int64_t H, int64_t W, int J,
+                           const float *const *outs, float *const *grads, float *sums, void *stream);
+
 /* DTWBlock / DWTBlock forward (diff_cifar/model.py:270-323; diff_mnist/mnist_diff/models.py:29-82;
  * twod_unetbase.py:173-193; wmh/model.py:72-95), fused:  out[n,k] = LL_J(x[n, k mod C]) / 2^J,
  * k < out_channels, J in [0,3] (J = 0 is the channel tile alone).  x [N,C,H,W] f32 ->

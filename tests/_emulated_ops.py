@@ -50,6 +50,17 @@ class EmulatedOps:
     def haar_idwt2d_multi(self, ll, highs):
         return torch.from_numpy(np.ascontiguousarray(haar_np.idwt2(ll.numpy(), [h.numpy() for h in highs])))
 
+    def multires_mse(self, noise, outs, want_grads):
+        J = len(outs) - 1
+        res = [torch.zeros(J + 1)]
+        grads = []
+        for k, o in enumerate(outs):
+            t = torch.from_numpy(haar_np.dwtblock(noise.numpy(), k, None)) if k else noise
+            d = o.detach() - t
+            res[0][k] = (d * d).sum()
+            grads.append(d * (2.0 / d.numel()))
+        return res + (grads if want_grads else [])
+
     def dwtblock_fwd(self, x, J, out_channels):
         return torch.from_numpy(haar_np.dwtblock(x.numpy(), J, out_channels))
 

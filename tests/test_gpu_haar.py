@@ -223,3 +223,28 @@ print("pad-at-start ok")
     env = dict(os.environ, UB200_HAAR_PAD_AT_START="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "pad-at-start ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("shape,J", [((128, 3, 32, 32), 3), ((4, 3, 32, 32), 2), ((2, 5, 16, 24), 1), ((2, 3, 64, 64), 3)])
+def test_fused_multires_loss_matches_oracle(ops, shape, J):
+    """ub200_multires_mse_f32: target pyramid LL_k(noise)/2^k + per-level MSE + gradients in one kernel, against the
+    level-by-level numpy oracle (diff_cifar/diffusion.py:52-91 builds the same targets with DWTForward per level)."""
+    torch.manual_seed(6)
+    n, c, h, w = shape
+    noise = torch.randn(*shape)
+    outs = [torch.randn(n, c, h >> k, w >> k) for k in range(J + 1)]
+    outs_gpu = [o.cuda().requires_grad_(True) for o in outs]
+    before = ops.launches()
+    res = ops.multires_mse(noise.cuda(), outs_gpu)
+    assert res is not None and ops.launches() - before == 1
+    loss, per_level = res
+    loss.backward()
+    ref_total = 0.0
+    for k, o in enumerate(outs):
+        t = torch.from_numpy(haar_np.dwtblock(noise.numpy(), k, None)) if k else noise
+        ref = float(((o - t) ** 2).mean())
+        ref_total += ref
+        assert abs(float(per_level[k]) - ref) < 1e-5 * max(1.0, ref)
+        assert rel_err(outs_gpu[k].grad, 2.0 * (o - t) / o.numel()) < 1e-6
+    assert abs(float(loss) - ref_total) < 1e-5 * ref_total
+    assert ops.multires_mse(noise.cuda()[..., :-1], outs_gpu) is None        # odd extent: caller goes level by level

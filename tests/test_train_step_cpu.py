@@ -237,14 +237,28 @@ def test_generic_train_step_adamw_matches_torch(emulated_ops):
         assert rel_err(p, q) < 2e-2, n
 
 
-def test_bucket_overlap_is_not_armed_while_a_second_stream_carries_weight_gradients(emulated_ops, monkeypatch):
-    """with ops._Side enabled (graph mode), an eager `_body` must fall back to one post-backward all-reduce."""
+def test_bucket_allreduce_waits_for_the_second_stream(emulated_ops, monkeypatch):
+    """weight-gradient kernels run on ops._Side.stream, so a bucket's collective must wait for that
+    stream as well as for the current one before it reads the gradient arena."""
+    import contextlib
     from unet_design_b200 import ops
+    from unet_design_b200 import train as tr
     state = _init_state()
     net, step = _make(state)
-    step.world, step.overlap = 2, True
-    armed = []
-    monkeypatch.setattr(step, "_arm_buckets", lambda: armed.append(1))
-    monkeypatch.setattr(ops._Side, "enabled", True)
-    step._fwd_bwd((torch.randn(2, 3, 16, 16),), {}, True)
-    assert not armed and step._overlapped is False
+
+    class FakeStream:
+        def __init__(self):
+            self.waited = []
+
+        def wait_stream(self, s):
+            self.waited.append(s)
+
+    comm, side, cur = FakeStream(), object(), object()
+    step._buckets, step._comm_stream = [(0, 16, (0,))], comm
+    monkeypatch.setattr(ops._Side, "stream", side)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: cur)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    reduced = []
+    monkeypatch.setattr(tr.dist, "all_reduce", lambda t, op=None, group=None: reduced.append(t.numel()))
+    step._launch_allreduce(0)
+    assert comm.waited == [cur, side] and reduced == [16]

@@ -39,7 +39,9 @@ struct FpropParams {
     int Cin, cblocks, taps, kb_main, kb_extra, stages;
     uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, tbl_bytes;
     int cluster_tiles;                // (channel tile, pixel-tile group) units walked by one cluster
-    int cluster;                      // CTAs per cluster: 1, or 2 with weight multicast
+    int cluster;                      // CTAs per cluster: 1, or 2 with weight multicast / as a cta_group::2 pair
+    int pair;                         // 1: the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 per k-step (M = 256: each CTA
+                                      // its own 128-pixel tile, HALF of the weight tile staged per CTA)
     int S;                            // convolution stride (1 or 2): input pixel = S * output pixel + tap offset
     const float *bias, *bias2, *rowadd;
     const __nv_bfloat16 *residual; int64_t ld_res;
@@ -69,7 +71,9 @@ __device__ __forceinline__ void sts_u4(uint32_t addr, const uint4 &v) {
 // resolved at compile time (RES: residual tensor, TBL: bias / per-sample row through the smem table) and both
 // epilogue groups working on alternate 64-channel chunks.  The generic path keeps all runtime options and uses
 // one group.  The epilogue is what bounds the 1x1 and short-K convolutions, so its instruction count matters.
-template <int BK, bool FAST, bool RES, bool TBL>
+// PAIR is a template parameter, not a run-time flag: a kernel that contains cta_group::2 instructions can only be launched
+// with an even cluster size (cudaErrorInvalidClusterSize otherwise, measured), so the single-CTA kernels must not contain any.
+template <int BK, bool FAST, bool RES, bool TBL, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                 const __grid_constant__ CUtensorMap tm_w,
                                                                 const __grid_constant__ CUtensorMap tm_a2,
@@ -100,11 +104,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         prefetch_tmap(&tm_w);
         if (p.kb_extra) { prefetch_tmap(&tm_a2); prefetch_tmap(&tm_w2); }
         if (p.has_out) prefetch_tmap(&tm_out);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, p.cluster); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 8); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, PAIR ? 1 : p.cluster); }
+        // pair: the leader's MMA may overwrite an accumulator only when the epilogue warps of BOTH CTAs have drained it
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, PAIR ? 16 : 8); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    if (warp == 1) { if constexpr (PAIR) tmem_alloc_pair(tmem_slot, p.tmem_cols); else tmem_alloc(tmem_slot, p.tmem_cols); }
     tc_fence_before();
     __syncthreads();
     if (p.cluster > 1) cluster_sync_all();   // the peer multicasts into our smem and arrives on our barriers
@@ -122,10 +127,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         // "waterfall"); only the instructions with side effects are issued by lane 0.
         {
             const bool leader = lane == 0;
-            const uint32_t tx_bytes = (uint32_t)p.msub * 128u * BK * 2u + (uint32_t)p.BN * BK * 2u;
+            constexpr bool pair = PAIR;
+            // pair: the leader's barrier counts the bytes of both CTAs (each: its A tiles + half of the weight tile)
+            const uint32_t tx_bytes = pair ? 2u * (uint32_t)p.msub * 128u * BK * 2u + (uint32_t)p.BN * BK * 2u
+                                           : (uint32_t)p.msub * 128u * BK * 2u + (uint32_t)p.BN * BK * 2u;
             const int half = p.BN / kCluster;                 // weight rows this CTA fetches for the pair
-            const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b) + (uint32_t)(crank * half * (BK * 2));
+            const uint32_t a0 = smem_u32(smem_a), b0 = smem_u32(smem_b) + (pair ? 0u : (uint32_t)(crank * half * (BK * 2)));
             const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+            uint32_t full_lead = full0;                                       // cluster address of the leader's `full` barriers
+            if constexpr (PAIR) full_lead = mapa_rank(full0, 0);
             const int cow = crank * half;
             int s = 0; uint32_t ph = 0;                       // ring position, carried across tiles
             for (int ct = cluster_id; ct < p.cluster_tiles; ct += num_clusters) {
@@ -151,7 +161,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                         for (int c = 0; c < p.Cin; c += BK, wk += BK) {
                             const uint32_t fb = full0 + 8u * s, sa = a0 + (uint32_t)s * p.a_stage_bytes;
                             mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
-                            if (leader) {
+                            if constexpr (PAIR) {
+                                if (leader) {
+                                    const uint32_t fl = full_lead + 8u * s;
+                                    if (crank == 0) mbar_arrive_expect_tx_a(fb, tx_bytes);
+                                    tma_load_4d_pair_a(sa, &tm_a, fl, c, p.S * xa + dx, p.S * ya + dy, na);
+                                    if (p.msub == 2) tma_load_4d_pair_a(sa + 128 * BK * 2, &tm_a, fl, c, p.S * xb + dx, p.S * yb + dy, nb);
+                                    tma_load_2d_pair_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w, fl, wk, co0);
+                                }
+                            } else if (leader) {
                                 mbar_arrive_expect_tx_a(fb, tx_bytes);
                                 tma_load_4d_a(sa, &tm_a, fb, c, p.S * xa + dx, p.S * ya + dy, na);
                                 if (p.msub == 2) tma_load_4d_a(sa + 128 * BK * 2, &tm_a, fb, c, p.S * xb + dx, p.S * yb + dy, nb);
@@ -164,7 +182,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                 for (int c = 0; c < p.kb_extra * BK; c += BK) {   // K slices of the fused 1x1 term
                     const uint32_t fb = full0 + 8u * s, sa = a0 + (uint32_t)s * p.a_stage_bytes;
                     mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
-                    if (leader) {
+                    if constexpr (PAIR) {
+                        if (leader) {
+                            const uint32_t fl = full_lead + 8u * s;
+                            if (crank == 0) mbar_arrive_expect_tx_a(fb, tx_bytes);
+                            tma_load_4d_pair_a(sa, &tm_a2, fl, c, xa, ya, na);
+                            if (p.msub == 2) tma_load_4d_pair_a(sa + 128 * BK * 2, &tm_a2, fl, c, xb, yb, nb);
+                            tma_load_2d_pair_a(b0 + (uint32_t)s * p.b_stage_bytes, &tm_w2, fl, c, co0);
+                        }
+                    } else if (leader) {
                         mbar_arrive_expect_tx_a(fb, tx_bytes);
                         tma_load_4d_a(sa, &tm_a2, fb, c, xa, ya, na);
                         if (p.msub == 2) tma_load_4d_a(sa + 128 * BK * 2, &tm_a2, fb, c, xb, yb, nb);
@@ -177,9 +203,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
         }
     } else if (warp == 1) {
         // ===================== MMA issuer: warp-uniform loop, tcgen05.mma / commit issued by lane 0 =====================
-        {
+        // (pair: only the leader CTA issues; its instruction drives the tensor cores of both SMs)
+        if (!(PAIR && crank != 0)) {
             const bool leader = lane == 0;
-            const uint32_t idesc = make_idesc(128, p.BN, 0, 0);
+            constexpr bool pair = PAIR;
+            const uint32_t idesc = make_idesc(pair ? 256 : 128, p.BN, 0, 0);
             constexpr uint32_t swz = swizzle_code(BK * 2);
             constexpr uint32_t sbo = 8u * BK * 2u;
             // descriptors differ between stages / k-steps only in the 14-bit start-address field (units of 16 bytes)
@@ -197,7 +225,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                     mbar_wait_a(full0 + 8u * s, ph);
                     tc_fence_after();
                     const uint64_t da = da0 + (uint64_t)(s * a_step), db = db0 + (uint64_t)(s * b_step);
-                    if (leader) {
+                    if constexpr (PAIR) {
+                        if (leader) {
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                            if (p.msub == 2) {
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    umma_bf16_pair(d_tmem + (uint32_t)p.BN, da + (128 * BK * 2 / 16) + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                            }
+                            umma_commit_pair_a(empty0 + 8u * s, (uint16_t)0x3);                  // frees the slot in both CTAs
+                        }
+                    } else if (leader) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
                         if (p.msub == 2) {
@@ -210,12 +249,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                     }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
-                if (leader) umma_commit(tmem_full + acc);              // accumulator complete
+                if (leader) {                                          // accumulator complete (pair: in both CTAs)
+                    if constexpr (PAIR) umma_commit_pair_a(smem_u32(tmem_full + acc), (uint16_t)0x3);
+                    else umma_commit(tmem_full + acc);
+                }
             }
         }
     } else {
         // ===================== epilogue: two groups of 4 warps, one TMEM lane quadrant per warp =====================
         const int grp = (warp - 2) >> 2;              // 0: warps 2..5, 1: warps 6..9
+        // "this accumulator is drained": on the own barrier, or (pair, follower CTA) on the leader's, whose MMA thread waits
+        auto arrive_tmem_empty = [&](uint32_t a) {
+            if constexpr (PAIR) {
+                if (crank != 0) { mbar_arrive_remote(mapa_rank(smem_u32(tmem_empty + a), 0)); return; }
+            }
+            mbar_arrive(tmem_empty + a);
+        };
         if constexpr (FAST) {
             const int qd = warp & 3;
             const int r = qd * 32 + lane;             // row of the tile == TMEM lane
@@ -289,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                     if (cc + 2 >= total) {                           // this group's last tcgen05.ld of the accumulator
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tmem_empty + acc);
+                        if (lane == 0) arrive_tmem_empty(acc);
                         arrived = true;
                     }
                     if (TBL) {
@@ -326,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                 if (!arrived) {                                      // no chunk of this tile was ours: stay in lock step
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty + acc);
+                    if (lane == 0) arrive_tmem_empty(acc);
                 }
             }
             if (issuer) tma_store_wait_all();
@@ -339,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                 tc_fence_after();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_empty + acc);
+                if (lane == 0) arrive_tmem_empty(acc);
             }
         } else {
         const int qd = warp & 3;
@@ -404,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
                     if (ch == nchunks - 1 && sub == p.msub - 1) {   // all tcgen05.ld of this accumulator are done
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tmem_empty + acc);
+                        if (lane == 0) arrive_tmem_empty(acc);
                     }
 #pragma unroll
                     for (int cg = 0; cg < 4; ++cg) {
@@ -485,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_fprop_kernel(const __grid_co
     if (p.cluster > 1) cluster_sync_all();   // nobody exits while the peer may still write our smem / barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, p.tmem_cols);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
     }
 }
 
@@ -520,13 +569,13 @@ int pick_bk(int64_t Cin, int64_t Cin2) {
 
 uint32_t pow2_at_least(uint32_t v, uint32_t lo) { uint32_t r = lo; while (r < v) r <<= 1; return r; }
 
-template <int BK, bool FAST, bool RES, bool TBL>
+template <int BK, bool FAST, bool RES, bool TBL, bool PAIR = false>
 int launch_fprop(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &ta2, const CUtensorMap &tw2,
                  const CUtensorMap &tout, const FpropParams &p, int grid, size_t smem, cudaStream_t s) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_fprop_kernel<BK, FAST, RES, TBL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        attr_err = cudaFuncSetAttribute(conv_fprop_kernel<BK, FAST, RES, TBL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         227 * 1024);
     });
     if (attr_err != cudaSuccess) return (int)attr_err;
@@ -540,7 +589,7 @@ int launch_fprop(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap
     attr[0].val.clusterDim.x = (unsigned)p.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     pdl_attr(attr[1]);
     cfg.attrs = attr; cfg.numAttrs = 2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BK, FAST, RES, TBL>, ta, tw, ta2, tw2, tout, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_fprop_kernel<BK, FAST, RES, TBL, PAIR>, ta, tw, ta2, tw2, tout, p);
     if (e != cudaSuccess) return (int)e;
     UB_LAUNCH_CHECK();
     return UB200_OK;
@@ -594,16 +643,23 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     // per MAC and the k-block count per MAC); 4 accumulators x BN <= 512 TMEM columns
     static const int env_cluster = [] { const char *e = getenv("UB200_FPROP_CLUSTER"); return e ? atoi(e) : 1; }();
     static const int env_msub = [] { const char *e = getenv("UB200_FPROP_MSUB"); return e ? atoi(e) : 2; }();
-    p.cluster = env_cluster == 2 ? 2 : 1;
+    // CTA pairs (cta_group::2; UB200_FPROP_PAIR=0 switches them off).  Each CTA stages half of the weight tile, so the per-SM
+    // shared-memory fill per MMA cycle drops by a third on the 256-channel layers (the L2 -> SM ingest, ~68 B/clk measured,
+    // is what caps cta_group::1 at ~72 % tensor-active there).  Measured on B200: 256->256 @ 32x32 1410 -> 1490 TFLOP/s,
+    // 512->256 @ 8x8 820 -> 897; the 1x1 convolutions (2-12 k-blocks, epilogue-bound) LOSE 10-25 % to the pair's extra
+    // hand-shakes, so only 3x3 convolutions with a long K loop are paired.
+    static const int env_pair = [] { const char *e = getenv("UB200_FPROP_PAIR"); return e ? atoi(e) : 1; }();
+    static const int env_fast = [] { const char *e = getenv("UB200_FPROP_FAST_EPI"); return e ? atoi(e) : 1; }();
+    const bool has_tbl = (a->bias || a->bias2 || a->rowadd);
+    const bool fast = env_fast && bk == 64 && a->out && !a->out_f32_nchw && a->Cout % 64 == 0 && p.BN % 64 == 0 &&
+                      (!has_tbl || p.BNI <= kTblRows);
+    p.pair = (env_pair == 2 || (env_pair && a->ksize == 3 && a->Cin / bk * 9 >= 16)) && fast && m_tiles >= 2 ? 1 : 0;   // fast epilogue only
+    p.cluster = (env_cluster == 2 || p.pair) ? 2 : 1;
     const int kCluster = p.cluster;
     p.msub = (env_msub == 2 && p.n_tiles == 1 && p.BN <= 128 && m_tiles >= 2 * ub::kSMs) ? 2 : 1;
     const int m_units = (m_tiles + p.msub - 1) / p.msub;
     p.num_tiles = m_units * p.n_tiles;
     p.cluster_tiles = ((m_units + kCluster - 1) / kCluster) * p.n_tiles;
-    static const int env_fast = [] { const char *e = getenv("UB200_FPROP_FAST_EPI"); return e ? atoi(e) : 1; }();
-    const bool has_tbl = (a->bias || a->bias2 || a->rowadd);
-    const bool fast = env_fast && bk == 64 && a->out && !a->out_f32_nchw && a->Cout % 64 == 0 && p.BN % 64 == 0 &&
-                      (!has_tbl || p.BNI <= kTblRows);
     // generic: [BNI][BN]; fast: [2 tile parities][msub][BNI][BN]
     p.tbl_bytes = ((uint32_t)((fast ? 2 * p.msub : 1) * (p.BNI <= kTblRows ? p.BNI : 1) * p.BN * 4) + 1023u) & ~1023u;
     p.Cin = (int)a->Cin;
@@ -612,7 +668,7 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     p.kb_main = p.taps * p.cblocks;
     p.kb_extra = extra ? (int)(a->Cin2 / bk) : 0;
     p.a_stage_bytes = (uint32_t)p.msub * 128u * bk * 2u;
-    p.b_stage_bytes = ((uint32_t)p.BN * bk * 2u + 1023u) & ~1023u;
+    p.b_stage_bytes = ((uint32_t)(p.pair ? p.BN / 2 : p.BN) * bk * 2u + 1023u) & ~1023u;
     const uint32_t stage = p.a_stage_bytes + p.b_stage_bytes;
     const uint32_t budget = 227u * 1024u - 1024u - kStagingBufs * kStagingBytes - p.tbl_bytes - 256u;
     int stages = (int)(budget / stage);
@@ -668,6 +724,13 @@ extern "C" int ub200_conv_fprop(const ub200_conv_args *a, void *stream) {
     const int grid = kCluster * (p.cluster_tiles < ub::kSMs / kCluster ? p.cluster_tiles : ub::kSMs / kCluster);
     const size_t smem = 1024 + kStagingBufs * kStagingBytes + p.tbl_bytes + (size_t)stages * stage + (2 * stages + 4) * sizeof(uint64_t) + 16;
     cudaStream_t s = ub::as_stream(stream);
+    if (fast && p.pair) {
+        const bool res = a->residual != nullptr;
+        if (res) return has_tbl ? launch_fprop<64, true, true, true, true>(ta, tw, ta2, tw2, tout, p, grid, smem, s)
+                                : launch_fprop<64, true, true, false, true>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
+        return has_tbl ? launch_fprop<64, true, false, true, true>(ta, tw, ta2, tw2, tout, p, grid, smem, s)
+                       : launch_fprop<64, true, false, false, true>(ta, tw, ta2, tw2, tout, p, grid, smem, s);
+    }
     if (fast) {
         const bool res = a->residual != nullptr;
         if (res) return has_tbl ? launch_fprop<64, true, true, true>(ta, tw, ta2, tw2, tout, p, grid, smem, s)

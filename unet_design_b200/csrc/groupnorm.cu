@@ -13,8 +13,6 @@
 
 #include <cstdlib>
 #include <mutex>
-#include <algorithm>
-#include <map>
 #include <unordered_set>
 
 #include "tc_common.cuh"
@@ -38,41 +36,51 @@ __device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t ctr) {
     return make_uint4(c0, c1, c2, c3);
 }
 
-// keep-mask for the 8 channels starting at element index `elem` (multiple of 8)
+// keep-mask for the 8 channels starting at element index `elem` (multiple of 8): ONE Philox call per 8 elements, 16 random
+// bits each (the keep probability is quantised to 1/65536: p = 0.1 -> 0.100006).  These kernels are instruction-issue bound
+// and the generator is ~60 of their ~115 instructions per 16-byte chunk, so two calls per chunk (32 bits per element) cost
+// a quarter of the dropout layers' time for resolution nobody needs.
 __device__ __forceinline__ void dropout_mask8(uint64_t seed, uint64_t offset, int64_t elem, float p, float (&m)[8]) {
-    const uint32_t thr = (uint32_t)fminf(p * 4294967296.0f, 4294967295.0f);
+    const uint32_t thr = (uint32_t)fminf(p * 65536.0f, 65535.0f);
     const float keep_scale = 1.0f / (1.0f - p);
-    const uint4 r0 = philox4(seed, offset + (uint64_t)(elem >> 2));
-    const uint4 r1 = philox4(seed, offset + (uint64_t)(elem >> 2) + 1);
-    const uint32_t r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const uint4 r0 = philox4(seed, offset + (uint64_t)(elem >> 3));
+    const uint32_t r[8] = {r0.x & 0xffffu, r0.x >> 16, r0.y & 0xffffu, r0.y >> 16, r0.z & 0xffffu, r0.z >> 16, r0.w & 0xffffu, r0.w >> 16};
 #pragma unroll
     for (int u = 0; u < 8; ++u) m[u] = r[u] >= thr ? keep_scale : 0.f;
 }
 
-// sigmoid through ONE special-function op: 0.5 * tanh(z/2) + 0.5  (tanh.approx.f32, relative error 2^-11: far below
-// the bf16 rounding of every value this feeds).  These kernels are issue-bound, not bandwidth-bound, on B200.
-__device__ __forceinline__ float fast_sigmoid(float z) {
+// The activation takes the PRE-SCALED argument h = kPre<ACT> * z: the factor is folded into the per-channel affine
+// coefficients (z = x*A + B is one fma per element either way), which removes the `0.5 * z` every SiLU evaluation starts
+// with.  SiLU through ONE special-function op (tanh.approx.f32, relative error 2^-11: far below the bf16 rounding of every
+// value this feeds), with h = z/2 and t = tanh(h):
+//     silu(z)  = z * (0.5 t + 0.5)              = h * t + h                       (1 MUFU + 1 FMA)
+//     silu'(z) = s + z s (1 - s),  s = 0.5t+0.5 = 0.5 * (1 + t + h (1 - t^2))     (1 MUFU + 3 FMA)
+// These kernels are instruction-issue bound, not bandwidth bound, on B200: every instruction per element counts.
+template <int ACT>
+__device__ __forceinline__ constexpr float act_pre_scale() { return ACT == UB200_ACT_SILU ? 0.5f : 1.0f; }
+
+__device__ __forceinline__ float tanh_approx(float h) {
     float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
-    return fmaf(t, 0.5f, 0.5f);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return t;
 }
 
 template <int ACT>
-__device__ __forceinline__ float act_fwd(float z) {
-    if constexpr (ACT == UB200_ACT_SILU) return z * fast_sigmoid(z);
-    else if constexpr (ACT == UB200_ACT_GELU) return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f));
-    else if constexpr (ACT == UB200_ACT_RELU) return fmaxf(z, 0.f);
-    else return z;
+__device__ __forceinline__ float act_fwd(float h) {
+    if constexpr (ACT == UB200_ACT_SILU) return fmaf(h, tanh_approx(h), h);
+    else if constexpr (ACT == UB200_ACT_GELU) return 0.5f * h * (1.0f + erff(h * 0.70710678118654752f));
+    else if constexpr (ACT == UB200_ACT_RELU) return fmaxf(h, 0.f);
+    else return h;
 }
 template <int ACT>
-__device__ __forceinline__ float act_bwd(float z) {   // d act / d z
+__device__ __forceinline__ float act_bwd(float h) {   // d act / d z at z = h / kPre
     if constexpr (ACT == UB200_ACT_SILU) {
-        const float s = fast_sigmoid(z);
-        return fmaf(z, fmaf(-s, s, s), s);          // s + z*s*(1-s)
+        const float t = tanh_approx(h);
+        return fmaf(fmaf(h, fmaf(-t, t, 1.0f), t), 0.5f, 0.5f);
     } else if constexpr (ACT == UB200_ACT_GELU) {
-        return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+        return 0.5f * (1.0f + erff(h * 0.70710678118654752f)) + h * 0.3989422804014327f * __expf(-0.5f * h * h);
     } else if constexpr (ACT == UB200_ACT_RELU) {
-        return z > 0.f ? 1.0f : 0.f;               // torch: relu'(0) = 0
+        return h > 0.f ? 1.0f : 0.f;               // torch: relu'(0) = 0
     } else return 1.0f;
 }
 
@@ -133,7 +141,8 @@ __device__ __forceinline__ void mean_rstd(const float *stats, int64_t n, int G, 
 }
 
 __device__ __forceinline__ Coef make_coef(const Shape &sh, int64_t n, int q, const float *stats, const float *gamma,
-                                          const float *beta, const float *scale, const float *shift, float eps) {
+                                          const float *beta, const float *scale, const float *shift, float eps,
+                                          float pre) {
     Coef k;
     const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
 #pragma unroll
@@ -143,8 +152,8 @@ __device__ __forceinline__ Coef make_coef(const Shape &sh, int64_t n, int q, con
         mean_rstd(stats, n, sh.G, c / sh.cpg, inv_cnt, eps, mean, rstd);
         const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
         const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f, sf = shift ? __ldg(shift + n * sh.C + c) : 0.f;
-        k.A[u] = rstd * ga * sc;
-        k.B[u] = (be - mean * rstd * ga) * sc + sf;
+        k.A[u] = pre * (rstd * ga * sc);
+        k.B[u] = pre * ((be - mean * rstd * ga) * sc + sf);
     }
     return k;
 }
@@ -161,7 +170,7 @@ __global__ void __launch_bounds__(256) gn_act_fwd_kernel(const __nv_bfloat16 *__
     const int64_t n = blockIdx.y;
     const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
     if (r >= sh.rows) return;
-    const Coef k = make_coef(sh, n, q, stats, gamma, beta, scale, shift, eps);
+    const Coef k = make_coef(sh, n, q, stats, gamma, beta, scale, shift, eps, act_pre_scale<ACT>());
     if (DROP && off_dev) offset += __ldg(off_dev);   // device-resident counter: CUDA-graph replays draw fresh masks
     const int64_t p0 = (int64_t)blockIdx.x * sh.pix_per_cta;
     int64_t p1 = p0 + sh.pix_per_cta;
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(256, 3) gn_act_bwd_reduce(const __nv_bfloat16 
     const int64_t n = blockIdx.y;
     const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
     if (r < sh.rows) {
-        const Coef k = make_coef(sh, n, q, stats, gamma, beta, scale, shift, eps);
+        const Coef k = make_coef(sh, n, q, stats, gamma, beta, scale, shift, eps, act_pre_scale<ACT>());
         if (DROP && off_dev) offset += __ldg(off_dev);   // device-resident counter: CUDA-graph replays draw fresh masks
         float q1[8], q2[8];
 #pragma unroll
@@ -365,6 +374,7 @@ constexpr uint32_t kBulkPiece = 16384;           // dense slabs are fetched in p
 
 struct FusedShape {
     int64_t HW; int C, G, cpg, chunks, rows, cs; int64_t pix_per_cta;
+    int packed;      // backward apply pass in packed bf16x2 FMAs (UB200_GN_BWD_PACKED=0: fp32 per element)
 };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -425,157 +435,125 @@ __device__ __forceinline__ void cta_channel_sums(const float (&v)[16], float4 *s
     __syncthreads();
 }
 
-// ---- persistent form.  A cluster walks the samples n = cluster index, + number of clusters, ...; with NBUF = 2 slab
-// buffers the bulk copies of the NEXT sample are in flight while the current one is reduced, normalised and stored, so an
-// SM reads and writes HBM at the same time instead of alternating between a load phase and a store phase (the
-// one-sample-per-cluster launch ran 2-4 phase-locked waves at 35-45 % of the copy bandwidth).  With one buffer and a grid
-// of N clusters it degenerates to one sample per cluster (small layers: everything is resident at once).
-struct Persist {
-    int N, num_clusters, nbuf;          // samples, clusters in the grid, slab buffers per CTA (1 or 2)
-    uint32_t slab_bytes;                // bytes of ONE slab buffer set (all tensors of one sample's CTA share)
-};
-
 template <int ACT, bool DROP>
 __global__ void __launch_bounds__(kFusedThreads) gn_fused_fwd_kernel(
-    const __nv_bfloat16 *__restrict__ x, int64_t ld_x, FusedShape sh, Persist ps, float *__restrict__ stats_out, float eps,
+    const __nv_bfloat16 *__restrict__ x, int64_t ld_x, FusedShape sh, float *__restrict__ stats_out, float eps,
     const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ scale,
     const float *__restrict__ shift, float p_drop, uint64_t seed, uint64_t offset, const uint64_t *__restrict__ off_dev,
     const __nv_bfloat16 *__restrict__ addend, int64_t ld_add, __nv_bfloat16 *__restrict__ y, int64_t ld_y) {
     extern __shared__ __align__(128) uint8_t fsm[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int cidx = blockIdx.x / sh.cs;
+    const int64_t n = blockIdx.x / sh.cs;
     const int gpad = (2 * sh.G + 3) & ~3;
     float4 *stage = reinterpret_cast<float4 *>(fsm + 16);
     float *chan = reinterpret_cast<float *>(fsm + kFusedFixedBytes);       // [C][2] this CTA
-    float *cta_gs = chan + 2 * sh.C;                                       // [2][G][2] this CTA, one per iteration parity
-    float *tot_gs = cta_gs + 2 * gpad;                                     // [G][2] whole sample
-    uint8_t *slab0 = reinterpret_cast<uint8_t *>(tot_gs + gpad);           // [nbuf][pix][chunks] x
-    const uint32_t bar0 = tc::smem_u32(fsm);                               // two mbarriers, 8 bytes each
+    float *cta_gs = chan + 2 * sh.C;                                       // [G][2] this CTA
+    float *tot_gs = cta_gs + gpad;                                         // [G][2] whole sample
+    uint4 *xs = reinterpret_cast<uint4 *>(tot_gs + gpad);                  // [pix][chunks]
+    const uint32_t bar = tc::smem_u32(fsm);
     const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
     const int64_t p0 = (int64_t)rank * sh.pix_per_cta;
     const int npx = (int)(min(p0 + sh.pix_per_cta, sh.HW) - p0);
-    const uint32_t bytes = (uint32_t)npx * (uint32_t)sh.C * 2u;
     if (threadIdx.x == 0) {
         tc::mbar_init(reinterpret_cast<uint64_t *>(fsm), 1);
-        tc::mbar_init(reinterpret_cast<uint64_t *>(fsm) + 1, 1);
         tc::fence_barrier_init();
+        tc::mbar_arrive_expect_tx_a(bar, (uint32_t)npx * (uint32_t)sh.C * 2u);
     }
     pdl_trigger();
     __syncthreads();
     pdl_wait();
+    if (threadIdx.x < 32) fetch_slab(tc::smem_u32(xs), x + (n * sh.HW + p0) * ld_x, ld_x, sh.C, npx, bar);
     const bool active = r < sh.rows;
     if (DROP && off_dev) offset += __ldg(off_dev);
-    auto issue = [&](int64_t n, int b) {                                    // warp 0: bulk copies of sample n into buffer b
-        if (threadIdx.x == 0) tc::mbar_arrive_expect_tx_a(bar0 + 8u * b, bytes);
-        __syncwarp();
-        fetch_slab(tc::smem_u32(slab0 + (size_t)b * ps.slab_bytes), x + (n * sh.HW + p0) * ld_x, ld_x, sh.C, npx, bar0 + 8u * b);
-    };
-    if (threadIdx.x < 32 && cidx < ps.N) issue(cidx, 0);
-    const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
+    tc::mbar_wait_a(bar, 0);
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = 0.f;
     const int step = sh.rows * sh.chunks;                                   // slab entries between a thread's pixels
-    int it = 0;
-    for (int64_t n = cidx; n < ps.N; n += ps.num_clusters, ++it) {
-        const int b = ps.nbuf == 2 ? (it & 1) : 0;
-        const uint32_t parity = ps.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
-        __syncthreads();                 // the previous iteration's readers of the other buffer / the tables are done
-        if (threadIdx.x < 32) {
-            if (ps.nbuf == 2) { if (n + ps.num_clusters < ps.N) issue(n + ps.num_clusters, b ^ 1); }
-            else if (it > 0) issue(n, 0);
-        }
-        const uint4 *xs = reinterpret_cast<const uint4 *>(slab0 + (size_t)b * ps.slab_bytes);
-        tc::mbar_wait_a(bar0 + 8u * b, parity);
-        float v[16];
+    if (active) {
+        const uint4 *xp = xs + r * sh.chunks + q;
+        for (int p = r; p < npx; p += sh.rows, xp += step) {
+            float f[8];
+            unpack8(*xp, f);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = 0.f;
-        if (active) {
-            const uint4 *xp = xs + r * sh.chunks + q;
-            for (int p = r; p < npx; p += sh.rows, xp += step) {
-                float f[8];
-                unpack8(*xp, f);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { v[u] += f[u]; v[8 + u] = fmaf(f[u], f[u], v[8 + u]); }
-            }
-        }
-        cta_channel_sums(v, stage, chan, sh, q, r);
-        float *my_gs = cta_gs + (it & 1) * gpad;
-        for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) {
-            const int g = i >> 1, kind = i & 1;
-            float acc = 0.f;
-            for (int c = g * sh.cpg; c < (g + 1) * sh.cpg; ++c) acc += chan[2 * c + kind];
-            my_gs[i] = acc;
-        }
-        // ONE cluster barrier per sample: the per-CTA group sums alternate between two buffers, so a peer still reading
-        // iteration it's sums cannot collide with this CTA writing iteration it+1's (it passes the next barrier first)
-        cluster.sync();
-        for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) {
-            float acc = 0.f;
-            for (int rk = 0; rk < sh.cs; ++rk) acc += cluster.map_shared_rank(my_gs, rk)[i];
-            tot_gs[i] = acc;
-            if (rank == 0) stats_out[n * 2 * sh.G + i] = acc;               // raw sums: what the backward consumes
-        }
-        __syncthreads();
-        // y = act(x * A[c] + B[c]): the per-channel coefficients are computed ONCE per CTA (one channel per thread, one
-        // integer division each) into the `chan` table instead of eight channels redundantly in every thread
-        for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
-            const int g = c / sh.cpg;
-            const float mean = tot_gs[2 * g] * inv_cnt;
-            const float var = fmaxf(tot_gs[2 * g + 1] * inv_cnt - mean * mean, 0.f);
-            const float rstd = rsqrtf(var + eps);
-            const float g0 = gamma ? __ldg(gamma + c) : 1.f, b0 = beta ? __ldg(beta + c) : 0.f;
-            const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f;
-            const float sf = shift ? __ldg(shift + n * sh.C + c) : 0.f;
-            const float a = rstd * g0 * sc;
-            chan[c] = a;
-            chan[sh.C + c] = fmaf(-mean, a, fmaf(b0, sc, sf));
-        }
-        __syncthreads();
-        if (active) {
-            float A[8], B[8];
-            {
-                const float4 a0 = *reinterpret_cast<const float4 *>(chan + 8 * q), a1 = *reinterpret_cast<const float4 *>(chan + 8 * q + 4);
-                const float4 b0 = *reinterpret_cast<const float4 *>(chan + sh.C + 8 * q), b1 = *reinterpret_cast<const float4 *>(chan + sh.C + 8 * q + 4);
-                A[0] = a0.x; A[1] = a0.y; A[2] = a0.z; A[3] = a0.w; A[4] = a1.x; A[5] = a1.y; A[6] = a1.z; A[7] = a1.w;
-                B[0] = b0.x; B[1] = b0.y; B[2] = b0.z; B[3] = b0.w; B[4] = b1.x; B[5] = b1.y; B[6] = b1.z; B[7] = b1.w;
-            }
-            __nv_bfloat16 *yp = y + (n * sh.HW + p0 + r) * ld_y + 8 * q;
-            const __nv_bfloat16 *ap = addend ? addend + (n * sh.HW + p0 + r) * ld_add + 8 * q : nullptr;
-            const int64_t ystep = (int64_t)sh.rows * ld_y, astep = (int64_t)sh.rows * ld_add;
-            const uint4 *xp = xs + r * sh.chunks + q;
-            int64_t elem = (n * sh.HW + p0 + r) * sh.C + 8 * q;             // dropout counter index
-            const int64_t estep = (int64_t)sh.rows * sh.C;
-#pragma unroll 2
-            for (int p = r; p < npx; p += sh.rows, xp += step, yp += ystep, elem += estep) {
-                float f[8];
-                unpack8(*xp, f);
-                float m[8];
-                if (DROP) dropout_mask8(seed, offset, elem, p_drop, m);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    f[u] = act_fwd<ACT>(fmaf(f[u], A[u], B[u]));
-                    if (DROP) f[u] *= m[u];
-                }
-                if (ap) {
-                    float r8[8];
-                    unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(ap)), r8);
-                    ap += astep;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) f[u] += r8[u];
-                }
-                *reinterpret_cast<uint4 *>(yp) = pack8(f);
-            }
+            for (int u = 0; u < 8; ++u) { v[u] += f[u]; v[8 + u] = fmaf(f[u], f[u], v[8 + u]); }
         }
     }
-    cluster.sync();                      // nobody leaves while a peer may still read its group sums through DSMEM
+    cta_channel_sums(v, stage, chan, sh, q, r);
+    for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) {
+        const int g = i >> 1, kind = i & 1;
+        float acc = 0.f;
+        for (int c = g * sh.cpg; c < (g + 1) * sh.cpg; ++c) acc += chan[2 * c + kind];
+        cta_gs[i] = acc;
+    }
+    cluster.sync();
+    for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) {
+        float acc = 0.f;
+        for (int rk = 0; rk < sh.cs; ++rk) acc += cluster.map_shared_rank(cta_gs, rk)[i];
+        tot_gs[i] = acc;
+        if (rank == 0) stats_out[n * 2 * sh.G + i] = acc;                   // raw sums: what the backward consumes
+    }
+    cluster.sync();                                                         // peers are done reading our cta_gs
+    // y = act(x * A[c] + B[c]): the per-channel coefficients are computed ONCE per CTA (one channel per thread, one
+    // integer division each) into the `chan` table instead of eight channels redundantly in every thread
+    const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        const int g = c / sh.cpg;
+        const float mean = tot_gs[2 * g] * inv_cnt;
+        const float var = fmaxf(tot_gs[2 * g + 1] * inv_cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        const float g0 = gamma ? __ldg(gamma + c) : 1.f, b0 = beta ? __ldg(beta + c) : 0.f;
+        const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f;
+        const float sf = shift ? __ldg(shift + n * sh.C + c) : 0.f;
+        const float a = rstd * g0 * sc;
+        chan[c] = act_pre_scale<ACT>() * a;
+        chan[sh.C + c] = act_pre_scale<ACT>() * fmaf(-mean, a, fmaf(b0, sc, sf));
+    }
+    __syncthreads();
+    if (!active) return;
+    float A[8], B[8];
+    {
+        const float4 a0 = *reinterpret_cast<const float4 *>(chan + 8 * q), a1 = *reinterpret_cast<const float4 *>(chan + 8 * q + 4);
+        const float4 b0 = *reinterpret_cast<const float4 *>(chan + sh.C + 8 * q), b1 = *reinterpret_cast<const float4 *>(chan + sh.C + 8 * q + 4);
+        A[0] = a0.x; A[1] = a0.y; A[2] = a0.z; A[3] = a0.w; A[4] = a1.x; A[5] = a1.y; A[6] = a1.z; A[7] = a1.w;
+        B[0] = b0.x; B[1] = b0.y; B[2] = b0.z; B[3] = b0.w; B[4] = b1.x; B[5] = b1.y; B[6] = b1.z; B[7] = b1.w;
+    }
+    __nv_bfloat16 *yp = y + (n * sh.HW + p0 + r) * ld_y + 8 * q;
+    const __nv_bfloat16 *ap = addend ? addend + (n * sh.HW + p0 + r) * ld_add + 8 * q : nullptr;
+    const int64_t ystep = (int64_t)sh.rows * ld_y, astep = (int64_t)sh.rows * ld_add;
+    const uint4 *xp = xs + r * sh.chunks + q;
+    int64_t elem = (n * sh.HW + p0 + r) * sh.C + 8 * q;                     // dropout counter index
+    const int64_t estep = (int64_t)sh.rows * sh.C;
+#pragma unroll 2
+    for (int p = r; p < npx; p += sh.rows, xp += step, yp += ystep, elem += estep) {
+        float f[8];
+        unpack8(*xp, f);
+        float m[8];
+        if (DROP) dropout_mask8(seed, offset, elem, p_drop, m);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            f[u] = act_fwd<ACT>(fmaf(f[u], A[u], B[u]));
+            if (DROP) f[u] *= m[u];
+        }
+        if (ap) {
+            float r8[8];
+            unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(ap)), r8);
+            ap += astep;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) f[u] += r8[u];
+        }
+        *reinterpret_cast<uint4 *>(yp) = pack8(f);
+    }
 }
 
 // XSLAB: x is kept in shared memory next to dz (small slabs: shortest latency chain).  Otherwise only gy -> dz lives in
 // shared memory and x is streamed from HBM in the sums pass and read again (L2-resident: the same CTA touched it
-// microseconds earlier) in the apply pass, which halves the footprint.
+// microseconds earlier) in the apply pass, which halves the footprint: large layers keep 3 CTAs per SM.
 template <int ACT, bool DROP, bool XSLAB>
 __global__ void __launch_bounds__(kFusedThreads, 3) gn_fused_bwd_kernel(
     const __nv_bfloat16 *__restrict__ gy, int64_t ld_gy, const __nv_bfloat16 *__restrict__ x, int64_t ld_x, FusedShape sh,
-    Persist ps, const float *__restrict__ stats, float eps, const float *__restrict__ gamma, const float *__restrict__ beta,
+    const float *__restrict__ stats, float eps, const float *__restrict__ gamma, const float *__restrict__ beta,
     const float *__restrict__ scale, const float *__restrict__ shift, float p_drop, uint64_t seed, uint64_t offset,
     const uint64_t *__restrict__ off_dev, __nv_bfloat16 *__restrict__ gx, int64_t ld_gx, float *__restrict__ dgamma,
     float *__restrict__ dbeta, float *__restrict__ dscale, float *__restrict__ dshift,
@@ -583,224 +561,230 @@ __global__ void __launch_bounds__(kFusedThreads, 3) gn_fused_bwd_kernel(
     extern __shared__ __align__(128) uint8_t fsm[];
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int cidx = blockIdx.x / sh.cs;
+    const int64_t n = blockIdx.x / sh.cs;
     float4 *stage = reinterpret_cast<float4 *>(fsm + 16);
-    float *cta_q = reinterpret_cast<float *>(fsm + kFusedFixedBytes);      // [2][C][2] this CTA: sum dz, sum dz*x (per parity)
-    float *tot_q = cta_q + 4 * sh.C;                                       // [C][2] whole sample / coefficient tables
-    float *scr = tot_q + 2 * sh.C;                                         // [C][2] local scratch tables
-    float *sg = scr + 2 * sh.C;                                            // [G][2]
-    uint8_t *slab0 = reinterpret_cast<uint8_t *>(sg + ((2 * sh.G + 3) & ~3));
-    const uint32_t bar0 = tc::smem_u32(fsm);
+    float *cta_q = reinterpret_cast<float *>(fsm + kFusedFixedBytes);      // [C][2] this CTA: sum dz, sum dz*x
+    float *tot_q = cta_q + 2 * sh.C;                                       // [C][2] whole sample
+    float *sg = tot_q + 2 * sh.C;                                          // [G][2]
+    uint4 *slab = reinterpret_cast<uint4 *>(sg + ((2 * sh.G + 3) & ~3));
+    uint4 *ds = slab;                                                      // [pix][chunks] gy, then dz in place
+    uint4 *xs = slab + (size_t)sh.pix_per_cta * sh.chunks;                 // [pix][chunks] x (XSLAB only)
+    const uint32_t bar = tc::smem_u32(fsm);
     const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
     const bool active = r < sh.rows;
     const int64_t p0 = (int64_t)rank * sh.pix_per_cta;
     const int npx = (int)(min(p0 + sh.pix_per_cta, sh.HW) - p0);
-    const uint32_t one_bytes = (uint32_t)npx * (uint32_t)sh.C * 2u;
-    const size_t xs_off = (size_t)sh.pix_per_cta * sh.chunks * 16;         // x follows dz inside one buffer set (XSLAB)
     if (threadIdx.x == 0) {
         tc::mbar_init(reinterpret_cast<uint64_t *>(fsm), 1);
-        tc::mbar_init(reinterpret_cast<uint64_t *>(fsm) + 1, 1);
         tc::fence_barrier_init();
+        tc::mbar_arrive_expect_tx_a(bar, (XSLAB ? 2u : 1u) * (uint32_t)npx * (uint32_t)sh.C * 2u);
     }
     pdl_trigger();
     __syncthreads();
     pdl_wait();
-    if (DROP && off_dev) offset += __ldg(off_dev);
-    auto issue = [&](int64_t n, int b) {
-        if (threadIdx.x == 0) tc::mbar_arrive_expect_tx_a(bar0 + 8u * b, (XSLAB ? 2u : 1u) * one_bytes);
-        __syncwarp();
-        uint8_t *base = slab0 + (size_t)b * ps.slab_bytes;
-        fetch_slab(tc::smem_u32(base), gy + (n * sh.HW + p0) * ld_gy, ld_gy, sh.C, npx, bar0 + 8u * b);
-        if (XSLAB) fetch_slab(tc::smem_u32(base + xs_off), x + (n * sh.HW + p0) * ld_x, ld_x, sh.C, npx, bar0 + 8u * b);
-    };
-    if (threadIdx.x < 32 && cidx < ps.N) issue(cidx, 0);
+    if (threadIdx.x < 32) {
+        fetch_slab(tc::smem_u32(ds), gy + (n * sh.HW + p0) * ld_gy, ld_gy, sh.C, npx, bar);
+        if (XSLAB) fetch_slab(tc::smem_u32(xs), x + (n * sh.HW + p0) * ld_x, ld_x, sh.C, npx, bar);
+    }
+    const __nv_bfloat16 *xb = x + (n * sh.HW + p0) * ld_x + 8 * q;
     const int step = sh.rows;
     const int sstep = sh.rows * sh.chunks;                                 // slab entries between a thread's pixels
     const int64_t xstep = (int64_t)step * ld_x;
+    uint4 xa = make_uint4(0, 0, 0, 0), xc = xa;
+    if (!XSLAB && active) {                                                // first two pixels travel with the bulk copy
+        if (r < npx) xa = *reinterpret_cast<const uint4 *>(xb + (int64_t)r * ld_x);
+        if (r + step < npx) xc = *reinterpret_cast<const uint4 *>(xb + (int64_t)(r + step) * ld_x);
+    }
     const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
-    const bool has_add = gadd != nullptr;
-    const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    int it = 0;
-    for (int64_t n = cidx; n < ps.N; n += ps.num_clusters, ++it) {
-        const int b = ps.nbuf == 2 ? (it & 1) : 0;
-        const uint32_t parity = ps.nbuf == 2 ? ((it >> 1) & 1) : (it & 1);
-        __syncthreads();                 // the previous iteration's readers of the other buffer / the tables are done
-        if (threadIdx.x < 32) {
-            if (ps.nbuf == 2) { if (n + ps.num_clusters < ps.N) issue(n + ps.num_clusters, b ^ 1); }
-            else if (it > 0) issue(n, 0);
-        }
-        uint4 *ds = reinterpret_cast<uint4 *>(slab0 + (size_t)b * ps.slab_bytes);          // [pix][chunks] gy, then dz in place
-        const uint4 *xs = reinterpret_cast<const uint4 *>(slab0 + (size_t)b * ps.slab_bytes + xs_off);
-        const __nv_bfloat16 *xb = x + (n * sh.HW + p0) * ld_x + 8 * q;
-        uint4 xa = zero4, xc = zero4;
-        if (!XSLAB && active) {                                            // first two pixels travel with the bulk copy
-            if (r < npx) xa = *reinterpret_cast<const uint4 *>(xb + (int64_t)r * ld_x);
-            if (r + step < npx) xc = *reinterpret_cast<const uint4 *>(xb + (int64_t)(r + step) * ld_x);
-        }
-        // z = x * A[c] + B[c]: per-channel coefficients computed once per CTA (one channel per thread) into the tot_q area,
-        // which is not needed before the cluster reduction
-        for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
-            float mean, rstd;
-            mean_rstd(stats, n, sh.G, c / sh.cpg, inv_cnt, eps, mean, rstd);
-            const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
-            const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f, sf = shift ? __ldg(shift + n * sh.C + c) : 0.f;
-            const float a = rstd * ga * sc;
-            tot_q[c] = a;
-            tot_q[sh.C + c] = (be - mean * rstd * ga) * sc + sf;
-        }
-        __syncthreads();
-        Coef k;
-        if (active) {
-            const float4 a0 = *reinterpret_cast<const float4 *>(tot_q + 8 * q), a1 = *reinterpret_cast<const float4 *>(tot_q + 8 * q + 4);
-            const float4 b0 = *reinterpret_cast<const float4 *>(tot_q + sh.C + 8 * q), b1 = *reinterpret_cast<const float4 *>(tot_q + sh.C + 8 * q + 4);
-            k.A[0] = a0.x; k.A[1] = a0.y; k.A[2] = a0.z; k.A[3] = a0.w; k.A[4] = a1.x; k.A[5] = a1.y; k.A[6] = a1.z; k.A[7] = a1.w;
-            k.B[0] = b0.x; k.B[1] = b0.y; k.B[2] = b0.z; k.B[3] = b0.w; k.B[4] = b1.x; k.B[5] = b1.y; k.B[6] = b1.z; k.B[7] = b1.w;
-        }
-        tc::mbar_wait_a(bar0 + 8u * b, parity);
-        float v[16];
+    // z = x * A[c] + B[c]: per-channel coefficients computed once per CTA (one channel per thread) into the tot_q area,
+    // which is not needed before the cluster reduction
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        float mean, rstd;
+        mean_rstd(stats, n, sh.G, c / sh.cpg, inv_cnt, eps, mean, rstd);
+        const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
+        const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f, sf = shift ? __ldg(shift + n * sh.C + c) : 0.f;
+        const float a = rstd * ga * sc;
+        tot_q[c] = act_pre_scale<ACT>() * a;
+        tot_q[sh.C + c] = act_pre_scale<ACT>() * ((be - mean * rstd * ga) * sc + sf);
+    }
+    __syncthreads();
+    Coef k;
+    if (active) {
+        const float4 a0 = *reinterpret_cast<const float4 *>(tot_q + 8 * q), a1 = *reinterpret_cast<const float4 *>(tot_q + 8 * q + 4);
+        const float4 b0 = *reinterpret_cast<const float4 *>(tot_q + sh.C + 8 * q), b1 = *reinterpret_cast<const float4 *>(tot_q + sh.C + 8 * q + 4);
+        k.A[0] = a0.x; k.A[1] = a0.y; k.A[2] = a0.z; k.A[3] = a0.w; k.A[4] = a1.x; k.A[5] = a1.y; k.A[6] = a1.z; k.A[7] = a1.w;
+        k.B[0] = b0.x; k.B[1] = b0.y; k.B[2] = b0.z; k.B[3] = b0.w; k.B[4] = b1.x; k.B[5] = b1.y; k.B[6] = b1.z; k.B[7] = b1.w;
+    }
+    if (DROP && off_dev) offset += __ldg(off_dev);
+    tc::mbar_wait_a(bar, 0);
+    float v[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = 0.f;
-        const int64_t ebase = (n * sh.HW + p0) * sh.C + 8 * q;              // dropout counter index of pixel 0
-        auto one = [&](int p, uint4 *dp, const uint4 &xv) {
-            float f[8], g[8], m[8];
-            unpack8(xv, f);
-            unpack8(*dp, g);
-            if (DROP) dropout_mask8(seed, offset, ebase + (int64_t)p * sh.C, p_drop, m);
+    for (int u = 0; u < 16; ++u) v[u] = 0.f;
+    const int64_t ebase = (n * sh.HW + p0) * sh.C + 8 * q;                  // dropout counter index of pixel 0
+    auto one = [&](int p, uint4 *dp, const uint4 &xv) {
+        float f[8], g[8], m[8];
+        unpack8(xv, f);
+        unpack8(*dp, g);
+        if (DROP) dropout_mask8(seed, offset, ebase + (int64_t)p * sh.C, p_drop, m);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
-                if (DROP) dz *= m[u];
-                v[u] += dz; v[8 + u] = fmaf(dz, f[u], v[8 + u]);
-                g[u] = dz;
-            }
-            *dp = pack8(g);
-        };
-        if (active) {
-            uint4 *dp = ds + r * sh.chunks + q;
-            if (XSLAB) {
-                const uint4 *xp = xs + r * sh.chunks + q;
+        for (int u = 0; u < 8; ++u) {
+            float dz = g[u] * act_bwd<ACT>(fmaf(f[u], k.A[u], k.B[u]));
+            if (DROP) dz *= m[u];
+            v[u] += dz; v[8 + u] = fmaf(dz, f[u], v[8 + u]);
+            g[u] = dz;
+        }
+        *dp = pack8(g);
+    };
+    if (active) {
+        uint4 *dp = ds + r * sh.chunks + q;
+        if (XSLAB) {
+            const uint4 *xp = xs + r * sh.chunks + q;
 #pragma unroll 2
-                for (int p = r; p < npx; p += step, dp += sstep, xp += sstep) one(p, dp, *xp);
-            } else {
-                const __nv_bfloat16 *xn = xb + (int64_t)(r + 2 * step) * ld_x;  // next pair to prefetch
-                for (int p = r; p < npx; p += 2 * step, dp += 2 * sstep, xn += 2 * xstep) {   // two pixels per turn, the next two in flight
-                    uint4 na = zero4, nc = zero4;
-                    if (p + 2 * step < npx) na = *reinterpret_cast<const uint4 *>(xn);
-                    if (p + 3 * step < npx) nc = *reinterpret_cast<const uint4 *>(xn + xstep);
-                    one(p, dp, xa);
-                    if (p + step < npx) one(p + step, dp + sstep, xc);
-                    xa = na; xc = nc;
-                }
-            }
-        }
-        float *my_q = cta_q + (it & 1) * 2 * sh.C;
-        cta_channel_sums(v, stage, my_q, sh, q, r);
-        cluster.sync();                  // one barrier per sample (the per-CTA sums alternate between two buffers)
-        for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) {
-            float acc = 0.f;
-            for (int rk = 0; rk < sh.cs; ++rk) acc += cluster.map_shared_rank(my_q, rk)[i];
-            tot_q[i] = acc;
-        }
-        __syncthreads();
-        for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
-            const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
-            const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f;
-            float mean, rstd;
-            mean_rstd(stats, n, sh.G, c / sh.cpg, inv_cnt, eps, mean, rstd);
-            const float Q1 = tot_q[2 * c];
-            const float Q2 = rstd * (tot_q[2 * c + 1] - mean * Q1);                  // sum dz * xhat
-            scr[2 * c] = ga * sc * Q1;
-            scr[2 * c + 1] = ga * sc * Q2;
-            if (rank == 0) {                                                          // parameter gradients: once per sample
-                if (dgamma) atomicAdd(dgamma + c, sc * Q2);
-                if (dbeta) atomicAdd(dbeta + c, sc * Q1);
-                if (dscale) dscale[n * sh.C + c] = ga * Q2 + be * Q1;
-                if (dshift) dshift[n * sh.C + c] = Q1;
-            }
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) {
-            const int g = i >> 1, kind = i & 1;
-            float acc = 0.f;
-            // without normalisation the statistics do not depend on x: no mean-subtraction terms
-            if (stats) for (int c = g * sh.cpg; c < (g + 1) * sh.cpg; ++c) acc += scr[2 * c + kind];
-            sg[i] = acc;
-        }
-        __syncthreads();
-        // dx = dz * P[c] + x * Qc[c] + R[c]: tables again, one channel per thread (tot_q and scr are free now)
-        for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
-            const int g = c / sh.cpg;
-            float mean, rstd;
-            mean_rstd(stats, n, sh.G, g, inv_cnt, eps, mean, rstd);
-            const float m1 = sg[2 * g] * inv_cnt, m2 = sg[2 * g + 1] * inv_cnt;
-            const float gs = (gamma ? __ldg(gamma + c) : 1.f) * (scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f);
-            const float qc = -rstd * rstd * m2;
-            tot_q[c] = rstd * gs;
-            tot_q[sh.C + c] = qc;
-            scr[c] = -rstd * m1 - mean * qc;
-        }
-        __syncthreads();
-        if (active) {
-            float P[8], Qc[8], R[8];
-            {
-                const float4 *tp = reinterpret_cast<const float4 *>(tot_q + 8 * q), *tq = reinterpret_cast<const float4 *>(tot_q + sh.C + 8 * q);
-                const float4 *tr = reinterpret_cast<const float4 *>(scr + 8 * q);
-                const float4 p0v = tp[0], p1v = tp[1], q0v = tq[0], q1v = tq[1], r0v = tr[0], r1v = tr[1];
-                P[0] = p0v.x; P[1] = p0v.y; P[2] = p0v.z; P[3] = p0v.w; P[4] = p1v.x; P[5] = p1v.y; P[6] = p1v.z; P[7] = p1v.w;
-                Qc[0] = q0v.x; Qc[1] = q0v.y; Qc[2] = q0v.z; Qc[3] = q0v.w; Qc[4] = q1v.x; Qc[5] = q1v.y; Qc[6] = q1v.z; Qc[7] = q1v.w;
-                R[0] = r0v.x; R[1] = r0v.y; R[2] = r0v.z; R[3] = r0v.w; R[4] = r1v.x; R[5] = r1v.y; R[6] = r1v.z; R[7] = r1v.w;
-            }
-            // gadd: a second gradient of x (the ResBlock's shortcut / residual branch), summed here instead of by a separate add
-            auto fin = [&](const uint4 *dp, __nv_bfloat16 *op, const uint4 &xv, const uint4 &av) {
-                float f[8], d[8];
-                unpack8(xv, f);
-                unpack8(*dp, d);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) d[u] = fmaf(d[u], P[u], fmaf(f[u], Qc[u], R[u]));
-                if (has_add) {
-                    float a[8];
-                    unpack8(av, a);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) d[u] += a[u];
-                }
-                *reinterpret_cast<uint4 *>(op) = pack8(d);
-            };
-            const uint4 *dp = ds + r * sh.chunks + q;
-            __nv_bfloat16 *op = gx + (n * sh.HW + p0 + r) * ld_gx + 8 * q;
-            const __nv_bfloat16 *ap = has_add ? gadd + (n * sh.HW + p0 + r) * ld_gadd + 8 * q : nullptr;
-            const int64_t ostep = (int64_t)step * ld_gx, astep = (int64_t)step * ld_gadd;
-            if (XSLAB) {
-                const uint4 *xp = xs + r * sh.chunks + q;
-                for (int p = r; p < npx; p += 2 * step, dp += 2 * sstep, xp += 2 * sstep, op += 2 * ostep) {
-                    const bool two = p + step < npx;
-                    uint4 a0 = zero4, a1 = zero4;
-                    if (has_add) {
-                        a0 = ld_stream_u4(reinterpret_cast<const uint4 *>(ap));
-                        if (two) a1 = ld_stream_u4(reinterpret_cast<const uint4 *>(ap + astep));
-                        ap += 2 * astep;
-                    }
-                    fin(dp, op, *xp, a0);
-                    if (two) fin(dp + sstep, op + ostep, xp[sstep], a1);
-                }
-            } else {
-                const __nv_bfloat16 *xp = xb + (int64_t)r * ld_x;
-                for (int p = r; p < npx; p += 4 * step, dp += 4 * sstep, xp += 4 * xstep, op += 4 * ostep) {   // four L2 reads in flight
-                    uint4 t[4], a[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (p + j * step < npx) {
-                            t[j] = *reinterpret_cast<const uint4 *>(xp + j * xstep);
-                            a[j] = has_add ? ld_stream_u4(reinterpret_cast<const uint4 *>(ap + j * astep)) : zero4;
-                        }
-                    if (has_add) ap += 4 * astep;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (p + j * step < npx) fin(dp + j * sstep, op + j * ostep, t[j], a[j]);
-                }
+            for (int p = r; p < npx; p += step, dp += sstep, xp += sstep) one(p, dp, *xp);
+        } else {
+            const __nv_bfloat16 *xn = xb + (int64_t)(r + 2 * step) * ld_x;  // next pair to prefetch
+            for (int p = r; p < npx; p += 2 * step, dp += 2 * sstep, xn += 2 * xstep) {   // two pixels per turn, the next two in flight
+                uint4 na = make_uint4(0, 0, 0, 0), nc = na;
+                if (p + 2 * step < npx) na = *reinterpret_cast<const uint4 *>(xn);
+                if (p + 3 * step < npx) nc = *reinterpret_cast<const uint4 *>(xn + xstep);
+                one(p, dp, xa);
+                if (p + step < npx) one(p + step, dp + sstep, xc);
+                xa = na; xc = nc;
             }
         }
     }
-    cluster.sync();                      // nobody leaves while a peer may still read its channel sums through DSMEM
+    cta_channel_sums(v, stage, cta_q, sh, q, r);
+    cluster.sync();
+    for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) {
+        float acc = 0.f;
+        for (int rk = 0; rk < sh.cs; ++rk) acc += cluster.map_shared_rank(cta_q, rk)[i];
+        tot_q[i] = acc;
+    }
+    cluster.sync();                                                         // peers are done reading our cta_q: reuse it
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
+        const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f;
+        float mean, rstd;
+        mean_rstd(stats, n, sh.G, c / sh.cpg, inv_cnt, eps, mean, rstd);
+        const float Q1 = tot_q[2 * c];
+        const float Q2 = rstd * (tot_q[2 * c + 1] - mean * Q1);                  // sum dz * xhat
+        cta_q[2 * c] = ga * sc * Q1;
+        cta_q[2 * c + 1] = ga * sc * Q2;
+        if (rank == 0) {                                                          // parameter gradients: once per sample
+            if (dgamma) atomicAdd(dgamma + c, sc * Q2);
+            if (dbeta) atomicAdd(dbeta + c, sc * Q1);
+            if (dscale) dscale[n * sh.C + c] = ga * Q2 + be * Q1;
+            if (dshift) dshift[n * sh.C + c] = Q1;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) {
+        const int g = i >> 1, kind = i & 1;
+        float acc = 0.f;
+        // without normalisation the statistics do not depend on x: no mean-subtraction terms
+        if (stats) for (int c = g * sh.cpg; c < (g + 1) * sh.cpg; ++c) acc += cta_q[2 * c + kind];
+        sg[i] = acc;
+    }
+    __syncthreads();
+    // dx = dz * P[c] + x * Qc[c] + R[c]: tables again, one channel per thread (tot_q and cta_q are free now)
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        const int g = c / sh.cpg;
+        float mean, rstd;
+        mean_rstd(stats, n, sh.G, g, inv_cnt, eps, mean, rstd);
+        const float m1 = sg[2 * g] * inv_cnt, m2 = sg[2 * g + 1] * inv_cnt;
+        const float gs = (gamma ? __ldg(gamma + c) : 1.f) * (scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f);
+        const float qc = -rstd * rstd * m2;
+        tot_q[c] = rstd * gs;
+        tot_q[sh.C + c] = qc;
+        cta_q[c] = -rstd * m1 - mean * qc;
+    }
+    __syncthreads();
+    if (!active) return;
+    float P[8], Qc[8], R[8];
+    {
+        const float4 *tp = reinterpret_cast<const float4 *>(tot_q + 8 * q), *tq = reinterpret_cast<const float4 *>(tot_q + sh.C + 8 * q);
+        const float4 *tr = reinterpret_cast<const float4 *>(cta_q + 8 * q);
+        const float4 p0v = tp[0], p1v = tp[1], q0v = tq[0], q1v = tq[1], r0v = tr[0], r1v = tr[1];
+        P[0] = p0v.x; P[1] = p0v.y; P[2] = p0v.z; P[3] = p0v.w; P[4] = p1v.x; P[5] = p1v.y; P[6] = p1v.z; P[7] = p1v.w;
+        Qc[0] = q0v.x; Qc[1] = q0v.y; Qc[2] = q0v.z; Qc[3] = q0v.w; Qc[4] = q1v.x; Qc[5] = q1v.y; Qc[6] = q1v.z; Qc[7] = q1v.w;
+        R[0] = r0v.x; R[1] = r0v.y; R[2] = r0v.z; R[3] = r0v.w; R[4] = r1v.x; R[5] = r1v.y; R[6] = r1v.z; R[7] = r1v.w;
+    }
+    // gadd: a second gradient of x (the ResBlock's shortcut / residual branch), summed here instead of by a separate add
+    const bool has_add = gadd != nullptr;
+    // The apply pass is instruction-issue bound (unpack + 2 fma + pack per element in fp32: ~44 instructions per 16-byte
+    // chunk).  dx = dz*P + (x*Qc + (R + gadd)) as packed bf16x2 FMAs (fp32 inside the FMA, one rounding each) is 8-12:
+    // the inputs and the output are bf16 anyway; the per-channel coefficients lose 2^-9 relative, within the bf16 bound.
+    __nv_bfloat162 P2[4], Q2[4], R2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        P2[u] = __floats2bfloat162_rn(P[2 * u], P[2 * u + 1]);
+        Q2[u] = __floats2bfloat162_rn(Qc[2 * u], Qc[2 * u + 1]);
+        R2[u] = __floats2bfloat162_rn(R[2 * u], R[2 * u + 1]);
+    }
+    const bool packed = sh.packed != 0;
+    auto fin = [&](const uint4 *dp, __nv_bfloat16 *op, const uint4 &xv, const uint4 &av) {
+        if (packed) {
+            const uint4 dv = *dp;
+            const __nv_bfloat162 *x2 = reinterpret_cast<const __nv_bfloat162 *>(&xv);
+            const __nv_bfloat162 *d2 = reinterpret_cast<const __nv_bfloat162 *>(&dv);
+            const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&av);
+            uint4 out;
+            __nv_bfloat162 *o2 = reinterpret_cast<__nv_bfloat162 *>(&out);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const __nv_bfloat162 rr = has_add ? __hadd2(R2[u], a2[u]) : R2[u];
+                o2[u] = __hfma2(d2[u], P2[u], __hfma2(x2[u], Q2[u], rr));
+            }
+            *reinterpret_cast<uint4 *>(op) = out;
+            return;
+        }
+        float f[8], d[8];
+        unpack8(xv, f);
+        unpack8(*dp, d);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = fmaf(d[u], P[u], fmaf(f[u], Qc[u], R[u]));
+        if (has_add) {
+            float a[8];
+            unpack8(av, a);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d[u] += a[u];
+        }
+        *reinterpret_cast<uint4 *>(op) = pack8(d);
+    };
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    const uint4 *dp = ds + r * sh.chunks + q;
+    __nv_bfloat16 *op = gx + (n * sh.HW + p0 + r) * ld_gx + 8 * q;
+    const __nv_bfloat16 *ap = has_add ? gadd + (n * sh.HW + p0 + r) * ld_gadd + 8 * q : nullptr;
+    const int64_t ostep = (int64_t)step * ld_gx, astep = (int64_t)step * ld_gadd;
+    if (XSLAB) {
+        const uint4 *xp = xs + r * sh.chunks + q;
+        for (int p = r; p < npx; p += 2 * step, dp += 2 * sstep, xp += 2 * sstep, op += 2 * ostep) {
+            const bool two = p + step < npx;
+            uint4 a0 = zero4, a1 = zero4;
+            if (has_add) {
+                a0 = ld_stream_u4(reinterpret_cast<const uint4 *>(ap));
+                if (two) a1 = ld_stream_u4(reinterpret_cast<const uint4 *>(ap + astep));
+                ap += 2 * astep;
+            }
+            fin(dp, op, *xp, a0);
+            if (two) fin(dp + sstep, op + ostep, xp[sstep], a1);
+        }
+    } else {
+        const __nv_bfloat16 *xp = xb + (int64_t)r * ld_x;
+        for (int p = r; p < npx; p += 4 * step, dp += 4 * sstep, xp += 4 * xstep, op += 4 * ostep) {   // four L2 reads in flight
+            uint4 t[4], a[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (p + j * step < npx) {
+                    t[j] = *reinterpret_cast<const uint4 *>(xp + j * xstep);
+                    a[j] = has_add ? ld_stream_u4(reinterpret_cast<const uint4 *>(ap + j * astep)) : zero4;
+                }
+            if (has_add) ap += 4 * astep;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (p + j * step < npx) fin(dp + j * sstep, op + j * ostep, t[j], a[j]);
+        }
+    }
 }
 
 // gx += gadd (the multi-pass fallback of the fused backward's second-gradient input)
@@ -820,50 +804,36 @@ __global__ void __launch_bounds__(256) add_rows_kernel(__nv_bfloat16 *__restrict
     }
 }
 
-// cluster size / smem plan for the fused kernels.  `one`: a single slab buffer per CTA (one sample per cluster, or a
-// persistent walk without prefetch); `two`: two buffers (persistent, the next sample's copy overlaps the current sample).
-struct Cand { FusedShape sh; size_t smem; uint32_t slab; bool ok; };
-
-bool fill_shape(int64_t N, int64_t HW, int64_t C, int G, FusedShape &sh) {
+// cluster size / smem plan for the fused kernels; returns false when the slab does not fit
+bool plan_fused(int64_t N, int64_t HW, int64_t C, int G, int tensors, size_t extra_floats, FusedShape &sh, size_t &smem,
+                int only_single_cta = 0) {
+    static const bool enabled = [] { const char *e = getenv("UB200_GN_FUSED"); return !(e && e[0] == '0'); }();   // A/B switch
+    if (!enabled) return false;
     if (C % 8 != 0 || C % G != 0 || C > 4 * kFusedThreads || N * 8 > 2147483647LL) return false;
     sh.HW = HW; sh.C = (int)C; sh.G = G; sh.cpg = (int)(C / G); sh.chunks = (int)(C / 8);
     sh.rows = (kFusedThreads / sh.chunks) & ~1;      // even, >= 2: the fold staging holds rows/2 * chunks <= 128 entries
-    return true;
-}
-
-void plan_fused(int64_t N, int64_t HW, int64_t C, int G, int tensors, size_t extra_floats, Cand &one, Cand &two,
-                int only_single_cta = 0) {
-    static const bool enabled = [] { const char *e = getenv("UB200_GN_FUSED"); return !(e && e[0] == '0'); }();   // A/B switches
-    static const bool persist = [] { const char *e = getenv("UB200_GN_PERSIST"); return !(e && e[0] == '0'); }();
-    one.ok = two.ok = false;
-    if (!enabled || !fill_shape(N, HW, C, G, one.sh)) return;
-    two.sh = one.sh;
+    static const int packed = [] { const char *e = getenv("UB200_GN_BWD_PACKED"); return (e && e[0] == '0') ? 0 : 1; }();
+    sh.packed = packed;
     const size_t fixed = (size_t)kFusedFixedBytes + extra_floats * 4;
     if (only_single_cta) {
-        const size_t slab = (size_t)tensors * HW * C * 2;
-        if (fixed + slab > 73 * 1024) return;
-        one.sh.cs = 1; one.sh.pix_per_cta = HW; one.smem = fixed + slab; one.slab = (uint32_t)slab; one.ok = true;
-        if (persist && fixed + 2 * slab <= 110 * 1024) { two = one; two.smem = fixed + 2 * slab; }
-        return;
+        const size_t bytes = fixed + (size_t)tensors * HW * C * 2;
+        if (bytes > 73 * 1024) return false;
+        sh.cs = 1; sh.pix_per_cta = HW; smem = bytes;
+        return true;
     }
     // (larger clusters were measured: 16x16x256 forward 18.4 us at the smallest fitting cluster vs 24.6 us at the largest,
     // and non-portable 16-CTA clusters are slower still -- cluster barriers and DSMEM reads cost more than balance gains)
     // smallest cluster whose per-CTA slab leaves room for 3, else 2 CTAs per SM; at 8 CTAs accept one per SM
     static const size_t limits[3] = {73 * 1024, 110 * 1024, 220 * 1024};
-    for (int nb = 1; nb <= (persist ? 2 : 1); ++nb) {
-        Cand &c = nb == 1 ? one : two;
-        for (int pass = 0; pass < 3 && !c.ok; ++pass) {
-            for (int cs = (pass == 2 ? 8 : 1); cs <= 8; cs *= 2) {
-                const int64_t ppc = (HW + cs - 1) / cs;
-                if (cs > 1 && (int64_t)(cs - 1) * ppc >= HW) continue;                 // would leave an empty CTA
-                const size_t slab = (size_t)tensors * ppc * C * 2;
-                if (fixed + nb * slab <= limits[pass]) {
-                    c.sh.cs = cs; c.sh.pix_per_cta = ppc; c.smem = fixed + nb * slab; c.slab = (uint32_t)slab; c.ok = true;
-                    break;
-                }
-            }
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int cs = (pass == 2 ? 8 : 1); cs <= 8; cs *= 2) {
+            const int64_t ppc = (HW + cs - 1) / cs;
+            if (cs > 1 && (int64_t)(cs - 1) * ppc >= HW) continue;                 // would leave an empty CTA
+            const size_t bytes = fixed + (size_t)tensors * ppc * C * 2;
+            if (bytes <= limits[pass]) { sh.cs = cs; sh.pix_per_cta = ppc; smem = bytes; return true; }
         }
     }
+    return false;
 }
 
 std::mutex g_attr_mu;
@@ -892,58 +862,6 @@ int launch_cluster(K kernel, int grid, int cs, size_t smem, cudaStream_t s, Args
     cfg.attrs = attr; cfg.numAttrs = 2;
     e = cudaLaunchKernelEx(&cfg, kernel, args...);
     return e == cudaSuccess ? (int)cudaPeekAtLastError() : (int)e;
-}
-
-// clusters of `cs` CTAs with `smem` bytes each that can be resident at once (cached per kernel / shape)
-template <typename K>
-int max_clusters(K kernel, int cs, size_t smem) {
-    struct Key { const void *k; int cs; size_t smem; bool operator<(const Key &o) const {
-        return k != o.k ? k < o.k : (cs != o.cs ? cs < o.cs : smem < o.smem); } };
-    static std::mutex mu;
-    static std::map<Key, int> cache;
-    const Key key{reinterpret_cast<const void *>(kernel), cs, smem};
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        auto it = cache.find(key);
-        if (it != cache.end()) return it->second;
-    }
-    {
-        std::lock_guard<std::mutex> lk(g_attr_mu);
-        if (!g_attr_done.count(key.k)) {
-            if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess)
-                g_attr_done.insert(key.k);
-        }
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(cs * 148), 1, 1);
-    cfg.blockDim = dim3(kFusedThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
-        (void)cudaGetLastError();
-        n = (148 / cs) * (int)((227 * 1024) / (smem + 1024) > 0 ? (227 * 1024) / (smem + 1024) : 1);   // estimate
-    }
-    std::lock_guard<std::mutex> lk(mu);
-    cache[key] = n;
-    return n;
-}
-
-// one sample per cluster when everything is resident at once; otherwise a persistent walk, double-buffered if it fits
-template <typename K, typename F>
-int launch_persistent(K kernel, const Cand &one, const Cand &two, int64_t N, F &&go) {
-    const int cap1 = std::max(1, max_clusters(kernel, one.sh.cs, one.smem));
-    if (N <= cap1 || !two.ok) {
-        const Persist ps{(int)N, (int)std::min<int64_t>(N, cap1), 1, one.slab};
-        return go(kernel, one.sh, ps, one.smem);
-    }
-    const int cap2 = std::max(1, max_clusters(kernel, two.sh.cs, two.smem));
-    const int rounds = (int)((N + cap2 - 1) / cap2);                  // equal rounds: no nearly-empty last one
-    const Persist ps{(int)N, (int)((N + rounds - 1) / rounds), 2, two.slab};
-    return go(kernel, two.sh, ps, two.smem);
 }
 
 int make_shape(int64_t N, int64_t HW, int64_t C, int G, Shape &sh, dim3 &grid) {
@@ -1055,14 +973,14 @@ int ub200_gn_act_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int
 }
 
 #define DISPATCH_FUSED(KERNEL, act, drop, ...)                                                                  \
-    ((drop) ? ((act) == UB200_ACT_SILU   ? launch_persistent(KERNEL(UB200_ACT_SILU, true), __VA_ARGS__)            \
-               : (act) == UB200_ACT_GELU ? launch_persistent(KERNEL(UB200_ACT_GELU, true), __VA_ARGS__)            \
-               : (act) == UB200_ACT_RELU ? launch_persistent(KERNEL(UB200_ACT_RELU, true), __VA_ARGS__)            \
-                                         : launch_persistent(KERNEL(UB200_ACT_NONE, true), __VA_ARGS__))           \
-            : ((act) == UB200_ACT_SILU   ? launch_persistent(KERNEL(UB200_ACT_SILU, false), __VA_ARGS__)           \
-               : (act) == UB200_ACT_GELU ? launch_persistent(KERNEL(UB200_ACT_GELU, false), __VA_ARGS__)           \
-               : (act) == UB200_ACT_RELU ? launch_persistent(KERNEL(UB200_ACT_RELU, false), __VA_ARGS__)           \
-                                         : launch_persistent(KERNEL(UB200_ACT_NONE, false), __VA_ARGS__)))
+    ((drop) ? ((act) == UB200_ACT_SILU   ? launch_cluster(KERNEL(UB200_ACT_SILU, true), __VA_ARGS__)            \
+               : (act) == UB200_ACT_GELU ? launch_cluster(KERNEL(UB200_ACT_GELU, true), __VA_ARGS__)            \
+               : (act) == UB200_ACT_RELU ? launch_cluster(KERNEL(UB200_ACT_RELU, true), __VA_ARGS__)            \
+                                         : launch_cluster(KERNEL(UB200_ACT_NONE, true), __VA_ARGS__))           \
+            : ((act) == UB200_ACT_SILU   ? launch_cluster(KERNEL(UB200_ACT_SILU, false), __VA_ARGS__)           \
+               : (act) == UB200_ACT_GELU ? launch_cluster(KERNEL(UB200_ACT_GELU, false), __VA_ARGS__)           \
+               : (act) == UB200_ACT_RELU ? launch_cluster(KERNEL(UB200_ACT_RELU, false), __VA_ARGS__)           \
+                                         : launch_cluster(KERNEL(UB200_ACT_NONE, false), __VA_ARGS__)))
 #define FUSED_FWD(A, D) gn_fused_fwd_kernel<A, D>
 #define FUSED_BWD_X(A, D) gn_fused_bwd_kernel<A, D, true>
 #define FUSED_BWD_S(A, D) gn_fused_bwd_kernel<A, D, false>
@@ -1074,26 +992,22 @@ int ub200_gn_act_fused_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int
                                      int64_t ld_y, void *stream) {
     UB_REQUIRE(x && y && stats && N > 0 && HW > 0 && C > 0 && G > 0 && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
     UB_REQUIRE(act >= UB200_ACT_NONE && act <= UB200_ACT_RELU, UB200_E_BADARG);
-    Cand one, two;
-    one.ok = two.ok = false;
+    FusedShape sh; size_t smem = 0;
     const size_t gpad = (size_t)((2 * G + 3) & ~3);
-    if (ld_x % 8 == 0 && ld_y % 8 == 0 && ld_x >= C && ld_y >= C && ub::aligned16(x) && ub::aligned16(y) &&
-        (!addend || (ld_add % 8 == 0 && ld_add >= C && ub::aligned16(addend))))
-        plan_fused(N, HW, C, G, 1, 2 * (size_t)C + 3 * gpad, one, two);
-    if (!one.ok) {      // slab too large for one cluster: statistics pass + apply pass
+    const bool ok = ld_x % 8 == 0 && ld_y % 8 == 0 && ld_x >= C && ld_y >= C && ub::aligned16(x) && ub::aligned16(y) &&
+                    (!addend || (ld_add % 8 == 0 && ld_add >= C && ub::aligned16(addend))) &&
+                    plan_fused(N, HW, C, G, 1, 2 * (size_t)C + 2 * gpad, sh, smem);
+    if (!ok) {      // slab too large for one cluster: statistics pass + apply pass
         int rc = ub200_gn_stats_nhwc_bf16(x, ld_x, N, HW, C, G, stats, stream);
         if (rc) return rc;
         return ub200_gn_act_fwd_nhwc_bf16(x, ld_x, N, HW, C, G, stats, eps, gamma, beta, scale, shift, act, dropout_p, seed,
                                           offset, offset_dev, addend, ld_add, y, ld_y, stream);
     }
     const bool drop = dropout_p > 0.f;
-    auto go = [&](auto kernel, const FusedShape &sh, const Persist &ps, size_t smem) {
-        return launch_cluster(kernel, ps.num_clusters * sh.cs, sh.cs, smem, ub::as_stream(stream),
-                              reinterpret_cast<const __nv_bfloat16 *>(x), ld_x, sh, ps, stats, eps, gamma, beta, scale, shift,
-                              dropout_p, seed, offset, offset_dev, reinterpret_cast<const __nv_bfloat16 *>(addend), ld_add,
-                              reinterpret_cast<__nv_bfloat16 *>(y), ld_y);
-    };
-    return DISPATCH_FUSED(FUSED_FWD, act, drop, one, two, N, go);
+    return DISPATCH_FUSED(FUSED_FWD, act, drop, (int)(N * sh.cs), sh.cs, smem, ub::as_stream(stream),
+                          reinterpret_cast<const __nv_bfloat16 *>(x), ld_x, sh, stats, eps, gamma, beta, scale, shift,
+                          dropout_p, seed, offset, offset_dev, reinterpret_cast<const __nv_bfloat16 *>(addend), ld_add,
+                          reinterpret_cast<__nv_bfloat16 *>(y), ld_y);
 }
 
 int ub200_gn_act_fused_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int64_t ld_x, int64_t N, int64_t HW,
@@ -1105,15 +1019,13 @@ int ub200_gn_act_fused_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *
     UB_REQUIRE(!gadd || (ld_gadd % 8 == 0 && ld_gadd >= C && ub::aligned16(gadd)), UB200_E_UNSUPPORTED);
     UB_REQUIRE(gy && x && gx && ws && N > 0 && HW > 0 && C > 0 && G > 0 && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
     UB_REQUIRE(act >= UB200_ACT_NONE && act <= UB200_ACT_RELU, UB200_E_BADARG);
-    Cand one, two;
-    one.ok = two.ok = false;
+    FusedShape sh; size_t smem = 0;
     const bool fits = ld_x % 8 == 0 && ld_gy % 8 == 0 && ld_gx % 8 == 0 && ld_x >= C && ld_gy >= C && ld_gx >= C &&
                       ub::aligned16(x) && ub::aligned16(gy) && ub::aligned16(gx);
-    const size_t extra = (size_t)(8 * C + ((2 * G + 3) & ~3));
-    if (fits) plan_fused(N, HW, C, G, 2, extra, one, two, 1);
-    const bool xslab = one.ok;
-    if (fits && !xslab) plan_fused(N, HW, C, G, 1, extra, one, two);
-    if (!one.ok) {
+    const size_t extra = (size_t)(4 * C + ((2 * G + 3) & ~3));
+    const bool xslab = fits && plan_fused(N, HW, C, G, 2, extra, sh, smem, 1);
+    const bool ok = xslab || (fits && plan_fused(N, HW, C, G, 1, extra, sh, smem));
+    if (!ok) {
         int rc = ub200_gn_act_bwd_nhwc_bf16(gy, ld_gy, x, ld_x, N, HW, C, G, stats, eps, gamma, beta, scale, shift, act,
                                             dropout_p, seed, offset, offset_dev, gx, ld_gx, 0, dgamma, dbeta, dscale, dshift,
                                             ws, stream);
@@ -1126,15 +1038,14 @@ int ub200_gn_act_fused_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *
         return UB200_OK;
     }
     const bool drop = dropout_p > 0.f;
-    auto go = [&](auto kernel, const FusedShape &sh, const Persist &ps, size_t smem) {
-        return launch_cluster(kernel, ps.num_clusters * sh.cs, sh.cs, smem, ub::as_stream(stream),
-                              reinterpret_cast<const __nv_bfloat16 *>(gy), ld_gy, reinterpret_cast<const __nv_bfloat16 *>(x), ld_x,
-                              sh, ps, stats, eps, gamma, beta, scale, shift, dropout_p, seed, offset, offset_dev,
-                              reinterpret_cast<__nv_bfloat16 *>(gx), ld_gx, dgamma, dbeta, dscale, dshift,
-                              reinterpret_cast<const __nv_bfloat16 *>(gadd), ld_gadd);
-    };
-    if (xslab) return DISPATCH_FUSED(FUSED_BWD_X, act, drop, one, two, N, go);
-    return DISPATCH_FUSED(FUSED_BWD_S, act, drop, one, two, N, go);
+#define BWD_ARGS                                                                                                      \
+    (int)(N * sh.cs), sh.cs, smem, ub::as_stream(stream), reinterpret_cast<const __nv_bfloat16 *>(gy), ld_gy,         \
+        reinterpret_cast<const __nv_bfloat16 *>(x), ld_x, sh, stats, eps, gamma, beta, scale, shift, dropout_p, seed, \
+        offset, offset_dev, reinterpret_cast<__nv_bfloat16 *>(gx), ld_gx, dgamma, dbeta, dscale, dshift,                 \
+        reinterpret_cast<const __nv_bfloat16 *>(gadd), ld_gadd
+    if (xslab) return DISPATCH_FUSED(FUSED_BWD_X, act, drop, BWD_ARGS);
+    return DISPATCH_FUSED(FUSED_BWD_S, act, drop, BWD_ARGS);
+#undef BWD_ARGS
 }
 
 }  // extern "C"

@@ -337,6 +337,100 @@ __global__ void __launch_bounds__(256) haar_idwt_vec2(const float *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Multi-resolution loss (diff_cifar/diffusion.py:52-91; diff_mnist/main.py:375-403; pdemodel.py:222-229), fused: the
+// target pyramid t_k = LL_k(noise) / 2^k (k = 0..J), the J+1 mean-squared errors against the model's per-level outputs and
+// their gradients in ONE pass over the noise (the reference rebuilds DWTForward modules and runs J transforms + J+1
+// mse_loss calls per step).  Same strip mapping as haar_dwt_multi: 2^J rows x 4 columns per thread, level 3 through one
+// lane-pair shuffle.  sums[k] += sum (out_k - t_k)^2;  grad_k = coef[k] * (out_k - t_k)  with coef[k] = 2 / numel_k.
+// ---------------------------------------------------------------------------------------------
+struct MrlArgs {
+    const float *out[4];     // model outputs, level 0 (finest) .. J
+    float *grad[4];          // gradients of the summed mean-squared errors, same shapes (may be NULL: loss only)
+    float coef[4];
+};
+
+template <int J>
+__global__ void __launch_bounds__(256) mrl_loss_kernel(const float *__restrict__ noise, int64_t planes, int H, int W,
+                                                      MrlArgs a, float *__restrict__ sums) {
+    constexpr int R = 1 << J;
+    const int wq = W >> 2, strips = H / R;
+    const int64_t items = planes * strips * wq;
+    const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2, H3 = H >> 3, W3 = W >> 3;
+    const int lane = threadIdx.x & 31;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t it0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x - lane; it0 < items; it0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t it = it0 + lane;
+        const bool live = it < items;
+        const int jq = (int)(it % wq);
+        const int64_t t = it / wq;
+        const int sidx = (int)(t % strips);
+        const int64_t p = t / strips;
+        float l1[R / 2 > 0 ? R / 2 : 1][2];
+        float l2[R / 4 > 0 ? R / 4 : 1];
+#pragma unroll
+        for (int r = 0; r < (R / 2 > 0 ? R / 2 : 1); ++r) l1[r][0] = l1[r][1] = 0.f;
+        if (live) {
+            const int64_t base0 = (p * H + (int64_t)sidx * R) * W + 4 * jq;
+#pragma unroll
+            for (int r = 0; r < R / 2; ++r) {
+                const float4 n0 = ld_stream(reinterpret_cast<const float4 *>(noise + base0 + (int64_t)(2 * r) * W));
+                const float4 n1 = ld_stream(reinterpret_cast<const float4 *>(noise + base0 + (int64_t)(2 * r + 1) * W));
+                const float4 o0 = ld_stream(reinterpret_cast<const float4 *>(a.out[0] + base0 + (int64_t)(2 * r) * W));
+                const float4 o1 = ld_stream(reinterpret_cast<const float4 *>(a.out[0] + base0 + (int64_t)(2 * r + 1) * W));
+                const float4 d0 = make_float4(o0.x - n0.x, o0.y - n0.y, o0.z - n0.z, o0.w - n0.w);
+                const float4 d1 = make_float4(o1.x - n1.x, o1.y - n1.y, o1.z - n1.z, o1.w - n1.w);
+                acc[0] += d0.x * d0.x + d0.y * d0.y + d0.z * d0.z + d0.w * d0.w + d1.x * d1.x + d1.y * d1.y + d1.z * d1.z + d1.w * d1.w;
+                if (a.grad[0]) {
+                    const float c = a.coef[0];
+                    st_stream(reinterpret_cast<float4 *>(a.grad[0] + base0 + (int64_t)(2 * r) * W), make_float4(c * d0.x, c * d0.y, c * d0.z, c * d0.w));
+                    st_stream(reinterpret_cast<float4 *>(a.grad[0] + base0 + (int64_t)(2 * r + 1) * W), make_float4(c * d1.x, c * d1.y, c * d1.z, c * d1.w));
+                }
+                l1[r][0] = analyse_ll(n0.x, n0.y, n1.x, n1.y);
+                l1[r][1] = analyse_ll(n0.z, n0.w, n1.z, n1.w);
+                // level 1 target: LL_1 / 2
+                const int64_t o = (p * H1 + (int64_t)sidx * (R / 2) + r) * W1 + 2 * jq;
+                const float2 ov = *reinterpret_cast<const float2 *>(a.out[1] + o);
+                const float e0 = ov.x - l1[r][0] * 0.5f, e1 = ov.y - l1[r][1] * 0.5f;
+                acc[1] += e0 * e0 + e1 * e1;
+                if (a.grad[1]) *reinterpret_cast<float2 *>(a.grad[1] + o) = make_float2(a.coef[1] * e0, a.coef[1] * e1);
+            }
+        }
+        if constexpr (J >= 2) {
+#pragma unroll
+            for (int r = 0; r < R / 4; ++r) {
+                l2[r] = analyse_ll(l1[2 * r][0], l1[2 * r][1], l1[2 * r + 1][0], l1[2 * r + 1][1]);
+                if (live) {
+                    const int64_t o = (p * H2 + (int64_t)sidx * (R / 4) + r) * W2 + jq;
+                    const float e = __ldg(a.out[2] + o) - l2[r] * 0.25f;
+                    acc[2] += e * e;
+                    if (a.grad[2]) a.grad[2][o] = a.coef[2] * e;
+                }
+            }
+        }
+        if constexpr (J == 3) {
+            const float o0 = __shfl_xor_sync(0xffffffffu, l2[0], 1), o1 = __shfl_xor_sync(0xffffffffu, l2[1], 1);
+            if (live && !(jq & 1)) {
+                const float l3 = analyse_ll(l2[0], o0, l2[1], o1);
+                const int64_t o = (p * H3 + sidx) * (int64_t)W3 + (jq >> 1);
+                const float e = __ldg(a.out[3] + o) - l3 * 0.125f;
+                acc[3] += e * e;
+                if (a.grad[3]) a.grad[3][o] = a.coef[3] * e;
+            }
+        }
+    }
+    __shared__ float part[8][4];
+#pragma unroll
+    for (int k = 0; k <= J; ++k) acc[k] = warp_sum(acc[k]);
+    if (lane == 0) { for (int k = 0; k <= J; ++k) part[threadIdx.x >> 5][k] = acc[k]; }
+    __syncthreads();
+    if (threadIdx.x <= J) {
+        float tsum = 0.f;
+        for (int w = 0; w < 8; ++w) tsum += part[w][threadIdx.x];
+        atomicAdd(sums + threadIdx.x, tsum);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // DTWBlock: LL_J / 2^J + channel tile.  Level extents are carried so that the zero extension of an
 // odd intermediate level is reproduced exactly (ll_at returns 0 outside a level's extent).
 // ---------------------------------------------------------------------------------------------
@@ -718,6 +812,29 @@ int ub200_haar_idwt2d_multi(const float *ll, const float *const *highs, int64_t 
     const int grid = ub::grid_for(planes * (H >> J) * (W / 4), 256, 8);
     if (J == 2) haar_idwt_multi<2><<<grid, 256, 0, s>>>(ll, highs[0], highs[1], nullptr, planes, (int)H, (int)W, out);
     else haar_idwt_multi<3><<<grid, 256, 0, s>>>(ll, highs[0], highs[1], highs[2], planes, (int)H, (int)W, out);
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+int ub200_multires_mse_f32(const float *noise, int64_t planes, int64_t H, int64_t W, int J, const float *const *outs,
+                           float *const *grads, float *sums, void *stream) {
+    UB_REQUIRE(noise && outs && sums && planes > 0 && H > 0 && W > 0, UB200_E_BADARG);
+    UB_REQUIRE(J >= 1 && J <= 3 && H % (1 << J) == 0 && W % 8 == 0 && H < (1 << 30) && W < (1 << 30), UB200_E_UNSUPPORTED);
+    MrlArgs a{};
+    bool al = ub::aligned16(noise);
+    for (int k = 0; k <= J; ++k) {
+        UB_REQUIRE(outs[k], UB200_E_BADARG);
+        a.out[k] = outs[k];
+        a.grad[k] = grads ? grads[k] : nullptr;
+        a.coef[k] = 2.0f / (float)((double)planes * (double)(H >> k) * (double)(W >> k));
+        al = al && ub::aligned16(outs[k]) && (!a.grad[k] || ub::aligned16(a.grad[k]));
+    }
+    UB_REQUIRE(al, UB200_E_UNSUPPORTED);
+    cudaStream_t s = ub::as_stream(stream);
+    const int grid = ub::grid_for(planes * (H >> J) * (W / 4), 256, 8);
+    if (J == 1) mrl_loss_kernel<1><<<grid, 256, 0, s>>>(noise, planes, (int)H, (int)W, a, sums);
+    else if (J == 2) mrl_loss_kernel<2><<<grid, 256, 0, s>>>(noise, planes, (int)H, (int)W, a, sums);
+    else mrl_loss_kernel<3><<<grid, 256, 0, s>>>(noise, planes, (int)H, (int)W, a, sums);
     UB_LAUNCH_CHECK();
     return UB200_OK;
 }

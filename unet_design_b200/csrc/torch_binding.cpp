@@ -63,6 +63,30 @@ const uint64_t *i64_opt(const c10::optional<Tensor> &t) {
 
 // ---------------------------------------------------------------- Haar
 
+// fused multi-resolution MSE: outs[k] at level k (0 = finest); returns {sums[J+1], grad_0 .. grad_J} or {} if not eligible
+std::vector<Tensor> multires_mse(const Tensor &noise, const std::vector<Tensor> &outs, bool want_grads) {
+    UB_GUARD(noise);
+    TORCH_CHECK(noise.dim() == 4, "multires_mse: noise must be [N,C,H,W]");
+    const int64_t J = (int64_t)outs.size() - 1;
+    const int64_t N = noise.size(0), C = noise.size(1), H = noise.size(2), W = noise.size(3);
+    if (J < 1 || J > 3 || H % (1 << J) != 0 || W % 8 != 0) return {};
+    const float *op[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *gp[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<Tensor> res;
+    res.push_back(at::zeros({J + 1}, noise.options()));
+    for (int64_t k = 0; k <= J; ++k) {
+        TORCH_CHECK(outs[k].dim() == 4 && outs[k].size(0) == N && outs[k].size(1) == C && outs[k].size(2) == (H >> k) && outs[k].size(3) == (W >> k),
+                    "multires_mse: output shape mismatch at level ", k);
+        op[k] = f32(outs[k], "out");
+        if (want_grads) { res.push_back(at::empty_like(outs[k])); gp[k] = res.back().data_ptr<float>(); }
+    }
+    const int rc = ub200_multires_mse_f32(f32(noise, "noise"), N * C, H, W, (int)J, op, want_grads ? gp : nullptr,
+                                          res[0].data_ptr<float>(), cur_stream());
+    if (rc == UB200_E_UNSUPPORTED) return {};
+    check_rc(rc, "multires_mse");
+    return res;
+}
+
 // J-level fused analysis; returns {ll, highs_1 (finest), ..., highs_J}; empty vector if the shape is not eligible
 std::vector<Tensor> haar_dwt2d_multi(const Tensor &x, int64_t J) {
     TORCH_CHECK(x.dim() == 4, "haar_dwt2d_multi: expected [N,C,H,W]");
@@ -465,6 +489,7 @@ TORCH_LIBRARY(unet_b200, m) {
           "Tensor? residual, Tensor? out, Tensor? out_nchw, Tensor? bias2, int stride=1) -> ()", &conv_fprop);
     m.def("conv_wgrad(Tensor gout, Tensor a, int ksize, Tensor dw, int stride=1) -> ()", &conv_wgrad);
     m.def("haar_dwt2d_multi", &haar_dwt2d_multi);
+    m.def("multires_mse", &multires_mse);
     m.def("haar_idwt2d_multi", &haar_idwt2d_multi);
     m.def("chansum", &chansum);
     m.def("pack_conv_weight", &pack_conv_weight);

@@ -41,6 +41,12 @@ class GaussianDiffusionTrainer(nn.Module):
                + extract(self.sqrt_one_minus_alphas_bar, t, x_0.shape) * noise)
         model_out = self.model(x_t, t, n_levels_used=n_levels_used)
         loss_list = []
+        if self.multi_res_loss and not self.sequ_train_algo and len(model_out) == self.model.n_levels:
+            # all levels present (coarse -> fine): target pyramid, the per-level MSEs and their gradients in ONE kernel
+            fused = ops.multires_mse(noise, list(model_out)[::-1])
+            if fused is not None:
+                loss, per_level = fused
+                return loss, list(per_level.flip(0).unbind(0))
         if self.multi_res_loss:
             targets = []
             for k in list(range(0, self.model.n_levels))[::-1]:

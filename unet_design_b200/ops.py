@@ -385,6 +385,44 @@ def dwtblock(x: torch.Tensor, J: int, out_channels: int) -> torch.Tensor:
     return _DwtBlock.apply(x, J, out_channels)
 
 
+class _MultiResMse(torch.autograd.Function):
+    """sum_k mse(out_k, LL_k(noise) / 2^k) and its gradients in ONE kernel (ub200_multires_mse_f32).  `outs` finest first."""
+
+    @staticmethod
+    def forward(ctx, noise, *outs):
+        want = any(o.requires_grad for o in outs)
+        res = _ops().multires_mse(noise.contiguous(), [o.contiguous() for o in outs], want)
+        _count()
+        sums = res[0]
+        numel = torch.tensor([o.numel() for o in outs], dtype=torch.float32, device=noise.device)
+        per_level = sums / numel
+        ctx.save_for_backward(*res[1:])
+        ctx.n = len(outs)
+        return (per_level.sum(), per_level)
+
+    @staticmethod
+    def backward(ctx, g_total, g_levels):
+        grads = ctx.saved_tensors
+        outs = []
+        for k, g in enumerate(grads):
+            scale = g_total if g_levels is None else g_total + g_levels[k]
+            outs.append(g * scale)
+        return (None, *outs)
+
+
+def multires_mse(noise: torch.Tensor, outs_fine_first):
+    """(sum of the per-level mean-squared errors, per-level losses [J+1], finest first) against the Haar target pyramid of
+    `noise`; None when the shapes are not eligible for the fused kernel (odd extents, more than 4 levels)."""
+    J = len(outs_fine_first) - 1
+    h, w = noise.shape[-2:]
+    if J < 1 or J > 3 or h % (1 << J) or w % 8 or noise.dtype != torch.float32:
+        return None
+    if any(tuple(o.shape) != (noise.shape[0], noise.shape[1], h >> k, w >> k) or o.dtype != torch.float32
+           for k, o in enumerate(outs_fine_first)):
+        return None
+    return _MultiResMse.apply(noise, *outs_fine_first)
+
+
 def dwtblock_nhwc(x: torch.Tensor, J: int, out: torch.Tensor, chmap: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Same forward written into an NHWC bf16 view (no autograd: the diffusion encoders see data only).
     `chmap` (int32 [C_out]) names the source channel of each output channel; None = k mod C."""

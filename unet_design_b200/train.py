@@ -194,21 +194,22 @@ class TrainStep:
         self.v = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.ema = self.arena.p.clone() if ema_decay is not None else None
         self.packed = PackedWeights(self.arena)
-        for p, off in zip(self.arena.params, self.arena.offsets):
-            ops.register_grad_sink(p, p.grad, None)
+        # gradient sinks: kernels that accumulate (wgrad, GroupNorm dgamma / dbeta, bias sums) write straight into the arena;
+        # `on_ready` tells the data-parallel bucket logic that the kernel producing this parameter's gradient is enqueued
+        # (autograd's post-accumulate hooks do not fire for them: their Function returns None for the parameter)
+        for i, (p, off) in enumerate(zip(self.arena.params, self.arena.offsets)):
+            ops.register_grad_sink(p, p.grad, self._make_hook(i))
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=self.device)
         if self.device.type == "cuda":
-            # second stream for the kernels that only feed the optimiser (ops._Side).  Not with the eager bucketed
-            # all-reduce: its hooks launch a bucket's collective as soon as autograd has passed the parameters, which
-            # would race with a weight gradient still queued on the side stream.
-            eager_overlap = self.world > 1 and overlap_allreduce and not use_cuda_graph
-            ops.enable_side_wgrad(os.environ.get("UB200_SIDE_WGRAD", "1") != "0" and not eager_overlap,
+            # second stream for the kernels that only feed the optimiser (ops._Side); the bucketed all-reduce waits for it
+            ops.enable_side_wgrad(os.environ.get("UB200_SIDE_WGRAD", "1") != "0",
                                   int(os.environ.get("UB200_SIDE_WGRAD_PIXELS", str(1 << 30))))
-            ops._Side.chansum = os.environ.get("UB200_SIDE_CHANSUM", "1") != "0" and not eager_overlap
+            ops._Side.chansum = os.environ.get("UB200_SIDE_CHANSUM", "1") != "0"
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)       # 1-based after the first bump
         self.steps_done = 0
         self.use_graph = use_cuda_graph and self.device.type == "cuda"
         self._graphs = {}              # (tensor shapes / dtypes, static kwargs) -> (graph, static inputs, static loss)
+        self._graph_has_tail = False   # the captured graph includes the collective + optimiser tail
         self._dgrad_stale = False      # the optimiser has moved the weights since the dgrad operands were packed
         self._pack_stream = None
         self._buckets: List[tuple] = []
@@ -246,17 +247,19 @@ class TrainStep:
             for i in mem:
                 self._bucket_of[i] = b
         self._pending = [0] * len(self._buckets)
+        self._seen = [False] * len(params)
         if self.device.type == "cuda":
             self._comm_stream = torch.cuda.Stream(device=self.device)
-        # note: post-accumulate hooks also fire for parameters whose Function returned None because its kernel
-        # accumulated straight into the arena (ops gradient sinks), and they fire after that kernel was enqueued
+        # parameters whose gradient arrives through autograd's AccumulateGrad (no sink kernel) report through this hook;
+        # the sink kernels report through `on_ready` (registered in __init__): whichever fires first counts, once per step
         for i, p in enumerate(params):
             p.register_post_accumulate_grad_hook(self._make_hook(i))
 
     def _make_hook(self, i: int):
-        def hook(_param):
-            if not self._hooks_live:
+        def hook(_param=None):
+            if not self._hooks_live or self._seen[i]:
                 return
+            self._seen[i] = True
             b = self._bucket_of[i]
             self._pending[b] -= 1
             if self._pending[b] == 0:
@@ -268,6 +271,8 @@ class TrainStep:
         view = self.arena.g[lo:hi]
         if self._comm_stream is not None:
             self._comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+            if ops._Side.stream is not None:      # weight-gradient kernels into this bucket may be queued on the second stream
+                self._comm_stream.wait_stream(ops._Side.stream)
             with torch.cuda.stream(self._comm_stream):
                 dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg)
         else:
@@ -276,6 +281,7 @@ class TrainStep:
     def _arm_buckets(self):
         for b, (_, _, mem) in enumerate(self._buckets):
             self._pending[b] = len(mem)
+        self._seen = [False] * len(self.arena.params)
 
     def _finish_allreduce(self):
         """After backward: reduce the buckets that hold parameters this step did not touch (e.g. the coarse
@@ -296,9 +302,8 @@ class TrainStep:
     def _fwd_bwd(self, inputs, static, overlap: bool) -> torch.Tensor:
         self.arena.g.zero_()
         self.step_dev.add_(1)
-        # a bucket must not be all-reduced while weight-gradient kernels into it are still queued on the second stream
-        # (ops._Side): the bucketed overlap is only armed when that stream is off
-        overlap = overlap and not ops._Side.enabled
+        # (a bucket's collective waits for the second stream too, see _launch_allreduce: weight-gradient kernels into it may
+        # still be queued there)
         self._hooks_live = overlap
         if overlap:
             self._arm_buckets()
@@ -366,7 +371,7 @@ class TrainStep:
         for dst, src in zip(static_in, inputs):
             dst.copy_(src, non_blocking=True)
         graph.replay()
-        if self.world > 1:             # the collective and the optimiser tail stay outside the graph (3 launches)
+        if self.world > 1 and not self._graph_has_tail:   # the collective and the optimiser tail follow the replay (3 launches)
             self._reduce_and_update(False)
         return static_loss
 
@@ -398,7 +403,12 @@ class TrainStep:
         """One CUDA graph for the whole step on a single GPU; forward + backward only when data-parallel (NCCL work
         captured into a graph dead-locked on this stack, so the gradient all-reduce is issued right after the replay)."""
         static_in = [t.clone() for t in inputs]
-        whole = self.world == 1
+        # data parallel: by default the graph holds forward + backward and the collective + optimiser follow the replay;
+        # UB200_DP_GRAPH_NCCL=1 captures the bucketed NCCL all-reduces (on the comm stream, forked from and joined to the
+        # capture stream, so they overlap the rest of backward) and the optimiser tail into the same graph.  The capture
+        # then runs in thread-local error mode: NCCL's watchdog thread polls CUDA events, which a global-mode capture forbids.
+        nccl_in_graph = self.world > 1 and os.environ.get("UB200_DP_GRAPH_NCCL", "0") == "1"
+        whole = self.world == 1 or nccl_in_graph
         # The warm-up runs real steps (allocator, tensor maps, cuBLAS handles): snapshot every piece of training state
         # they touch and put it back, so that the first replay is step 1 of the run exactly as in eager mode.
         state = self._training_state()
@@ -416,10 +426,11 @@ class TrainStep:
         del saved
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_loss = self._fwd_bwd(static_in, static, False)
+        with torch.cuda.graph(graph, capture_error_mode="thread_local" if nccl_in_graph else "global"):
+            static_loss = self._fwd_bwd(static_in, static, nccl_in_graph and self.overlap)
             if whole:
-                self._reduce_and_update(False)
+                self._reduce_and_update(self._overlapped)
+        self._graph_has_tail = whole
         entry = (graph, static_in, static_loss)
         self._graphs[key] = entry
         return entry
