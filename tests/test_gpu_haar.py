@@ -244,7 +244,7 @@ def test_fused_multires_loss_matches_oracle(ops, shape, J):
         t = torch.from_numpy(haar_np.dwtblock(noise.numpy(), k, None)) if k else noise
         ref = float(((o - t) ** 2).mean())
         ref_total += ref
-        assert abs(float(per_level[k]) - ref) < 1e-5 * max(1.0, ref)
+        assert abs(float(per_level[k].detach()) - ref) < 1e-5 * max(1.0, ref)
         assert rel_err(outs_gpu[k].grad, 2.0 * (o - t) / o.numel()) < 1e-6
-    assert abs(float(loss) - ref_total) < 1e-5 * ref_total
+    assert abs(float(loss.detach()) - ref_total) < 1e-5 * ref_total
     assert ops.multires_mse(noise.cuda()[..., :-1], outs_gpu) is None        # odd extent: caller goes level by level

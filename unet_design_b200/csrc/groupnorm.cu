@@ -374,7 +374,6 @@ constexpr uint32_t kBulkPiece = 16384;           // dense slabs are fetched in p
 
 struct FusedShape {
     int64_t HW; int C, G, cpg, chunks, rows, cs; int64_t pix_per_cta;
-    int packed;      // backward apply pass in packed bf16x2 FMAs (UB200_GN_BWD_PACKED=0: fp32 per element)
 };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -711,33 +710,7 @@ __global__ void __launch_bounds__(kFusedThreads, 3) gn_fused_bwd_kernel(
     }
     // gadd: a second gradient of x (the ResBlock's shortcut / residual branch), summed here instead of by a separate add
     const bool has_add = gadd != nullptr;
-    // The apply pass is instruction-issue bound (unpack + 2 fma + pack per element in fp32: ~44 instructions per 16-byte
-    // chunk).  dx = dz*P + (x*Qc + (R + gadd)) as packed bf16x2 FMAs (fp32 inside the FMA, one rounding each) is 8-12:
-    // the inputs and the output are bf16 anyway; the per-channel coefficients lose 2^-9 relative, within the bf16 bound.
-    __nv_bfloat162 P2[4], Q2[4], R2[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        P2[u] = __floats2bfloat162_rn(P[2 * u], P[2 * u + 1]);
-        Q2[u] = __floats2bfloat162_rn(Qc[2 * u], Qc[2 * u + 1]);
-        R2[u] = __floats2bfloat162_rn(R[2 * u], R[2 * u + 1]);
-    }
-    const bool packed = sh.packed != 0;
     auto fin = [&](const uint4 *dp, __nv_bfloat16 *op, const uint4 &xv, const uint4 &av) {
-        if (packed) {
-            const uint4 dv = *dp;
-            const __nv_bfloat162 *x2 = reinterpret_cast<const __nv_bfloat162 *>(&xv);
-            const __nv_bfloat162 *d2 = reinterpret_cast<const __nv_bfloat162 *>(&dv);
-            const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&av);
-            uint4 out;
-            __nv_bfloat162 *o2 = reinterpret_cast<__nv_bfloat162 *>(&out);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const __nv_bfloat162 rr = has_add ? __hadd2(R2[u], a2[u]) : R2[u];
-                o2[u] = __hfma2(d2[u], P2[u], __hfma2(x2[u], Q2[u], rr));
-            }
-            *reinterpret_cast<uint4 *>(op) = out;
-            return;
-        }
         float f[8], d[8];
         unpack8(xv, f);
         unpack8(*dp, d);
@@ -812,8 +785,6 @@ bool plan_fused(int64_t N, int64_t HW, int64_t C, int G, int tensors, size_t ext
     if (C % 8 != 0 || C % G != 0 || C > 4 * kFusedThreads || N * 8 > 2147483647LL) return false;
     sh.HW = HW; sh.C = (int)C; sh.G = G; sh.cpg = (int)(C / G); sh.chunks = (int)(C / 8);
     sh.rows = (kFusedThreads / sh.chunks) & ~1;      // even, >= 2: the fold staging holds rows/2 * chunks <= 128 entries
-    static const int packed = [] { const char *e = getenv("UB200_GN_BWD_PACKED"); return (e && e[0] == '0') ? 0 : 1; }();
-    sh.packed = packed;
     const size_t fixed = (size_t)kFusedFixedBytes + extra_floats * 4;
     if (only_single_cta) {
         const size_t bytes = fixed + (size_t)tensors * HW * C * 2;
