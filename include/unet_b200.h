@@ -272,6 +272,31 @@ int ub200_pack_conv_weight(const float *w, int64_t Cout, int64_t Cin, int ksize,
                            int transpose_flip, void *out_bf16, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Attention core of AttnBlock (diff_cifar/model.py:100-119; diff_mnist layers.py:371-391 with one head): one batched GEMM
+ * kernel on tcgen05 (M = 256 rows per CTA, N, K <= 256) with fused epilogues; forward = 2 calls, backward = 4 (see
+ * csrc/attention.cu).  All matrices are row-major bf16 [R = 256 * groups rows, ld]; a group of 256 rows holds 256 / T
+ * whole samples of T tokens (T divides 256), scores between different samples of a group are masked.
+ *   a_mn_major = 0: A[m, k] = a[row0 + m, k]   (K columns)      1: A[m, k] = a[row0 + k, m]   (256 columns, K = 256)
+ *   b_mn_major = 0: B[n, k] = b[row0 + n, k]   (N = 256 rows)   1: B[n, k] = b[row0 + k, n]   (N columns, K = 256)
+ *   out[row0 + m, n] = epilogue( sum_k A[m, k] * B[n, k] ):
+ *     UB200_BGEMM_PLAIN        alpha * acc
+ *     UB200_BGEMM_SOFTMAX      row softmax of acc * scale over the sample's own T keys; pass alpha = scale * log2(e)
+ *     UB200_BGEMM_SOFTMAX_BWD  p o (acc - rowsum(p o acc)) * alpha     with p [R, 256] the saved softmax
+ * ------------------------------------------------------------------------------------------ */
+#define UB200_BGEMM_PLAIN 0
+#define UB200_BGEMM_SOFTMAX 1
+#define UB200_BGEMM_SOFTMAX_BWD 2
+typedef struct ub200_bgemm_args {
+    const void *a; int64_t ld_a; int a_mn_major;
+    const void *b; int64_t ld_b; int b_mn_major;
+    void *out; int64_t ld_out;
+    int64_t groups, N, K;
+    int epilogue; float alpha; int T;
+    const void *p; int64_t ld_p;
+} ub200_bgemm_args;
+int ub200_bgemm256(const ub200_bgemm_args *args, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Train-step tail (diff_cifar/main.py:425-429, :57-77): global-norm clip + Adam + EMA over a
  * flat fp32 parameter arena, no host synchronisation.
  * ------------------------------------------------------------------------------------------ */

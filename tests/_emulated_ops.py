@@ -210,6 +210,27 @@ class EmulatedOps:
         else:
             dw.view(cout, k, k, cin).add_(gw.permute(0, 2, 3, 1))
 
+    def bgemm256(self, a, a_mn, b, b_mn, out, K, epilogue, alpha, T, p):
+        """Contract of ub200_bgemm256 (csrc/attention.cu): per group of 256 rows, out = epilogue(A @ B^T), fp32 math."""
+        R, N = out.shape
+        for g in range(R // 256):
+            rows = slice(256 * g, 256 * g + 256)
+            A = a[rows].float().t() if a_mn else a[rows, :K].float()            # [256, K]
+            B = b[rows, :N].float().t() if b_mn else b[rows, :K].float()        # [N, K]
+            acc = A @ B.t()
+            if epilogue == 1:
+                idx = torch.arange(256)
+                mask = (idx[:, None] // T) == (idx[None, :] // T)
+                z = (acc * alpha).masked_fill(~mask, float("-inf"))
+                acc = torch.exp2(z - z.max(dim=1, keepdim=True).values)
+                acc = acc / acc.sum(dim=1, keepdim=True)
+            elif epilogue == 2:
+                pp = p[rows].float()
+                acc = pp * (acc - (pp * acc).sum(dim=1, keepdim=True)) * alpha
+            else:
+                acc = acc * alpha
+            out[rows] = _bf(acc)
+
     def chansum(self, x, per_sample, total, total2=None):
         s = x.float().sum(dim=(1, 2))
         per_sample.copy_(s)

@@ -4,6 +4,8 @@
 // Encoded maps are cached by (address, shape, strides, box): the caching allocator hands the same
 // buffers back every step, so steady-state training encodes nothing.  The cache is the library's only
 // global state; it is immutable per key and guarded by a mutex (threading).
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -89,7 +91,23 @@ int encode_bf16_tensor_map(CUtensorMap *out, const void *base, int rank, const i
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, gbox,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return UB200_E_UNSUPPORTED;
+    if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+        // A thread that has made no runtime call yet (autograd runs backward on its own worker threads) has no current
+        // driver context, and this is a DRIVER entry point: let the runtime bind the primary context, then retry once.
+        (void)cudaFree(nullptr);
+        r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, gbox, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) {
+        if (getenv("UB200_DEBUG")) {
+            fprintf(stderr, "cuTensorMapEncodeTiled failed (%d): base %p rank %d", (int)r, base, rank);
+            for (int i = 0; i < rank; ++i)
+                fprintf(stderr, " | dim %llu box %u es %u stride %llu", (unsigned long long)gdim[i], gbox[i], estr[i],
+                        (unsigned long long)(i + 1 < rank ? gstr[i] : 0));
+            fprintf(stderr, "\n");
+        }
+        return UB200_E_UNSUPPORTED;
+    }
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (g_cache.size() > 65536) g_cache.clear();   // bounded; a changing allocator pattern just re-encodes

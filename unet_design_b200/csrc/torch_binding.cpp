@@ -379,6 +379,34 @@ void pack_conv_weight(const Tensor &w, bool transpose_flip, const Tensor &out) {
                                     transpose_flip ? 1 : 0, out.data_ptr(), cur_stream()), "pack_conv_weight");
 }
 
+// ---------------------------------------------------------------- attention core (batched 256-row GEMM)
+struct Mat2 { void *ptr; int64_t rows, cols, ld; };
+Mat2 mat2(const Tensor &t, const char *name) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.dim() == 2 && t.stride(1) == 1, name,
+                ": expected a CUDA bf16 [rows, cols] matrix with unit column stride");
+    return {t.data_ptr(), t.size(0), t.size(1), t.size(0) > 1 ? t.stride(0) : t.size(1)};
+}
+
+void bgemm256(const Tensor &a, bool a_mn, const Tensor &b, bool b_mn, const Tensor &out, int64_t K, int64_t epilogue,
+              double alpha, int64_t T, const c10::optional<Tensor> &p) {
+    UB_GUARD(a);
+    const Mat2 A = mat2(a, "a"), B = mat2(b, "b"), O = mat2(out, "out");
+    TORCH_CHECK(A.rows == B.rows && A.rows == O.rows && A.rows % 256 == 0, "bgemm256: all matrices need the same multiple of 256 rows");
+    ub200_bgemm_args g{};
+    g.a = A.ptr; g.ld_a = A.ld; g.a_mn_major = a_mn ? 1 : 0;
+    g.b = B.ptr; g.ld_b = B.ld; g.b_mn_major = b_mn ? 1 : 0;
+    g.out = O.ptr; g.ld_out = O.ld;
+    g.groups = A.rows / 256; g.N = O.cols; g.K = K;
+    g.epilogue = (int)epilogue; g.alpha = (float)alpha; g.T = (int)T;
+    TORCH_CHECK(A.cols == (a_mn ? 256 : K) && B.cols == (b_mn ? O.cols : K), "bgemm256: operand column counts do not match N / K");
+    if (p.has_value()) {
+        const Mat2 P = mat2(*p, "p");
+        TORCH_CHECK(P.rows == A.rows && P.cols == 256, "bgemm256: p must be [R, 256]");
+        g.p = P.ptr; g.ld_p = P.ld;
+    }
+    check_rc(ub200_bgemm256(&g, cur_stream()), "bgemm256");
+}
+
 // ---------------------------------------------------------------- optimiser tail
 void sumsq(const Tensor &g, const Tensor &acc) {
     UB_GUARD(g);
@@ -490,6 +518,7 @@ TORCH_LIBRARY(unet_b200, m) {
     m.def("conv_wgrad(Tensor gout, Tensor a, int ksize, Tensor dw, int stride=1) -> ()", &conv_wgrad);
     m.def("haar_dwt2d_multi", &haar_dwt2d_multi);
     m.def("multires_mse", &multires_mse);
+    m.def("bgemm256", &bgemm256);
     m.def("haar_idwt2d_multi", &haar_idwt2d_multi);
     m.def("chansum", &chansum);
     m.def("pack_conv_weight", &pack_conv_weight);

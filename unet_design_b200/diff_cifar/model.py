@@ -175,11 +175,15 @@ class AttnBlock(nn.Module):
             wqkv = torch.cat([self.proj_q.weight, self.proj_k.weight, self.proj_v.weight], dim=0)
             bqkv = torch.cat([self.proj_q.bias, self.proj_k.bias, self.proj_v.bias], dim=0)
             qkv = ops.conv(y, wqkv, bqkv)
-        qkv = qkv.reshape(n, 1, h * w, 3 * c)
-        q, k, v = ops.split3(qkv)
-        o = F.scaled_dot_product_attention(q, k, v, scale=int(c) ** (-0.5))
+        if ops.attention_core_supported(n * h * w, h * w, c):
+            # softmax(Q K^T / sqrt(C)) V and its backward on the tcgen05 batched-GEMM kernel (csrc/attention.cu)
+            o = ops.attention_core(qkv)
+        else:       # shapes the kernel does not tile (token counts that do not divide 256, C not a multiple of 64)
+            qkv = qkv.reshape(n, 1, h * w, 3 * c)
+            q, k, v = ops.split3(qkv)
+            o = F.scaled_dot_product_attention(q, k, v, scale=int(c) ** (-0.5)).reshape(n, h, w, c)
         # x + proj(o): the residual add rides in the conv epilogue
-        return ops.conv(o.reshape(n, h, w, c), self.proj.weight, self.proj.bias, residual=x, out=out)
+        return ops.conv(o, self.proj.weight, self.proj.bias, residual=x, out=out)
 
     def forward(self, x):
         return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x)))

@@ -876,6 +876,68 @@ def rowlin_batch(xs, ws, bs, silu: bool):
     return list(_RowLinBatch.apply(silu, n, *xs, *ws, *bs))
 
 
+# --------------------------------------------------------------------------------------------------
+# attention core: softmax(Q K^T / sqrt(C)) V on tcgen05 (csrc/attention.cu), one head
+# --------------------------------------------------------------------------------------------------
+BGEMM_PLAIN, BGEMM_SOFTMAX, BGEMM_SOFTMAX_BWD = 0, 1, 2
+_LOG2E = 1.4426950408889634
+
+
+def attention_core_supported(n_tokens_total: int, tokens: int, channels: int) -> bool:
+    """One CTA owns 256 rows = 256 / T whole samples; channels in 64-element chunks, at most 256."""
+    import os
+    return (os.environ.get("UB200_ATTN_CORE", "1") != "0" and tokens <= 256 and 256 % tokens == 0
+            and n_tokens_total % 256 == 0 and channels % 64 == 0 and channels <= 256)
+
+
+class _AttnCore(torch.autograd.Function):
+    """o = softmax(q k^T * C^-0.5) v from the fused projection qkv [R, 3C] (R = samples * T rows).  Forward: two batched GEMM
+    launches (scores + softmax epilogue, P V); backward: four (dS with the softmax-backward epilogue, dV, dQ, dK).  The
+    softmax P (bf16 [R, 256]) is saved, so nothing is recomputed."""
+
+    @staticmethod
+    def forward(ctx, qkv2d, T):
+        o_ = _ops()
+        R, c3 = qkv2d.shape
+        C = c3 // 3
+        q, k, v = qkv2d[:, :C], qkv2d[:, C:2 * C], qkv2d[:, 2 * C:]
+        P = torch.empty((R, 256), dtype=torch.bfloat16, device=qkv2d.device)
+        o_.bgemm256(q, False, k, False, P, C, BGEMM_SOFTMAX, float(C) ** -0.5 * _LOG2E, T, None)
+        out = torch.empty((R, C), dtype=torch.bfloat16, device=qkv2d.device)
+        o_.bgemm256(P, False, v, True, out, 256, BGEMM_PLAIN, 1.0, T, None)
+        _count(2)
+        ctx.save_for_backward(qkv2d, P)
+        ctx.T = T
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        o_ = _ops()
+        qkv2d, P = ctx.saved_tensors
+        T = ctx.T
+        R, c3 = qkv2d.shape
+        C = c3 // 3
+        q, k, v = qkv2d[:, :C], qkv2d[:, C:2 * C], qkv2d[:, 2 * C:]
+        if go.stride(1) != 1 or go.stride(0) % 8 != 0 or go.data_ptr() % 16 != 0:
+            go = go.contiguous()
+        dS = torch.empty((R, 256), dtype=torch.bfloat16, device=go.device)
+        o_.bgemm256(go, False, v, False, dS, C, BGEMM_SOFTMAX_BWD, float(C) ** -0.5, T, P)
+        dqkv = torch.empty((R, c3), dtype=torch.bfloat16, device=go.device)
+        o_.bgemm256(P, True, go, True, dqkv[:, 2 * C:], 256, BGEMM_PLAIN, 1.0, T, None)          # dV = P^T dO
+        o_.bgemm256(dS, False, k, True, dqkv[:, :C], 256, BGEMM_PLAIN, 1.0, T, None)             # dQ = dS K
+        o_.bgemm256(dS, True, q, True, dqkv[:, C:2 * C], 256, BGEMM_PLAIN, 1.0, T, None)          # dK = dS^T Q
+        _count(4)
+        return dqkv, None
+
+
+def attention_core(qkv: torch.Tensor) -> torch.Tensor:
+    """qkv: NHWC bf16 [N, H, W, 3C] (the fused q|k|v projection) -> o [N, H, W, C]."""
+    n, h, w, c3 = qkv.shape
+    qkv = _dense_nhwc(qkv)
+    out = _AttnCore.apply(qkv.reshape(n * h * w, c3), h * w)
+    return out.reshape(n, h, w, c3 // 3)
+
+
 class _Split3(torch.autograd.Function):
     """Three channel-slice views of a fused q|k|v projection; backward gathers the three gradients into one
     buffer with strided copies (no zero-fill + add chain as plain slicing would record)."""
