@@ -40,6 +40,8 @@ struct WgradParams {
     // MMA slab is a run of 16 consecutive 128-byte rows starting at an arbitrary row (not an 8-row swizzle atom)
     int halo, bo_mode;
     int S;                              // conv stride: A pixel = S * G pixel + tap offset (TMA traversal stride S)
+    int k1wide;                         // 1x1 conv: the CTA's `ntaps` accumulators are consecutive 128-channel ci tiles, so one
+                                        // G tile feeds 2-3 of them (a lone 128x128 accumulator needs 128 B/clk of operand fill)
     uint32_t a_chunk_stride, a_halo_bytes;
     float *dw;
 };
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     int t = blockIdx.x;
     const int cit = t % p.ci_tiles; t /= p.ci_tiles;
     const int kyg = t % p.ky_groups; t /= p.ky_groups;
-    const int co0 = t * 128, ci0 = cit * 128;
+    const int co0 = t * 128, ci0 = cit * 128 * (p.k1wide ? p.ntaps : 1);
     const int ncols = (p.Cin - ci0 < 128 ? p.Cin - ci0 : 128);          // multiple of 16
     const int mrows = (p.Cout - co0 < 128 ? p.Cout - co0 : 128);
     const int chunks_g = (mrows + p.cw_g - 1) / p.cw_g, chunks_a = (ncols + p.cw_a - 1) / p.cw_a;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                         const int kx = p.ksize == 3 ? tp - 1 : 0;
                         const uint32_t sa = sg + p.g_stage_bytes + tp * p.a_tap_bytes;
                         for (int c = 0; c < chunks_a; ++c)
-                            if (leader) tma_load_4d_a(sa + c * a_chunk_bytes, &tm_a, fb, ci0 + c * p.cw_a, p.S * x0 + kx, p.S * y0 + ky, n0);
+                            if (leader) tma_load_4d_a(sa + c * a_chunk_bytes, &tm_a, fb, ci0 + c * p.cw_a + (p.k1wide ? tp * 128 : 0), p.S * x0 + kx, p.S * y0 + ky, n0);
                     }
                 }
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                 float v[16];
                 tmem_ld16(trow + tp * 128 + cg * 16, v);
                 if (co < p.Cout) {
-                    float4 *dst = reinterpret_cast<float4 *>(p.dw + ((int64_t)co * taps_total + tap) * p.Cin + ci0 + cg * 16);
+                    float4 *dst = reinterpret_cast<float4 *>(p.dw + ((int64_t)co * taps_total + tap) * p.Cin + ci0 + (p.k1wide ? tp * 128 : 0) + cg * 16);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         atomicAdd(dst + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
@@ -396,6 +398,15 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
     p.ci_tiles = (int)((Cin + 127) / 128);
     p.ky_groups = ksize == 3 ? 3 : 1;
     p.ntaps = ksize == 3 ? 3 : 1;
+    // measured on B200: 256->768 @ 16x16 27.3 -> 24.5 us, but 384->128 @ 32x32 29.3 -> 38.0 us (one output tile: 148 pixel
+    // splits, each paying a 3x larger atomic epilogue) and the config-2 step 6.42 -> 6.45 ms: off unless asked for
+    static const int env_k1wide = [] { const char *e = getenv("UB200_WGRAD_K1WIDE"); return e ? atoi(e) : 0; }();
+    if (env_k1wide && ksize == 1 && Cin % 128 == 0 && Cin >= 256) {
+        p.k1wide = 1;
+        p.ntaps = (p.ci_tiles % 3 == 0) ? 3 : (p.ci_tiles % 2 == 0 ? 2 : 1);
+        if (p.ntaps == 1) p.k1wide = 0;
+        p.ci_tiles /= p.ntaps;
+    }
     const int co_tiles = (int)((Cout + 127) / 128);
     const int out_tiles = p.ci_tiles * p.ky_groups * co_tiles;
     // one CTA per SM (the smem ring takes the whole SM): keep the grid within ONE wave of 148 CTAs so there is no
@@ -425,7 +436,7 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
     if (stages > p.tiles_per_split) stages = p.tiles_per_split;
     if (stages < 1) stages = 1;
     p.stages = stages;
-    p.tmem_cols = p.ntaps == 3 ? 512 : 128;
+    p.tmem_cols = p.ntaps == 3 ? 512 : (p.ntaps == 2 ? 256 : 128);
     p.dw = dw;
 
     CUtensorMap tg, ta;
