@@ -515,6 +515,12 @@ def run_gpu_arm_generic(args):
     launches_per_step = ops.launches() - l0
     for i in range(max(args.warmup, 3)):
         step(*devb[i % 4])
+    if args.profile_step:            # ncu --profile-from-start off: exactly one (eager) step between start/stop
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step._body(*devb[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
