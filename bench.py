@@ -464,13 +464,16 @@ def run_gpu_arm(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": BATCH_PER_GPU * world, "parallelism": f"dp{world}",
-                       "cuda_graph": not args.no_graph, "allreduce": ("none" if world == 1 else (("bucketed NCCL all-reduces captured inside the step graph, overlapped with backward" if step._graph_has_tail else "one NCCL all-reduce of the gradient arena after the forward+backward graph") if not args.no_graph else ("tail" if args.no_overlap else "bucketed, overlapped with backward"))), "l2_policy": "4 rotating input batches; activations+weights per step "
+                       "cuda_graph": not args.no_graph, "allreduce": ("none" if world == 1 else (((("bucketed peer-memory (NVLink P2P) all-reduce kernels" if step._p2p is not None else "bucketed NCCL all-reduces") + " captured inside the step graph, overlapped with backward") if step._graph_has_tail else ("one " + ("peer-memory" if step._p2p is not None else "NCCL") + " all-reduce of the gradient arena after the forward+backward graph")) if not args.no_graph else ("tail" if args.no_overlap else "bucketed, overlapped with backward"))), "l2_policy": "4 rotating input batches; activations+weights per step "
                        "(~3 GB) exceed the 126 MB L2", "loss": loss_val},
             "clocks": clocks,
             "e2e": {"value": imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": BATCH_PER_GPU * 3 * 32 * 32 * 4,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,
             "dp_phases": phases,
+            "dp_bucket_trace": ({"gradients": len(step.arena.params), "launched_after": [n for _, n in step.bucket_trace],
+                                 "bucket_mb": [round((hi - lo) * 4 / 2**20, 1) for lo, hi, _ in step._buckets]}
+                                if world > 1 and step._buckets else None),
             "roofline": roofline, "haar_roofline": haar, "cpu_baseline": cpu, "gpu_library_baseline": lib,
         }
     if world > 1:

@@ -199,6 +199,30 @@ int ub200_gn_act_fused_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *
                                      const void *gadd, int64_t ld_gadd,   /* nullable: gx = backward(gy) + gadd */
                                      float *ws, void *stream);
 
+/* Streaming variants of the same two calls: a sums launch and an apply launch, both plain streams over the tensor
+ * (no clusters, no shared-memory slab); the apply launch re-reads from L2 what the sums launch just touched, so HBM
+ * still sees every tensor once.  Faster than the cluster kernels once a sample's slab is larger than what one or two
+ * CTAs hold (ub200_gn_stream_preferred: the policy the torch binding follows; UB200_GN_STREAM=0/1 forces it).
+ * Same arguments and results; ws = ub200_gn_stream_ws_floats(N, HW, C, G) floats of scratch, no zeroing needed:
+ * sums travel between the launches as per-CTA partials that are reduced in a fixed order (bit-reproducible). */
+size_t ub200_gn_stream_ws_floats(int64_t N, int64_t HW, int64_t C, int G);
+int ub200_gn_stream_preferred(int64_t N, int64_t HW, int64_t C, int G, int backward);
+int ub200_gn_act_stream_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t HW, int64_t C, int G,
+                                      float *stats, float eps, const float *gamma, const float *beta,
+                                      const float *scale, const float *shift, int act,
+                                      float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                                      const void *addend, int64_t ld_add, void *y, int64_t ld_y,
+                                      float *ws, void *stream);
+int ub200_gn_act_stream_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int64_t ld_x,
+                                      int64_t N, int64_t HW, int64_t C, int G,
+                                      const float *stats, float eps, const float *gamma, const float *beta,
+                                      const float *scale, const float *shift, int act,
+                                      float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                                      void *gx, int64_t ld_gx,
+                                      float *dgamma, float *dbeta, float *dscale, float *dshift,
+                                      const void *gadd, int64_t ld_gadd,
+                                      float *ws, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * 3x3 / 1x1 convolution, stride 1, "same" zero padding, as tcgen05/TMEM implicit GEMM fed by TMA
  * (replaces nn.Conv2d fprop / dgrad / wgrad; diff_cifar/model.py:69,:133,:143,:146,:396;
@@ -356,6 +380,28 @@ typedef struct ub200_rowlin_item {
 
 int ub200_rowlin_fwd(const ub200_rowlin_item *items, int n_items, int64_t N, int64_t K, int silu, void *stream);
 int ub200_rowlin_bwd(const ub200_rowlin_item *items, int n_items, int64_t N, int64_t K, int silu, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Gradient all-reduce over NVLink peer memory (replaces the implicit gradient exchange of the reference's
+ * data-parallel wrappers: nn.DataParallel at diff_cifar/main.py:235-238, Lightning DDP in pdearena).
+ * One process per GPU.  Each rank allocates one "symmetric" block [flag area | fp32 gradient arena] with
+ * ub200_p2p_alloc (cudaMalloc, zeroed; `handle64` = its 64-byte CUDA IPC handle, to be exchanged between the
+ * ranks by any host channel), maps every other rank's block with ub200_p2p_open, and then calls
+ * ub200_p2p_allreduce_sum_f32 with the table of the `world` base pointers (its own at index `rank`):
+ * arena[offset .. offset + count) of EVERY rank becomes the sum over ranks, bitwise identical on all of
+ * them (two-shot, summed in rank order).  A plain kernel launch: stream-ordered, capturable in a CUDA
+ * graph, no host synchronisation; all ranks must issue the same sequence of calls (same ranges, same `ctas`).
+ * world <= 8, offset and count multiples of 4 floats.  `ctas` = thread blocks of the launch (0: default 148; a
+ * bucket that overlaps other kernels can be throttled to a few dozen so that it does not disturb them).
+ * The arena starts ub200_p2p_flag_bytes() bytes into the block.
+ * ------------------------------------------------------------------------------------------ */
+size_t ub200_p2p_flag_bytes(void);
+int ub200_p2p_alloc(size_t bytes, void **ptr, unsigned char *handle64);
+int ub200_p2p_free(void *ptr);
+int ub200_p2p_open(const unsigned char *handle64, void **peer_ptr);
+int ub200_p2p_close(void *peer_ptr);
+int ub200_p2p_allreduce_sum_f32(void *const *bases, int rank, int world, int64_t offset_floats, int64_t count,
+                                int ctas, void *stream);
 
 #ifdef __cplusplus
 }

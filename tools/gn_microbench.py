@@ -29,7 +29,7 @@ def timeit(fn, iters=20):
 
 def main():
     ops = _lib.ops()
-    out = {"fused": os.environ.get("UB200_GN_FUSED", "1"), "persist": os.environ.get("UB200_GN_PERSIST", "1"), "rows": []}
+    out = {"fused": os.environ.get("UB200_GN_FUSED", "1"), "stream": os.environ.get("UB200_GN_STREAM", "policy"), "rows": []}
     for (n, h, w, c) in SHAPES:
         x = torch.randn(n, h, w, c, device="cuda").to(torch.bfloat16)
         gy = torch.randn_like(x)
@@ -46,7 +46,7 @@ def main():
         print(row, flush=True)
         out["rows"].append(row)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open(f"gpurun_out/gn_microbench_fused{out['fused']}_persist{os.environ.get('UB200_GN_PERSIST', '1')}.json", "w"), indent=1)
+    json.dump(out, open(f"gpurun_out/gn_microbench_fused{out['fused']}_stream{out['stream']}.json", "w"), indent=1)
 
 
 if __name__ == "__main__":

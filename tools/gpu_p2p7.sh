@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=${N:-2}
+tr() { timeout -s KILL ${T:-300} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 500)) "$@"; }
+b() { name=$1; T=400 tr bench.py --gpus $N --steps 30 --warmup 5 --skip-cpu --skip-haar --skip-lib > gpurun_out/dp${N}_$name.log 2>&1
+  echo -n "$name exit=$? "; grep -a '^{' gpurun_out/dp${N}_$name.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],3),'ms/step', round(d['value']),'img/s', d.get('dp_phases'))" 2>/dev/null || tail -8 gpurun_out/dp${N}_$name.log | cut -c1-300; }
+b carve_overlap
+UB200_P2P_EARLY_CTAS=48 b carve_overlap_early48
+UB200_P2P_DEBUG=2 b carve_barriers_only
+UB200_MAX_CARVEOUT=0 b nocarve_overlap
+UB200_DP_OVERLAP=0 b carve_tail

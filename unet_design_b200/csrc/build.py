@@ -20,7 +20,7 @@ TORCH_LIB = os.path.join(OUT_DIR, "libunet_b200_torch.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
 CU_SOURCES = ["api.cu", "haar.cu", "layout.cu", "groupnorm.cu", "optim.cu", "tc_host.cu", "conv_fprop.cu",
-              "conv_wgrad.cu", "rowlin.cu", "attention.cu"]
+              "conv_wgrad.cu", "rowlin.cu", "attention.cu", "p2p.cu"]
 HEADERS = ["common.cuh", "tc_common.cuh", os.path.join(INCLUDE, "unet_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -5,6 +5,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <unordered_set>
+
 #include "unet_b200.h"
 
 #define UB_LAUNCH_CHECK()                                  \
@@ -52,9 +55,25 @@ inline void pdl_attr(cudaLaunchAttribute &a) {
     a.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
 }
 
+// Shared-memory carve-out.  Two kernels are resident on one SM together only when they agree on the SM's L1 / shared-memory
+// split; a kernel that wants another split waits until the SM has drained.  The persistent conv kernels need the largest
+// shared-memory configuration, so every kernel that is meant to run NEXT TO them on another stream (weight-gradient side
+// stream, column sums, all-reduce buckets, the streaming GroupNorm kernels) asks for the same one.  None of them lives off L1:
+// their global accesses are streaming.  UB200_MAX_CARVEOUT=0 switches the request off (A/B).
+inline void prefer_max_smem_carveout(const void *kernel) {
+    static const bool on = [] { const char *e = getenv("UB200_MAX_CARVEOUT"); return !(e && e[0] == '0'); }();
+    if (!on) return;
+    static std::mutex mu;
+    static std::unordered_set<const void *> done;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.insert(kernel).second)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 // kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute (the kernel must call pdl_trigger / pdl_wait)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    prefer_max_smem_carveout(reinterpret_cast<const void *>(kernel));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];

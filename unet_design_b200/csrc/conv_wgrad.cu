@@ -470,6 +470,7 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
     cudaLaunchAttribute attr[1];
     ub::pdl_attr(attr[0]);
     cfg.attrs = attr; cfg.numAttrs = 1;
+    ub::prefer_max_smem_carveout(reinterpret_cast<const void *>(conv_wgrad_kernel));
     cudaError_t le = cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, tg, ta, p);
     if (le != cudaSuccess) return (int)le;
     UB_LAUNCH_CHECK();
@@ -500,6 +501,8 @@ int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, in
             attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             ub::pdl_attr(attr[1]);
             cfg.attrs = attr; cfg.numAttrs = 2;
+            ub::prefer_max_smem_carveout(reinterpret_cast<const void *>(chansum_cluster_kernel));   // runs next to the conv kernels
+            ub::prefer_max_smem_carveout(reinterpret_cast<const void *>(colsum_rows_kernel));
             cudaError_t e = cudaLaunchKernelEx(&cfg, chansum_cluster_kernel, reinterpret_cast<const __nv_bfloat16 *>(x), ld, HW,
                                                (int)C, chunks, rows, ppc, cs, per_sample);
             if (e != cudaSuccess) return (int)e;
@@ -528,6 +531,8 @@ int ub200_chansum_nhwc_bf16(const void *x, int64_t ld, int64_t N, int64_t HW, in
     const int64_t ppc = (HW + splits - 1) / splits;
     splits = (HW + ppc - 1) / ppc;
     dim3 grid((unsigned)splits, (unsigned)N, 1);
+    ub::prefer_max_smem_carveout(reinterpret_cast<const void *>(chansum_kernel));
+    ub::prefer_max_smem_carveout(reinterpret_cast<const void *>(colsum_rows_kernel));
     chansum_kernel<<<grid, 256, 256 * 8 * sizeof(float), s>>>(reinterpret_cast<const __nv_bfloat16 *>(x), ld, HW, (int)C, chunks,
                                                        rows, ppc, per_sample);
     UB_LAUNCH_CHECK();

@@ -777,6 +777,391 @@ __global__ void __launch_bounds__(256) add_rows_kernel(__nv_bfloat16 *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming two-launch variants.  The cluster kernels above read every tensor once, but each CTA walks a chain of ~8
+// dependent phases (bulk copy -> sums -> fold -> cluster barrier -> DSMEM -> table -> apply) on a 32-64 KB slab: ~10 us of
+// latency per CTA, which caps them at 2.3-3.2 TB/s forward and 1.5-1.8 TB/s backward on the 32x32 layers (cold cache).
+// Here the chain is cut at a kernel boundary instead: a sums kernel and an apply kernel, both pure streams with four
+// 16-byte loads in flight per thread and no barrier inside the loop.  The second kernel's reads are L2 hits (the first
+// kernel touched the same lines microseconds earlier; a layer's tensors are 17-100 MB against 126 MB of L2), so HBM
+// still sees each tensor once.  Sums travel between the two launches as per-CTA partials [N][splits][...] that every
+// apply CTA reduces itself in a fixed order: no atomics, no memset, bit-reproducible.
+//   forward : gn_stream_stats_kernel (partials [N][splits][2G]) -> gn_stream_fwd_kernel (writes stats [N,G,2] too)
+//   backward: gn_stream_bwd_reduce   (dz parked in gx, partials [N][splits][2C]) -> gn_stream_bwd_apply
+// The forward apply kernel with splits = 1 and part = stats is the "statistics already known" entry
+// (ub200_gn_act_fwd_nhwc_bf16; a conv epilogue that accumulates ub200_conv_args.gn_partial feeds it directly).
+// ---------------------------------------------------------------------------------------------
+constexpr int kStreamThreads = 256;
+constexpr int kStreamMaxSplits = 64;
+
+struct StreamShape {
+    int64_t HW; int C, G, cpg, chunks, rows, splits, iters;   // one CTA: `iters` turns of `rows` pixels
+};
+
+// per-thread 16 values (8 channels x 2 kinds) -> chan[2*c + kind] summed over the threads that share a chunk
+__device__ __forceinline__ void stream_channel_sums(const float (&v)[16], float *sp, float *chan, const StreamShape &sh, bool active) {
+    if (active) {
+        float4 *dst = reinterpret_cast<float4 *>(sp + (size_t)threadIdx.x * 16);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]); dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        dst[2] = make_float4(v[8], v[9], v[10], v[11]); dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) {
+        const int c = i >> 1, kind = i & 1, cq = c >> 3, u = c & 7;
+        float acc = 0.f;
+        for (int rr = 0; rr < sh.rows; ++rr) acc += sp[(size_t)(rr * sh.chunks + cq) * 16 + kind * 8 + u];
+        chan[i] = acc;
+    }
+    __syncthreads();
+}
+
+// out[2*g + kind] = sum over the channels of group g of chan[2*c + kind]; a warp per item for wide groups
+__device__ __forceinline__ void stream_group_sums(const float *chan, const StreamShape &sh, float *out_smem, float *out_gmem) {
+    if (sh.cpg >= 64) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int i = warp; i < 2 * sh.G; i += blockDim.x >> 5) {
+            const int g = i >> 1, kind = i & 1;
+            float acc = 0.f;
+            for (int k = lane; k < sh.cpg; k += 32) acc += chan[2 * (g * sh.cpg + k) + kind];
+            acc = warp_sum(acc);
+            if (lane == 0) { if (out_smem) out_smem[i] = acc; if (out_gmem) out_gmem[i] = acc; }
+        }
+    } else {
+        for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) {
+            const int g = i >> 1, kind = i & 1;
+            float acc = 0.f;
+            for (int k = 0; k < sh.cpg; ++k) acc += chan[2 * (g * sh.cpg + k) + kind];
+            if (out_smem) out_smem[i] = acc;
+            if (out_gmem) out_gmem[i] = acc;
+        }
+    }
+}
+
+__device__ __forceinline__ void load_tab8(const float *tab, int q, float (&o)[8]) {
+    const float4 a = *reinterpret_cast<const float4 *>(tab + 8 * q), b = *reinterpret_cast<const float4 *>(tab + 8 * q + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+__global__ void __launch_bounds__(kStreamThreads, 4) gn_stream_stats_kernel(const __nv_bfloat16 *__restrict__ x, int64_t ld,
+                                                                            StreamShape sh, float *__restrict__ part) {
+    extern __shared__ __align__(16) float ssm[];      // sp [256][16] | chan [2C]
+    float *sp = ssm, *chan = ssm + kStreamThreads * 16;
+    const int64_t n = blockIdx.y;
+    const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
+    const bool active = r < sh.rows;
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = 0.f;
+    pdl_trigger();
+    pdl_wait();
+    if (active) {
+        const int64_t p0 = (int64_t)blockIdx.x * sh.iters * sh.rows;
+        const int64_t p1 = min(p0 + (int64_t)sh.iters * sh.rows, sh.HW);
+        const __nv_bfloat16 *base = x + n * sh.HW * ld + 8 * q;
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        for (int64_t p = p0 + r; p < p1; p += 4 * sh.rows) {
+            uint4 t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t pj = p + (int64_t)j * sh.rows;
+                t[j] = pj < p1 ? ld_stream_u4(reinterpret_cast<const uint4 *>(base + pj * ld)) : zero4;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float f[8];
+                unpack8(t[j], f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { v[u] += f[u]; v[8 + u] = fmaf(f[u], f[u], v[8 + u]); }
+            }
+        }
+    }
+    stream_channel_sums(v, sp, chan, sh, active);
+    stream_group_sums(chan, sh, nullptr, part + (n * sh.splits + blockIdx.x) * 2 * sh.G);
+}
+
+// y = addend + dropout(act(x * A[n,c] + B[n,c])) with the statistics given as `nparts` partial sums per (sample, group)
+template <int ACT, bool DROP>
+__global__ void __launch_bounds__(kStreamThreads, DROP ? 3 : 4) gn_stream_fwd_kernel(
+    const __nv_bfloat16 *__restrict__ x, int64_t ld_x, StreamShape sh, const float *__restrict__ part, int nparts,
+    float *__restrict__ stats_out, float eps, const float *__restrict__ gamma, const float *__restrict__ beta,
+    const float *__restrict__ scale, const float *__restrict__ shift, float p_drop, uint64_t seed, uint64_t offset,
+    const uint64_t *__restrict__ off_dev, const __nv_bfloat16 *__restrict__ addend, int64_t ld_add,
+    __nv_bfloat16 *__restrict__ y, int64_t ld_y) {
+    extern __shared__ __align__(16) float ssm[];      // gs [2G padded] | tab [2C]
+    float *gs = ssm, *tab = ssm + ((2 * sh.G + 3) & ~3);
+    const int64_t n = blockIdx.y;
+    const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
+    pdl_trigger();
+    pdl_wait();
+    if (part) {
+        for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) {
+            const float *src = part + n * nparts * 2 * sh.G + i;
+            float acc = 0.f;
+            for (int s = 0; s < nparts; ++s) acc += __ldg(src + (int64_t)s * 2 * sh.G);
+            gs[i] = acc;
+            if (stats_out && blockIdx.x == 0) stats_out[n * 2 * sh.G + i] = acc;
+        }
+    }
+    __syncthreads();
+    const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        float mean = 0.f, rstd = 1.f;
+        if (part) {
+            const int g = c / sh.cpg;
+            mean = gs[2 * g] * inv_cnt;
+            rstd = rsqrtf(fmaxf(gs[2 * g + 1] * inv_cnt - mean * mean, 0.f) + eps);
+        }
+        const float g0 = gamma ? __ldg(gamma + c) : 1.f, b0 = beta ? __ldg(beta + c) : 0.f;
+        const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f, sf = shift ? __ldg(shift + n * sh.C + c) : 0.f;
+        const float a = rstd * g0 * sc;
+        tab[c] = act_pre_scale<ACT>() * a;
+        tab[sh.C + c] = act_pre_scale<ACT>() * fmaf(-mean, a, fmaf(b0, sc, sf));
+    }
+    __syncthreads();
+    if (r >= sh.rows) return;
+    float A[8], B[8];
+    load_tab8(tab, q, A); load_tab8(tab + sh.C, q, B);
+    if (DROP && off_dev) offset += __ldg(off_dev);   // device-resident counter: CUDA-graph replays draw fresh masks
+    const int64_t p0 = (int64_t)blockIdx.x * sh.iters * sh.rows;
+    const int64_t p1 = min(p0 + (int64_t)sh.iters * sh.rows, sh.HW);
+    const __nv_bfloat16 *xb = x + n * sh.HW * ld_x + 8 * q;
+    const __nv_bfloat16 *ab = addend ? addend + n * sh.HW * ld_add + 8 * q : nullptr;
+    __nv_bfloat16 *yb = y + n * sh.HW * ld_y + 8 * q;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    for (int64_t p = p0 + r; p < p1; p += 4 * sh.rows) {
+        uint4 t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t pj = p + (int64_t)j * sh.rows;
+            t[j] = pj < p1 ? ld_stream_u4(reinterpret_cast<const uint4 *>(xb + pj * ld_x)) : zero4;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t pj = p + (int64_t)j * sh.rows;
+            if (pj >= p1) break;
+            float f[8], m[8];
+            unpack8(t[j], f);
+            if (DROP) dropout_mask8(seed, offset, (n * sh.HW + pj) * sh.C + 8 * q, p_drop, m);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                f[u] = act_fwd<ACT>(fmaf(f[u], A[u], B[u]));
+                if (DROP) f[u] *= m[u];
+            }
+            if (ab) {
+                float r8[8];
+                unpack8(ld_stream_u4(reinterpret_cast<const uint4 *>(ab + pj * ld_add)), r8);   // post-norm blocks only: not prefetched
+#pragma unroll
+                for (int u = 0; u < 8; ++u) f[u] += r8[u];
+            }
+            *reinterpret_cast<uint4 *>(yb + pj * ld_y) = pack8(f);
+        }
+    }
+}
+
+// backward launch 1: dz = gy * mask * act'(z) computed once, parked (bf16) in the gx buffer, and reduced to per-CTA
+// partials part[n][split][c] = (sum dz, sum dz*x)
+template <int ACT, bool DROP>
+__global__ void __launch_bounds__(kStreamThreads, DROP ? 2 : 3) gn_stream_bwd_reduce(
+    const __nv_bfloat16 *__restrict__ gy, int64_t ld_gy, const __nv_bfloat16 *__restrict__ x, int64_t ld_x, StreamShape sh,
+    const float *__restrict__ stats, float eps, const float *__restrict__ gamma, const float *__restrict__ beta,
+    const float *__restrict__ scale, const float *__restrict__ shift, float p_drop, uint64_t seed, uint64_t offset,
+    const uint64_t *__restrict__ off_dev, __nv_bfloat16 *__restrict__ dzbuf, int64_t ld_dz, float *__restrict__ part) {
+    extern __shared__ __align__(16) float ssm[];      // sp [256][16] | chan [2C] (first the A/B table, then the sums)
+    float *sp = ssm, *chan = ssm + kStreamThreads * 16;
+    const int64_t n = blockIdx.y;
+    const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
+    const bool active = r < sh.rows;
+    const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
+    pdl_trigger();
+    pdl_wait();
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        float mean, rstd;
+        mean_rstd(stats, n, sh.G, c / sh.cpg, inv_cnt, eps, mean, rstd);
+        const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
+        const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f, sf = shift ? __ldg(shift + n * sh.C + c) : 0.f;
+        const float a = rstd * ga * sc;
+        chan[c] = act_pre_scale<ACT>() * a;
+        chan[sh.C + c] = act_pre_scale<ACT>() * ((be - mean * rstd * ga) * sc + sf);
+    }
+    __syncthreads();
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = 0.f;
+    if (active) {
+        float A[8], B[8];
+        load_tab8(chan, q, A); load_tab8(chan + sh.C, q, B);
+        if (DROP && off_dev) offset += __ldg(off_dev);
+        const int64_t p0 = (int64_t)blockIdx.x * sh.iters * sh.rows;
+        const int64_t p1 = min(p0 + (int64_t)sh.iters * sh.rows, sh.HW);
+        const __nv_bfloat16 *xb = x + n * sh.HW * ld_x + 8 * q;
+        const __nv_bfloat16 *gb = gy + n * sh.HW * ld_gy + 8 * q;
+        __nv_bfloat16 *db = dzbuf + n * sh.HW * ld_dz + 8 * q;
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        for (int64_t p = p0 + r; p < p1; p += 2 * sh.rows) {          // two pixels per turn: four 16-byte loads in flight
+            const int64_t pb = p + sh.rows;
+            const bool two = pb < p1;
+            const uint4 xa = ld_stream_u4(reinterpret_cast<const uint4 *>(xb + p * ld_x));
+            const uint4 ga = ld_stream_u4(reinterpret_cast<const uint4 *>(gb + p * ld_gy));
+            const uint4 xc = two ? ld_stream_u4(reinterpret_cast<const uint4 *>(xb + pb * ld_x)) : zero4;
+            const uint4 gc = two ? ld_stream_u4(reinterpret_cast<const uint4 *>(gb + pb * ld_gy)) : zero4;
+            float f[8], g[8], m[8];
+            unpack8(xa, f); unpack8(ga, g);
+            if (DROP) dropout_mask8(seed, offset, (n * sh.HW + p) * sh.C + 8 * q, p_drop, m);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float dz = g[u] * act_bwd<ACT>(fmaf(f[u], A[u], B[u]));
+                if (DROP) dz *= m[u];
+                v[u] += dz; v[8 + u] = fmaf(dz, f[u], v[8 + u]);
+                g[u] = dz;
+            }
+            *reinterpret_cast<uint4 *>(db + p * ld_dz) = pack8(g);
+            if (two) {
+                unpack8(xc, f); unpack8(gc, g);
+                if (DROP) dropout_mask8(seed, offset, (n * sh.HW + pb) * sh.C + 8 * q, p_drop, m);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    float dz = g[u] * act_bwd<ACT>(fmaf(f[u], A[u], B[u]));
+                    if (DROP) dz *= m[u];
+                    v[u] += dz; v[8 + u] = fmaf(dz, f[u], v[8 + u]);
+                    g[u] = dz;
+                }
+                *reinterpret_cast<uint4 *>(db + pb * ld_dz) = pack8(g);
+            }
+        }
+    }
+    __syncthreads();                                                   // every thread is done with the A/B table in chan
+    stream_channel_sums(v, sp, chan, sh, active);
+    float *dst = part + (n * sh.splits + blockIdx.x) * 2 * sh.C;
+    for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) dst[i] = chan[i];
+}
+
+// backward launch 2.  With Q1 = sum dz, Q2x = sum dz*x per (n,c):  sum dz*xhat = rstd*(Q2x - mean*Q1), and
+//   dx = rstd*(dz*gs - m1 - xhat*m2) = dz*P + x*Qc + R     (P, Qc, R per channel; gs = gamma*(1+scale))
+// dz is read back from the gx buffer and overwritten in place: three fmas per element.
+__global__ void __launch_bounds__(kStreamThreads, 4) gn_stream_bwd_apply(
+    const __nv_bfloat16 *__restrict__ x, int64_t ld_x, StreamShape sh, const float *__restrict__ stats,
+    const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ scale, float eps,
+    const float *__restrict__ part, __nv_bfloat16 *__restrict__ gx, int64_t ld_gx, float *__restrict__ dgamma,
+    float *__restrict__ dbeta, float *__restrict__ dscale, float *__restrict__ dshift,
+    const __nv_bfloat16 *__restrict__ gadd, int64_t ld_gadd) {
+    extern __shared__ __align__(16) float ssm[];      // chan [2C] | tab [3C] | sg [2G]
+    float *chan = ssm, *tab = ssm + 2 * sh.C, *sg = tab + 3 * sh.C;
+    const int64_t n = blockIdx.y;
+    const int q = threadIdx.x % sh.chunks, r = threadIdx.x / sh.chunks;
+    const float inv_cnt = 1.0f / ((float)sh.cpg * (float)sh.HW);
+    pdl_trigger();
+    pdl_wait();
+    // Q[c] = sum of the per-CTA partials (fixed order), folded with gamma*(1+scale) for the group sums
+    for (int i = threadIdx.x; i < 2 * sh.C; i += blockDim.x) {
+        const float *src = part + n * sh.splits * 2 * sh.C + i;
+        float acc = 0.f;
+        for (int s = 0; s < sh.splits; ++s) acc += __ldg(src + (int64_t)s * 2 * sh.C);
+        tab[i] = acc;                                                  // raw (Q1, Q2x) parked in tab[0 .. 2C)
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        const float ga = gamma ? __ldg(gamma + c) : 1.f, be = beta ? __ldg(beta + c) : 0.f;
+        const float sc = scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f;
+        float mean, rstd;
+        mean_rstd(stats, n, sh.G, c / sh.cpg, inv_cnt, eps, mean, rstd);
+        const float Q1 = tab[2 * c];
+        const float Q2 = rstd * (tab[2 * c + 1] - mean * Q1);          // sum dz * xhat
+        chan[2 * c] = ga * sc * Q1;
+        chan[2 * c + 1] = ga * sc * Q2;
+        if (blockIdx.x == 0) {                                         // parameter gradients: once per sample
+            if (dgamma) atomicAdd(dgamma + c, sc * Q2);
+            if (dbeta) atomicAdd(dbeta + c, sc * Q1);
+            if (dscale) dscale[n * sh.C + c] = ga * Q2 + be * Q1;
+            if (dshift) dshift[n * sh.C + c] = Q1;
+        }
+    }
+    __syncthreads();
+    if (stats) stream_group_sums(chan, sh, sg, nullptr);
+    else for (int i = threadIdx.x; i < 2 * sh.G; i += blockDim.x) sg[i] = 0.f;   // no normalisation: no mean-subtraction terms
+    __syncthreads();
+    for (int c = threadIdx.x; c < sh.C; c += blockDim.x) {
+        const int g = c / sh.cpg;
+        float mean, rstd;
+        mean_rstd(stats, n, sh.G, g, inv_cnt, eps, mean, rstd);
+        const float m1 = sg[2 * g] * inv_cnt, m2 = sg[2 * g + 1] * inv_cnt;
+        const float gs = (gamma ? __ldg(gamma + c) : 1.f) * (scale ? 1.f + __ldg(scale + n * sh.C + c) : 1.f);
+        const float qc = -rstd * rstd * m2;
+        tab[c] = rstd * gs;
+        tab[sh.C + c] = qc;
+        tab[2 * sh.C + c] = -rstd * m1 - mean * qc;
+    }
+    __syncthreads();
+    if (r >= sh.rows) return;
+    float P[8], Qc[8], R[8];
+    load_tab8(tab, q, P); load_tab8(tab + sh.C, q, Qc); load_tab8(tab + 2 * sh.C, q, R);
+    const int64_t p0 = (int64_t)blockIdx.x * sh.iters * sh.rows;
+    const int64_t p1 = min(p0 + (int64_t)sh.iters * sh.rows, sh.HW);
+    const __nv_bfloat16 *xb = x + n * sh.HW * ld_x + 8 * q;
+    const __nv_bfloat16 *ab = gadd ? gadd + n * sh.HW * ld_gadd + 8 * q : nullptr;
+    __nv_bfloat16 *gb = gx + n * sh.HW * ld_gx + 8 * q;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    for (int64_t p = p0 + r; p < p1; p += 2 * sh.rows) {
+        const int64_t pb = p + sh.rows;
+        const bool two = pb < p1;
+        const uint4 xa = ld_stream_u4(reinterpret_cast<const uint4 *>(xb + p * ld_x));
+        const uint4 da = *reinterpret_cast<const uint4 *>(gb + p * ld_gx);
+        const uint4 xc = two ? ld_stream_u4(reinterpret_cast<const uint4 *>(xb + pb * ld_x)) : zero4;
+        const uint4 dc = two ? *reinterpret_cast<const uint4 *>(gb + pb * ld_gx) : zero4;
+        uint4 aa = zero4, ac = zero4;
+        if (ab) {
+            aa = ld_stream_u4(reinterpret_cast<const uint4 *>(ab + p * ld_gadd));
+            if (two) ac = ld_stream_u4(reinterpret_cast<const uint4 *>(ab + pb * ld_gadd));
+        }
+        float f[8], d[8], a[8];
+        unpack8(xa, f); unpack8(da, d); unpack8(aa, a);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = fmaf(d[u], P[u], fmaf(f[u], Qc[u], R[u])) + a[u];
+        *reinterpret_cast<uint4 *>(gb + p * ld_gx) = pack8(d);
+        if (two) {
+            unpack8(xc, f); unpack8(dc, d); unpack8(ac, a);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) d[u] = fmaf(d[u], P[u], fmaf(f[u], Qc[u], R[u])) + a[u];
+            *reinterpret_cast<uint4 *>(gb + pb * ld_gx) = pack8(d);
+        }
+    }
+}
+
+// CTA plan of the streaming kernels; false when the shape is not eligible
+bool plan_stream(int64_t N, int64_t HW, int64_t C, int G, StreamShape &sh) {
+    if (N <= 0 || HW <= 0 || C <= 0 || G <= 0 || C % 8 != 0 || C % G != 0 || C > 8 * kStreamThreads || N > 65535) return false;
+    sh.HW = HW; sh.C = (int)C; sh.G = G; sh.cpg = (int)(C / G); sh.chunks = (int)(C / 8);
+    sh.rows = kStreamThreads / sh.chunks;
+    const int64_t turns = (HW + sh.rows - 1) / sh.rows;              // row-turns per sample
+    // about one wave of 4 resident CTAs per SM, at least 4 turns per CTA; among [want, 2*want] the split that wastes least
+    int64_t want = (ub::kSMs * 4 + N - 1) / N;
+    const int64_t most = turns / 4 > 1 ? turns / 4 : 1;
+    if (want > most) want = most;
+    if (want > kStreamMaxSplits) want = kStreamMaxSplits;
+    int64_t best = want, best_waste = -1;
+    for (int64_t s = want; s <= 2 * want && s <= most && s <= kStreamMaxSplits; ++s) {
+        const int64_t it = (turns + s - 1) / s, waste = it * s - turns;
+        if ((turns + it - 1) / it != s) continue;                     // would leave an empty CTA
+        if (best_waste < 0 || waste < best_waste) { best = s; best_waste = waste; }
+    }
+    sh.iters = (int)((turns + best - 1) / best);
+    sh.splits = (int)((turns + sh.iters - 1) / sh.iters);
+    return true;
+}
+
+// policy: the cluster kernels win on small slabs (one or two CTAs hold a sample: short chain, one launch)
+bool stream_preferred(int64_t HW, int64_t C, bool backward) {
+    static const int mode = [] { const char *e = getenv("UB200_GN_STREAM"); return e ? atoi(e) : -1; }();   // A/B switch
+    if (mode == 0) return false;
+    if (mode == 1) return true;
+    static const long min_slab = [] { const char *e = getenv("UB200_GN_STREAM_MIN_SLAB"); return e ? atol(e) : 0L; }();
+    static const long max_slab = [] { const char *e = getenv("UB200_GN_STREAM_MAX_SLAB"); return e ? atol(e) : (1L << 40); }();
+    // 1 forward, 2 backward, 3 both.  Measured in the config-2 step graph (B200, ms/step): neither 6.42, both 6.32,
+    // backward only 6.25, forward only 6.48 -- the one-launch cluster forward stays, the backward streams.
+    static const int dir = [] { const char *e = getenv("UB200_GN_STREAM_DIR"); return e ? atoi(e) : 2; }();
+    if (!(dir & (backward ? 2 : 1))) return false;
+    return HW * C * 2 >= min_slab && HW * C * 2 <= max_slab;
+}
+
 // cluster size / smem plan for the fused kernels; returns false when the slab does not fit
 bool plan_fused(int64_t N, int64_t HW, int64_t C, int G, int tensors, size_t extra_floats, FusedShape &sh, size_t &smem,
                 int only_single_cta = 0) {
@@ -821,6 +1206,7 @@ int launch_cluster(K kernel, int grid, int cs, size_t smem, cudaStream_t s, Args
         }
     }
     if (e != cudaSuccess) return (int)e;
+    prefer_max_smem_carveout(reinterpret_cast<const void *>(kernel));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.blockDim = dim3(kFusedThreads, 1, 1);
@@ -866,6 +1252,16 @@ int make_shape(int64_t N, int64_t HW, int64_t C, int G, Shape &sh, dim3 &grid) {
         }                                                                                            \
     } while (0)
 
+#define STREAM_ACT_DROP(KERNEL, act, drop, ...)                                                                   \
+    ((drop) ? ((act) == UB200_ACT_SILU   ? launch_pdl(KERNEL<UB200_ACT_SILU, true>, __VA_ARGS__)                  \
+               : (act) == UB200_ACT_GELU ? launch_pdl(KERNEL<UB200_ACT_GELU, true>, __VA_ARGS__)                  \
+               : (act) == UB200_ACT_RELU ? launch_pdl(KERNEL<UB200_ACT_RELU, true>, __VA_ARGS__)                  \
+                                         : launch_pdl(KERNEL<UB200_ACT_NONE, true>, __VA_ARGS__))                 \
+            : ((act) == UB200_ACT_SILU   ? launch_pdl(KERNEL<UB200_ACT_SILU, false>, __VA_ARGS__)                 \
+               : (act) == UB200_ACT_GELU ? launch_pdl(KERNEL<UB200_ACT_GELU, false>, __VA_ARGS__)                 \
+               : (act) == UB200_ACT_RELU ? launch_pdl(KERNEL<UB200_ACT_RELU, false>, __VA_ARGS__)                 \
+                                         : launch_pdl(KERNEL<UB200_ACT_NONE, false>, __VA_ARGS__)))
+
 }  // namespace
 
 extern "C" {
@@ -899,6 +1295,18 @@ int ub200_gn_act_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t H
     UB_REQUIRE(!addend || (ld_add % 8 == 0 && ld_add >= C && ub::aligned16(addend)), UB200_E_UNSUPPORTED);
     cudaStream_t s = ub::as_stream(stream);
     const bool drop = dropout_p > 0.f;
+    StreamShape st;
+    if (plan_stream(N, HW, C, G, st)) {      // per-CTA coefficient table + four loads in flight; part = stats, one partial
+        cudaError_t e = STREAM_ACT_DROP(gn_stream_fwd_kernel, act, drop, dim3((unsigned)st.splits, (unsigned)N, 1),
+                                        dim3(kStreamThreads), (size_t)(((2 * G + 3) & ~3) + 2 * C) * 4, s,
+                                        reinterpret_cast<const __nv_bfloat16 *>(x), ld_x, st, stats, 1, (float *)nullptr, eps, gamma,
+                                        beta, scale, shift, dropout_p, seed, offset, offset_dev,
+                                        reinterpret_cast<const __nv_bfloat16 *>(addend), ld_add,
+                                        reinterpret_cast<__nv_bfloat16 *>(y), ld_y);
+        if (e != cudaSuccess) return (int)e;
+        UB_LAUNCH_CHECK();
+        return UB200_OK;
+    }
     DISPATCH_ACT_DROP(gn_act_fwd_kernel, act, drop,
                       <<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16 *>(x), ld_x, sh, stats, gamma, beta,
                                             scale, shift, eps, dropout_p, seed, offset, offset_dev,
@@ -1017,6 +1425,77 @@ int ub200_gn_act_fused_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *
     if (xslab) return DISPATCH_FUSED(FUSED_BWD_X, act, drop, BWD_ARGS);
     return DISPATCH_FUSED(FUSED_BWD_S, act, drop, BWD_ARGS);
 #undef BWD_ARGS
+}
+
+/* ---- streaming two-launch variants (see the kernel comment) ---- */
+size_t ub200_gn_stream_ws_floats(int64_t N, int64_t HW, int64_t C, int G) {
+    StreamShape sh;
+    if (!plan_stream(N, HW, C, G, sh)) return 0;
+    return (size_t)N * (size_t)sh.splits * 2 * (size_t)C;      // backward partials; the forward uses [N][splits][2G] of it
+}
+
+int ub200_gn_stream_preferred(int64_t N, int64_t HW, int64_t C, int G, int backward) {
+    StreamShape sh;
+    return plan_stream(N, HW, C, G, sh) && stream_preferred(HW, C, backward != 0) ? 1 : 0;
+}
+
+int ub200_gn_act_stream_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t HW, int64_t C, int G, float *stats,
+                                      float eps, const float *gamma, const float *beta, const float *scale,
+                                      const float *shift, int act, float dropout_p, uint64_t seed, uint64_t offset,
+                                      const uint64_t *offset_dev, const void *addend, int64_t ld_add, void *y,
+                                      int64_t ld_y, float *ws, void *stream) {
+    UB_REQUIRE(x && y && stats && ws && N > 0 && HW > 0 && C > 0 && G > 0 && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
+    UB_REQUIRE(act >= UB200_ACT_NONE && act <= UB200_ACT_RELU, UB200_E_BADARG);
+    StreamShape sh;
+    UB_REQUIRE(plan_stream(N, HW, C, G, sh), UB200_E_UNSUPPORTED);
+    UB_REQUIRE(ld_x % 8 == 0 && ld_y % 8 == 0 && ld_x >= C && ld_y >= C && ub::aligned16(x) && ub::aligned16(y) &&
+                   (!addend || (ld_add % 8 == 0 && ld_add >= C && ub::aligned16(addend))),
+               UB200_E_UNSUPPORTED);
+    cudaStream_t s = ub::as_stream(stream);
+    const dim3 grid((unsigned)sh.splits, (unsigned)N, 1);
+    const __nv_bfloat16 *xp = reinterpret_cast<const __nv_bfloat16 *>(x);
+    cudaError_t e = launch_pdl(gn_stream_stats_kernel, grid, dim3(kStreamThreads), (size_t)(kStreamThreads * 16 + 2 * C) * 4, s,
+                               xp, ld_x, sh, ws);
+    if (e != cudaSuccess) return (int)e;
+    const size_t smem = (size_t)(((2 * G + 3) & ~3) + 2 * C) * 4;
+    const bool drop = dropout_p > 0.f;
+    e = STREAM_ACT_DROP(gn_stream_fwd_kernel, act, drop, grid, dim3(kStreamThreads), smem, s, xp, ld_x, sh, (const float *)ws,
+                        sh.splits, stats, eps, gamma, beta, scale, shift, dropout_p, seed, offset, offset_dev,
+                        reinterpret_cast<const __nv_bfloat16 *>(addend), ld_add, reinterpret_cast<__nv_bfloat16 *>(y), ld_y);
+    if (e != cudaSuccess) return (int)e;
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
+}
+
+int ub200_gn_act_stream_bwd_nhwc_bf16(const void *gy, int64_t ld_gy, const void *x, int64_t ld_x, int64_t N, int64_t HW,
+                                      int64_t C, int G, const float *stats, float eps, const float *gamma,
+                                      const float *beta, const float *scale, const float *shift, int act,
+                                      float dropout_p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                                      void *gx, int64_t ld_gx, float *dgamma, float *dbeta, float *dscale, float *dshift,
+                                      const void *gadd, int64_t ld_gadd, float *ws, void *stream) {
+    UB_REQUIRE(gy && x && gx && ws && N > 0 && HW > 0 && C > 0 && G > 0 && dropout_p >= 0.f && dropout_p < 1.f, UB200_E_BADARG);
+    UB_REQUIRE(act >= UB200_ACT_NONE && act <= UB200_ACT_RELU, UB200_E_BADARG);
+    StreamShape sh;
+    UB_REQUIRE(plan_stream(N, HW, C, G, sh), UB200_E_UNSUPPORTED);
+    UB_REQUIRE(ld_x % 8 == 0 && ld_gy % 8 == 0 && ld_gx % 8 == 0 && ld_x >= C && ld_gy >= C && ld_gx >= C &&
+                   ub::aligned16(x) && ub::aligned16(gy) && ub::aligned16(gx) &&
+                   (!gadd || (ld_gadd % 8 == 0 && ld_gadd >= C && ub::aligned16(gadd))),
+               UB200_E_UNSUPPORTED);
+    cudaStream_t s = ub::as_stream(stream);
+    const dim3 grid((unsigned)sh.splits, (unsigned)N, 1);
+    const __nv_bfloat16 *gyp = reinterpret_cast<const __nv_bfloat16 *>(gy), *xp = reinterpret_cast<const __nv_bfloat16 *>(x);
+    __nv_bfloat16 *gxp = reinterpret_cast<__nv_bfloat16 *>(gx);
+    const bool drop = dropout_p > 0.f;
+    cudaError_t e = STREAM_ACT_DROP(gn_stream_bwd_reduce, act, drop, grid, dim3(kStreamThreads),
+                                    (size_t)(kStreamThreads * 16 + 2 * C) * 4, s, gyp, ld_gy, xp, ld_x, sh, stats, eps, gamma, beta,
+                                    scale, shift, dropout_p, seed, offset, offset_dev, gxp, ld_gx, ws);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_pdl(gn_stream_bwd_apply, grid, dim3(kStreamThreads), (size_t)(5 * C + 2 * G) * 4, s, xp, ld_x, sh, stats, gamma,
+                   beta, scale, eps, (const float *)ws, gxp, ld_gx, dgamma, dbeta, dscale, dshift,
+                   reinterpret_cast<const __nv_bfloat16 *>(gadd), ld_gadd);
+    if (e != cudaSuccess) return (int)e;
+    UB_LAUNCH_CHECK();
+    return UB200_OK;
 }
 
 }  // extern "C"

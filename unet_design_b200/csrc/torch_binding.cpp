@@ -254,8 +254,18 @@ void gn_act_fwd(const Tensor &x, int64_t G, const c10::optional<Tensor> &stats, 
         TORCH_CHECK(a.N == i.N && a.H == i.H && a.W == i.W && a.C == i.C, "gn_act_fwd: addend shape mismatch");
         addp = a.ptr; ld_add = a.ld;
     }
-    if (compute_stats) {     // statistics + apply in one cluster kernel (falls back to two passes for huge slabs)
+    if (compute_stats) {     // statistics + apply: two streaming launches, or one cluster kernel for small slabs
         TORCH_CHECK(stats.has_value(), "gn_act_fwd: compute_stats needs a stats buffer");
+        if (ub200_gn_stream_preferred(i.N, i.H * i.W, i.C, (int)G, 0)) {
+            Tensor ws = at::empty({(int64_t)ub200_gn_stream_ws_floats(i.N, i.H * i.W, i.C, (int)G)}, x.options().dtype(at::kFloat));
+            check_rc(ub200_gn_act_stream_fwd_nhwc_bf16(i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_mut(*stats, "stats"), (float)eps,
+                                                       f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
+                                                       f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed,
+                                                       (uint64_t)offset, i64_opt(offset_dev), addp, ld_add, o.ptr, o.ld,
+                                                       ws.data_ptr<float>(), cur_stream()),
+                     "gn_act_stream_fwd");
+            return;
+        }
         check_rc(ub200_gn_act_fused_fwd_nhwc_bf16(i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_mut(*stats, "stats"), (float)eps,
                                                   f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
                                                   f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed,
@@ -285,9 +295,20 @@ void gn_act_bwd(const Tensor &gy, const Tensor &x, int64_t G, const c10::optiona
     }
     TORCH_CHECK(g.N == i.N && g.H == i.H && g.W == i.W && g.C == i.C && o.N == i.N && o.H == i.H && o.W == i.W && o.C == i.C,
                 "gn_act_bwd: shape mismatch");
-    Tensor ws = at::empty({(int64_t)ub200_gn_act_bwd_ws_floats(i.N, i.C, (int)G)}, x.options().dtype(at::kFloat));
     auto mut = [](const c10::optional<Tensor> &t, const char *n) -> float * { return t.has_value() ? f32_mut(*t, n) : nullptr; };
     TORCH_CHECK(!accumulate, "gn_act_bwd: accumulate is not supported");
+    if (ub200_gn_stream_preferred(i.N, i.H * i.W, i.C, (int)G, 1)) {
+        Tensor ws = at::empty({(int64_t)ub200_gn_stream_ws_floats(i.N, i.H * i.W, i.C, (int)G)}, x.options().dtype(at::kFloat));
+        check_rc(ub200_gn_act_stream_bwd_nhwc_bf16(g.ptr, g.ld, i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_opt(stats, "stats"),
+                                                   (float)eps, f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
+                                                   f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed,
+                                                   (uint64_t)offset, i64_opt(offset_dev), o.ptr, o.ld, mut(dgamma, "dgamma"),
+                                                   mut(dbeta, "dbeta"), mut(dscale, "dscale"), mut(dshift, "dshift"), gap, ld_ga,
+                                                   ws.data_ptr<float>(), cur_stream()),
+                 "gn_act_stream_bwd");
+        return;
+    }
+    Tensor ws = at::empty({(int64_t)ub200_gn_act_bwd_ws_floats(i.N, i.C, (int)G)}, x.options().dtype(at::kFloat));
     check_rc(ub200_gn_act_fused_bwd_nhwc_bf16(g.ptr, g.ld, i.ptr, i.ld, i.N, i.H * i.W, i.C, (int)G, f32_opt(stats, "stats"),
                                               (float)eps, f32_opt(gamma, "gamma"), f32_opt(beta, "beta"), f32_opt(scale, "scale"),
                                               f32_opt(shift, "shift"), (int)act, (float)dropout_p, (uint64_t)seed,
@@ -496,6 +517,46 @@ void rowlin_bwd(at::TensorList x, at::TensorList w, at::TensorList gy, const Opt
     check_rc(ub200_rowlin_bwd(items.data(), (int)n, N, K, silu ? 1 : 0, cur_stream()), "rowlin_bwd");
 }
 
+// ---------------------------------------------------------------- peer-memory gradient all-reduce
+// (arena fp32 [floats] living in a symmetric block, 64-byte IPC handle as a CPU uint8 tensor, base pointer of the block)
+std::tuple<Tensor, Tensor, int64_t> p2p_alloc(int64_t floats, int64_t device) {
+    TORCH_CHECK(floats > 0 && floats % 4 == 0, "p2p_alloc: the arena must be a positive multiple of 4 floats");
+    const c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+    const size_t fb = ub200_p2p_flag_bytes();
+    void *base = nullptr;
+    Tensor handle = at::empty({64}, at::TensorOptions().dtype(at::kByte));
+    check_rc(ub200_p2p_alloc(fb + (size_t)floats * 4, &base, handle.data_ptr<uint8_t>()), "p2p_alloc");
+    Tensor arena = at::from_blob(reinterpret_cast<uint8_t *>(base) + fb, {floats}, [base](void *) { ub200_p2p_free(base); },
+                                 at::TensorOptions().dtype(at::kFloat).device(at::kCUDA, (c10::DeviceIndex)device));
+    return {arena, handle, (int64_t)reinterpret_cast<uintptr_t>(base)};
+}
+
+int64_t p2p_open(const Tensor &handle, int64_t device) {
+    TORCH_CHECK(!handle.is_cuda() && handle.scalar_type() == at::kByte && handle.numel() == 64 && handle.is_contiguous(),
+                "p2p_open: the handle is a CPU uint8[64] tensor");
+    const c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+    void *peer = nullptr;
+    check_rc(ub200_p2p_open(handle.data_ptr<uint8_t>(), &peer), "p2p_open");
+    return (int64_t)reinterpret_cast<uintptr_t>(peer);
+}
+
+void p2p_close(int64_t ptr, int64_t device) {
+    const c10::cuda::CUDAGuard guard((c10::DeviceIndex)device);
+    check_rc(ub200_p2p_close(reinterpret_cast<void *>((uintptr_t)ptr)), "p2p_close");
+}
+
+void p2p_allreduce(const Tensor &arena, std::vector<int64_t> bases, int64_t rank, int64_t offset, int64_t count, int64_t ctas) {
+    UB_GUARD(arena);
+    TORCH_CHECK(arena.scalar_type() == at::kFloat && arena.is_contiguous() && offset >= 0 && offset + count <= arena.numel(),
+                "p2p_allreduce: range outside the arena");
+    TORCH_CHECK(bases.size() >= 2 && bases.size() <= 8 && rank >= 0 && rank < (int64_t)bases.size(), "p2p_allreduce: bad world / rank");
+    TORCH_CHECK((uintptr_t)bases[rank] + ub200_p2p_flag_bytes() == (uintptr_t)arena.data_ptr(),
+                "p2p_allreduce: `arena` is not the arena of this rank's symmetric block");
+    void *ptrs[8];
+    for (size_t i = 0; i < bases.size(); ++i) ptrs[i] = reinterpret_cast<void *>((uintptr_t)bases[i]);
+    check_rc(ub200_p2p_allreduce_sum_f32(ptrs, (int)rank, (int)bases.size(), offset, count, (int)ctas, cur_stream()), "p2p_allreduce");
+}
+
 }  // namespace
 
 TORCH_LIBRARY(unet_b200, m) {
@@ -527,4 +588,8 @@ TORCH_LIBRARY(unet_b200, m) {
     m.def("pack_dgrad_weights_batched", &pack_dgrad_weights_batched);
     m.def("rowlin_fwd", &rowlin_fwd);
     m.def("rowlin_bwd", &rowlin_bwd);
+    m.def("p2p_alloc", &p2p_alloc);
+    m.def("p2p_open", &p2p_open);
+    m.def("p2p_close", &p2p_close);
+    m.def("p2p_allreduce(Tensor(a!) arena, int[] bases, int rank, int offset, int count, int ctas=0) -> ()", &p2p_allreduce);
 }

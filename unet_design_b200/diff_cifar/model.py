@@ -403,6 +403,15 @@ class UNetWaveletEnc(nn.Module):
             return layer.forward_nhwc(h, out=out)
         return layer.forward_nhwc(h)
 
+    def late_grad_params(self):
+        """Parameters of the batched time path (time embeddings + every ResBlock's temb projection): their gradients come
+        from the launches at the very end of backward (train.FlatArena keeps them out of the early all-reduce buckets)."""
+        out = [p for te in self.time_embedding_list for p in te.parameters() if p.requires_grad]
+        for m in self.modules():
+            if isinstance(m, ResBlock):
+                out += [p for p in m.temb_proj.parameters() if p.requires_grad]
+        return out
+
     def forward(self, x, t, n_levels_used=-1):
         if n_levels_used == -1:
             n_levels_used = self.n_levels

@@ -54,7 +54,7 @@ class FlatArena:
     """Trainable parameters of `model` re-homed into one flat fp32 buffer (and a matching gradient buffer).
     Conv weights (4-D) keep channels_last order: the arena slice is viewed as [Cout,kh,kw,Cin] and permuted."""
 
-    def __init__(self, model: nn.Module):
+    def __init__(self, model: nn.Module, grad_factory=None):
         params = [p for p in model.parameters() if p.requires_grad]
         assert params, "model has no trainable parameters"
         dev = params[0].device
@@ -76,6 +76,15 @@ class FlatArena:
             for q in member_of.get(id(p), [p]):
                 ordered.append(q)
                 seen.add(id(q))
+        # parameters whose gradients only appear at the very end of backward (a model says which: e.g. the batched time-embedding
+        # path of diff_cifar, whose ONE backward launch serves every ResBlock) go to the front of the arena = into the LAST
+        # data-parallel bucket; left in place they would hold every bucket back until backward is over
+        late = set()
+        for m in model.modules():
+            if hasattr(m, "late_grad_params"):
+                late.update(id(p) for p in m.late_grad_params())
+        if late:
+            ordered = [p for p in ordered if id(p) in late] + [p for p in ordered if id(p) not in late]
         params = ordered
         self.fused_groups = groups
         self.params = params
@@ -85,7 +94,9 @@ class FlatArena:
             self.offsets.append(self.offsets[-1] + s)
         total = self.offsets[-1]
         self.p = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.g = torch.zeros(total, dtype=torch.float32, device=dev)
+        # grad_factory(total) -> zeroed fp32 [total] buffer on `dev`: data parallel puts the gradients in peer-mapped memory
+        self.g = grad_factory(total) if grad_factory is not None else torch.zeros(total, dtype=torch.float32, device=dev)
+        assert self.g.numel() == total and self.g.dtype == torch.float32 and self.g.device == dev
         for p, off in zip(params, self.offsets):
             view = self._view(self.p, p, off)
             view.copy_(p.data)
@@ -160,6 +171,37 @@ class PackedWeights:
         self.refresh_dgrad()
 
 
+class PeerAllReduce:
+    """Sum all-reduce of ranges of a gradient arena over NVLink peer memory (csrc/p2p.cu): each rank's arena lives in a
+    symmetric block that every other rank of the box has mapped through CUDA IPC, and one kernel launch per range does
+    the two-shot reduce in place.  Being a plain launch it is captured into the step's CUDA graph on the comm stream,
+    which is what NCCL could not be on this stack.  torch.distributed only carries the 64-byte handles."""
+
+    def __init__(self, device: torch.device, group=None):
+        self.device, self.group = device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert 2 <= self.world <= 8, "peer all-reduce: 2..8 ranks of one box"
+        self.arena = None
+        self.bases: List[int] = []
+
+    def allocate(self, floats: int) -> torch.Tensor:
+        o = ops._ops()
+        self.arena, handle, base = o.p2p_alloc(int(floats), self.device.index)
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, (os.uname().nodename, bytes(handle.numpy().tobytes())), group=self.group)
+        if any(b[0] != blobs[self.rank][0] for b in blobs):
+            raise RuntimeError("peer all-reduce: ranks on different hosts")
+        for r, (_, h) in enumerate(blobs):
+            self.bases.append(int(base) if r == self.rank else
+                              int(o.p2p_open(torch.frombuffer(bytearray(h), dtype=torch.uint8), self.device.index)))
+        dist.barrier(group=self.group)          # every rank has mapped every block before the first launch
+        return self.arena
+
+    def __call__(self, lo: int, hi: int, ctas: int = 0) -> None:
+        ops._ops().p2p_allreduce(self.arena, self.bases, self.rank, int(lo), int(hi - lo), int(ctas))
+        ops._count(1)
+
+
 class TrainStep:
     """Model-agnostic fast training step: flat arenas, packed bf16 weight shadow, gradient sinks, the fused
     clip + Adam(W) + EMA tail and (optionally) the whole step as one CUDA graph, data-parallel over `process_group`.
@@ -188,7 +230,25 @@ class TrainStep:
         if self.world > 1:      # identical replicas: rank 0's initial weights everywhere (one broadcast)
             for t in list(model.parameters()) + list(model.buffers()):
                 dist.broadcast(t.data, src=0, group=process_group)
-        self.arena = FlatArena(model)
+        # data parallel on one box: gradients live in peer-mapped memory and are reduced by our own kernel (UB200_DP_P2P=0:
+        # NCCL).  Any failure to set the peer mapping up (no IPC in this container, different hosts) falls back to NCCL.
+        self._p2p = None
+        grad_factory = None
+        if self.world > 1 and self.device.type == "cuda" and self.world <= 8 and os.environ.get("UB200_DP_P2P", "1") != "0":
+            ok = torch.zeros(1, device=self.device)
+            try:
+                peer = PeerAllReduce(self.device, process_group)
+                n_floats = sum((p.numel() + 3) // 4 * 4 for p in model.parameters() if p.requires_grad)
+                peer.allocate(n_floats)
+                ok.fill_(1)
+            except Exception as e:          # noqa: BLE001 -- reported, then the NCCL path runs
+                peer = None
+                print(f"[unet_design_b200] peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", flush=True)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)       # all ranks or none
+            if float(ok) == 1.0:
+                self._p2p = peer
+                grad_factory = lambda total: peer.arena                     # noqa: E731
+        self.arena = FlatArena(model, grad_factory)
         n = self.arena.p.numel()
         self.m = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.v = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -215,8 +275,12 @@ class TrainStep:
         self._buckets: List[tuple] = []
         self._comm_stream = None
         self._hooks_live = False
-        self.overlap = overlap_allreduce
+        self._probe, self._silent, self.bucket_trace, self._launched = False, frozenset(), [], []
+        self._early_ctas = int(os.environ.get("UB200_P2P_EARLY_CTAS", "0"))
+        self.overlap = overlap_allreduce and os.environ.get("UB200_DP_OVERLAP", "1") != "0"
         if self.world > 1 and self.overlap:
+            # (peer-memory buckets pay two cross-GPU barriers each: 32 MB measured better than 16 MB at 2 GPUs)
+            bucket_mb = float(os.environ.get("UB200_DP_BUCKET_MB", 32.0 if self._p2p is not None and bucket_mb == 16.0 else bucket_mb))
             self._build_buckets(int(bucket_mb * (1 << 20) / 4))
         # `model.load_state_dict(...)` after this point writes the fp32 masters in place (they are arena views); the
         # bf16 operands forward / backward actually read must follow, and before any training the EMA is by definition
@@ -247,7 +311,11 @@ class TrainStep:
             for i in mem:
                 self._bucket_of[i] = b
         self._pending = [0] * len(self._buckets)
+        self._launched = [False] * len(self._buckets)
         self._seen = [False] * len(params)
+        self._silent = frozenset()     # parameters the current step is known not to touch (found by a probe pass, see _capture)
+        self._probe = False
+        self.bucket_trace: List[tuple] = []   # (bucket, gradients reported so far) in launch order: diagnostic
         if self.device.type == "cuda":
             self._comm_stream = torch.cuda.Stream(device=self.device)
         # parameters whose gradient arrives through autograd's AccumulateGrad (no sink kernel) report through this hook;
@@ -260,37 +328,66 @@ class TrainStep:
             if not self._hooks_live or self._seen[i]:
                 return
             self._seen[i] = True
+            if self._probe:
+                return
+            if i in self._silent:
+                raise RuntimeError("data-parallel buckets: a parameter the probe pass saw no gradient for has produced one")
             b = self._bucket_of[i]
             self._pending[b] -= 1
-            if self._pending[b] == 0:
+            if self._pending[b] == 0 and not self._launched[b]:
                 self._launch_allreduce(b)
         return hook
 
-    def _launch_allreduce(self, b: int):
+    def _allreduce_range(self, lo: int, hi: int, early: bool = False):
+        if self._p2p is not None:
+            # a bucket launched from a gradient hook runs NEXT TO backward kernels and has slack: throttled to a few CTAs
+            self._p2p(lo, hi, self._early_ctas if early else 0)
+        else:
+            dist.all_reduce(self.arena.g[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _launch_allreduce(self, b: int, early: bool = True):
         lo, hi, _ = self._buckets[b]
-        view = self.arena.g[lo:hi]
+        self._launch_range(lo, hi, [b], early)
+
+    def _launch_range(self, lo: int, hi: int, members, early: bool):
+        if len(self._launched) != len(self._buckets):
+            self._launched = [False] * len(self._buckets)
+        for b in members:
+            self._launched[b] = True
+            self.bucket_trace.append((b, sum(getattr(self, "_seen", ()))))
         if self._comm_stream is not None:
             self._comm_stream.wait_stream(torch.cuda.current_stream(self.device))
             if ops._Side.stream is not None:      # weight-gradient kernels into this bucket may be queued on the second stream
                 self._comm_stream.wait_stream(ops._Side.stream)
             with torch.cuda.stream(self._comm_stream):
-                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg)
+                self._allreduce_range(lo, hi, early)
         else:
-            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.pg)
+            self._allreduce_range(lo, hi, early)
 
     def _arm_buckets(self):
         for b, (_, _, mem) in enumerate(self._buckets):
-            self._pending[b] = len(mem)
+            self._pending[b] = sum(1 for i in mem if i not in self._silent)
+        self._launched = [False] * len(self._buckets)
         self._seen = [False] * len(self.arena.params)
+        self.bucket_trace = []
 
     def _finish_allreduce(self):
         """After backward: reduce the buckets that hold parameters this step did not touch (e.g. the coarse
         tails without the multi-resolution loss; their hooks never fire), then join the side stream.  The set of
         untouched parameters is the same on every rank, so the collective order stays consistent."""
-        for b in range(len(self._buckets)):
-            if self._pending[b] > 0:
-                self._pending[b] = 0
-                self._launch_allreduce(b)
+        # what is left when backward ends (the buckets that hold the last gradients, parameters this step did not touch) goes
+        # out as ONE launch per contiguous arena range: each launch costs two cross-GPU barriers on the critical path
+        left = sorted((self._buckets[b][0], self._buckets[b][1], b) for b in range(len(self._buckets)) if not self._launched[b])
+        runs: List[list] = []
+        for lo, hi, b in left:
+            self._pending[b] = 0
+            if runs and runs[-1][1] == lo:
+                runs[-1][1] = hi
+                runs[-1][2].append(b)
+            else:
+                runs.append([lo, hi, [b]])
+        for lo, hi, members in runs:
+            self._launch_range(lo, hi, members, early=False)
         if self._comm_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
 
@@ -337,7 +434,7 @@ class TrainStep:
             if overlapped:
                 self._finish_allreduce()
             else:                      # one all-reduce of the whole arena after backward
-                dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM, group=self.pg)
+                self._allreduce_range(0, self.arena.g.numel())
         self._update()
 
     def _update(self):
@@ -355,6 +452,7 @@ class TrainStep:
 
     def _body(self, *inputs, **static) -> torch.Tensor:
         """Eager step; with several ranks the bucketed all-reduce overlaps backward (when no second stream is in use)."""
+        self._silent = frozenset()      # no probe pass in eager mode: untouched parameters are flushed after backward
         loss = self._fwd_bwd(inputs, static, self.world > 1 and self.overlap)
         self._reduce_and_update(self._overlapped)
         return loss
@@ -387,7 +485,7 @@ class TrainStep:
             ev[r][0].record()
             graph.replay()
             ev[r][1].record()
-            dist.all_reduce(self.arena.g, op=dist.ReduceOp.SUM, group=self.pg)
+            self._allreduce_range(0, self.arena.g.numel())
             ev[r][2].record()
             self._update()
             ev[r][3].record()
@@ -407,7 +505,9 @@ class TrainStep:
         # UB200_DP_GRAPH_NCCL=1 captures the bucketed NCCL all-reduces (on the comm stream, forked from and joined to the
         # capture stream, so they overlap the rest of backward) and the optimiser tail into the same graph.  The capture
         # then runs in thread-local error mode: NCCL's watchdog thread polls CUDA events, which a global-mode capture forbids.
-        nccl_in_graph = self.world > 1 and os.environ.get("UB200_DP_GRAPH_NCCL", "0") == "1"
+        # With the peer-memory all-reduce (self._p2p) the collectives are ordinary kernel launches: always captured.
+        nccl_in_graph = self.world > 1 and (os.environ.get("UB200_DP_GRAPH_NCCL", "0") == "1" or
+                                            (self._p2p is not None and os.environ.get("UB200_DP_GRAPH_P2P", "1") != "0"))
         whole = self.world == 1 or nccl_in_graph
         # The warm-up runs real steps (allocator, tensor maps, cuBLAS handles): snapshot every piece of training state
         # they touch and put it back, so that the first replay is step 1 of the run exactly as in eager mode.
@@ -416,8 +516,15 @@ class TrainStep:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):           # warm-up on a side stream
-            for _ in range(3):
-                self._fwd_bwd(static_in, static, False)
+            for it in range(3):
+                # the first warm-up step doubles as a probe: which parameters report a gradient at all with these static
+                # arguments (coarse tails without the multi-resolution loss never do).  The silent ones must not hold their
+                # bucket back until the end of backward.
+                self._probe = nccl_in_graph and self.overlap and it == 0
+                self._fwd_bwd(static_in, static, self._probe)
+                if self._probe:
+                    self._silent = frozenset(i for i, seen in enumerate(self._seen) if not seen)
+                    self._probe = False
                 self._reduce_and_update(False)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
@@ -426,7 +533,7 @@ class TrainStep:
         del saved
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, capture_error_mode="thread_local" if nccl_in_graph else "global"):
+        with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
             static_loss = self._fwd_bwd(static_in, static, nccl_in_graph and self.overlap)
             if whole:
                 self._reduce_and_update(self._overlapped)
