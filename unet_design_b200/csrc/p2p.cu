@@ -17,7 +17,7 @@
 // written to peers, against 2*(world-1)/world * B for a ring.
 //
 // Barriers are per CTA (CTA b of every rank meets CTA b of every other rank) through monotonically increasing epochs kept in
-// device memory: nothing is reset between launches, so the kernel replays from a CUDA graph.  Waits are bounded (~4 s): a
+// device memory: nothing is reset between launches, so the kernel replays from a CUDA graph.  Waits are bounded (~30 s): a
 // lost peer traps instead of hanging the GPU.
 #include <string.h>
 
@@ -85,7 +85,7 @@ __device__ __forceinline__ void cta_barrier(const Peers &P, int rank, int world,
         const uint32_t *mine = P.flags[rank] + word + peer;
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-            if (clock64() - t0 > 8000000000LL) __trap();                 // ~4 s at 1.9 GHz: a peer is gone
+            if (clock64() - t0 > 60000000000LL) __trap();                // ~30 s at 1.9 GHz: a peer is gone
         }
     }
     __syncthreads();

@@ -391,6 +391,13 @@ class TrainStep:
         if self._comm_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
 
+    def _rank_sync(self):
+        """Host-level rendezvous of the ranks (one-off places only: warm-up, end of capture).  The peer-memory all-reduce
+        spins on flags in device memory with a bounded wait, so ranks must not reach it tens of seconds apart."""
+        if self.world > 1 and self._p2p is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.pg)
+
     # ------------------------------------------------------------------ one step
     def _loss(self, inputs, static) -> torch.Tensor:
         out = self.loss_fn(*inputs, **static)
@@ -525,6 +532,7 @@ class TrainStep:
                 if self._probe:
                     self._silent = frozenset(i for i, seen in enumerate(self._seen) if not seen)
                     self._probe = False
+                self._rank_sync()       # first-call initialisation skews the ranks by seconds; the peer kernel's waits are bounded
                 self._reduce_and_update(False)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
@@ -538,6 +546,7 @@ class TrainStep:
             if whole:
                 self._reduce_and_update(self._overlapped)
         self._graph_has_tail = whole
+        self._rank_sync()               # capture time differs per rank: line the ranks up before the first replay
         entry = (graph, static_in, static_loss)
         self._graphs[key] = entry
         return entry
