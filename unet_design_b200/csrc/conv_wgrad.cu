@@ -14,6 +14,7 @@
 // Replaces the wgrad half of nn.Conv2d backward at the sites listed in conv_fprop.cu.
 #include <cooperative_groups.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -42,17 +43,20 @@ struct WgradParams {
     int S;                              // conv stride: A pixel = S * G pixel + tap offset (TMA traversal stride S)
     int k1wide;                         // 1x1 conv: the CTA's `ntaps` accumulators are consecutive 128-channel ci tiles, so one
                                         // G tile feeds 2-3 of them (a lone 128x128 accumulator needs 128 B/clk of operand fill)
-    uint32_t a_chunk_stride, a_halo_bytes;
+    uint32_t a_chunk_stride, a_halo_bytes, ring_bytes;
+    int dbg;                            // diagnostics (UB200_WGRAD_DEBUG): 1 = no atomics, 2 = no TMEM loads either
+    int tma_red;                        // split-K partials leave through TMA reduce-add boxes instead of per-thread atomics
     float *dw;
 };
 
 __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g,
                                                              const __grid_constant__ CUtensorMap tm_a,
+                                                             const __grid_constant__ CUtensorMap tm_dw,
                                                              const WgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t stage_bytes = p.g_stage_bytes + (p.halo ? p.a_halo_bytes : p.ntaps * p.a_tap_bytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + p.ring_bytes);        // behind the ring (>= stages * stage_bytes)
     uint64_t *empty = full + p.stages;
     uint64_t *tmem_full = empty + p.stages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tm_g);
         prefetch_tmap(&tm_a);
+        if (p.tma_red) prefetch_tmap(&tm_dw);
         for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
@@ -183,11 +188,47 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16);
         const int taps_total = p.ksize * p.ksize;
+        if (p.tma_red) {
+            // Split-K partials through the TMA unit: each warp stages its 32 rows x 32 fp32 columns (4 KB, 128-byte swizzle) in
+            // the drained pipeline ring and lane 0 issues ONE reduce-add box; the L2 does the adds.  The per-thread path below
+            // issues 96 16-byte reds per thread, and an SM retires ~0.8 red lanes per clock: 12288 lane-ops = 8 us per CTA.
+            constexpr int kBufs = 4;
+            const uint32_t ring = smem_u32(smem) + (uint32_t)(warp - 2) * (kBufs * 4096u);
+            const uint32_t row_off = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+            int c = 0;
+            for (int tp = 0; tp < p.ntaps; ++tp) {
+                const int tap = p.ksize == 3 ? kyg * 3 + tp : 0;
+                const int col0 = tap * p.Cin + ci0 + (p.k1wide ? tp * 128 : 0);
+                for (int cg = 0; cg < ncols / 32; ++cg, ++c) {
+                    const uint32_t buf = ring + (uint32_t)(c % kBufs) * 4096u;
+                    if (c >= kBufs) {                       // the box that last used this buffer has been read
+                        if (lane == 0) tma_store_wait_read<kBufs - 1>();
+                        __syncwarp();
+                    }
+                    float v[32];
+                    tmem_ld32(trow + tp * 128 + cg * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + row_off + (((uint32_t)j ^ sw) << 4)),
+                                     "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_reduce_add_2d(&tm_dw, buf, col0 + cg * 32, co0 + qd * 32);
+                        tma_store_commit();
+                    }
+                }
+            }
+            if (lane == 0) tma_store_wait_all();
+            __syncwarp();
+        } else
         for (int tp = 0; tp < p.ntaps; ++tp) {
             const int tap = p.ksize == 3 ? kyg * 3 + tp : 0;
             for (int cg = 0; cg < ncols / 16; ++cg) {
                 float v[16];
+                if (p.dbg == 2) continue;
                 tmem_ld16(trow + tp * 128 + cg * 16, v);
+                if (p.dbg == 1) { if (v[0] == 12345.678f) p.dw[0] = v[1]; continue; }
                 if (co < p.Cout) {
                     float4 *dst = reinterpret_cast<float4 *>(p.dw + ((int64_t)co * taps_total + tap) * p.Cin + ci0 + (p.k1wide ? tp * 128 : 0) + cg * 16);
 #pragma unroll
@@ -438,6 +479,8 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
     p.stages = stages;
     p.tmem_cols = p.ntaps == 3 ? 512 : (p.ntaps == 2 ? 256 : 128);
     p.dw = dw;
+    static const int env_dbg = [] { const char *e = getenv("UB200_WGRAD_DEBUG"); return e ? atoi(e) : 0; }();
+    p.dbg = env_dbg;
 
     CUtensorMap tg, ta;
     {
@@ -455,13 +498,46 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
         int rc = encode_bf16_tensor_map(&ta, a, 4, dims, str, box, es);
         if (rc) return rc;
     }
+    // TMA reduce-add epilogue: every 128-channel ci tile must be whole 32-column boxes (a box past the tile would land in the next tap)
+    static const int env_tma_red = [] { const char *e = getenv("UB200_WGRAD_TMA_RED"); return e ? atoi(e) : 1; }();
+    p.tma_red = (env_tma_red && Cin % 32 == 0 && !env_dbg) ? 1 : 0;
+    CUtensorMap tdw = tg;
+    if (p.tma_red) {
+        const int64_t taps_total = (int64_t)ksize * ksize;
+        const int64_t dims[2] = {taps_total * Cin, Cout};
+        const int64_t str[1] = {taps_total * Cin};
+        const int box[2] = {32, 32};
+        int rc = encode_f32_tensor_map(&tdw, dw, 2, dims, str, box);
+        if (rc) return rc;
+    }
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
         attr_err = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     });
     if (attr_err != cudaSuccess) return (int)attr_err;
-    const size_t smem = 1024 + (size_t)stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
+    // (the epilogue's staging ring -- 4 warps x 4 boxes x 4 KB -- re-uses the pipeline ring, which must be at least that large;
+    // the mbarriers behind the ring are not touched)
+    size_t ring_bytes = (size_t)stages * stage;
+    if (p.tma_red && ring_bytes < 64 * 1024) ring_bytes = 64 * 1024;
+    p.ring_bytes = (uint32_t)ring_bytes;
+    const size_t smem = 1024 + ring_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
+    if (env_dbg == 3) {                 // how many clusters of 2 / 4 / 8 one-per-SM CTAs can be resident (printed once)
+        static std::once_flag once2;
+        std::call_once(once2, [&] {
+            for (int cs : {1, 2, 4, 8}) {
+                cudaLaunchConfig_t q{};
+                q.gridDim = dim3(8, 8, 1); q.blockDim = dim3(kThreads, 1, 1); q.dynamicSmemBytes = 200 * 1024;
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = 1; qa[0].val.clusterDim.y = (unsigned)cs; qa[0].val.clusterDim.z = 1;
+                q.attrs = qa; q.numAttrs = 1;
+                int nc = -1;
+                cudaError_t qe = cudaOccupancyMaxActiveClusters(&nc, conv_wgrad_kernel, &q);
+                fprintf(stderr, "[ub200] max active clusters of %d CTAs (200 KB smem): %d (%s)\n", cs, nc, cudaGetErrorString(qe));
+            }
+        });
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)out_tiles, (unsigned)splits, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
@@ -471,7 +547,7 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
     ub::pdl_attr(attr[0]);
     cfg.attrs = attr; cfg.numAttrs = 1;
     ub::prefer_max_smem_carveout(reinterpret_cast<const void *>(conv_wgrad_kernel));
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, tg, ta, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, tg, ta, tdw, p);
     if (le != cudaSuccess) return (int)le;
     UB_LAUNCH_CHECK();
     return UB200_OK;

@@ -202,6 +202,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, const void *s
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+// TMA tiled reduction (smem tile ADDED into global memory by the L2, element type from the tensor map), bulk-group completion
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {   // at most N bulk groups still reading shared memory
@@ -251,6 +258,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread, one wait
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // 32 lanes x 64 consecutive fp32 columns -> 64 registers per thread, one wait
@@ -308,6 +332,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // (the driver's bounding box is box[i] * elem_strides[i]) -- how the stride-2 convolutions fetch every second pixel.
 int encode_bf16_tensor_map(CUtensorMap *out, const void *base, int rank, const int64_t *dims,
                            const int64_t *strides_elems, const int *box, const int *elem_strides = nullptr);
+// fp32 variant (swizzle span = box[0] * 4 bytes): destination of the TMA reduce-add epilogues
+int encode_f32_tensor_map(CUtensorMap *out, const void *base, int rank, const int64_t *dims,
+                          const int64_t *strides_elems, const int *box);
 
 }  // namespace tc
 }  // namespace ub

@@ -49,12 +49,29 @@ std::unordered_map<Key, CUtensorMap, KeyHash> g_cache;
 
 }  // namespace
 
+namespace {
+int encode_tensor_map(CUtensorMap *out, const void *base, int rank, const int64_t *dims, const int64_t *strides_elems,
+                      const int *box, const int *elem_strides, int esize);
+}
+
 int encode_bf16_tensor_map(CUtensorMap *out, const void *base, int rank, const int64_t *dims,
                            const int64_t *strides_elems, const int *box, const int *elem_strides) {
+    return encode_tensor_map(out, base, rank, dims, strides_elems, box, elem_strides, 2);
+}
+
+int encode_f32_tensor_map(CUtensorMap *out, const void *base, int rank, const int64_t *dims,
+                          const int64_t *strides_elems, const int *box) {
+    return encode_tensor_map(out, base, rank, dims, strides_elems, box, nullptr, 4);
+}
+
+namespace {
+int encode_tensor_map(CUtensorMap *out, const void *base, int rank, const int64_t *dims, const int64_t *strides_elems,
+                      const int *box, const int *elem_strides, int esize) {
     if (!out || !base || rank < 2 || rank > 4) return UB200_E_BADARG;
+    const CUtensorMapDataType dtype = esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     Key key{};
     key.v[0] = reinterpret_cast<uint64_t>(base);
-    key.v[1] = (uint64_t)rank;
+    key.v[1] = (uint64_t)rank | ((uint64_t)esize << 8);
     for (int i = 0; i < rank; ++i) {
         key.v[2 + i] = (uint64_t)dims[i];
         key.v[6 + i] = (uint64_t)box[i];
@@ -77,25 +94,25 @@ int encode_bf16_tensor_map(CUtensorMap *out, const void *base, int rank, const i
         gbox[i] = (cuuint32_t)(box[i] * es);      // bounding box; ceil(gbox / es) = box elements are loaded
         estr[i] = (cuuint32_t)es;
         if (i + 1 < rank) {
-            if (strides_elems[i] <= 0 || (strides_elems[i] * 2) % 16 != 0) return UB200_E_UNSUPPORTED;
-            gstr[i] = (cuuint64_t)strides_elems[i] * 2;
+            if (strides_elems[i] <= 0 || (strides_elems[i] * esize) % 16 != 0) return UB200_E_UNSUPPORTED;
+            gstr[i] = (cuuint64_t)strides_elems[i] * esize;
         }
     }
-    const int row_bytes = box[0] * 2;
+    const int row_bytes = box[0] * esize;
     CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                            : row_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
                            : row_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
                                               : CU_TENSOR_MAP_SWIZZLE_NONE;
     if (swz == CU_TENSOR_MAP_SWIZZLE_NONE) return UB200_E_UNSUPPORTED;
     CUtensorMap m;
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, gbox,
+    CUresult r = enc(&m, dtype, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, gbox,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
         // A thread that has made no runtime call yet (autograd runs backward on its own worker threads) has no current
         // driver context, and this is a DRIVER entry point: let the runtime bind the primary context, then retry once.
         (void)cudaFree(nullptr);
-        r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, gbox, estr,
+        r = enc(&m, dtype, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, gbox, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) {
@@ -116,6 +133,7 @@ int encode_bf16_tensor_map(CUtensorMap *out, const void *base, int rank, const i
     *out = m;
     return UB200_OK;
 }
+}  // namespace
 
 }  // namespace tc
 }  // namespace ub
