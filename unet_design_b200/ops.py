@@ -9,6 +9,7 @@ Nothing here has a CPU or eager fallback: every function ends in a hand-written 
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import weakref
@@ -92,6 +93,9 @@ def clear_registry() -> None:
     _Registry.owner.clear()
 
 
+_SKIP_CHANSUM = os.environ.get("UB200_DEBUG_SKIP_CHANSUM", "0") == "1"
+
+
 class _Side:
     """Weight-gradient launches on a second stream.  A wgrad only feeds the optimiser, so it need not sit on the
     backward critical path; at the coarse levels every kernel covers a fraction of the 148 SMs and is bound by
@@ -132,6 +136,9 @@ def _chansum(o, g, per, tot, tot2, side_ok: bool) -> None:
     """Bias / time-row column sums of a conv's output gradient.  Like the wgrad they only feed the optimiser (and, for
     `per`, the batched time-embedding backward, which waits for the side stream): off the critical path when both
     destinations are arena sinks or fresh buffers nobody reads before the join."""
+    if _SKIP_CHANSUM:               # timing diagnostic only (UB200_DEBUG_SKIP_CHANSUM=1): results are wrong
+        per.zero_()
+        return
     if side_ok and _Side.enabled and _Side.chansum and g.is_cuda:
         if _Side.stream is None:
             _Side.stream = torch.cuda.Stream(device=g.device)
