@@ -1436,7 +1436,17 @@ size_t ub200_gn_stream_ws_floats(int64_t N, int64_t HW, int64_t C, int G) {
 
 int ub200_gn_stream_preferred(int64_t N, int64_t HW, int64_t C, int G, int backward) {
     StreamShape sh;
-    return plan_stream(N, HW, C, G, sh) && stream_preferred(HW, C, backward != 0) ? 1 : 0;
+    if (!plan_stream(N, HW, C, G, sh)) return 0;
+    if (stream_preferred(HW, C, backward != 0)) return 1;
+    // A slab no cluster can hold (pdearena / wmh: GroupNorm(1, C) over 128x128 or 200x200 pixels) used to fall back to memset +
+    // atomic statistics (gn_stats_kernel: 66 us for 17 MB at batch 8, 0.25 TB/s) + apply; the streaming pair does the same two
+    // passes with per-CTA partials at 4x the bandwidth.  UB200_GN_STREAM=0 keeps the old fallback for A/B.
+    static const bool never = [] { const char *e = getenv("UB200_GN_STREAM"); return e && atoi(e) == 0; }();
+    if (never) return 0;
+    FusedShape fs; size_t smem = 0;
+    if (!backward) return plan_fused(N, HW, C, G, 1, 2 * (size_t)C + 2 * (size_t)((2 * G + 3) & ~3), fs, smem) ? 0 : 1;
+    const size_t extra = (size_t)(4 * C + ((2 * G + 3) & ~3));
+    return (plan_fused(N, HW, C, G, 2, extra, fs, smem, 1) || plan_fused(N, HW, C, G, 1, extra, fs, smem)) ? 0 : 1;
 }
 
 int ub200_gn_act_stream_fwd_nhwc_bf16(const void *x, int64_t ld_x, int64_t N, int64_t HW, int64_t C, int G, float *stats,
