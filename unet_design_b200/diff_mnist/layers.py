@@ -162,7 +162,8 @@ class ResBlock(TimestepBlock):
         gn1, conv1 = self.in_layers[0], self.in_layers[2]
         gn2, drop, conv2 = self.out_layers[0], self.out_layers[2], self.out_layers[3]
         a1 = ops.gn_act(x, gn1.weight, gn1.bias, gn1.num_groups, act="silu", eps=gn1.eps)
-        emb_out = self.emb_layers(emb).float()
+        pre = self.__dict__.pop("_emb_pre", None)       # one-shot: set by precompute_emb_layers for this forward only
+        emb_out = pre if pre is not None else self.emb_layers(emb).float()
         p = drop.p if self.training else 0.0
         if self.use_scale_shift_norm:
             h = ops.conv(a1, conv1.weight, conv1.bias)
@@ -182,6 +183,25 @@ class ResBlock(TimestepBlock):
 
     def forward(self, x, emb):
         return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x), emb))
+
+
+def precompute_emb_layers(pairs):
+    """`emb_layers(emb)` (SiLU + Linear, layers.py:305-312 of the reference) of every ResBlock that is about to run, as ONE
+    batched launch (ops.rowlin_batch) instead of four framework kernels per block (sigmoid, mul, GEMM, bias add) and their
+    backward.  `pairs`: [(ResBlock, emb)]; each block picks its row up once in forward_nhwc."""
+    pairs = [(b, e) for b, e in pairs if isinstance(b, ResBlock)]
+    if not pairs:
+        return
+    lins = [b.emb_layers[1] for b, _ in pairs]
+    outs = ops.rowlin_batch([e for _, e in pairs], [l.weight for l in lins], [l.bias for l in lins], silu=True)
+    for (b, _), o in zip(pairs, outs):
+        b.__dict__["_emb_pre"] = o
+
+
+def batched_time_embed(seqs, sin_emb):
+    """[seq(sin_emb) for seq in seqs] for `nn.Sequential(linear, SiLU, linear)` time-embedding MLPs: two batched launches."""
+    h = ops.rowlin_batch([sin_emb] * len(seqs), [s[0].weight for s in seqs], [s[0].bias for s in seqs], silu=False)
+    return ops.rowlin_batch(h, [s[2].weight for s in seqs], [s[2].bias for s in seqs], silu=True)
 
 
 class QKVAttention(nn.Module):

@@ -16,8 +16,8 @@ from torch import nn
 
 from .. import ops
 from ..diff_cifar.model import DTWBlock, _PyramidView, _conv_param  # DTWBlock: same logic as mnist_diff/models.py:12-82
-from .layers import (AttentionBlock, Downsample, ResBlock, SiLU, TimestepEmbedSequential, Upsample, linear, normalization,
-                     timestep_embedding)
+from .layers import (AttentionBlock, Downsample, ResBlock, SiLU, TimestepEmbedSequential, Upsample, batched_time_embed, linear,
+                     normalization, precompute_emb_layers, timestep_embedding)
 
 
 def compute_norm(tensor):
@@ -180,6 +180,26 @@ class UNet_wavelet(nn.Module):
         ins = [self.input_blocks[0]] + list(self.input_blocks[::-1][:upper_range][::-1])
         start_level = self.n_levels - n_levels_used
 
+        # Time-embedding path of the whole forward in three batched launches: the reference re-evaluates
+        # `compute_time_embedding` (sin/cos + Linear, SiLU, Linear) before every block (unet.py:440-520) and every ResBlock
+        # runs its own SiLU + Linear; here each level's embedding is computed once and all ResBlock rows together.
+        up_levels = list(range(len(self.channel_mult)))[::-1][:n_levels_used]
+        plan = []                                   # (ResBlock, level) in execution order
+        if not self.dwt_encoder:
+            for i, module in enumerate(ins):
+                if i > 0:
+                    plan += [(blk, start_level + int((i - 1) / (self.num_res_blocks + 1))) for blk in module]
+        plan += [(blk, self.n_levels - 1) for blk in self.middle_block]
+        for level in up_levels:
+            for out_block in self.out_f_list[level]:
+                plan += [(blk, level) for blk in out_block]
+        plan = [(blk, max(lv, 0)) for blk, lv in plan if isinstance(blk, ResBlock)]
+        lv_used = sorted({lv for _, lv in plan})
+        embs = dict(zip(lv_used, batched_time_embed([self.time_embed_list[lv] for lv in lv_used],
+                                                    timestep_embedding(timesteps, self.model_channels))))
+        precompute_emb_layers([(blk, embs[lv]) for blk, lv in plan])
+        time_emb = lambda level: embs.get(max(level, 0))     # noqa: E731  (None where no ResBlock consumes it)
+
         hs = []
         if self.dwt_encoder:
             # every encoder tensor is a channel tile of the image pyramid LL_l(x)/2^l: compute the pyramid only
@@ -202,7 +222,7 @@ class UNet_wavelet(nn.Module):
             h = None
             for i, module in enumerate(ins):
                 level = start_level + int((i - 1) / (self.num_res_blocks + 1))
-                emb = self.compute_time_embedding(timesteps=timesteps, level=level, y=y)
+                emb = time_emb(level)
                 if i == 0:
                     blk = module[0]
                     h = ops.dwtblock_nhwc(x, 0, torch.empty((x.shape[0], x.shape[2], x.shape[3], blk.out_channels),
@@ -214,8 +234,7 @@ class UNet_wavelet(nn.Module):
                 hs.append(h)
             fetch = lambda v: v
 
-        emb = self.compute_time_embedding(timesteps=timesteps, level=self.n_levels - 1, y=y)
-        h = self.middle_block.forward_nhwc(h, emb)
+        h = self.middle_block.forward_nhwc(h, time_emb(self.n_levels - 1))
         if u_net_norm:
             norms["middle"].append(compute_norm(h))
 
@@ -226,8 +245,7 @@ class UNet_wavelet(nn.Module):
         for i, level in enumerate(list(range(len(self.channel_mult)))[::-1][:n_levels_used]):
             for out_block in self.out_f_list[level]:
                 cat_in = th.cat([h, fetch(hs.pop())], dim=3)
-                emb = self.compute_time_embedding(timesteps=timesteps, level=level, y=y)
-                h = out_block.forward_nhwc(cat_in, emb)
+                h = out_block.forward_nhwc(cat_in, time_emb(level))
                 if u_net_norm:
                     norms["up"][level].append(compute_norm(h))
             gn = self.out_activation_list[i][0]
@@ -245,8 +263,7 @@ class UNet_wavelet(nn.Module):
                 if u_net_norm:
                     norms["up"][level].append(compute_norm(h))
             if not last:
-                emb = self.compute_time_embedding(timesteps=timesteps, level=level - 1, y=y)
-                h = self.out_upsample_list[level][0].forward_nhwc(h, emb)
+                h = self.out_upsample_list[level][0].forward_nhwc(h, None)      # Upsample / Identity: no embedding use
                 if u_net_norm:
                     norms["up"][level].append(compute_norm(h))
             level_inv += 1
@@ -329,10 +346,13 @@ class UNetModel(nn.Module):
             timesteps = timesteps[None]
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
-        emb = self.time_embed(timestep_embedding(timesteps, self.model_channels))
+        emb = batched_time_embed([self.time_embed], timestep_embedding(timesteps, self.model_channels))[0]
         if self.num_classes is not None:
             assert y.shape == (x.shape[0],)
             emb = emb + self.label_emb(y)
+        n_in, n_out = n_levels_used * (self.num_res_blocks + 1), n_levels_used * (self.num_res_blocks + 1) - 1
+        running = [m for m in self.input_blocks[1:n_in]] + [self.middle_block] + list(self.output_blocks[:n_out])
+        precompute_emb_layers([(blk, emb) for m in running for blk in m])       # every ResBlock's SiLU + Linear: one launch
         hs = []
         cin = x.shape[1]
         h = ops.to_nhwc(x.float(), (cin + 15) // 16 * 16)
