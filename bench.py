@@ -438,10 +438,10 @@ def run_gpu_arm(args):
         roofline = {"bound": "tensor", "kernel": "conv_fprop_kernel (fprop + dgrad launches)", "achieved": ach, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": ach / peak_tf, "frac_of_burst_peak": ach / peaks["bf16_tflops"],
                     "achieved_event_overhead_adjusted": ach_adj,
-                    # DRAM bytes of the largest launch (256->256 @ 32x32, batch 128, 111 us) in the ncu --set full capture
-                    # profiles/r01_ncu_full_conv_fprop_final_raw.csv: 68.3 MB read + 26.8 MB written (67 + 67 MB
-                    # algorithmic; part of the output is still in L2 when the kernel ends)
-                    "traffic": 95.1e6, "traffic_source": "profiles/r01_ncu_full_conv_fprop_final_raw.csv (largest launch)",
+                    # DRAM bytes of the largest launch (256->256 @ 32x32, batch 128, 106 us under ncu) in the per-launch metrics
+                    # pass profiles/r02_conv_traffic_all_launches.csv: 68.3 MB read + 21.8 MB written (67 + 67 MB
+                    # algorithmic; part of the output is still in L2 when the kernel ends), tensor pipe 83 % active
+                    "traffic": 90.1e6, "traffic_source": "profiles/r02_conv_traffic_all_launches.csv (largest launch)",
                     "event_overhead_us_subtracted": 1e3 * timer.overhead_ms(),
                     "launches_per_step": fp["launches"],
                     "flops_per_step": fp["flops"], "ms_per_step": fp["ms"],
