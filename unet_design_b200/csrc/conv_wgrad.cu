@@ -33,6 +33,7 @@ struct WgradParams {
     int N, H, W, Cin, Cout, ksize;
     int BW, BH, BNI, tiles_w, tiles_h, pix_tiles, tiles_per_split;
     int ci_tiles, ky_groups, ntaps;     // ntaps = taps handled by one CTA (3 or 1)
+    int co_tiles, pair;
     int cw_g, cw_a;                     // channel chunk width (elements) of the G and A boxes
     int stages;
     uint32_t g_stage_bytes, a_tap_bytes, tmem_cols;
@@ -49,6 +50,12 @@ struct WgradParams {
     float *dw;
 };
 
+// PAIR (template, not a run-time flag: a kernel that contains cta_group::2 instructions only launches with an even cluster
+// size): two CTAs with ADJACENT co tiles, the same ci tile / filter row / pixel range form a cluster; ONE tcgen05.mma
+// .cta_group::2 of M = 256 drives both.  Each CTA stages its own 128-channel G tile and HALF of the activation halo box (64 of
+// the 128 ci), so per MMA cycle an SM reads 96 instead of 128 bytes of operands and fills 33 instead of 45: the M = N = 128
+// single-CTA shape sits at the 128 B/clk shared-memory port.
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g,
                                                              const __grid_constant__ CUtensorMap tm_a,
                                                              const __grid_constant__ CUtensorMap tm_dw,
@@ -65,11 +72,19 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     pdl_trigger();
 
-    // blockIdx.x -> (ci tile, ky group, co tile); blockIdx.y -> pixel split
+    // blockIdx.x -> (ci tile, ky group, co tile); blockIdx.y -> pixel split.  PAIR: the co tile is the fastest index, so the two
+    // CTAs of a cluster (consecutive blockIdx.x) hold co tiles 2j and 2j + 1
     int t = blockIdx.x;
-    const int cit = t % p.ci_tiles; t /= p.ci_tiles;
-    const int kyg = t % p.ky_groups; t /= p.ky_groups;
-    const int co0 = t * 128, ci0 = cit * 128 * (p.k1wide ? p.ntaps : 1);
+    int cit, kyg, cot;
+    if constexpr (PAIR) {
+        cot = t % p.co_tiles; t /= p.co_tiles;
+        kyg = t % p.ky_groups; cit = t / p.ky_groups;
+    } else {
+        cit = t % p.ci_tiles; t /= p.ci_tiles;
+        kyg = t % p.ky_groups; cot = t / p.ky_groups;
+    }
+    const int crank = PAIR ? (int)cluster_ctarank() : 0;
+    const int co0 = cot * 128, ci0 = cit * 128 * (p.k1wide ? p.ntaps : 1);
     const int ncols = (p.Cin - ci0 < 128 ? p.Cin - ci0 : 128);          // multiple of 16
     const int mrows = (p.Cout - co0 < 128 ? p.Cout - co0 : 128);
     const int chunks_g = (mrows + p.cw_g - 1) / p.cw_g, chunks_a = (ncols + p.cw_a - 1) / p.cw_a;
@@ -86,9 +101,10 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+    if (warp == 1) { if constexpr (PAIR) tmem_alloc_pair(tmem_slot, p.tmem_cols); else tmem_alloc(tmem_slot, p.tmem_cols); }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();      // the peer's TMA loads and commits arrive on our barriers
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     pdl_wait();
@@ -100,9 +116,13 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
         {
             const bool leader = lane == 0;
             const uint32_t halo_box_bytes = (uint32_t)((p.BW + 2) * p.BH * p.BNI) * 128u;
-            const uint32_t tx_bytes = chunks_g * g_chunk_bytes +
-                                      (p.halo ? chunks_a * halo_box_bytes : p.ntaps * chunks_a * a_chunk_bytes);
+            // pair: the leader's barrier counts the bytes of both CTAs (each: its G tile + ONE 64-channel chunk of the halo box)
+            const uint32_t tx_bytes = PAIR ? 2u * (chunks_g * g_chunk_bytes + halo_box_bytes)
+                                           : chunks_g * g_chunk_bytes +
+                                                 (p.halo ? chunks_a * halo_box_bytes : p.ntaps * chunks_a * a_chunk_bytes);
             const uint32_t base = smem_u32(smem), full0 = smem_u32(full), empty0 = smem_u32(empty);
+            uint32_t full_lead = full0;                                       // cluster address of the leader's `full` barriers
+            if constexpr (PAIR) full_lead = mapa_rank(full0, 0);
             // first pixel tile of this split, then advance (x fastest, then y, then image group) incrementally
             int pt = pt0;
             int tw = pt % p.tiles_w; pt /= p.tiles_w;
@@ -114,6 +134,18 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                 const int x0 = tw * p.BW, y0 = th * p.BH, n0 = tn * p.BNI;
                 const uint32_t fb = full0 + 8u * s, sg = base + (uint32_t)s * stage_bytes;
                 mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
+                if constexpr (PAIR) {
+                    if (leader) {
+                        const uint32_t fl = full_lead + 8u * s;
+                        if (crank == 0) mbar_arrive_expect_tx_a(fb, tx_bytes);
+                        for (int c = 0; c < chunks_g; ++c)
+                            tma_load_4d_pair_a(sg + c * g_chunk_bytes, &tm_g, fl, co0 + c * p.cw_g, x0, y0, n0);
+                        tma_load_4d_pair_a(sg + p.g_stage_bytes, &tm_a, fl, ci0 + crank * 64, x0 - 1, y0 + ky, n0);
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
+                    continue;
+                }
                 if (leader) mbar_arrive_expect_tx_a(fb, tx_bytes);
                 for (int c = 0; c < chunks_g; ++c)
                     if (leader) tma_load_4d_a(sg + c * g_chunk_bytes, &tm_g, fb, co0 + c * p.cw_g, x0, y0, n0);
@@ -134,9 +166,10 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer: warp-uniform loop, lane 0 issues =====================
-        {
+        // (pair: only the leader CTA issues; its instruction drives the tensor cores of both SMs)
+        if (!(PAIR && crank != 0)) {
             const bool leader = lane == 0;
-            const uint32_t idesc = make_idesc(128, ncols, 1, 1);
+            const uint32_t idesc = make_idesc(PAIR ? 256 : 128, ncols, 1, 1);
             const uint32_t swz_g = swizzle_code(p.cw_g * 2), swz_a = swizzle_code(p.cw_a * 2);
             const uint32_t row_g = p.cw_g * 2, row_a = p.cw_a * 2;
             const uint32_t base = smem_u32(smem), full0 = smem_u32(full), empty0 = smem_u32(empty);
@@ -154,7 +187,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                 mbar_wait_a(full0 + 8u * s, ph);
                 tc_fence_after();
                 const uint64_t dg = dg0 + (uint64_t)(s * stage_step), da = da0 + (uint64_t)(s * stage_step);
-                if (p.halo) {
+                if (PAIR || p.halo) {
                     const uint64_t dh = dh0 + (uint64_t)(s * stage_step);
                     for (int tp = 0; tp < 3; ++tp) {
 #pragma unroll
@@ -163,10 +196,14 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                             // swizzle phase of a start address that is not 1024-byte aligned (descriptor bits 49..51)
                             const uint32_t bo = p.bo_mode == 0 ? 0u : p.bo_mode == 1 ? (row & 7u) : ((8u - (row & 7u)) & 7u);
                             const uint64_t db = (dh + (uint64_t)(row * 8u)) | ((uint64_t)bo << 49);
-                            if (leader) umma_bf16(tmem_base + tp * 128, dg + k * kstep_g, db, idesc, (accum | (uint32_t)k) != 0 ? 1u : 0u);
+                            if constexpr (PAIR) {
+                                if (leader) umma_bf16_pair(tmem_base + tp * 128, dg + k * kstep_g, db, idesc, (accum | (uint32_t)k) != 0 ? 1u : 0u);
+                            } else {
+                                if (leader) umma_bf16(tmem_base + tp * 128, dg + k * kstep_g, db, idesc, (accum | (uint32_t)k) != 0 ? 1u : 0u);
+                            }
                         }
                     }
-                } else
+                } else if constexpr (!PAIR) {
                 for (int tp = 0; tp < p.ntaps; ++tp) {
                     if (leader) {
 #pragma unroll
@@ -175,11 +212,16 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                                       (accum | (uint32_t)k) != 0 ? 1u : 0u);
                     }
                 }
+                }
                 accum = 1;
-                if (leader) umma_commit_a(empty0 + 8u * s);
+                if constexpr (PAIR) { if (leader) umma_commit_pair_a(empty0 + 8u * s, (uint16_t)0x3); }   // frees the slot in both CTAs
+                else if (leader) umma_commit_a(empty0 + 8u * s);
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
-            if (iters > 0 && leader) umma_commit(tmem_full);
+            if (iters > 0 && leader) {
+                if constexpr (PAIR) umma_commit_pair_a(smem_u32(tmem_full), (uint16_t)0x3);     // accumulators complete in both CTAs
+                else umma_commit(tmem_full);
+            }
         }
     } else if (iters > 0) {
         const int qd = warp & 3;
@@ -240,9 +282,10 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
         tc_fence_before();
     }
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();      // nobody exits while the leader's MMAs may still read the peer's shared memory
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, p.tmem_cols);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
     }
 }
 
@@ -449,6 +492,7 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
         p.ci_tiles /= p.ntaps;
     }
     const int co_tiles = (int)((Cout + 127) / 128);
+    p.co_tiles = co_tiles;
     const int out_tiles = p.ci_tiles * p.ky_groups * co_tiles;
     // one CTA per SM (the smem ring takes the whole SM): keep the grid within ONE wave of 148 CTAs so there is no
     // tail wave, and give every split the same number of pixel tiles
@@ -471,6 +515,12 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
     p.bo_mode = env_bo;
     p.a_chunk_stride = (uint32_t)(((p.BW + 2) * p.BH * p.BNI * 128 + 1023) & ~1023);
     p.a_halo_bytes = (uint32_t)((ncols_max + 63) / 64) * p.a_chunk_stride;
+    // CTA pairs (cta_group::2, see the kernel): halo mode, whole 128-channel ci tiles, an even number of whole co tiles.
+    // Measured on B200 (profiles/r02_wgrad_pair_probe.txt): 256->256 @ 32x32 1,200 -> 1,437 TFLOP/s, 256->256 @ 16x16 1,000 -> 1,180,
+    // 512->256 @ 16x16 1,122 -> 1,358; config-2 step 6.05 -> 5.98 ms.  UB200_WGRAD_PAIR=0 switches them off.
+    static const int env_pair = [] { const char *e = getenv("UB200_WGRAD_PAIR"); return e ? atoi(e) : 1; }();
+    p.pair = (env_pair && p.halo && !p.k1wide && Cin % 128 == 0 && Cout % 256 == 0) ? 1 : 0;
+    if (p.pair) p.a_halo_bytes = p.a_chunk_stride;          // each CTA stages ONE 64-channel chunk of the halo box
     const uint32_t stage = p.g_stage_bytes + (p.halo ? p.a_halo_bytes : p.ntaps * p.a_tap_bytes);
     int stages = (int)((200u * 1024u) / stage);
     if (stages > 6) stages = 6;
@@ -513,7 +563,9 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_err = cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     });
     if (attr_err != cudaSuccess) return (int)attr_err;
     // (the epilogue's staging ring -- 4 warps x 4 boxes x 4 KB -- re-uses the pipeline ring, which must be at least that large;
@@ -533,7 +585,7 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
                 qa[0].val.clusterDim.x = 1; qa[0].val.clusterDim.y = (unsigned)cs; qa[0].val.clusterDim.z = 1;
                 q.attrs = qa; q.numAttrs = 1;
                 int nc = -1;
-                cudaError_t qe = cudaOccupancyMaxActiveClusters(&nc, conv_wgrad_kernel, &q);
+                cudaError_t qe = cudaOccupancyMaxActiveClusters(&nc, conv_wgrad_kernel<false>, &q);
                 fprintf(stderr, "[ub200] max active clusters of %d CTAs (200 KB smem): %d (%s)\n", cs, nc, cudaGetErrorString(qe));
             }
         });
@@ -543,11 +595,15 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ub::as_stream(stream);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     ub::pdl_attr(attr[0]);
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    ub::prefer_max_smem_carveout(reinterpret_cast<const void *>(conv_wgrad_kernel));
-    cudaError_t le = cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, tg, ta, tdw, p);
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = p.pair ? 2 : 1;
+    ub::prefer_max_smem_carveout(reinterpret_cast<const void *>(conv_wgrad_kernel<false>));
+    ub::prefer_max_smem_carveout(reinterpret_cast<const void *>(conv_wgrad_kernel<true>));
+    cudaError_t le = p.pair ? cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<true>, tg, ta, tdw, p)
+                            : cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<false>, tg, ta, tdw, p);
     if (le != cudaSuccess) return (int)le;
     UB_LAUNCH_CHECK();
     return UB200_OK;
