@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
             const bool leader = lane == 0;
             const uint32_t halo_box_bytes = (uint32_t)((p.BW + 2) * p.BH * p.BNI) * 128u;
             // pair: the leader's barrier counts the bytes of both CTAs (each: its G tile + ONE 64-channel chunk of the halo box)
-            const uint32_t tx_bytes = PAIR ? 2u * (chunks_g * g_chunk_bytes + halo_box_bytes)
+            const uint32_t tx_bytes = PAIR ? 2u * (chunks_g * g_chunk_bytes + (p.halo ? halo_box_bytes : p.ntaps * a_chunk_bytes))
                                            : chunks_g * g_chunk_bytes +
                                                  (p.halo ? chunks_a * halo_box_bytes : p.ntaps * chunks_a * a_chunk_bytes);
             const uint32_t base = smem_u32(smem), full0 = smem_u32(full), empty0 = smem_u32(empty);
@@ -140,7 +140,15 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                         if (crank == 0) mbar_arrive_expect_tx_a(fb, tx_bytes);
                         for (int c = 0; c < chunks_g; ++c)
                             tma_load_4d_pair_a(sg + c * g_chunk_bytes, &tm_g, fl, co0 + c * p.cw_g, x0, y0, n0);
-                        tma_load_4d_pair_a(sg + p.g_stage_bytes, &tm_a, fl, ci0 + crank * 64, x0 - 1, y0 + ky, n0);
+                        if (p.halo) {
+                            tma_load_4d_pair_a(sg + p.g_stage_bytes, &tm_a, fl, ci0 + crank * 64, x0 - 1, y0 + ky, n0);
+                        } else {
+                            for (int tp = 0; tp < p.ntaps; ++tp) {            // one 64-channel chunk per tap and CTA
+                                const int kx = p.ksize == 3 ? tp - 1 : 0;
+                                tma_load_4d_pair_a(sg + p.g_stage_bytes + tp * p.a_tap_bytes, &tm_a, fl, ci0 + crank * 64,
+                                                   p.S * x0 + kx, p.S * y0 + ky, n0);
+                            }
+                        }
                     }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                     if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tn; } }
@@ -187,7 +195,18 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
                 mbar_wait_a(full0 + 8u * s, ph);
                 tc_fence_after();
                 const uint64_t dg = dg0 + (uint64_t)(s * stage_step), da = da0 + (uint64_t)(s * stage_step);
-                if (PAIR || p.halo) {
+                if (PAIR && !p.halo) {
+                    if constexpr (PAIR) {
+                        for (int tp = 0; tp < p.ntaps; ++tp) {
+                            if (leader) {
+#pragma unroll
+                                for (int k = 0; k < kPix / 16; ++k)
+                                    umma_bf16_pair(tmem_base + tp * 128, dg + k * kstep_g, da + tp * tap_step + k * kstep_a, idesc,
+                                                   (accum | (uint32_t)k) != 0 ? 1u : 0u);
+                            }
+                        }
+                    }
+                } else if (p.halo) {
                     const uint64_t dh = dh0 + (uint64_t)(s * stage_step);
                     for (int tp = 0; tp < 3; ++tp) {
 #pragma unroll
@@ -518,12 +537,16 @@ int ub200_conv_wgrad_strided(const void *gout, int64_t ld_g, const void *a, int6
     // CTA pairs (cta_group::2, see the kernel): halo mode, whole 128-channel ci tiles, an even number of whole co tiles.
     // Measured on B200 (profiles/r02_wgrad_pair_probe.txt): 256->256 @ 32x32 1,200 -> 1,437 TFLOP/s, 256->256 @ 16x16 1,000 -> 1,180,
     // 512->256 @ 16x16 1,122 -> 1,358; config-2 step 6.05 -> 5.98 ms.  UB200_WGRAD_PAIR=0 switches them off.
-    static const int env_pair = [] { const char *e = getenv("UB200_WGRAD_PAIR"); return e ? atoi(e) : 1; }();
-    p.pair = (env_pair && p.halo && !p.k1wide && Cin % 128 == 0 && Cout % 256 == 0) ? 1 : 0;
-    if (p.pair) p.a_halo_bytes = p.a_chunk_stride;          // each CTA stages ONE 64-channel chunk of the halo box
+    static const int env_pair = [] { const char *e = getenv("UB200_WGRAD_PAIR"); return e ? atoi(e) : 2; }();   // 1: halo layers only, 2: every eligible layer
+    p.pair = (env_pair && (p.halo || env_pair >= 2) && p.cw_a == 64 && p.cw_g == 64 && !p.k1wide && Cin % 128 == 0 && Cout % 256 == 0) ? 1 : 0;
+    if (p.pair) {           // each CTA stages ONE 64-channel chunk of the halo box / of every tap tile
+        p.a_halo_bytes = p.a_chunk_stride;
+        p.a_tap_bytes = (uint32_t)(kPix * 64 * 2);
+    }
     const uint32_t stage = p.g_stage_bytes + (p.halo ? p.a_halo_bytes : p.ntaps * p.a_tap_bytes);
+    static const int env_stages = [] { const char *e = getenv("UB200_WGRAD_STAGES"); return e ? atoi(e) : 6; }();
     int stages = (int)((200u * 1024u) / stage);
-    if (stages > 6) stages = 6;
+    if (stages > env_stages) stages = env_stages;
     if (stages > p.tiles_per_split) stages = p.tiles_per_split;
     if (stages < 1) stages = 1;
     p.stages = stages;
