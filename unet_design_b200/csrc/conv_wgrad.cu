@@ -7,9 +7,11 @@
 // CW contiguous channels (M or N) -- exactly the canonical MN-major swizzled layout -- and is consumed
 // in place.  One CTA owns a [128 co] x [<=128 ci] x [3 taps of one filter row] slab of dW: three fp32
 // accumulators in TMEM (3 x 128 columns), fed by one G tile and three shifted A tiles per 64-pixel stage
-// (the shifts are TMA coordinates; zero padding is the TMA out-of-bounds fill).  The pixel range is split
-// across CTAs (split-K) and the partial slabs are reduced with 128-bit fp32 atomics into dW, which is kept
-// in the packed [Cout, k, k, Cin] layout (= the channels_last memory of the torch weight).
+// (the shifts are TMA coordinates; zero padding is the TMA out-of-bounds fill; in halo mode the three taps are
+// row offsets into ONE haloed box).  The pixel range is split across CTAs (split-K) and the partial slabs are
+// added into dW -- kept in the packed [Cout, k, k, Cin] layout (= the channels_last memory of the torch weight)
+// -- as TMA reduce-add boxes (cp.reduce.async.bulk.tensor; per-thread 128-bit fp32 atomics only where a ci tile
+// is not whole 32-column boxes).  Layers with an even number of whole co tiles run as CTA pairs (cta_group::2).
 //
 // Replaces the wgrad half of nn.Conv2d backward at the sites listed in conv_fprop.cu.
 #include <cooperative_groups.h>
