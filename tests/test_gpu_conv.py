@@ -167,3 +167,26 @@ def test_stride2_fprop_dgrad_wgrad(ops, case):
     assert rel_err(a.grad, ar.grad.permute(0, 2, 3, 1)) < TOL
     assert rel_err(wt.grad, wr.grad) < TOL
     assert rel_err(bias.grad, br.grad) < TOL
+
+
+def test_batched_dgrad_weight_repack_is_exact(ops):
+    """`pack_dgrad_weights_batched_` (the tiled-transpose kernel that re-packs every conv's dgrad operand from the bf16 shadow
+    arena once per step) against the definition dst[ci][ky][kx][co] = src[co][k-1-ky][k-1-kx][ci]: bit-exact."""
+    torch.manual_seed(11)
+    shapes = [(256, 256, 3), (128, 384, 3), (768, 256, 1), (16, 128, 3), (128, 16, 3), (272, 80, 3), (64, 64, 1)]
+    src_off, dst_off, rows, srcs = 0, 0, [], []
+    for cout, cin, k in shapes:
+        w = torch.randn(cout, k, k, cin, device="cuda").to(torch.bfloat16)
+        srcs.append(w)
+        rows.append([src_off, dst_off, cout, cin, k])
+        src_off += (w.numel() + 7) // 8 * 8
+        dst_off += ((cin + 15) // 16 * 16 * k * k * cout + 7) // 8 * 8
+    shadow = torch.zeros(src_off, dtype=torch.bfloat16, device="cuda")
+    for w, r in zip(srcs, rows):
+        shadow[r[0]:r[0] + w.numel()] = w.reshape(-1)
+    dst = torch.full((dst_off,), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.pack_dgrad_weights_batched_(shadow, dst, torch.tensor(rows, dtype=torch.int64, device="cuda"))
+    for w, (s0, d0, cout, cin, k) in zip(srcs, rows):
+        want = w.flip(1, 2).permute(3, 1, 2, 0).contiguous()                      # [Cin, k, k, Cout], taps rotated by 180 degrees
+        got = dst[d0:d0 + want.numel()].view(cin, k, k, cout)
+        assert torch.equal(got, want), f"re-pack mismatch for Cout={cout} Cin={cin} k={k}"

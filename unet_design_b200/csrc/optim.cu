@@ -101,6 +101,45 @@ __global__ void __launch_bounds__(256) pack_dgrad_batched_kernel(const __nv_bflo
     __nv_bfloat16 *dst = dst_arena + row[1];
     const int Cout = (int)row[2], Cin = (int)row[3], k = (int)row[4];
     const int rows_pad = (Cin + 15) / 16 * 16;
+    if (Cin % 8 == 0 && Cout % 8 == 0 && ((row[0] | row[1]) & 7) == 0) {
+        // Tiled transpose, one filter tap at a time: a [64 co] x [64 ci] tile is read as 128-byte rows of the source, turned in
+        // shared memory, and written as 128-byte rows of the destination (16 bytes per thread on both sides; all index
+        // arithmetic is per tile).  The element-wise loop below needs ~100 instructions per bf16 and was issue-bound at ~150 us
+        // for 53 MB, on a second stream next to the forward pass whose GroupNorm kernels are issue-bound themselves.
+        __shared__ uint32_t tile[64][33];                     // [co][ci pair], one pad word per row
+        const int kk = k * k, co_tiles = (Cout + 63) / 64, ci_tiles = (rows_pad + 63) / 64;
+        const int ntiles = kk * co_tiles * ci_tiles;
+        const int r = threadIdx.x >> 3, q = threadIdx.x & 7;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int cit = t % ci_tiles, rest = t / ci_tiles, cot = rest % co_tiles, tap = rest / co_tiles;
+            const int ky = tap / k, kx = tap - ky * k;
+            const int src_tap = (k - 1 - ky) * k + (k - 1 - kx);
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int col = pass * 32 + r, co = cot * 64 + col, ci0 = cit * 64 + q * 8;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (co < Cout && ci0 < Cin)
+                    v = *reinterpret_cast<const uint4 *>(src + ((long long)co * kk + src_tap) * Cin + ci0);
+                uint32_t *d = &tile[col][q * 4];
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int cil = pass * 32 + r, ci = cit * 64 + cil, co0 = cot * 64 + q * 8;
+                if (ci < rows_pad && co0 < Cout) {
+                    const int w = cil >> 1, sh = (cil & 1) * 16;
+                    uint32_t h[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) h[j] = (tile[q * 8 + j][w] >> sh) & 0xffffu;
+                    const uint4 o = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                    *reinterpret_cast<uint4 *>(dst + ((long long)ci * kk + tap) * Cout + co0) = o;
+                }
+            }
+            __syncthreads();
+        }
+        return;
+    }
     const long long total = (long long)rows_pad * k * k * Cout;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int co = (int)(i % Cout);
