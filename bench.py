@@ -572,8 +572,6 @@ def run_gpu_arm_generic(args):
         t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
-        if phases is not None and "whole_step_graph_ms" in phases:
-            phases["whole_step_graph_ms"] = ms / args.steps
 
     timer = KernelTimer(_lib.ops())
     _lib._ops = timer
