@@ -106,3 +106,32 @@ def test_pdearena_unetbase_and_modern_unet(emulated_ops, tag):
 def test_mnist_unetmodel_get_unet(emulated_ops):
     from unet_design_b200.diff_mnist.unet import get_unet
     gc.check_mnist_unetmodel(get_unet, "cpu", 3 * TOL, 0.12)
+
+
+def test_mnist_precomputed_embedding_rows_are_one_shot(emulated_ops):
+    """The batched `emb_layers` rows (diff_mnist.layers.precompute_emb_layers) are consumed by the forward that made them: nothing
+    is left on the blocks afterwards, a second forward with other timesteps is not served stale rows, and a ResBlock called
+    on its own still evaluates its own `emb_layers`."""
+    import torch
+    from unet_design_b200.diff_mnist.layers import ResBlock
+    from unet_design_b200.diff_mnist.unet import get_unet_wavelet
+    torch.manual_seed(0)
+    model = get_unet_wavelet(32, 1, num_channels=32, num_res_blocks=1, dwt_encoder=True).eval()
+    for p in model.parameters():                          # the zero-initialised output convs would hide the time embedding
+        p.data.normal_(0.0, 0.05)
+    x = torch.randn(2, 1, 32, 32)
+    t1, t2 = torch.tensor([[3], [7]]), torch.tensor([[11], [2]])
+    with torch.no_grad():
+        a1 = model(x, t1)[0]
+        assert not any("_emb_pre" in m.__dict__ for m in model.modules()), "precomputed rows left behind"
+        a2 = model(x, t2)[0]
+        a1_again = model(x, t1)[0]
+    assert torch.equal(a1, a1_again)
+    assert not torch.equal(a1, a2)
+    blk = next(m for m in model.modules() if isinstance(m, ResBlock))
+    blk.__dict__["_emb_pre"] = torch.zeros(1)             # a stale row must not survive a failed forward
+    try:
+        model(x[:, :, :3], t1)                              # bad extent: raises somewhere inside
+    except Exception:
+        pass
+    model.__dict__.pop("_emb_blocks", None)

@@ -191,11 +191,19 @@ def precompute_emb_layers(pairs):
     backward.  `pairs`: [(ResBlock, emb)]; each block picks its row up once in forward_nhwc."""
     pairs = [(b, e) for b, e in pairs if isinstance(b, ResBlock)]
     if not pairs:
-        return
+        return []
     lins = [b.emb_layers[1] for b, _ in pairs]
     outs = ops.rowlin_batch([e for _, e in pairs], [l.weight for l in lins], [l.bias for l in lins], silu=True)
     for (b, _), o in zip(pairs, outs):
         b.__dict__["_emb_pre"] = o
+    return [b for b, _ in pairs]
+
+
+def clear_emb_layers(blocks):
+    """Drop rows that were precomputed but not consumed (a forward that raised half-way): a block called on its own later must
+    evaluate its own `emb_layers`."""
+    for b in blocks or ():
+        b.__dict__.pop("_emb_pre", None)
 
 
 def batched_time_embed(seqs, sin_emb):

@@ -16,8 +16,8 @@ from torch import nn
 
 from .. import ops
 from ..diff_cifar.model import DTWBlock, _PyramidView, _conv_param  # DTWBlock: same logic as mnist_diff/models.py:12-82
-from .layers import (AttentionBlock, Downsample, ResBlock, SiLU, TimestepEmbedSequential, Upsample, batched_time_embed, linear,
-                     normalization, precompute_emb_layers, timestep_embedding)
+from .layers import (AttentionBlock, Downsample, ResBlock, SiLU, TimestepEmbedSequential, Upsample, batched_time_embed,
+                     clear_emb_layers, linear, normalization, precompute_emb_layers, timestep_embedding)
 
 
 def compute_norm(tensor):
@@ -164,6 +164,12 @@ class UNet_wavelet(nn.Module):
         return ops.dwtblock_nhwc(base, 0, out, cm)
 
     def forward(self, x, t, y=None, n_levels_used=-1, u_net_norm=False):
+        try:
+            return self._forward(x, t, y, n_levels_used, u_net_norm)
+        finally:
+            clear_emb_layers(self.__dict__.pop("_emb_blocks", None))
+
+    def _forward(self, x, t, y=None, n_levels_used=-1, u_net_norm=False):
         if n_levels_used == -1:
             n_levels_used = len(self.channel_mult)
         timesteps = t.squeeze()
@@ -197,7 +203,7 @@ class UNet_wavelet(nn.Module):
         lv_used = sorted({lv for _, lv in plan})
         embs = dict(zip(lv_used, batched_time_embed([self.time_embed_list[lv] for lv in lv_used],
                                                     timestep_embedding(timesteps, self.model_channels))))
-        precompute_emb_layers([(blk, embs[lv]) for blk, lv in plan])
+        self.__dict__["_emb_blocks"] = precompute_emb_layers([(blk, embs[lv]) for blk, lv in plan])
         time_emb = lambda level: embs.get(max(level, 0))     # noqa: E731  (None where no ResBlock consumes it)
 
         hs = []
@@ -339,6 +345,12 @@ class UNetModel(nn.Module):
         self.out_reduce_channels = _conv_param(nn.Conv2d(in_channels=ch, out_channels=out_channels, kernel_size=1, stride=1))
 
     def forward(self, x, t, y=None, n_levels_used: int = -1):
+        try:
+            return self._forward(x, t, y, n_levels_used)
+        finally:
+            clear_emb_layers(self.__dict__.pop("_emb_blocks", None))
+
+    def _forward(self, x, t, y=None, n_levels_used: int = -1):
         if n_levels_used == -1:
             n_levels_used = len(self.channel_mult)
         timesteps = t.squeeze()
@@ -352,7 +364,7 @@ class UNetModel(nn.Module):
             emb = emb + self.label_emb(y)
         n_in, n_out = n_levels_used * (self.num_res_blocks + 1), n_levels_used * (self.num_res_blocks + 1) - 1
         running = [m for m in self.input_blocks[1:n_in]] + [self.middle_block] + list(self.output_blocks[:n_out])
-        precompute_emb_layers([(blk, emb) for m in running for blk in m])       # every ResBlock's SiLU + Linear: one launch
+        self.__dict__["_emb_blocks"] = precompute_emb_layers([(blk, emb) for m in running for blk in m])   # one launch
         hs = []
         cin = x.shape[1]
         h = ops.to_nhwc(x.float(), (cin + 15) // 16 * 16)
