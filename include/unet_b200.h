@@ -267,8 +267,9 @@ int ub200_conv_fprop(const ub200_conv_args *args, void *stream);
 
 /* dW[co,ky,kx,ci] += sum_{n,y,x} gout[n,y,x,co] * a[n,y+ky-p,x+kx-p,ci]   (fp32, packed layout
  * [Cout,k,k,Cin] = the channels_last memory of the torch weight).  The pixel range is split across
- * CTAs and reduced with fp32 atomics, so the call ACCUMULATES: zero dw first for a plain gradient.
- * Cin, Cout multiples of 16. */
+ * CTAs and the partial sums are ADDED into dw by the L2 (TMA reduce-add boxes; per-thread fp32 atomics
+ * when Cin is not a multiple of 32), so the call ACCUMULATES: zero dw first for a plain gradient, and
+ * the summation order is not fixed.  Cin, Cout multiples of 16; dw 16-byte aligned. */
 int ub200_conv_wgrad(const void *gout, int64_t ld_g, const void *a, int64_t ld_a,
                      int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize,
                      float *dw, void *stream);
